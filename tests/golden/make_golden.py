@@ -1,0 +1,158 @@
+"""Generate golden vectors by running the UNMODIFIED reference modules from /root/reference.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+Each reference sub-project is imported in its own process (they share flat module names
+``Module``/``Model``/``utils_``).  Shims: empty ``matplotlib``/``soundfile`` modules (plotting / IO
+only).  The script also asserts that ``oracle.seeded_*_state_dict`` reproduces the
+reference modules' default-init weights bit for bit, so fixtures only store inputs' seeds and the
+reference OUTPUTS (weights are re-generated from the seed at test time).
+"""
+import os
+import subprocess
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+
+def _shim():
+    for m in ["matplotlib", "matplotlib.pyplot", "soundfile", "webrtcvad"]:
+        sys.modules[m] = types.ModuleType(m)
+
+
+def _randn(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float32)
+
+
+def gen_fnssl():
+    _shim()
+    sys.path.insert(0, os.path.join(REF, "FN-SSL", "Lightning"))
+    import Model as ref_model          # FN-SSL/Lightning/Model.py
+    import Module as ref_module        # FN-SSL/Lightning/Module.py
+    import utils_ as ref_utils         # FN-SSL/Lightning/utils_.py
+    from oracle import fnssl_oracle as orc
+
+    out = {}
+    # ---- front end: STFT / AddChToBatch / forgetting_norm / data_preprocess (main.py:206-225)
+    sig = _randn((2, 512 + 256 * 30 + 77, 3), 11)
+    stft = ref_module.STFT(win_len=512, win_shift_ratio=0.5, nfft=512)(sig)
+    out["fe_stft_re"], out["fe_stft_im"] = stft.real.numpy(), stft.imag.numpy()
+    for mode in ("M", "MM"):
+        st = stft.permute(0, 3, 1, 2)
+        reb = ref_module.AddChToBatch(ch_mode=mode)(st)
+        mag = torch.abs(reb)
+        mu = ref_utils.forgetting_norm(mag)               # default sample_length=298
+        mu8 = ref_utils.forgetting_norm(mag, sample_length=8)
+        re = torch.real(reb) / (mu + 1e-6)
+        im = torch.imag(reb) / (mu + 1e-6)
+        feat = torch.cat((re, im), dim=1)[:, :, range(1, 257), :]
+        out[f"fe_mu_{mode}"] = mu.numpy()
+        out[f"fe_mu8_{mode}"] = mu8.numpy()
+        out[f"fe_feat_{mode}"] = feat.numpy()
+    # ---- network: FN_SSL online / offline / doa on a short clip (nt=26 -> 2 pooled frames)
+    x = _randn((2, 4, 256, 26), 12)
+    for tag, kw in (("on", dict(is_online=True)), ("off", dict(is_online=False)),
+                    ("doa", dict(is_online=True, is_doa=True))):
+        torch.manual_seed(3)
+        net = ref_model.FN_SSL(**kw).eval()
+        sd = orc.seeded_fnssl_state_dict(3, **kw)
+        ref_sd = net.state_dict()
+        assert list(sd.keys()) == list(ref_sd.keys()), (tag, "state_dict key order")
+        for k in sd:
+            assert torch.equal(sd[k], ref_sd[k]), (tag, k)
+        with torch.no_grad():
+            out[f"net_{tag}"] = net(x).numpy()
+    # ---- one FNblock (cfg1), first and non-first, small hidden
+    torch.manual_seed(5)
+    blk = ref_model.FNblock(input_size=4, hidden_size=64, is_online=True, is_first=True).eval()
+    xb = _randn((1, 10, 16, 4), 13)
+    with torch.no_grad():
+        y, fb, nbs = blk(xb)
+    out["blk_first_y"], out["blk_first_fb"], out["blk_first_nb"] = y.numpy(), fb.numpy(), nbs.numpy()
+    for k, v in blk.state_dict().items():
+        out["blk_first_sd." + k] = v.numpy()
+    torch.manual_seed(6)
+    blk2 = ref_model.FNblock(input_size=64, hidden_size=64, is_online=False, is_first=False).eval()
+    with torch.no_grad():
+        y2, fb2, nbs2 = blk2(y, fb_skip=fb, nb_skip=nbs)
+    out["blk_next_y"], out["blk_next_fb"], out["blk_next_nb"] = y2.numpy(), fb2.numpy(), nbs2.numpy()
+    for k, v in blk2.state_dict().items():
+        out["blk_next_sd." + k] = v.numpy()
+    # FN_lightning wrapper key names (FN-SSL/Model.py:92-99, loaded with expandtabs because of the TabError at :61)
+    src = open(os.path.join(REF, "FN-SSL", "Model.py")).read().expandtabs(8)
+    ns = {"__name__": "ref_fnssl_model"}
+    exec(compile(src, "FN-SSL/Model.py", "exec"), ns)
+    torch.manual_seed(0)
+    out["lightning_keys"] = np.array(list(ns["FN_lightning"]().state_dict().keys()))
+    np.savez_compressed(os.path.join(HERE, "fnssl_golden.npz"), **out)
+    print("wrote fnssl_golden.npz:", {k: v.shape for k, v in out.items() if not k.startswith('blk_') or 'sd.' not in k})
+
+
+def gen_ipdnet():
+    _shim()
+    sys.path.insert(0, os.path.join(REF, "IPDnet"))
+    import FixedAarryIPDnet as ref_ipd
+    import Module as ref_module
+    import utils_ as ref_utils
+    from oracle import fnssl_oracle as orc
+
+    out = {}
+    # front end (runIPDnetOn.py:240-254, runIPDnetOff.py:248-251); IPDnet/Module.py STFT allocates on CPU
+    sig = _randn((2, 512 + 256 * 20 + 5, 4), 21)
+    stft = ref_module.STFT(win_len=512, win_shift_ratio=0.5, nfft=512)(sig)
+    st = stft.permute(0, 3, 1, 2)
+    mag = torch.abs(st)
+    mu = ref_utils.forgetting_norm(mag, sample_length=280)
+    feat_on = torch.cat((torch.real(st) / (mu + 1e-6), torch.imag(st) / (mu + 1e-6)), dim=1)[:, :, range(1, 257), :]
+    mo = torch.mean(mag.reshape(mag.shape[0], -1), dim=1)
+    mo = mo[:, np.newaxis, np.newaxis, np.newaxis].expand(mag.shape)
+    feat_off = torch.cat((torch.real(st) / (mo + 1e-6), torch.imag(st) / (mo + 1e-6)), dim=1)[:, :, range(1, 257), :]
+    out["fe_feat_on"], out["fe_feat_off"] = feat_on.numpy(), feat_off.numpy()
+    # networks
+    cfgs = {
+        "d2": dict(input_size=4, hidden_size=128, max_track=2, is_online=True),      # default 2-mic
+        "m4": dict(input_size=8, hidden_size=256, max_track=2, is_online=True),      # cfg3 4-mic
+        "off": dict(input_size=4, hidden_size=128, max_track=2, is_online=False),
+    }
+    for tag, kw in cfgs.items():
+        torch.manual_seed(4)
+        net = ref_ipd.IPDnet(**kw).eval()
+        sd = orc.seeded_ipdnet_state_dict(4, **kw)
+        ref_sd = net.state_dict()
+        assert list(sd.keys()) == list(ref_sd.keys()), (tag, list(sd.keys()), list(ref_sd.keys()))
+        for k in sd:
+            assert torch.equal(sd[k], ref_sd[k]), (tag, k)
+        x = _randn((2, kw["input_size"], 64, 26), 22)
+        with torch.no_grad():
+            out[f"net_{tag}"] = net(x).numpy()
+            if tag == "off":
+                net.n = 12        # n_seg: 26 frames -> 3 zero-padded chunks of 12
+                out["net_off_chunked"] = net(x, offline_inference=True).numpy()
+    # CausCnnBlock alone
+    torch.manual_seed(9)
+    cnn = ref_ipd.CausCnnBlock(inp_dim=20, out_dim=4, cnn_hidden_dim=128).eval()
+    xc = _randn((2, 20, 12, 37), 23)
+    with torch.no_grad():
+        out["cnn_y"] = cnn(xc).numpy()
+    for k, v in cnn.state_dict().items():
+        out["cnn_sd." + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "ipdnet_golden.npz"), **out)
+    print("wrote ipdnet_golden.npz:", {k: v.shape for k, v in out.items() if 'sd.' not in k})
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        {"fnssl": gen_fnssl, "ipdnet": gen_ipdnet}[sys.argv[1]]()
+    else:
+        for which in ("fnssl", "ipdnet"):
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), which])

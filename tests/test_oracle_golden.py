@@ -1,0 +1,84 @@
+"""Pin the CPU oracle against outputs of the unmodified reference (tests/golden/*.npz)."""
+import numpy as np
+import torch
+
+from oracle import fnssl_oracle as orc
+
+
+def _randn(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float32)
+
+
+def _close(a, b, rel=1e-5):
+    a = torch.as_tensor(np.asarray(a)); b = torch.as_tensor(np.asarray(b))
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = float((a - b).abs().max()); ref = float(b.abs().max())
+    assert err <= rel * ref, (err, ref)
+
+
+def test_stft_matches_reference(golden_fnssl):
+    sig = _randn((2, 512 + 256 * 30 + 77, 3), 11)
+    s = orc.stft(sig)
+    assert s.shape == (2, 257, 31, 3)
+    # bit-exact frame indexing and (measured) bit-identical values vs torch.stft(center=False)
+    assert np.array_equal(s.real.numpy(), golden_fnssl["fe_stft_re"])
+    assert np.array_equal(s.imag.numpy(), golden_fnssl["fe_stft_im"])
+
+
+def test_frontend_matches_reference(golden_fnssl):
+    sig = _randn((2, 512 + 256 * 30 + 77, 3), 11)
+    spec = orc.stft(sig).permute(0, 3, 1, 2)
+    for mode in ("M", "MM"):
+        reb = orc.add_ch_to_batch(spec, mode)
+        _close(orc.forgetting_norm(reb.abs()), golden_fnssl[f"fe_mu_{mode}"], 1e-6)
+        _close(orc.forgetting_norm(reb.abs(), 8), golden_fnssl[f"fe_mu8_{mode}"], 1e-6)
+        _close(orc.preprocess_fnssl(sig, mode), golden_fnssl[f"fe_feat_{mode}"], 1e-6)
+
+
+def test_fnssl_network_matches_reference(golden_fnssl):
+    x = _randn((2, 4, 256, 26), 12)
+    for tag, kw in (("on", dict(is_online=True)), ("off", dict(is_online=False)),
+                    ("doa", dict(is_online=True, is_doa=True))):
+        sd = orc.seeded_fnssl_state_dict(3, **kw)
+        for fast in (False, True):
+            _close(orc.fnssl_forward(x, sd, fast=fast), golden_fnssl[f"net_{tag}"], 2e-5)
+
+
+def test_fnblock_matches_reference(golden_fnssl):
+    g = golden_fnssl
+    sd1 = {k[len("blk_first_sd."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("blk_first_sd.")}
+    sd2 = {k[len("blk_next_sd."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("blk_next_sd.")}
+    xb = _randn((1, 10, 16, 4), 13)
+    y, fb, nbs = orc.fnssl_block(xb, sd1, "", True)
+    _close(y, g["blk_first_y"]); _close(fb, g["blk_first_fb"]); _close(nbs, g["blk_first_nb"])
+    y2, fb2, nbs2 = orc.fnssl_block(y, sd2, "", False, nbs, fb)
+    _close(y2, g["blk_next_y"]); _close(fb2, g["blk_next_fb"]); _close(nbs2, g["blk_next_nb"])
+
+
+def test_ipdnet_frontend_matches_reference(golden_ipdnet):
+    sig = _randn((2, 512 + 256 * 20 + 5, 4), 21)
+    _close(orc.preprocess_ipdnet(sig), golden_ipdnet["fe_feat_on"], 1e-6)
+    _close(orc.preprocess_ipdnet(sig, offline=True), golden_ipdnet["fe_feat_off"], 1e-6)
+
+
+def test_ipdnet_network_matches_reference(golden_ipdnet):
+    cfgs = {
+        "d2": dict(input_size=4, hidden_size=128, max_track=2, is_online=True),
+        "m4": dict(input_size=8, hidden_size=256, max_track=2, is_online=True),
+        "off": dict(input_size=4, hidden_size=128, max_track=2, is_online=False),
+    }
+    for tag, kw in cfgs.items():
+        sd = orc.seeded_ipdnet_state_dict(4, **kw)
+        x = _randn((2, kw["input_size"], 64, 26), 22)
+        _close(orc.ipdnet_forward(x, sd, is_online=kw["is_online"]), golden_ipdnet[f"net_{tag}"], 2e-5)
+        if tag == "off":
+            _close(orc.ipdnet_forward(x, sd, is_online=False, offline_inference=True, n_seg=12, fast=True),
+                   golden_ipdnet["net_off_chunked"], 2e-5)
+
+
+def test_causcnn_matches_reference(golden_ipdnet):
+    g = golden_ipdnet
+    sd = {"conv." + k[len("cnn_sd."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("cnn_sd.")}
+    xc = _randn((2, 20, 12, 37), 23)
+    _close(orc.causcnn(xc, sd), g["cnn_y"], 1e-5)
