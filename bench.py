@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""Benchmark of the FN-SSL forward hot path (BASELINE.json: TF-frames/s, 2ch, 4 s @ 16 kHz, 512/256 STFT).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU (oracle port)
+
+A "step" = one pass of the whole path (STFT -> features -> 3 FN blocks -> DP-IPD head) over one batch of
+synthetic white-noise utterances.  1 TF-frame = one STFT frame of one network batch row through the whole path.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NSAMPLE, NCH, NT = 64000, 2, 249          # 4 s @ 16 kHz, 2 mics -> 249 frames (512/256, center=False)
+PER_GPU_BATCH = 16                        # BASELINE.json configs[1]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", default="offline", choices=["offline", "online"],
+                    help="narrow-band layer: offline = BLSTM (BASELINE configs[1] wording), online = uni-LSTM (code default)")
+    ap.add_argument("--engine", default=None, help="auto / tcgen05 / simt")
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="utterances per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def flops_per_frame(online: bool) -> float:
+    mac = 2498560 if online else 2105344          # MAC per TF-bin, SURVEY.md section 8d
+    return 2.0 * mac * 256
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(online: bool, steps: int, warmup: int, nb: int = 1):
+    """Reference algorithm on the host cores: oracle port (torch CPU kernels = what the reference's nn.LSTM /
+    torch.stft dispatch to), all host threads, one 4-s utterance per step (a bounded sample of the workload)."""
+    import torch
+    from oracle import fnssl_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = orc.seeded_fnssl_state_dict(0, is_online=online)
+    sig = orc.white_noise(nb, NSAMPLE, NCH)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            out = orc.fnssl_forward(orc.preprocess_fnssl(sig), sd, fast=True)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    assert out.shape == (nb, NT // 12, 512)
+    total = sum(times)
+    return {"value": nb * NT * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": torch.get_num_threads(),
+            "sample": f"{nb} utterance(s) of 4 s per step, {len(times)} timed steps after {warmup} warm-up"}
+
+
+def main():
+    args = parse()
+    online = args.variant == "online"
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = (f"FN-SSL 2-mic, 3 FN blocks, batch {args.batch}x4s@16kHz per GPU, 512/256 STFT, DP-IPD head, "
+                f"narrow-band={'uni-LSTM(256)' if online else 'BLSTM(2x128)'}")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(online, max(1, args.steps), max(0, args.warmup))
+        line = {"impl": "reference", "metric": "TF-frames/sec", "value": r["value"], "unit": "frames/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "variant": args.variant},
+                "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import fn_ssl_b200 as F
+    from fn_ssl_b200 import config, ops
+    from fn_ssl_b200 import distributed as D
+    from oracle import fnssl_oracle as orc   # synthetic-input generator + seeded weights + cpu_baseline only
+
+    rank, world, local = D.init_from_env("nccl")
+    if world != args.gpus and rank == 0 and world > 1:
+        print(f"[bench] note: WORLD_SIZE={world} differs from --gpus {args.gpus}", file=sys.stderr)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    net = F.FN_SSL(is_online=online).eval()
+    if rank == 0:
+        net.load_state_dict(orc.seeded_fnssl_state_dict(0, is_online=online))
+    net.to(dev)
+    wbytes = D.broadcast_weights(net, src=0)               # thin weight broadcast (NCCL)
+    net.engine = args.engine
+    eng = net._engine()
+    pipe = F.FNSSLPipeline(net)
+
+    B = args.batch
+    sig_host = orc.white_noise(B, NSAMPLE, NCH, seed=1234 + rank).pin_memory()
+    sig_dev = sig_host.to(dev)
+    counts = [B] * world
+    out_host = torch.empty((B * world, NT // 12, 512), dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        out = pipe(sig_dev)
+        return D.all_gather_outputs(out, counts)           # per-utterance outputs gathered on every rank
+
+    def step_e2e():
+        x = sig_host.to(dev, non_blocking=True)
+        out = D.all_gather_outputs(pipe(x), counts)
+        out_host.copy_(out, non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l0 = ops.LAUNCHES
+        if profile:
+            ops.profile_start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        rec = ops.profile_stop() if profile else []
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), ops.LAUNCHES - l0, rec
+
+    W, K = max(3, args.warmup), max(1, args.steps)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches, rec = timed(step_resident, K, W, profile=True)
+    ms_e2e, _, _ = timed(step_e2e, K, 1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    frames_per_step = B * world * NT
+    value = frames_per_step * K / (ms_total * 1e-3)
+    e2e_value = frames_per_step * K / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (per-launch CUDA-event durations recorded inside the timed region)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    by = {}
+    for label, flops, nbytes, a, b in rec:
+        d = by.setdefault(label, {"ms": 0.0, "n": 0, "flops": flops, "bytes": nbytes})
+        d["ms"] += a.elapsed_time(b); d["n"] += 1
+    kernels = []
+    for label, d in sorted(by.items(), key=lambda kv: -kv[1]["ms"]):
+        avg = d["ms"] / d["n"]
+        kernels.append({"kernel": label, "launches": d["n"], "avg_ms": round(avg, 4), "share_of_step": round(d["ms"] / ms_total, 4),
+                        "tflops": round(d["flops"] / (avg * 1e-3) / 1e12, 2), "hbm_gbs": round(d["bytes"] / (avg * 1e-3) / 1e9, 1)})
+    roof = None
+    if kernels:
+        top = kernels[0]
+        tensor_bound = eng == "tcgen05"
+        # SIMT engine: fp32 CUDA cores; its roof is the FP32 FMA pipe (148 SMs x 128 lanes x 2 x clock), not the tensor pipe
+        fp32_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+        peak = tf_peak if tensor_bound else fp32_peak
+        roof = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["tflops"], "peak": round(peak, 1), "unit": "TFLOP/s",
+                "frac": round(top["tflops"] / peak, 4), "traffic": None,
+                "peak_source": (peak_src + ", bf16/fp16 dense sustained") if tensor_bound else "FP32 FMA pipe, 148 SMs x 128 x 2 x max clock",
+                "hbm_achieved_gbs": top["hbm_gbs"], "hbm_peak_gbs": hbm_peak, "hbm_frac": round(top["hbm_gbs"] / hbm_peak, 4),
+                "note": "LSTM layers are tensor-pipe bound (AI 260-512 FLOP/B); hbm_frac is the figure BASELINE.json names"}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference_run(online, 3, 1)
+        cpu = {"value": round(r["value"], 1), "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    line = {
+        "metric": "TF-frames/sec", "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands / f32 accumulate+state (tcgen05)" if eng == "tcgen05" else "f32",
+        "data": "synthetic",
+        "config": {"workload": workload, "variant": args.variant, "engine": eng, "global_batch": B * world,
+                   "l2": "per-step activations (>2 GB) exceed the 126 MB L2; no explicit flush", "weights_broadcast_bytes": wbytes,
+                   "flop_per_frame": flops_per_frame(online)},
+        "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": sig_host.numel() * 4,
+                "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": round(ms_e2e / K, 4)},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels[:8], "cpu_baseline": cpu,
+        "model_tflops": round(value * flops_per_frame(online) / 1e12, 2),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,153 @@
+"""IPDnet (fixed array): drop-in for IPDnet/FixedAarryIPDnet.py (file name spelled as in the reference).
+
+    FNblock       (reference :7-40)      CausCnnBlock (:42-73)  alias CausalConv1dBlock
+    IPDnet        (:76-120)              alias FixedArrayIPDnet
+Same constructor arguments, forward layouts and state_dict keys; inference only.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import config, ops
+from .Model import _require_eval
+from .packing import LSTMParams
+
+Tensor = torch.Tensor
+
+
+class FNblock(nn.Module):
+    """Full-band BiLSTM + narrow-band LSTM with *concatenated* raw-input skips.
+    forward(x (nb,nt,nf,nc), fb_skip (nb*nt,nf,skip), nb_skip (nb*nf,nt,skip)) -> (nb, nt, nf, hidden+skip)."""
+
+    def __init__(self, input_size, hidden_size=128, dropout=0.2, add_skip_dim=4, is_online=False, is_first=False):
+        super().__init__()
+        self.input_size = input_size
+        self.full_hidden_size = hidden_size // 2
+        self.is_first = is_first
+        self.is_online = is_online
+        self.narr_hidden_size = hidden_size if is_online else hidden_size // 2
+        self.add_skip_dim = add_skip_dim
+        self.dropout = dropout
+        self.dropout_full = nn.Dropout(p=dropout)
+        self.dropout_narr = nn.Dropout(p=dropout)
+        full_in = input_size if is_first else input_size + add_skip_dim
+        self.fullLstm = LSTMParams(full_in, self.full_hidden_size, bidirectional=True)
+        self.narrLstm = LSTMParams(2 * self.full_hidden_size + add_skip_dim, self.narr_hidden_size,
+                                   bidirectional=not is_online)
+        self.engine = None
+
+    def _run(self, eng: str, x: Tensor, cx: int, raw: Tensor, craw: int) -> Tensor:
+        """x: grid with cx channels (block 1: the raw grid itself; block 2: previous narrow output), raw: raw grid.
+        Returns the narrow-band output grid N (hidden channels); the [N | raw] concat stays virtual."""
+        ec = config.engine_code(eng)
+        fh, nh = self.full_hidden_size, self.narr_hidden_size
+        if self.is_first:
+            F_, _ = ops.lstm(ec, ops.ALONG_FREQ, x, cx, None, 0, self.fullLstm.packed(ec, (cx,)), fh, 2)
+        else:
+            F_, _ = ops.lstm(ec, ops.ALONG_FREQ, x, cx, raw, craw, self.fullLstm.packed(ec, (cx, craw)), fh, 2)
+        N_, _ = ops.lstm(ec, ops.ALONG_TIME, F_, 2 * fh, raw, craw, self.narrLstm.packed(ec, (2 * fh, craw)), nh,
+                         self.narrLstm.num_dirs)
+        return N_
+
+    def forward(self, x: Tensor, fb_skip: Tensor, nb_skip: Tensor) -> Tensor:
+        _require_eval(self)
+        nb, nt, nf, nc = x.shape
+        eng = config.resolve(self.engine, (self.full_hidden_size, self.narr_hidden_size))
+        dt = config.grid_dtype(eng)
+        skip = fb_skip.reshape(nb, nt, nf, -1)
+        cs = skip.shape[-1]
+        rawg = ops.grid_copy(skip, cs, dt)
+        if self.is_first:
+            xg, cx = ops.grid_copy(x, nc, dt), nc
+        else:   # reference block input = [previous narrow output | raw skip]; feed the two parts separately
+            xg, cx = ops.grid_copy(x, nc - cs, dt), nc - cs
+        N_ = self._run(eng, xg, cx, rawg, cs)
+        return torch.cat((N_.float(), nb_skip.reshape(nb, nf, nt, -1).permute(0, 2, 1, 3).float()), dim=-1)
+
+
+class CausCnnBlock(nn.Module):
+    """3 x (Conv2d 3x3, pad (1,2), no bias, crop 2 frames) with ReLU+AvgPool(1,3), ReLU+AvgPool(1,4), tanh.
+    forward(x (nb, C, F, T)) -> (nb, out_dim, F, T//12)."""
+
+    def __init__(self, inp_dim, out_dim, cnn_hidden_dim=128, kernel=(3, 3), stride=(1, 1), padding=(1, 2)):
+        super().__init__()
+        if tuple(kernel) != (3, 3) or tuple(stride) != (1, 1) or tuple(padding) != (1, 2):
+            raise Exception("fn_ssl_b200.CausCnnBlock: only kernel (3,3), stride (1,1), padding (1,2) is implemented")
+        self.conv1 = nn.Conv2d(inp_dim, cnn_hidden_dim, kernel_size=kernel, stride=stride, padding=padding, bias=False)
+        self.conv2 = nn.Conv2d(cnn_hidden_dim, cnn_hidden_dim, kernel_size=kernel, stride=stride, padding=padding, bias=False)
+        self.conv3 = nn.Conv2d(cnn_hidden_dim, out_dim, kernel_size=kernel, stride=stride, padding=padding, bias=False)
+        self.pooling1 = nn.AvgPool2d(kernel_size=(1, 3))   # module-tree parity; fused into the conv kernels
+        self.pooling2 = nn.AvgPool2d(kernel_size=(1, 4))
+        self.pad = padding
+        self.relu = nn.ReLU(inplace=True)
+        self.tanh = nn.Tanh()
+
+    def forward_grid(self, src0: Tensor, c0: int, src1: Optional[Tensor], c1: int) -> Tensor:
+        return ops.causcnn(src0, c0, src1, c1, self.conv1.weight, self.conv2.weight, self.conv3.weight)
+
+    def forward(self, x: Tensor) -> Tensor:
+        _require_eval(self)
+        g = ops.cfirst_to_grid(x, torch.float32)
+        return self.forward_grid(g, x.shape[1], None, 0)
+
+
+class IPDnet(nn.Module):
+    """forward(x (nb, 2M, nf, nt), offline_inference=False) -> (nb, nt//12, 2*nf, M-1, 2)   (reference :91-120)."""
+
+    def __init__(self, input_size=4, hidden_size=128, max_track=2, is_online=True, n_seg=312):
+        super().__init__()
+        self.is_online = is_online
+        self.input_size = input_size
+        self.hidden_size = hidden_size
+        self.block_1 = FNblock(input_size=input_size, hidden_size=hidden_size, add_skip_dim=input_size,
+                               is_online=is_online, is_first=True)
+        self.block_2 = FNblock(input_size=hidden_size, hidden_size=hidden_size, add_skip_dim=input_size,
+                               is_online=is_online, is_first=False)
+        self.cnn_out_dim = 2 * ((input_size // 2) - 1) * max_track
+        self.cnn_inp_dim = hidden_size + input_size
+        self.conv = CausCnnBlock(inp_dim=self.cnn_inp_dim, out_dim=self.cnn_out_dim)
+        self.n = n_seg
+        self.engine = None
+
+    def _engine(self) -> str:
+        b = self.block_1
+        return config.resolve(self.engine, (b.full_hidden_size, b.narr_hidden_size))
+
+    def forward_grid(self, g0: Tensor, eng: str, nt_real: int, chunked: bool) -> Tensor:
+        """g0: raw feature grid (nb, nt, nf, ld); for chunked offline inference nt is already padded to a multiple of n_seg."""
+        _require_eval(self)
+        nb, nt, nf, _ = g0.shape
+        ci = self.input_size
+        ou_frame = nt_real // 12
+        nseg = 1
+        if chunked:                                   # fold ceil(T/n) zero-padded chunks into the batch (:97-101) -- a view
+            nseg = nt // self.n
+            g0 = g0.reshape(nb * nseg, self.n, nf, g0.shape[-1])
+        N1 = self.block_1._run(eng, g0, ci, g0, ci)
+        N2 = self.block_2._run(eng, N1, self.hidden_size, g0, ci)
+        y = self.conv.forward_grid(N2, self.hidden_size, g0, ci)                    # (nb', cout, nf, nt2)
+        nbp, nt2 = y.shape[0], y.shape[3]
+        x = y.permute(0, 3, 2, 1).reshape(nbp, nt2, nf, 2, -1).permute(0, 1, 3, 2, 4)   # :114 (tiny output tensor)
+        if chunked:
+            x = x.reshape(nbp // nseg, nt2 * nseg, 2, nf * 2, -1).permute(0, 1, 3, 4, 2)
+            return x[:, :ou_frame, :, :, :]
+        return x.reshape(nbp, nt2, 2, nf * 2, -1).permute(0, 1, 3, 4, 2)
+
+    def forward(self, x: Tensor, offline_inference: bool = False) -> Tensor:
+        _require_eval(self)
+        if x.dim() != 4 or x.shape[1] != self.input_size:
+            raise RuntimeError(f"IPDnet: expected (nb, {self.input_size}, nf, nt), got {tuple(x.shape)}")
+        eng = self._engine()
+        nt = x.shape[3]
+        chunked = (not self.is_online) and offline_inference
+        nt_alloc = (nt + self.n - 1) // self.n * self.n if chunked else None
+        g0 = ops.cfirst_to_grid(x, config.grid_dtype(eng), nt_alloc=nt_alloc)
+        return self.forward_grid(g0, eng, nt, chunked)
+
+
+FixedArrayIPDnet = IPDnet          # names used by BASELINE.json's north_star
+CausalConv1dBlock = CausCnnBlock
+FullNarrowBlock = FNblock

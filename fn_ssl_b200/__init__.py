@@ -1,0 +1,16 @@
+"""fn_ssl_b200 -- B200-native (sm_100a) forward hot path of FN-SSL / IPDnet.
+
+Drop-in module surface (same names as the reference, Audio-WestlakeU/FN-SSL):
+    fn_ssl_b200.Module            STFT, AddChToBatch, RemoveChFromBatch, forgetting_norm
+    fn_ssl_b200.Model             FNblock, FN_SSL, FN_lightning
+    fn_ssl_b200.FixedAarryIPDnet  FNblock, CausCnnBlock, IPDnet
+plus the fused end-to-end pipelines (fn_ssl_b200.pipeline) and the multi-GPU helpers (fn_ssl_b200.distributed).
+All arithmetic runs in libfnssl_b200.so (hand-written CUDA, C ABI in include/fnssl_b200.h).
+"""
+from . import config  # noqa: F401
+from .FixedAarryIPDnet import CausalConv1dBlock, CausCnnBlock, FixedArrayIPDnet, IPDnet  # noqa: F401
+from .Model import FN_SSL, FN_lightning, FNblock, FullNarrowBlock  # noqa: F401
+from .Module import STFT, AddChToBatch, RemoveChFromBatch, forgetting_norm  # noqa: F401
+from .pipeline import FNSSLPipeline, IPDnetPipeline, data_preprocess_fnssl, data_preprocess_ipdnet  # noqa: F401
+
+__version__ = "0.1.0"

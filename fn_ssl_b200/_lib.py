@@ -1,0 +1,83 @@
+"""ctypes binding of libfnssl_b200.so (include/fnssl_b200.h).  Fails loudly: there is no CPU path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfnssl_b200.so")
+_lock = threading.Lock()
+_lib = None
+
+F32, F16 = 0, 1
+ALONG_FREQ, ALONG_TIME = 0, 1
+ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
+PAIRS_M, PAIRS_MM, PAIRS_ALL = 0, 1, 2
+NORM_NONE, NORM_FORGETTING, NORM_GLOBAL = 0, 1, 2
+
+
+class LstmArgs(C.Structure):
+    """struct fnssl_lstm_args (include/fnssl_b200.h)."""
+    _fields_ = [
+        ("engine", C.c_int32), ("axis", C.c_int32),
+        ("nb", C.c_int32), ("nt", C.c_int32), ("nf", C.c_int32),
+        ("hidden", C.c_int32), ("num_dirs", C.c_int32), ("dtype", C.c_int32),
+        ("src0", C.c_void_p), ("c0", C.c_int32), ("ld0", C.c_int32),
+        ("src1", C.c_void_p), ("c1", C.c_int32), ("ld1", C.c_int32),
+        ("weights", C.c_void_p), ("weights_bytes", C.c_int64),
+        ("out0", C.c_void_p), ("out0_ld", C.c_int32), ("out0_off", C.c_int32),
+        ("addend", C.c_void_p), ("addend_ld", C.c_int32),
+        ("out1", C.c_void_p), ("out1_ld", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/fnssl_b200.h declares
+_vp, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
+SIGNATURES = {
+    "fnssl_abi_version": (_i, []),
+    "fnssl_last_error": (C.c_char_p, []),
+    "fnssl_stft_num_frames": (_i, [_i, _i, _i]),
+    "fnssl_stft_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "fnssl_norm_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "fnssl_feature_rows": (_i, [_i, _i, _i]),
+    "fnssl_feature_channels": (_i, [_i, _i]),
+    "fnssl_features_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _i, _i, _vp, _vp]),
+    "fnssl_cfirst_to_grid": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    "fnssl_grid_to_cfirst": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "fnssl_grid_copy": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i64, _i, _vp]),
+    "fnssl_grid_add": (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
+    "fnssl_lstm_forward": (_i, [C.POINTER(LstmArgs), _vp]),
+    "fnssl_ipd_head_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "fnssl_linear_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "fnssl_causcnn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "fnssl_causcnn_forward": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+}
+
+
+def load(build_if_missing: bool = True):
+    """Load the C-ABI library (building it with nvcc if it is absent and nvcc exists)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if not build_if_missing:
+                raise RuntimeError(f"{LIB_PATH} is missing: run `python -m fn_ssl_b200.build`")
+            from . import build as _build
+            _build.build()
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError if the header and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        if lib.fnssl_abi_version() != 1:
+            raise RuntimeError("libfnssl_b200.so: ABI version mismatch, rebuild it")
+        _lib = lib
+        return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().fnssl_last_error()
+        raise RuntimeError("fnssl_b200: " + (msg.decode() if msg else f"error {rc}"))

@@ -1,0 +1,490 @@
+// Front end of the FN-SSL / IPDnet hot path: batched multi-channel STFT (512/256, periodic Hann,
+// center=False), magnitude normaliser (forgetting_norm / global mean) and feature assembly.
+//
+// Reference call sites replaced (Audio-WestlakeU/FN-SSL):
+//   STFT.forward            FN-SSL/Lightning/Module.py:48-68, IPDnet/Module.py:45-63
+//   AddChToBatch.forward    FN-SSL/Lightning/Module.py:384-405
+//   forgetting_norm         FN-SSL/Lightning/utils_.py:9-55
+//   data_preprocess         FN-SSL/Lightning/main.py:206-225, IPDnet/runIPDnetOn.py:240-254, runIPDnetOff.py:248-251
+//
+// All three kernels are HBM-bound (about 4 FLOP/B); algorithmic bytes per TF-frame: 3080*M.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace fnssl {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// STFT
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kWin = 512;
+constexpr int kBins = 257;
+constexpr int kStftThreads = 256;
+constexpr int kStftWarps = kStftThreads / 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// One CTA = FR consecutive frames of one utterance, all channels.
+//  1. the sample span [(t0*hop)*nch, ...) is staged in shared memory with ONE 1-D TMA bulk copy
+//     (cp.async.bulk, completion on an mbarrier) when 16-byte aligned, else with plain loads;
+//  2. each warp runs 512-point radix-2 FFTs (one (frame, channel) job at a time) out of shared memory;
+//  3. the (FR*nch) x 257 results are transposed through shared memory so that every bin row of the
+//     (nb, 257, nt, nch) output is written as one contiguous FR*nch*8-byte run.
+__global__ void __launch_bounds__(kStftThreads)
+stft512_kernel(const float* __restrict__ signal, int nsample, int nch, int hop, int nt, int FR, int use_bulk,
+               float2* __restrict__ spec, float* __restrict__ magsum) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * FR;
+  const int nfr = min(FR, nt - t0);
+  const int span = ((nfr - 1) * hop + kWin) * nch;  // floats
+
+  float2* tw = reinterpret_cast<float2*>(smem_raw);                         // 256
+  float* hann = reinterpret_cast<float*>(tw + 256);                          // 512
+  float2* fftbuf = reinterpret_cast<float2*>(hann + kWin);                   // kStftWarps * 512
+  float2* stage = fftbuf + kStftWarps * kWin;                                // FR*nch*257
+  float* samples = reinterpret_cast<float*>(stage + (((size_t)FR * nch * kBins + 1) & ~(size_t)1));  // 16B aligned
+  __shared__ __align__(8) unsigned long long mbar;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* src = signal + ((size_t)b * nsample + (size_t)t0 * hop) * nch;
+
+  if (use_bulk) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)span * 4u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(samples)),
+          "l"(src), "r"(bytes), "r"(smem_u32(&mbar))
+          : "memory");
+    }
+  } else {
+    for (int i = tid; i < span; i += kStftThreads) samples[i] = src[i];
+  }
+  // twiddles exp(-2*pi*i*k/512) and the periodic Hann window, computed with exact-argument sinpi/cospi
+  {
+    float s, c;
+    sincospif((float)tid * (1.0f / 256.0f), &s, &c);
+    tw[tid] = make_float2(c, -s);
+    for (int n = tid; n < kWin; n += kStftThreads) hann[n] = 0.5f - 0.5f * cospif((float)n * (1.0f / 256.0f));
+  }
+  if (use_bulk) {
+    // wait for the bulk copy (phase 0); bounded spin, then trap instead of hanging the GPU
+    uint32_t done = 0;
+    for (int it = 0; it < (1 << 22) && !done; ++it) {
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+          : "=r"(done)
+          : "r"(smem_u32(&mbar)), "r"(0u)
+          : "memory");
+    }
+    if (!done) __trap();
+  }
+  __syncthreads();
+
+  float2* buf = fftbuf + warp * kWin;
+  const int njobs = nfr * nch;
+  for (int job = warp; job < njobs; job += kStftWarps) {
+    const int tl = job / nch, ch = job - tl * nch;
+    const float* x = samples + (size_t)tl * hop * nch + ch;
+    // windowed load in bit-reversed order
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int n = lane + 32 * i;
+      const int r = __brev((unsigned)n) >> 23;  // 9-bit reversal
+      buf[r] = make_float2(x[(size_t)n * nch] * hann[n], 0.0f);
+    }
+    __syncwarp();
+    // 9 radix-2 DIT stages, 256 butterflies each (8 per lane)
+#pragma unroll 1
+    for (int s = 1; s <= 9; ++s) {
+      const int half = 1 << (s - 1);
+      const int tstep = 256 >> (s - 1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = lane + 32 * i;
+        const int pos = j & (half - 1);
+        const int i0 = ((j >> (s - 1)) << s) + pos;
+        const int i1 = i0 + half;
+        const float2 w = tw[pos * tstep];
+        const float2 a = buf[i0], c = buf[i1];
+        const float2 t = make_float2(w.x * c.x - w.y * c.y, w.x * c.y + w.y * c.x);
+        buf[i0] = make_float2(a.x + t.x, a.y + t.y);
+        buf[i1] = make_float2(a.x - t.x, a.y - t.y);
+      }
+      __syncwarp();
+    }
+    // bins 0..256 -> staging; magnitude sum for the normaliser
+    float2* st = stage + (size_t)job * kBins;
+    float msum = 0.0f;
+    for (int f = lane; f < kBins; f += 32) {
+      const float2 v = buf[f];
+      st[f] = v;
+      msum += sqrtf(v.x * v.x + v.y * v.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
+    if (lane == 0 && magsum) magsum[((size_t)b * nch + ch) * nt + t0 + tl] = msum;
+    __syncwarp();
+  }
+  __syncthreads();
+  // transposed, coalesced write: spec[b][f][t0 + tl][ch], (tl, ch) fastest
+  const int run = nfr * nch;
+  for (int idx = tid; idx < kBins * run; idx += kStftThreads) {
+    const int f = idx / run, j = idx - f * run;
+    spec[((size_t)b * kBins + f) * nt * nch + (size_t)t0 * nch + j] = stage[(size_t)j * kBins + f];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// normaliser: one thread per feature row, sequential over frames (utils_.py:27-44)
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void row_channels(int r, int nch, int pairing, int& b, int& ci, int& cj) {
+  if (pairing == FNSSL_PAIRS_ALL) { b = r; ci = 0; cj = 0; return; }
+  const int P = (pairing == FNSSL_PAIRS_M) ? (nch - 1) : nch * (nch - 1) / 2;
+  b = r / P;
+  int p = r - b * P;
+  if (pairing == FNSSL_PAIRS_M) { ci = 0; cj = p + 1; return; }
+  int i = 0;
+  while (p >= nch - 1 - i) { p -= nch - 1 - i; ++i; }   // lexicographic (i<j), Module.py:398-404
+  ci = i; cj = i + 1 + p;
+}
+
+__global__ void norm_scan_kernel(const float* __restrict__ magsum, int R, int nt, int nch, int nbins, int pairing, int norm,
+                                 int sample_length, float* __restrict__ mu_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  int b, ci, cj;
+  row_channels(r, nch, pairing, b, ci, cj);
+  const int C = (pairing == FNSSL_PAIRS_ALL) ? nch : 2;
+  const float cnt = (float)(C * nbins);
+  auto frame_mean = [&](int t) {
+    float s;
+    if (pairing == FNSSL_PAIRS_ALL) {
+      s = 0.0f;
+      for (int c = 0; c < nch; ++c) s += magsum[((size_t)b * nch + c) * nt + t];
+    } else {
+      s = magsum[((size_t)b * nch + ci) * nt + t] + magsum[((size_t)b * nch + cj) * nt + t];
+    }
+    return s / cnt;
+  };
+  float* mu_row = mu_out + (size_t)r * nt;
+  if (norm == FNSSL_NORM_GLOBAL) {
+    float s = 0.0f;
+    for (int t = 0; t < nt; ++t) s += frame_mean(t);
+    const float m = s / (float)nt;
+    for (int t = 0; t < nt; ++t) mu_row[t] = m;
+    return;
+  }
+  const double alpha = (double)(sample_length - 1) / (double)(sample_length + 1);
+  float mu = 0.0f;
+  for (int t = 0; t < nt; ++t) {
+    float a, om;
+    if (t < sample_length) {
+      a = (float)fmin((double)(t - 1) / (double)(t + 1), alpha);  // fp32 tensor in the reference (:31)
+      om = 1.0f - a;
+    } else {
+      a = (float)alpha;
+      om = (float)(1.0 - alpha);
+    }
+    mu = a * mu + om * frame_mean(t);
+    mu_row[t] = mu;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// feature assembly: (nb, 257, nt, nch) complex -> grid (R, nt, 256, ld) [+ (R, C, 256, nt) f32]
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kAsmTF = 16;  // bins per tile
+constexpr int kAsmTT = 32;  // frames per tile
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+assemble_kernel(const float2* __restrict__ spec, const float* __restrict__ mu, int nb, int nt, int nch, int pairing,
+                int norm, float eps, T* __restrict__ feat, int ld, float* __restrict__ feat_cfirst) {
+  extern __shared__ float2 tile[];  // [kAsmTF][kAsmTT][nch]
+  const int b = blockIdx.z;
+  const int f0 = 1 + blockIdx.y * kAsmTF;  // spectrum bin of the first feature bin in the tile
+  const int t0 = blockIdx.x * kAsmTT;
+  const int tn = min(kAsmTT, nt - t0);
+  const int tid = threadIdx.x;
+  // coalesced read: for each bin a contiguous run of tn*nch complex values
+  const int runlen = tn * nch;
+  for (int idx = tid; idx < kAsmTF * runlen; idx += blockDim.x) {
+    const int fl = idx / runlen, j = idx - fl * runlen;
+    tile[(size_t)fl * kAsmTT * nch + j] = spec[((size_t)b * kBins + f0 + fl) * nt * nch + (size_t)t0 * nch + j];
+  }
+  __syncthreads();
+  const bool all = (pairing == FNSSL_PAIRS_ALL);
+  const int P = all ? 1 : (pairing == FNSSL_PAIRS_M ? nch - 1 : nch * (nch - 1) / 2);
+  const int C = all ? 2 * nch : 4;
+  const int half = C / 2;
+  for (int p = 0; p < P; ++p) {
+    const int r = b * P + p;
+    int bb, ci, cj;
+    row_channels(r, nch, pairing, bb, ci, cj);
+    // grid write: (t, f, c), c fastest
+    for (int idx = tid; idx < tn * kAsmTF * ld; idx += blockDim.x) {
+      const int c = idx % ld;
+      const int fl = (idx / ld) % kAsmTF;
+      const int tl = idx / (ld * kAsmTF);
+      float v = 0.0f;
+      if (c < C) {
+        const int k = (c < half) ? c : c - half;
+        const int ch = all ? k : (k == 0 ? ci : cj);
+        const float2 x = tile[((size_t)fl * kAsmTT + tl) * nch + ch];
+        v = (c < half) ? x.x : x.y;
+        if (norm != FNSSL_NORM_NONE) v = v / (mu[(size_t)r * nt + t0 + tl] + eps);
+      }
+      st_act<T>(feat + (((size_t)r * nt + t0 + tl) * 256 + (f0 - 1 + fl)) * ld + c, v);
+    }
+    if (feat_cfirst) {
+      for (int idx = tid; idx < C * kAsmTF * tn; idx += blockDim.x) {
+        const int tl = idx % tn;
+        const int fl = (idx / tn) % kAsmTF;
+        const int c = idx / (tn * kAsmTF);
+        const int k = (c < half) ? c : c - half;
+        const int ch = all ? k : (k == 0 ? ci : cj);
+        const float2 x = tile[((size_t)fl * kAsmTT + tl) * nch + ch];
+        float v = (c < half) ? x.x : x.y;
+        if (norm != FNSSL_NORM_NONE) v = v / (mu[(size_t)r * nt + t0 + tl] + eps);
+        feat_cfirst[(((size_t)r * C + c) * 256 + (f0 - 1 + fl)) * nt + t0 + tl] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout converters
+// ------------------------------------------------------------------------------------------------
+
+// (nb, C, nf, nt) f32 -> grid (nb, nt, nf, ld)[ch_off + c].  CTA = (b, f, 32 frames), all channels.
+template <typename T>
+__global__ void cfirst_to_grid_kernel(const float* __restrict__ src, int C, int nf, int nt, T* __restrict__ dst, int ld,
+                                      int ch_off) {
+  extern __shared__ float ctile[];  // [C][33]
+  const int b = blockIdx.z, f = blockIdx.y, t0 = blockIdx.x * 32;
+  const int tn = min(32, nt - t0);
+  for (int idx = threadIdx.x; idx < C * 32; idx += blockDim.x) {
+    const int c = idx >> 5, tl = idx & 31;
+    if (tl < tn) ctile[c * 33 + tl] = src[(((size_t)b * C + c) * nf + f) * nt + t0 + tl];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < tn * C; idx += blockDim.x) {
+    const int tl = idx / C, c = idx - tl * C;
+    st_act<T>(dst + (((size_t)b * nt + t0 + tl) * nf + f) * ld + ch_off + c, ctile[c * 33 + tl]);
+  }
+}
+
+template <typename T>
+__global__ void grid_to_cfirst_kernel(const T* __restrict__ src, int ld, int ch_off, int C, int nf, int nt,
+                                      float* __restrict__ dst) {
+  extern __shared__ float ctile[];  // [C][33]
+  const int b = blockIdx.z, f = blockIdx.y, t0 = blockIdx.x * 32;
+  const int tn = min(32, nt - t0);
+  for (int idx = threadIdx.x; idx < tn * C; idx += blockDim.x) {
+    const int tl = idx / C, c = idx - tl * C;
+    ctile[c * 33 + tl] = ld_act<T>(src + (((size_t)b * nt + t0 + tl) * nf + f) * ld + ch_off + c);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < C * 32; idx += blockDim.x) {
+    const int c = idx >> 5, tl = idx & 31;
+    if (tl < tn) dst[(((size_t)b * C + c) * nf + f) * nt + t0 + tl] = ctile[c * 33 + tl];
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void grid_copy_kernel(const TS* __restrict__ src, int src_ld, int src_off, TD* __restrict__ dst, int dst_ld,
+                                 int dst_off, int64_t npos, int C) {
+  const int64_t total = npos * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / C;
+    const int c = (int)(i - p * C);
+    st_act<TD>(dst + p * dst_ld + dst_off + c, ld_act<TS>(src + p * src_ld + src_off + c));
+  }
+}
+
+template <typename T>
+__global__ void grid_add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    st_act<T>(dst + i, ld_act<T>(a + i) + ld_act<T>(b + i));
+}
+
+}  // namespace fnssl
+
+using namespace fnssl;
+
+extern "C" {
+
+int fnssl_abi_version(void) { return FNSSL_ABI_VERSION; }
+const char* fnssl_last_error(void) { return fnssl::g_err; }
+
+int fnssl_stft_num_frames(int nsample, int win_len, int hop) {
+  if (nsample < win_len || hop <= 0) return 0;
+  return (nsample - win_len) / hop + 1;
+}
+
+int fnssl_stft_forward(const float* signal, int nb, int nsample, int nch, int win_len, int hop, int nfft, float* spec,
+                       float* magsum, void* stream) {
+  FNSSL_REQUIRE(win_len == 512 && nfft == 512, "stft: only win_len = nfft = 512 is implemented (got %d/%d)", win_len, nfft);
+  FNSSL_REQUIRE(hop > 0 && hop <= 512, "stft: hop must be in (0, 512] (got %d)", hop);
+  FNSSL_REQUIRE(nb > 0 && nch > 0 && nch <= 64, "stft: bad nb/nch (%d/%d)", nb, nch);
+  const int nt = fnssl_stft_num_frames(nsample, win_len, hop);
+  FNSSL_REQUIRE(nt > 0, "stft: signal shorter than one window (nsample=%d)", nsample);
+  FNSSL_REQUIRE(signal && spec, "stft: null pointer");
+  int FR = 16 / nch;
+  if (FR < 1) FR = 1;
+  if (FR > nt) FR = nt;
+  const size_t span = ((size_t)(FR - 1) * hop + kWin) * nch;
+  const size_t smem = 256 * sizeof(float2) + kWin * sizeof(float) + (size_t)kStftWarps * kWin * sizeof(float2) +
+                      (((size_t)FR * nch * kBins + 1) & ~(size_t)1) * sizeof(float2) + span * sizeof(float);
+  FNSSL_REQUIRE(smem <= 200 * 1024, "stft: too many channels for one CTA (%d)", nch);
+  const int use_bulk = ((reinterpret_cast<uintptr_t>(signal) & 15) == 0) && (((size_t)hop * nch * 4) % 16 == 0) &&
+                       (((size_t)nsample * nch * 4) % 16 == 0) && (((size_t)kWin * nch * 4) % 16 == 0);
+  FNSSL_CUDA(cudaFuncSetAttribute(stft512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((nt + FR - 1) / FR, nb);
+  stft512_kernel<<<grid, kStftThreads, smem, (cudaStream_t)stream>>>(signal, nsample, nch, hop, nt, FR, use_bulk,
+                                                                    reinterpret_cast<float2*>(spec), magsum);
+  FNSSL_LAUNCH_CHECK("stft512_kernel");
+  return 0;
+}
+
+int fnssl_feature_rows(int nb, int nch, int pairing) {
+  if (pairing == FNSSL_PAIRS_M) return nb * (nch - 1);
+  if (pairing == FNSSL_PAIRS_MM) return nb * (nch * (nch - 1) / 2);
+  return nb;
+}
+int fnssl_feature_channels(int nch, int pairing) { return pairing == FNSSL_PAIRS_ALL ? 2 * nch : 4; }
+
+int fnssl_norm_forward(const float* magsum, int nb, int nch, int nt, int nbins, int pairing, int norm, int sample_length,
+                       float* mu, void* stream) {
+  FNSSL_REQUIRE(magsum && mu && nb > 0 && nch > 0 && nt > 0 && nbins > 0, "norm: bad arguments");
+  FNSSL_REQUIRE(pairing >= 0 && pairing <= 2, "norm: bad pairing %d", pairing);
+  FNSSL_REQUIRE(norm == FNSSL_NORM_FORGETTING || norm == FNSSL_NORM_GLOBAL, "norm: bad norm %d", norm);
+  FNSSL_REQUIRE(pairing == FNSSL_PAIRS_ALL || nch >= 2, "norm: pair modes need >= 2 channels");
+  const int R = fnssl_feature_rows(nb, nch, pairing);
+  norm_scan_kernel<<<(R + 127) / 128, 128, 0, (cudaStream_t)stream>>>(magsum, R, nt, nch, nbins, pairing, norm, sample_length, mu);
+  FNSSL_LAUNCH_CHECK("norm_scan_kernel");
+  return 0;
+}
+
+int fnssl_features_forward(const float* spec, const float* magsum, int nb, int nt, int nch, int pairing, int norm,
+                           int sample_length, float eps, float* mu, void* feat, int dtype, int ld, float* feat_cfirst,
+                           void* stream) {
+  FNSSL_REQUIRE(pairing >= 0 && pairing <= 2, "features: bad pairing %d", pairing);
+  FNSSL_REQUIRE(norm >= 0 && norm <= 2, "features: bad norm %d", norm);
+  FNSSL_REQUIRE(pairing == FNSSL_PAIRS_ALL || nch >= 2, "features: pair modes need >= 2 channels");
+  FNSSL_REQUIRE(dtype == FNSSL_F32 || dtype == FNSSL_F16, "features: bad dtype %d", dtype);
+  const int C = fnssl_feature_channels(nch, pairing);
+  const int R = fnssl_feature_rows(nb, nch, pairing);
+  FNSSL_REQUIRE(ld >= C, "features: ld (%d) < channels (%d)", ld, C);
+  FNSSL_REQUIRE(spec && feat && (norm == FNSSL_NORM_NONE || (magsum && mu)), "features: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (norm != FNSSL_NORM_NONE) {
+    if (fnssl_norm_forward(magsum, nb, nch, nt, kBins, pairing, norm, sample_length, mu, stream)) return 1;
+  }
+  dim3 grid((nt + kAsmTT - 1) / kAsmTT, 256 / kAsmTF, nb);
+  const size_t smem = (size_t)kAsmTF * kAsmTT * nch * sizeof(float2);
+  if (dtype == FNSSL_F32) {
+    FNSSL_CUDA(cudaFuncSetAttribute(assemble_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    assemble_kernel<float><<<grid, 256, smem, st>>>(reinterpret_cast<const float2*>(spec), mu, nb, nt, nch, pairing, norm,
+                                                    eps, (float*)feat, ld, feat_cfirst);
+  } else {
+    FNSSL_CUDA(cudaFuncSetAttribute(assemble_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    assemble_kernel<__half><<<grid, 256, smem, st>>>(reinterpret_cast<const float2*>(spec), mu, nb, nt, nch, pairing, norm,
+                                                     eps, (__half*)feat, ld, feat_cfirst);
+  }
+  FNSSL_LAUNCH_CHECK("assemble_kernel");
+  return 0;
+}
+
+int fnssl_cfirst_to_grid(const float* src, int nb, int C, int nf, int nt, void* dst, int dtype, int ld, int ch_off,
+                         void* stream) {
+  FNSSL_REQUIRE(src && dst && nb > 0 && C > 0 && nf > 0 && nt > 0, "cfirst_to_grid: bad arguments");
+  FNSSL_REQUIRE(ld >= ch_off + C && ch_off >= 0, "cfirst_to_grid: ld %d < ch_off %d + C %d", ld, ch_off, C);
+  FNSSL_REQUIRE(nf <= 65535 && nb <= 65535, "cfirst_to_grid: grid too large");
+  dim3 grid((nt + 31) / 32, nf, nb);
+  const size_t smem = (size_t)C * 33 * sizeof(float);
+  FNSSL_REQUIRE(smem <= 200 * 1024, "cfirst_to_grid: too many channels (%d)", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FNSSL_F32) {
+    FNSSL_CUDA(cudaFuncSetAttribute(cfirst_to_grid_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfirst_to_grid_kernel<float><<<grid, 128, smem, st>>>(src, C, nf, nt, (float*)dst, ld, ch_off);
+  } else if (dtype == FNSSL_F16) {
+    FNSSL_CUDA(cudaFuncSetAttribute(cfirst_to_grid_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfirst_to_grid_kernel<__half><<<grid, 128, smem, st>>>(src, C, nf, nt, (__half*)dst, ld, ch_off);
+  } else {
+    FNSSL_FAIL("cfirst_to_grid: bad dtype %d", dtype);
+  }
+  FNSSL_LAUNCH_CHECK("cfirst_to_grid_kernel");
+  return 0;
+}
+
+int fnssl_grid_to_cfirst(const void* src, int dtype, int ld, int ch_off, int nb, int C, int nf, int nt, float* dst,
+                         void* stream) {
+  FNSSL_REQUIRE(src && dst && nb > 0 && C > 0 && nf > 0 && nt > 0, "grid_to_cfirst: bad arguments");
+  FNSSL_REQUIRE(ld >= ch_off + C && ch_off >= 0, "grid_to_cfirst: ld %d < ch_off %d + C %d", ld, ch_off, C);
+  FNSSL_REQUIRE(nf <= 65535 && nb <= 65535, "grid_to_cfirst: grid too large");
+  dim3 grid((nt + 31) / 32, nf, nb);
+  const size_t smem = (size_t)C * 33 * sizeof(float);
+  FNSSL_REQUIRE(smem <= 200 * 1024, "grid_to_cfirst: too many channels (%d)", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FNSSL_F32) {
+    FNSSL_CUDA(cudaFuncSetAttribute(grid_to_cfirst_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    grid_to_cfirst_kernel<float><<<grid, 128, smem, st>>>((const float*)src, ld, ch_off, C, nf, nt, dst);
+  } else if (dtype == FNSSL_F16) {
+    FNSSL_CUDA(cudaFuncSetAttribute(grid_to_cfirst_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    grid_to_cfirst_kernel<__half><<<grid, 128, smem, st>>>((const __half*)src, ld, ch_off, C, nf, nt, dst);
+  } else {
+    FNSSL_FAIL("grid_to_cfirst: bad dtype %d", dtype);
+  }
+  FNSSL_LAUNCH_CHECK("grid_to_cfirst_kernel");
+  return 0;
+}
+
+int fnssl_grid_copy(const void* src, int src_dtype, int src_ld, int src_off, void* dst, int dst_dtype, int dst_ld,
+                    int dst_off, int64_t npos, int C, void* stream) {
+  FNSSL_REQUIRE(src && dst && npos > 0 && C > 0, "grid_copy: bad arguments");
+  FNSSL_REQUIRE(src_ld >= src_off + C && dst_ld >= dst_off + C, "grid_copy: channel window out of range");
+  const int64_t total = npos * C;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+#define FNSSL_GC(TS, TD) \
+  grid_copy_kernel<TS, TD><<<blocks, 256, 0, st>>>((const TS*)src, src_ld, src_off, (TD*)dst, dst_ld, dst_off, npos, C)
+  if (src_dtype == FNSSL_F32 && dst_dtype == FNSSL_F32) FNSSL_GC(float, float);
+  else if (src_dtype == FNSSL_F32 && dst_dtype == FNSSL_F16) FNSSL_GC(float, __half);
+  else if (src_dtype == FNSSL_F16 && dst_dtype == FNSSL_F32) FNSSL_GC(__half, float);
+  else if (src_dtype == FNSSL_F16 && dst_dtype == FNSSL_F16) FNSSL_GC(__half, __half);
+  else FNSSL_FAIL("grid_copy: bad dtype %d/%d", src_dtype, dst_dtype);
+#undef FNSSL_GC
+  FNSSL_LAUNCH_CHECK("grid_copy_kernel");
+  return 0;
+}
+
+int fnssl_grid_add(const void* a, const void* b, void* dst, int dtype, int64_t n, void* stream) {
+  FNSSL_REQUIRE(a && b && dst && n > 0, "grid_add: bad arguments");
+  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  if (dtype == FNSSL_F32) grid_add_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)a, (const float*)b, (float*)dst, n);
+  else if (dtype == FNSSL_F16) grid_add_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (__half*)dst, n);
+  else FNSSL_FAIL("grid_add: bad dtype %d", dtype);
+  FNSSL_LAUNCH_CHECK("grid_add_kernel");
+  return 0;
+}
+
+}  // extern "C"

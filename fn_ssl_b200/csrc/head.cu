@@ -1,0 +1,96 @@
+// Output heads of the FN-SSL path.
+//   fnssl_ipd_head_forward : AvgPool2d((12,1)) -> Linear(C,2) -> tanh -> [ch0 over f | ch1 over f]
+//                            (FN-SSL/Lightning/Model.py:79-87)
+//   fnssl_linear_forward   : the DOA classifier Linear(512,180) (Model.py:71,88-89)
+// Both are HBM-bound single-pass kernels; the head reads the last narrow-band output exactly once.
+#include "common.cuh"
+
+namespace fnssl {
+
+// one warp per (b, t2, f): 12 frames x C channels -> 2 outputs
+template <typename T>
+__global__ void __launch_bounds__(256)
+ipd_head_kernel(const T* __restrict__ x, int ld, int nb, int nt, int nf, int C, const float* __restrict__ w,
+                const float* __restrict__ bias, float* __restrict__ out) {
+  const int nt2 = nt / 12;
+  const int64_t total = (int64_t)nb * nt2 * nf;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= total) return;
+  const int f = (int)(warp % nf);
+  const int t2 = (int)((warp / nf) % nt2);
+  const int b = (int)(warp / ((int64_t)nf * nt2));
+  float a0 = 0.0f, a1 = 0.0f;
+  for (int c = lane; c < C; c += 32) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) s += ld_act<T>(x + (((int64_t)b * nt + t2 * 12 + k) * nf + f) * ld + c);
+    s *= (1.0f / 12.0f);
+    a0 = fmaf(s, w[c], a0);
+    a1 = fmaf(s, w[C + c], a1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  if (lane == 0) {
+    float* o = out + ((int64_t)b * nt2 + t2) * (2 * nf);
+    o[f] = tanhf(a0 + bias[0]);
+    o[nf + f] = tanhf(a1 + bias[1]);
+  }
+}
+
+// y[r][o] = b[o] + sum_k x[r][k] w[o][k]; one CTA per row, x row staged in shared memory
+__global__ void __launch_bounds__(256)
+linear_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, int in_f,
+                   int out_f, float* __restrict__ y) {
+  extern __shared__ float xs[];
+  const int r = blockIdx.x;
+  for (int k = threadIdx.x; k < in_f; k += blockDim.x) xs[k] = x[(size_t)r * in_f + k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int o = warp; o < out_f; o += nwarp) {
+    float a = 0.0f;
+    for (int k = lane; k < in_f; k += 32) a = fmaf(xs[k], w[(size_t)o * in_f + k], a);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+    if (lane == 0) y[(size_t)r * out_f + o] = a + b[o];
+  }
+}
+
+}  // namespace fnssl
+
+using namespace fnssl;
+
+extern "C" {
+
+int fnssl_ipd_head_forward(const void* x, int dtype, int ld, int nb, int nt, int nf, int C, const float* w, const float* b,
+                           float* out, void* stream) {
+  FNSSL_REQUIRE(x && w && b && out, "ipd_head: null pointer");
+  FNSSL_REQUIRE(nb > 0 && nf > 0 && C > 0 && ld >= C, "ipd_head: bad shape");
+  if (nt / 12 == 0) return 0;
+  const int64_t warps = (int64_t)nb * (nt / 12) * nf;
+  const int64_t blocks = (warps * 32 + 255) / 256;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FNSSL_F32)
+    ipd_head_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, ld, nb, nt, nf, C, w, b, out);
+  else if (dtype == FNSSL_F16)
+    ipd_head_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, ld, nb, nt, nf, C, w, b, out);
+  else
+    FNSSL_FAIL("ipd_head: bad dtype %d", dtype);
+  FNSSL_LAUNCH_CHECK("ipd_head_kernel");
+  return 0;
+}
+
+int fnssl_linear_forward(const float* x, const float* w, const float* b, int rows, int in_features, int out_features,
+                         float* y, void* stream) {
+  FNSSL_REQUIRE(x && w && b && y, "linear: null pointer");
+  FNSSL_REQUIRE(rows >= 0 && in_features > 0 && out_features > 0 && in_features <= 12288, "linear: bad shape");
+  if (rows == 0) return 0;
+  linear_rows_kernel<<<rows, 256, in_features * sizeof(float), (cudaStream_t)stream>>>(x, w, b, in_features, out_features, y);
+  FNSSL_LAUNCH_CHECK("linear_rows_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+"""Multi-GPU inference plumbing: one process per GPU (torch.distributed, NCCL over NVLink 5 / NVSwitch).
+
+The path shards over utterances with no data-path exchange (every utterance / mic pair is independent through
+the whole forward); the only collectives are
+    * one broadcast of the flat weight buffer at start-up (what Lightning's DDP wrapper does at wrap time,
+      FN-SSL/Lightning/main.py:286-288), and
+    * one all-gather of the per-utterance outputs per batch (<= 1.3 MB per rank).
+Works with the gloo backend on CPU tensors too (used by the world_size-2 tests).
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+Tensor = torch.Tensor
+
+
+def init_from_env(backend: str = "nccl") -> Tuple[int, int, int]:
+    """Initialise the default process group from torchrun's environment; returns (rank, world, local_rank)."""
+    import os
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend="nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of n_items for `rank`; the first n_items % world ranks get one extra item."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+@torch.no_grad()
+def broadcast_weights(module: nn.Module, src: int = 0) -> int:
+    """Broadcast every parameter and buffer of `module` from rank `src` as ONE flat buffer; returns bytes sent."""
+    tensors = [p.data for p in module.parameters()] + [b.data for b in module.buffers()]
+    if not tensors:
+        return 0
+    flat = torch.cat([t.reshape(-1).float() for t in tensors])
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(flat, src=src)
+        off = 0
+        for t in tensors:
+            n = t.numel()
+            t.copy_(flat[off:off + n].reshape(t.shape).to(t.dtype))
+            off += n
+    return flat.numel() * 4
+
+
+@torch.no_grad()
+def all_gather_outputs(local_out: Tensor, counts: List[int]) -> Tensor:
+    """Gather per-rank output shards (counts[r] utterances each, identical trailing shape) in rank order."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local_out
+    world = dist.get_world_size()
+    assert len(counts) == world and local_out.shape[0] == counts[dist.get_rank()]
+    mx = max(counts)
+    tail = tuple(local_out.shape[1:])
+    padded = local_out.new_zeros((mx,) + tail)
+    padded[: local_out.shape[0]] = local_out
+    out = local_out.new_empty((world * mx,) + tail)
+    dist.all_gather_into_tensor(out, padded.contiguous())
+    if all(c == mx for c in counts):
+        return out
+    return torch.cat([out[r * mx: r * mx + counts[r]] for r in range(world)], dim=0)

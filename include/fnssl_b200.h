@@ -1,0 +1,163 @@
+/*
+ * fnssl_b200 -- C ABI of the B200-native (sm_100a) FN-SSL / IPDnet forward hot path.
+ *
+ * The reference (Audio-WestlakeU/FN-SSL) has no FFI: its "plugin surface" for this path is the
+ * Python nn.Module contract.  This header is the drop-in boundary one level
+ * below it: plain device pointers and sizes, no torch types.  Each entry point names the reference
+ * call site it replaces.  fn_ssl_b200/{Module,Model,FixedAarryIPDnet}.py bind these through ctypes
+ * and re-create the reference's module classes on top.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated; `stream` is a cudaStream_t passed as void*;
+ *   - all functions enqueue work on `stream` and return immediately; 0 = ok, non-zero = error
+ *     (message via fnssl_last_error(), thread-local); nothing aborts, nothing falls back to the CPU;
+ *   - "grid" tensors are channels-last  (nb, nt, nf, C)  with a channel stride `ld >= C`
+ *     (element (b,t,f,c) at ((b*nt + t)*nf + f)*ld + c) in fp32 or fp16 (FNSSL_F32 / FNSSL_F16);
+ *   - the reference's own layouts ((nb,C,nf,nt) network input, (nb,nf,nt,nch) complex STFT,
+ *     (nb,nt//12,2nf) IPD output ...) are produced / consumed by the entry points below as documented.
+ */
+#ifndef FNSSL_B200_H_
+#define FNSSL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FNSSL_ABI_VERSION 1
+
+/* element types of grid tensors */
+#define FNSSL_F32 0
+#define FNSSL_F16 1
+
+/* recurrence axis of an LSTM pass over a (nb, nt, nf, C) grid */
+#define FNSSL_ALONG_FREQ 0 /* full-band:   sequences = (b,t) rows, steps = f   (Model.py:35-38)  */
+#define FNSSL_ALONG_TIME 1 /* narrow-band: sequences = (b,f) rows, steps = t   (Model.py:41-46)  */
+
+/* LSTM engine */
+#define FNSSL_ENGINE_SIMT 0    /* fp32 CUDA-core kernel, fp32 or fp16 grids, any shape            */
+#define FNSSL_ENGINE_TCGEN05 1 /* tcgen05/TMEM/TMA kernel, fp16 operands, fp32 accumulate + state */
+
+/* channel pairing of the feature front end */
+#define FNSSL_PAIRS_M 0   /* AddChToBatch('M'):  rows (ref 0, m)          Module.py:390-396 */
+#define FNSSL_PAIRS_MM 1  /* AddChToBatch('MM'): all i<j pairs            Module.py:398-404 */
+#define FNSSL_PAIRS_ALL 2 /* IPDnet: no re-batching, all mics as channels runIPDnetOn.py:246 */
+
+/* magnitude normalisation */
+#define FNSSL_NORM_NONE 0
+#define FNSSL_NORM_FORGETTING 1 /* utils_.py:9-55  */
+#define FNSSL_NORM_GLOBAL 2     /* runIPDnetOff.py:248-251 */
+
+int fnssl_abi_version(void);
+const char* fnssl_last_error(void);
+
+/* ---- front end ------------------------------------------------------------------------------ */
+
+/* nt = floor((nsample - win_len) / hop + 1), FN-SSL/Module.py:56 */
+int fnssl_stft_num_frames(int nsample, int win_len, int hop);
+
+/* Replaces STFT.forward (FN-SSL/Lightning/Module.py:48-68; IPDnet/Module.py:45-63): framed,
+ * periodic-Hann-windowed, un-normalised one-sided 512-point FFT, center=False.
+ *   signal : (nb, nsample, nch) f32        spec : (nb, 257, nt, nch) complex64 (interleaved re,im)
+ *   magsum : optional (nb, nch, nt) f32 = sum over the 257 bins of |X| (feeds the normaliser), or NULL
+ * Only win_len = nfft = 512 is implemented (the value hard-coded by every caller, main.py:38-44). */
+int fnssl_stft_forward(const float* signal, int nb, int nsample, int nch, int win_len, int hop, int nfft,
+                       float* spec, float* magsum, void* stream);
+
+/* The normaliser alone (forgetting_norm, FN-SSL/Lightning/utils_.py:9-55; global mean, runIPDnetOff.py:248-251).
+ *   magsum : (nb, nch, nt) f32 sums of |X| over `nbins` bins;  mu : (R, nt) f32, R = fnssl_feature_rows() */
+int fnssl_norm_forward(const float* magsum, int nb, int nch, int nt, int nbins, int pairing, int norm,
+                       int sample_length, float* mu, void* stream);
+
+/* rows of the feature tensor for a pairing mode: nb*(nch-1), nb*nch*(nch-1)/2 or nb */
+int fnssl_feature_rows(int nb, int nch, int pairing);
+/* channels of the feature tensor: 4 for pair modes, 2*nch for FNSSL_PAIRS_ALL */
+int fnssl_feature_channels(int nch, int pairing);
+
+/* Replaces the body of data_preprocess (FN-SSL/Lightning/main.py:206-225; IPDnet/runIPDnetOn.py:240-254;
+ * runIPDnetOff.py:248-251): pair re-batching + |X| + forgetting_norm / global mean + re,im / (mu+eps) +
+ * cat + bins 1..256.
+ *   spec, magsum : outputs of fnssl_stft_forward
+ *   mu    : workspace AND output, (R, nt) f32 -- the normaliser the reference returns from forgetting_norm
+ *   feat  : grid (R, nt, 256, ld) of `dtype`; channels [re_0..re_{C/2-1}, im_0..im_{C/2-1}], channels
+ *           C..ld-1 are written as zero (padding for the tensor-core path)
+ *   feat_cfirst : optional (R, C, 256, nt) f32 in the reference's own layout, or NULL */
+int fnssl_features_forward(const float* spec, const float* magsum, int nb, int nt, int nch, int pairing,
+                           int norm, int sample_length, float eps, float* mu, void* feat, int dtype, int ld,
+                           float* feat_cfirst, void* stream);
+
+/* (nb, C, nf, nt) f32  <->  grid (nb, nt, nf, ld) of dtype at channel offset `ch_off`
+ * (FN_SSL.forward's x.permute(0,3,2,1), Model.py:73; IPDnet :93,:111). */
+int fnssl_cfirst_to_grid(const float* src, int nb, int C, int nf, int nt, void* dst, int dtype, int ld,
+                         int ch_off, void* stream);
+int fnssl_grid_to_cfirst(const void* src, int dtype, int ld, int ch_off, int nb, int C, int nf, int nt,
+                         float* dst, void* stream);
+/* grid copy / convert / zero-pad: dst[..., dst_off + c] = src[..., src_off + c] for c < C */
+int fnssl_grid_copy(const void* src, int src_dtype, int src_ld, int src_off, void* dst, int dst_dtype,
+                    int dst_ld, int dst_off, int64_t npos, int C, void* stream);
+
+/* dst = a + b, elementwise over n elements of `dtype` (FNblock's standalone residual add, Model.py:36-37,44-45) */
+int fnssl_grid_add(const void* a, const void* b, void* dst, int dtype, int64_t n, void* stream);
+
+/* ---- LSTM ----------------------------------------------------------------------------------- */
+
+/* One uni- or bi-directional LSTM layer over a grid; replaces nn.LSTM as called at
+ * FN-SSL/Lightning/Model.py:38,46 and IPDnet/FixedAarryIPDnet.py:32,36 *including* the surrounding
+ * layout glue (reshape/permute :35,:41,:49), the channel concat of a skip (:42-43; IPDnet :34,:38) and
+ * the residual add feeding the NEXT layer (:36-37,:44-45).
+ *
+ *   input   x_t  = concat(src0[c0 channels], src1[c1 channels])         (src1 may be NULL, c1 = 0)
+ *   output  out0 = h                  (dirs*hidden channels at channel offset out0_off, stride out0_ld)
+ *           out1 = h + addend         (optional; same channel count, its own stride)  -- the operand of
+ *                                      the next layer in FN-SSL's additive-skip blocks
+ *   weights: engine-specific packed buffer produced by fn_ssl_b200.packing (layout in DESIGN.md) from
+ *            nn.LSTM-shaped weight_ih_l0 (4H,in), weight_hh_l0 (4H,H), bias_ih_l0, bias_hh_l0 [+ _reverse];
+ *            gate order i,f,g,o; zero initial state.
+ */
+typedef struct fnssl_lstm_args {
+  int32_t engine;   /* FNSSL_ENGINE_* */
+  int32_t axis;     /* FNSSL_ALONG_*  */
+  int32_t nb, nt, nf;
+  int32_t hidden;   /* H per direction */
+  int32_t num_dirs; /* 1 or 2; direction 1 runs the sequence in reverse */
+  int32_t dtype;    /* element type of every grid in this call */
+  const void* src0; int32_t c0; int32_t ld0;
+  const void* src1; int32_t c1; int32_t ld1;
+  const void* weights; int64_t weights_bytes;
+  void* out0; int32_t out0_ld; int32_t out0_off;
+  const void* addend; int32_t addend_ld;
+  void* out1; int32_t out1_ld;
+} fnssl_lstm_args;
+
+int fnssl_lstm_forward(const fnssl_lstm_args* args, void* stream);
+
+/* ---- heads ---------------------------------------------------------------------------------- */
+
+/* FN_SSL head (Model.py:79-87): AvgPool over 12 frames -> Linear(C,2) -> tanh -> [ch0 over f | ch1 over f].
+ *   x : grid (nb, nt, nf, ld) of dtype, C channels used;  w : (2, C) f32, b : (2) f32
+ *   out : (nb, nt/12, 2*nf) f32 */
+int fnssl_ipd_head_forward(const void* x, int dtype, int ld, int nb, int nt, int nf, int C, const float* w,
+                           const float* b, float* out, void* stream);
+
+/* y = x @ w^T + b for small row counts; the DOA classifier Linear(512,180) (Model.py:71,88-89).
+ *   x : (rows, in) f32, w : (out, in) f32, b : (out) f32, y : (rows, out) f32 */
+int fnssl_linear_forward(const float* x, const float* w, const float* b, int rows, int in_features,
+                         int out_features, float* y, void* stream);
+
+/* CausCnnBlock.forward (IPDnet/FixedAarryIPDnet.py:61-73): 3x (Conv2d 3x3, pad (1,2), no bias, crop 2)
+ * with ReLU+AvgPool(1,3), ReLU+AvgPool(1,4), tanh.
+ *   input  = concat(src0[c0], src1[c1]) grids (nb, nt, nf, ld*) of dtype
+ *   w1 : (hid, c0+c1, 3, 3), w2 : (hid, hid, 3, 3), w3 : (cout, hid, 3, 3)  f32, PyTorch layout
+ *   work : scratch, fnssl_causcnn_workspace_bytes() bytes
+ *   out : (nb, cout, nf, nt/12) f32 -- the reference's layout */
+size_t fnssl_causcnn_workspace_bytes(int nb, int nt, int nf, int cin, int hid, int cout);
+int fnssl_causcnn_forward(const void* src0, int c0, int ld0, const void* src1, int c1, int ld1, int dtype,
+                          int nb, int nt, int nf, const float* w1, const float* w2, const float* w3, int hid,
+                          int cout, void* work, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FNSSL_B200_H_ */

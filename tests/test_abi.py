@@ -1,0 +1,108 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol include/fnssl_b200.h declares;
+host-side logic (state_dict surface, seeded init, error behaviour) matches the reference contract."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "fnssl_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(fnssl_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from fn_ssl_b200 import _lib
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/fnssl_b200.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(syms)
+    assert lib.fnssl_abi_version() == 1
+
+
+def test_host_only_entry_points():
+    from fn_ssl_b200 import _lib
+    lib = _lib.load()
+    assert lib.fnssl_stft_num_frames(64000, 512, 256) == 249          # 4 s @ 16 kHz
+    assert lib.fnssl_stft_num_frames(76640, 512, 256) == 298          # FN-SSL training clip (utils_.py:9)
+    assert lib.fnssl_stft_num_frames(511, 512, 256) == 0
+    assert lib.fnssl_feature_rows(3, 4, _lib.PAIRS_M) == 9
+    assert lib.fnssl_feature_rows(3, 4, _lib.PAIRS_MM) == 18
+    assert lib.fnssl_feature_rows(3, 4, _lib.PAIRS_ALL) == 3
+    assert lib.fnssl_feature_channels(4, _lib.PAIRS_ALL) == 8
+    assert lib.fnssl_feature_channels(4, _lib.PAIRS_MM) == 4
+    # argument validation happens before any CUDA call
+    assert lib.fnssl_stft_forward(None, 1, 64000, 2, 400, 160, 400, None, None, None) != 0
+    assert b"512" in lib.fnssl_last_error()
+    args = _lib.LstmArgs()
+    args.axis = 7
+    import ctypes
+    assert lib.fnssl_lstm_forward(ctypes.byref(args), None) != 0
+    assert b"axis" in lib.fnssl_last_error()
+
+
+def test_state_dict_surface_matches_reference(golden_fnssl):
+    import fn_ssl_b200 as F
+    from oracle import fnssl_oracle as orc
+    for kw in (dict(is_online=True), dict(is_online=False), dict(is_online=True, is_doa=True)):
+        torch.manual_seed(3)
+        net = F.FN_SSL(**kw)
+        sd = orc.seeded_fnssl_state_dict(3, **kw)              # == reference's seeded state_dict (make_golden.py)
+        assert list(net.state_dict().keys()) == list(sd.keys())
+        for k, v in net.state_dict().items():
+            assert torch.equal(v, sd[k]), k
+        net.load_state_dict(sd, strict=True)
+    assert list(F.FN_lightning().state_dict().keys()) == list(golden_fnssl["lightning_keys"])
+    for kw in (dict(), dict(input_size=8, hidden_size=256), dict(is_online=False)):
+        torch.manual_seed(4)
+        net = F.IPDnet(**kw)
+        sd = orc.seeded_ipdnet_state_dict(4, kw.get("input_size", 4), kw.get("hidden_size", 128), 2, kw.get("is_online", True))
+        assert list(net.state_dict().keys()) == list(sd.keys())
+        for k, v in net.state_dict().items():
+            assert torch.equal(v, sd[k]), k
+
+
+def test_aliases_and_errors():
+    import fn_ssl_b200 as F
+    assert F.FullNarrowBlock is F.FNblock and F.FixedArrayIPDnet is F.IPDnet and F.CausalConv1dBlock is F.CausCnnBlock
+    net = F.FN_SSL()
+    with pytest.raises(RuntimeError, match="eval"):
+        net(torch.zeros(1, 4, 8, 24))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net.eval()(torch.zeros(1, 4, 8, 24))                # CPU tensor: no fallback, loud failure
+    with pytest.raises(RuntimeError, match="CUDA"):
+        F.STFT(512, 0.5, 512)(torch.zeros(1, 4096, 2))
+    with pytest.raises(Exception):
+        F.AddChToBatch("XX")(torch.zeros(1, 3, 4, 5))
+
+
+def test_simt_weight_packing_layout():
+    from fn_ssl_b200.packing import LSTMParams, pack_lstm_simt
+    torch.manual_seed(0)
+    p = LSTMParams(5, 32, bidirectional=True)
+    buf = pack_lstm_simt([tuple(t.detach() for t in d) for d in p.directions()])
+    H, I, Kp = 32, 5, 40
+    assert buf.numel() == 2 * Kp * H * 4 + 2 * H * 4
+    w4 = buf[: 2 * Kp * H * 4].reshape(2, Kp, H, 4)
+    b4 = buf[2 * Kp * H * 4:].reshape(2, H, 4)
+    wi, wh, bi, bh = [t.detach() for t in p.directions()[1]]
+    assert w4[1, 3, 7, 2] == wi[2 * H + 7, 3]                 # gate g, unit 7, input 3
+    assert w4[1, I + 9, 7, 3] == wh[3 * H + 7, 9]             # gate o, unit 7, hidden 9
+    assert torch.all(w4[:, I + H:] == 0)
+    assert torch.allclose(b4[1, 7, 1], bi[H + 7] + bh[H + 7])
+
+
+def test_addchtobatch_cpu_matches_oracle():
+    # pure indexing: also valid on CPU tensors
+    import fn_ssl_b200 as F
+    from oracle import fnssl_oracle as orc
+    x = torch.randn(2, 4, 3, 5, dtype=torch.complex64)
+    for mode in ("M", "MM"):
+        assert torch.equal(F.AddChToBatch(mode)(x), orc.add_ch_to_batch(x, mode))

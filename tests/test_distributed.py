@@ -1,0 +1,56 @@
+"""world_size-2 gloo test of the multi-GPU host logic (weight broadcast, utterance sharding, output all-gather)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from fn_ssl_b200 import FN_SSL
+    from fn_ssl_b200 import distributed as D
+    D.init_from_env(backend="gloo")
+    torch.manual_seed(100 + rank)                       # different init per rank ...
+    net = FN_SSL()
+    nbytes = D.broadcast_weights(net, src=0)            # ... equalised by the broadcast
+    ref = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    gathered = [torch.empty_like(ref) for _ in range(world)]
+    dist.all_gather(gathered, ref)
+    same = all(torch.equal(g, gathered[0]) for g in gathered)
+    n_utt = 5                                           # uneven shard: 3 + 2
+    lo, hi = D.shard_range(n_utt, rank, world)
+    counts = [D.shard_range(n_utt, r, world)[1] - D.shard_range(n_utt, r, world)[0] for r in range(world)]
+    full = torch.arange(n_utt * 20 * 4, dtype=torch.float32).reshape(n_utt, 20, 4)
+    out = D.all_gather_outputs(full[lo:hi].clone(), counts)
+    q.put((rank, same, nbytes, torch.equal(out, full), (lo, hi)))
+    dist.destroy_process_group()
+
+
+def test_broadcast_shard_allgather_gloo():
+    world, port = 2, 29731
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(60)
+    assert [r[4] for r in res] == [(0, 3), (3, 5)]
+    for rank, same, nbytes, ok, _ in res:
+        assert same and ok
+        assert nbytes == 2511362 * 4                     # FN_SSL online parameter count
+
+
+def test_shard_range_covers_everything():
+    from fn_ssl_b200.distributed import shard_range
+    for n in (1, 7, 16, 256):
+        for w in (1, 2, 4, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
