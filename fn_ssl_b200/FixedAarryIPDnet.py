@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import config, ops
 from .Model import _require_eval
-from .packing import LSTMParams
+from .packing import LSTMParams, run_lstm
 
 Tensor = torch.Tensor
 
@@ -42,14 +42,12 @@ class FNblock(nn.Module):
     def _run(self, eng: str, x: Tensor, cx: int, raw: Tensor, craw: int) -> Tensor:
         """x: grid with cx channels (block 1: the raw grid itself; block 2: previous narrow output), raw: raw grid.
         Returns the narrow-band output grid N (hidden channels); the [N | raw] concat stays virtual."""
-        ec = config.engine_code(eng)
-        fh, nh = self.full_hidden_size, self.narr_hidden_size
+        fh = self.full_hidden_size
         if self.is_first:
-            F_, _ = ops.lstm(ec, ops.ALONG_FREQ, x, cx, None, 0, self.fullLstm.packed(ec, (cx,)), fh, 2)
+            F_, _ = run_lstm(self.fullLstm, eng, ops.ALONG_FREQ, x, cx, None, 0)
         else:
-            F_, _ = ops.lstm(ec, ops.ALONG_FREQ, x, cx, raw, craw, self.fullLstm.packed(ec, (cx, craw)), fh, 2)
-        N_, _ = ops.lstm(ec, ops.ALONG_TIME, F_, 2 * fh, raw, craw, self.narrLstm.packed(ec, (2 * fh, craw)), nh,
-                         self.narrLstm.num_dirs)
+            F_, _ = run_lstm(self.fullLstm, eng, ops.ALONG_FREQ, x, cx, raw, craw)
+        N_, _ = run_lstm(self.narrLstm, eng, ops.ALONG_TIME, F_, 2 * fh, raw, craw)
         return N_
 
     def forward(self, x: Tensor, fb_skip: Tensor, nb_skip: Tensor) -> Tensor:

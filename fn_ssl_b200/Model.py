@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import config, ops
-from .packing import LSTMParams
+from .packing import LSTMParams, run_lstm
 
 Tensor = torch.Tensor
 
@@ -55,20 +55,15 @@ class FNblock(nn.Module):
         raw: first block only -- the raw feature grid concatenated to the narrow-band input.
         narr_addend: non-first blocks -- the block input (narrow-band residual, :44-45).
         Returns (N, N + F [if next_full_addend], F)."""
-        ec = config.engine_code(eng)
-        fh, nh = self.full_hidden_size, self.narr_hidden_size
-        ndn = self.narrLstm.num_dirs
-        wf = self.fullLstm.packed(ec, (c_in,))
+        fh = self.full_hidden_size
         if self.is_first:
-            F_, _ = ops.lstm(ec, ops.ALONG_FREQ, x_full_in, c_in, None, 0, wf, fh, 2)
-            wn = self.narrLstm.packed(ec, (2 * fh, c_in))
-            N_, S_ = ops.lstm(ec, ops.ALONG_TIME, F_, 2 * fh, raw, c_in, wn, nh, ndn,
+            F_, _ = run_lstm(self.fullLstm, eng, ops.ALONG_FREQ, x_full_in, c_in, None, 0)
+            N_, S_ = run_lstm(self.narrLstm, eng, ops.ALONG_TIME, F_, 2 * fh, raw, c_in,
                               addend=F_ if next_full_addend else None)
         else:
-            F_, U_ = ops.lstm(ec, ops.ALONG_FREQ, x_full_in, c_in, None, 0, wf, fh, 2, addend=narr_addend,
+            F_, U_ = run_lstm(self.fullLstm, eng, ops.ALONG_FREQ, x_full_in, c_in, None, 0, addend=narr_addend,
                               want_h=need_fb)
-            wn = self.narrLstm.packed(ec, (2 * fh,))
-            N_, S_ = ops.lstm(ec, ops.ALONG_TIME, U_, 2 * fh, None, 0, wn, nh, ndn,
+            N_, S_ = run_lstm(self.narrLstm, eng, ops.ALONG_TIME, U_, 2 * fh, None, 0,
                               addend=F_ if next_full_addend else None)
         return N_, S_, F_
 

@@ -11,8 +11,7 @@ import os
 import torch
 
 DEFAULT_ENGINE = os.environ.get("FNSSL_ENGINE", "auto")
-TC_HIDDEN = (64, 128, 256)        # hidden sizes the tcgen05 engine is instantiated for
-TC_AVAILABLE = False              # flipped to True by lstm_tc once the engine is compiled in
+TC_AVAILABLE = True               # the tcgen05 engine is compiled into libfnssl_b200.so
 
 
 def resolve(engine: str, hidden_sizes) -> str:
@@ -20,8 +19,9 @@ def resolve(engine: str, hidden_sizes) -> str:
     if engine not in ("auto", "tcgen05", "simt"):
         raise RuntimeError(f"unknown engine {engine!r} (auto / tcgen05 / simt)")
     if engine == "auto":
-        ok = TC_AVAILABLE and all(h in TC_HIDDEN for h in hidden_sizes)
-        return "tcgen05" if ok else "simt"
+        # fp16 grids + tensor cores; layers the tcgen05 kernel is not built for run the CUDA-core kernel on the
+        # same grids (packing.run_lstm).  Hidden sizes the CUDA-core kernel does not know either -> error there.
+        return "tcgen05" if TC_AVAILABLE else "simt"
     if engine == "tcgen05" and not TC_AVAILABLE:
         raise RuntimeError("the tcgen05 engine is not compiled into libfnssl_b200.so")
     return engine

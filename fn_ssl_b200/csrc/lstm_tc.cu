@@ -1,5 +1,589 @@
-// placeholder until the tcgen05 engine lands (next commit)
+// tcgen05 / TMEM / TMA LSTM engine (FNSSL_ENGINE_TCGEN05) for sm_100a.
+//
+// Replaces nn.LSTM at FN-SSL/Lightning/Model.py:38,46 and IPDnet/FixedAarryIPDnet.py:32,36 plus the layout
+// glue around it (Model.py:35-37,41-45,49): one persistent launch time-steps ALL sequences of a layer.
+//
+// Work decomposition.  A CTA owns a tile of 128 sequences ("rows": (b,t) pairs for the full-band pass,
+// (b,f) pairs for the narrow-band pass) of one direction for all L steps -- there is no inter-CTA
+// communication.  Per step the gate pre-activations  G[128, 4H] = [x_t | h_{t-1}] . W^T  are produced by
+// tcgen05.mma (kind::f16: fp16 operands, fp32 accumulation in TMEM) in chunks of 32 hidden units
+// (N = 128 gate columns = i,f,g,o of those units); the cell state c (fp32) lives in TMEM for the whole
+// launch, h_t goes to shared memory as the next step's A operand (fp16, 128B-swizzled K-major) and to HBM.
+//
+//   warp 0        TMA producer: x_t slabs (HBM -> smem, once per step) and the weight slab ring (L2 -> smem)
+//   warp 1        MMA issuer (one elected lane), TMEM allocator
+//   warps 2..9    epilogue: tcgen05.ld gates, sigmoid/tanh, c/h update, tcgen05.st c, h -> smem + global
+//
+// Pipelines (all mbarrier based): weight ring full/empty, per-slab x full/empty, 3 accumulator buffers
+// full/empty (MMA of chunk k+1.. overlaps the epilogue of chunk k), h_t complete -> MMA of step t+1.
+// The x-part of a chunk is issued before its h-part so the tensor pipe has work while h_t is finished.
+//
+// Every mbarrier wait is bounded (~1 s) and traps on timeout: a protocol bug fails the launch instead of
+// hanging the GPU.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
+
 namespace fnssl {
-int lstm_forward_tc(const fnssl_lstm_args*, cudaStream_t) { FNSSL_FAIL("lstm: tcgen05 engine not built yet"); }
+
+constexpr int kTcThreads = 320;
+constexpr int kRows = 128;             // sequences per CTA (UMMA M)
+constexpr int kSlabK = 64;             // fp16 elements per 128-byte swizzle row
+constexpr int kSlabBytes = kRows * 128;  // one [128 x 64] fp16 operand tile
+constexpr int kChunkUnits = 32;
+constexpr int kChunkN = 4 * kChunkUnits;  // 128 gate columns per chunk (UMMA N)
+constexpr int kNumAcc = 3;             // accumulator buffers in TMEM
+constexpr int kMaxXSlabs = 6;
+constexpr int kMaxWStages = 6;
+constexpr int kSmemLimit = 232448;     // 227 KB
+
+struct TcParams {
+  int nxs;                        // x slabs
+  int xs_src[kMaxXSlabs];         // 0 = src0, 1 = src1
+  int xs_k0[kMaxXSlabs];          // first channel of the slab within its source
+  int xs_nk16[kMaxXSlabs];        // valid K=16 steps in the slab (1..4)
+  int wstages;
+  int steps, axis, nf, nt;
+  long long rows;
+  int tiles_per_b;                // narrow-band: row tiles per utterance
+  const float* bias;              // [dirs][4H] in accumulator column order [chunk][gate][unit]
+  __half* out0; int out0_ld; int out0_off;
+  const __half* addend; int addend_ld;
+  __half* out1; int out1_ld;
+  int* error_flag;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: ~1 s of SM clock, then record the site and trap (fails the launch, never hangs the box)
+__device__ __noinline__ void mbar_timeout(int* flag, int site) {
+  if (flag) { *reinterpret_cast<volatile int*>(flag) = site; }   // host-mapped: survives the trap
+  __threadfence_system();
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* flag, int site) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 2000000000LL) mbar_timeout(flag, site);
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 operands, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.ld is asynchronous: its destination registers are valid only after tcgen05.wait::ld.  Threading the
+// registers through an (empty) volatile asm placed after the wait gives the compiler a true dependency, so no
+// consumer can be scheduled above the wait.
+__device__ __forceinline__ void tmem_ld_dep(float (&v)[8]) {
+  asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])::"memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// K-major, 128B-swizzled operand tile descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+//   start address >> 4 | LBO (unused for swizzled K-major, =1) << 16 | SBO = 1024 B (8 rows x 128 B) >> 4 << 32
+//   | version 1 << 46 | layout SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor, kind::f16: D = f32 (bit 4), A = B = f16 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kChunkN >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+
+template <int H>
+__global__ void __launch_bounds__(kTcThreads, 1)
+lstm_tc_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_constant__ CUtensorMap map_src1,
+               const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  constexpr int NCH = H / kChunkUnits;  // chunks per step
+  constexpr int NHS = H / kSlabK;       // h slabs (H = 64 -> 1, 128 -> 2)
+  static_assert(H == 64 || H == 128, "this build keeps M = 128 row tiles: H in {64, 128}");
+
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) unsigned long long bars[2 * kMaxWStages + 2 * kMaxXSlabs + 2 * kNumAcc + 2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.y;
+  const int tile = blockIdx.x;
+  const int nxs = p.nxs, S = p.wstages, L = p.steps;
+
+  // carve dynamic smem (1024-byte aligned operand tiles)
+  const uint32_t dyn0 = (smem_addr(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t xs_base = dyn0;                                   // nxs tiles
+  const uint32_t hs_base = xs_base + (uint32_t)nxs * kSlabBytes;   // 2 * NHS tiles
+  const uint32_t ws_base = hs_base + 2u * NHS * kSlabBytes;        // S tiles
+  const uint32_t bias_base = ws_base + (uint32_t)S * kSlabBytes;   // 4H floats
+  unsigned char* dyn_gen = smem_dyn + (dyn0 - smem_addr(smem_dyn));
+  float* bias_s = reinterpret_cast<float*>(dyn_gen + (bias_base - dyn0));
+  unsigned char* hs_gen = dyn_gen + (hs_base - dyn0);
+
+  // barrier map
+  const uint32_t bar0 = smem_addr(bars);
+  auto W_FULL = [&](int i) { return bar0 + 8u * i; };
+  auto W_EMPTY = [&](int i) { return bar0 + 8u * (kMaxWStages + i); };
+  auto X_FULL = [&](int i) { return bar0 + 8u * (2 * kMaxWStages + i); };
+  auto X_EMPTY = [&](int i) { return bar0 + 8u * (2 * kMaxWStages + kMaxXSlabs + i); };
+  auto ACC_FULL = [&](int i) { return bar0 + 8u * (2 * kMaxWStages + 2 * kMaxXSlabs + i); };
+  auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (2 * kMaxWStages + 2 * kMaxXSlabs + kNumAcc + i); };
+  auto H_FULL = [&](int i) { return bar0 + 8u * (2 * kMaxWStages + 2 * kMaxXSlabs + 2 * kNumAcc + i); };
+
+  if (tid == 0) {
+    for (int i = 0; i < kMaxWStages; ++i) { mbar_init(W_FULL(i), 1); mbar_init(W_EMPTY(i), 1); }
+    for (int i = 0; i < kMaxXSlabs; ++i) { mbar_init(X_FULL(i), 1); mbar_init(X_EMPTY(i), 1); }
+    for (int i = 0; i < kNumAcc; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), 256); }
+    for (int i = 0; i < 2; ++i) mbar_init(H_FULL(i), 256 * NCH);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&map_src0); prefetch_tmap(&map_src1); prefetch_tmap(&map_w); }
+  if (warp == 1) {  // TMEM: all 512 columns (1 CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < 4 * H; i += kTcThreads) bias_s[i] = p.bias[dir * 4 * H + i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tmem_c = tmem;                 // cell state: columns [0, H)
+  const uint32_t tmem_acc = tmem + 128;         // accumulators: 3 x 128 columns
+
+  // tile coordinates
+  int coord_b = 0, coord_r0 = 0;
+  long long row0;
+  int valid_rows;
+  if (p.axis == FNSSL_ALONG_FREQ) {
+    row0 = (long long)tile * kRows;
+    coord_r0 = (int)row0;
+    valid_rows = (int)min((long long)kRows, p.rows - row0);
+  } else {
+    coord_b = tile / p.tiles_per_b;
+    coord_r0 = (tile % p.tiles_per_b) * kRows;  // first bin of the tile
+    row0 = (long long)coord_b * p.nf + coord_r0;
+    valid_rows = min(kRows, p.nf - coord_r0);
+  }
+  const int nslabs = nxs + NHS;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wphase = 0;
+      for (int t = 0; t < L; ++t) {
+        const int s = dir ? (L - 1 - t) : t;
+        for (int c = 0; c < NCH; ++c) {
+          for (int j = 0; j < nslabs; ++j) {
+            if (j >= nxs && t == 0) continue;  // h_{-1} = 0: no recurrent term at the first step
+            if (c == 0 && j < nxs) {
+              if (t > 0) mbar_wait(X_EMPTY(j), (uint32_t)((t - 1) & 1), p.error_flag, 100 + j);
+              mbar_expect_tx(X_FULL(j), kSlabBytes);
+              const CUtensorMap* m = p.xs_src[j] ? &map_src1 : &map_src0;
+              if (p.axis == FNSSL_ALONG_FREQ) tma_load_4d(xs_base + j * kSlabBytes, m, X_FULL(j), p.xs_k0[j], s, coord_r0, 0);
+              else tma_load_4d(xs_base + j * kSlabBytes, m, X_FULL(j), p.xs_k0[j], coord_r0, s, coord_b);
+            }
+            mbar_wait(W_EMPTY(ws), wphase ^ 1u, p.error_flag, 110);
+            mbar_expect_tx(W_FULL(ws), kSlabBytes);
+            tma_load_2d(ws_base + ws * kSlabBytes, &map_w, W_FULL(ws), j * kSlabK, (dir * NCH + c) * kChunkN);
+            if (++ws == S) { ws = 0; wphase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wphase = 0;
+      int g = 0;
+      for (int t = 0; t < L; ++t) {
+        for (int c = 0; c < NCH; ++c, ++g) {
+          const int buf = g % kNumAcc;
+          const int use = g / kNumAcc;
+          if (use > 0) mbar_wait(ACC_EMPTY(buf), (uint32_t)((use - 1) & 1), p.error_flag, 200 + buf);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_acc + (uint32_t)buf * kChunkN;
+          uint32_t accumulate = 0;
+          for (int j = 0; j < nslabs; ++j) {
+            if (j >= nxs && t == 0) continue;
+            uint32_t a_tile;
+            int nk16;
+            if (j < nxs) {
+              if (c == 0) mbar_wait(X_FULL(j), (uint32_t)(t & 1), p.error_flag, 210 + j);
+              a_tile = xs_base + j * kSlabBytes;
+              nk16 = p.xs_nk16[j];
+            } else {
+              if (c == 0 && j == nxs) mbar_wait(H_FULL((t - 1) & 1), (uint32_t)(((t - 1) >> 1) & 1), p.error_flag, 220);
+              a_tile = hs_base + (uint32_t)(((t - 1) & 1) * NHS + (j - nxs)) * kSlabBytes;
+              nk16 = 4;
+            }
+            mbar_wait(W_FULL(ws), wphase, p.error_flag, 230);
+            tc_fence_after();
+            const uint64_t a_desc = make_sw128_desc(a_tile);
+            const uint64_t b_desc = make_sw128_desc(ws_base + ws * kSlabBytes);
+            for (int k = 0; k < nk16; ++k) {
+              umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, accumulate);  // +32 B per K=16 step
+              accumulate = 1;
+            }
+            umma_commit(W_EMPTY(ws));                       // weight stage free once these MMAs retire
+            if (c == NCH - 1 && j < nxs) umma_commit(X_EMPTY(j));  // x_t slab free for x_{t+1}
+            if (++ws == S) { ws = 0; wphase ^= 1u; }
+          }
+          umma_commit(ACC_FULL(buf));
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== epilogue warps ==============================
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;       // which 16 of the chunk's 32 units
+    const int r = q * 32 + lane;            // row inside the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const bool valid = r < valid_rows;
+    long long base;
+    long long sstride;
+    if (p.axis == FNSSL_ALONG_FREQ) { base = (row0 + r) * p.nf; sstride = 1; }
+    else { base = (long long)coord_b * p.nt * p.nf + coord_r0 + r; sstride = p.nf; }
+
+    {  // c_0 = 0
+      float z[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z[i] = 0.0f;
+      for (int col = half * (H / 2); col < (half + 1) * (H / 2); col += 8) tmem_st8(tmem_c + lane_off + col, z);
+      tmem_wait_st();
+    }
+    const float kL2E = 1.4426950408889634f;
+    int g = 0;
+    for (int t = 0; t < L; ++t) {
+      const int s = dir ? (L - 1 - t) : t;
+      const long long pos = base + (long long)s * sstride;
+      unsigned char* hbuf = hs_gen + (size_t)((t & 1) * NHS) * kSlabBytes;
+      for (int c = 0; c < NCH; ++c, ++g) {
+        const int buf = g % kNumAcc;
+        mbar_wait(ACC_FULL(buf), (uint32_t)((g / kNumAcc) & 1), p.error_flag, 300 + buf);
+        tc_fence_after();
+        const uint32_t acc = tmem_acc + (uint32_t)buf * kChunkN + lane_off;
+#pragma unroll
+        for (int sb = 0; sb < 2; ++sb) {
+          const int u0 = half * 16 + sb * 8;          // unit offset inside the chunk
+          const int ua = c * kChunkUnits + u0;        // absolute hidden unit
+          float gi[8], gf[8], gg[8], go[8], cc[8];
+          tmem_ld8(acc + 0 * kChunkUnits + u0, gi);
+          tmem_ld8(acc + 1 * kChunkUnits + u0, gf);
+          tmem_ld8(acc + 2 * kChunkUnits + u0, gg);
+          tmem_ld8(acc + 3 * kChunkUnits + u0, go);
+          tmem_ld8(tmem_c + lane_off + ua, cc);
+          uint4 addv = make_uint4(0, 0, 0, 0);
+          if (p.out1 && valid) addv = __ldg(reinterpret_cast<const uint4*>(p.addend + pos * p.addend_ld + dir * H + ua));
+          tmem_wait_ld();
+          tmem_ld_dep(gi); tmem_ld_dep(gf); tmem_ld_dep(gg); tmem_ld_dep(go); tmem_ld_dep(cc);
+          const float* bs = bias_s + c * kChunkN + u0;
+          float hv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float xi = fminf(fmaxf(gi[e] + bs[e], -30.f), 30.f);
+            const float xf = fminf(fmaxf(gf[e] + bs[kChunkUnits + e], -30.f), 30.f);
+            const float xg = fminf(fmaxf(gg[e] + bs[2 * kChunkUnits + e], -15.f), 15.f);
+            const float xo = fminf(fmaxf(go[e] + bs[3 * kChunkUnits + e], -30.f), 30.f);
+            const float ei = ex2_approx(-kL2E * xi);
+            const float ef = ex2_approx(-kL2E * xf);
+            const float eg = ex2_approx(-2.0f * kL2E * xg);
+            const float eo = ex2_approx(-kL2E * xo);
+            // c' = sigmoid(f) c + sigmoid(i) tanh(g);  h = sigmoid(o) tanh(c')
+            const float cn = cc[e] * rcp_approx(1.0f + ef) + (1.0f - eg) * rcp_approx((1.0f + ei) * (1.0f + eg));
+            cc[e] = cn;
+            const float ec = ex2_approx(-2.0f * kL2E * fminf(fmaxf(cn, -15.f), 15.f));
+            hv[e] = (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
+          }
+          tmem_st8(tmem_c + lane_off + ua, cc);
+          // h_t -> fp16: operand tile of the next step (128B swizzle: 16-byte chunk index ^= row & 7) and HBM
+          __half2 h01 = __floats2half2_rn(hv[0], hv[1]), h23 = __floats2half2_rn(hv[2], hv[3]);
+          __half2 h45 = __floats2half2_rn(hv[4], hv[5]), h67 = __floats2half2_rn(hv[6], hv[7]);
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
+          pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
+          {
+            const int slab = ua >> 6;
+            const int chunk16 = (ua & 63) >> 3;
+            unsigned char* dst = hbuf + (size_t)slab * kSlabBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk16 ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = pk;
+          }
+          if (valid) {
+            if (p.out0) *reinterpret_cast<uint4*>(p.out0 + pos * p.out0_ld + p.out0_off + dir * H + ua) = pk;
+            if (p.out1) {
+              const __half2* av = reinterpret_cast<const __half2*>(&addv);
+              __half2 o0 = __floats2half2_rn(hv[0] + __low2float(av[0]), hv[1] + __high2float(av[0]));
+              __half2 o1 = __floats2half2_rn(hv[2] + __low2float(av[1]), hv[3] + __high2float(av[1]));
+              __half2 o2 = __floats2half2_rn(hv[4] + __low2float(av[2]), hv[5] + __high2float(av[2]));
+              __half2 o3 = __floats2half2_rn(hv[6] + __low2float(av[3]), hv[7] + __high2float(av[3]));
+              uint4 ok;
+              ok.x = *reinterpret_cast<uint32_t*>(&o0); ok.y = *reinterpret_cast<uint32_t*>(&o1);
+              ok.z = *reinterpret_cast<uint32_t*>(&o2); ok.w = *reinterpret_cast<uint32_t*>(&o3);
+              *reinterpret_cast<uint4*>(p.out1 + pos * p.out1_ld + dir * H + ua) = ok;
+            }
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(ACC_EMPTY(buf));   // accumulator drained (all tcgen05.ld of this thread completed)
+        fence_async_smem();            // h_t writes (generic proxy) -> visible to the tensor core (async proxy)
+        mbar_arrive(H_FULL(t & 1));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// 4-D fp16 tensor map over a grid, 128B swizzle, zero OOB fill
+static int make_map4(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                     const uint32_t box[4]) {
+  auto enc = get_encode();
+  FNSSL_REQUIRE(enc, "lstm(tcgen05): cuTensorMapEncodeTiled is unavailable in this driver");
+  const uint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FNSSL_REQUIRE(r == CUDA_SUCCESS, "lstm(tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+static int make_grid_map(CUtensorMap* m, const void* base, int c, int ld, int nb, int nt, int nf, int axis) {
+  FNSSL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld % 8) == 0, "lstm(tcgen05): grid base / channel stride not 16-byte aligned");
+  if (axis == FNSSL_ALONG_FREQ) {
+    const uint64_t dims[4] = {(uint64_t)c, (uint64_t)nf, (uint64_t)nb * nt, 1};
+    const uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)nf * ld * 2, (uint64_t)nb * nt * nf * ld * 2};
+    const uint32_t box[4] = {kSlabK, 1, kRows, 1};
+    return make_map4(m, base, dims, str, box);
+  }
+  const uint64_t dims[4] = {(uint64_t)c, (uint64_t)nf, (uint64_t)nt, (uint64_t)nb};
+  const uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)nf * ld * 2, (uint64_t)nt * nf * ld * 2};
+  const uint32_t box[4] = {kSlabK, kRows, 1, 1};
+  return make_map4(m, base, dims, str, box);
+}
+
+static int* g_flag_host = nullptr;
+static int* tc_error_flag() {   // one host-mapped int per process; written by mbar_timeout, readable after a trap
+  static int* flag_dev = nullptr;
+  if (!flag_dev) {
+    if (cudaHostAlloc(&g_flag_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    *g_flag_host = 0;
+    if (cudaHostGetDevicePointer(&flag_dev, g_flag_host, 0) != cudaSuccess) { flag_dev = nullptr; return nullptr; }
+  }
+  return flag_dev;
+}
+
+bool lstm_tc_supports(const fnssl_lstm_args* a) {
+  if (a->dtype != FNSSL_F16) return false;
+  if (a->hidden != 64 && a->hidden != 128) return false;
+  if (a->c0 % 16 || a->c1 % 16) return false;
+  const int nxs = (a->c0 + 63) / 64 + (a->c1 + 63) / 64;
+  return nxs <= kMaxXSlabs;
+}
+
+template <int H>
+static int launch_tc(const fnssl_lstm_args* a, cudaStream_t st) {
+  constexpr int NCH = H / kChunkUnits, NHS = H / kSlabK;
+  TcParams p{};
+  int nxs = 0;
+  for (int src = 0; src < 2; ++src) {
+    const int c = src ? a->c1 : a->c0;
+    for (int k0 = 0; k0 < c; k0 += kSlabK) {
+      p.xs_src[nxs] = src; p.xs_k0[nxs] = k0;
+      p.xs_nk16[nxs] = (((c - k0) < kSlabK ? (c - k0) : kSlabK) + 15) / 16;
+      ++nxs;
+    }
+  }
+  p.nxs = nxs;
+  const int nslabs = nxs + NHS;
+  const int64_t wbytes = (int64_t)a->num_dirs * NCH * kChunkN * nslabs * kSlabK * 2;
+  const int64_t need = wbytes + (int64_t)a->num_dirs * 4 * H * 4;
+  FNSSL_REQUIRE(a->weights_bytes == need, "lstm(tcgen05): packed weight buffer is %lld bytes, expected %lld",
+                (long long)a->weights_bytes, (long long)need);
+  FNSSL_REQUIRE((reinterpret_cast<uintptr_t>(a->weights) & 15) == 0, "lstm(tcgen05): weights not 16-byte aligned");
+  const int fixed = (nxs + 2 * NHS) * kSlabBytes + 4 * H * 4 + 1024;
+  int S = (kSmemLimit - 2048 - fixed) / kSlabBytes;
+  if (S > kMaxWStages) S = kMaxWStages;
+  FNSSL_REQUIRE(S >= 2, "lstm(tcgen05): layer does not fit in shared memory (c0=%d c1=%d H=%d)", a->c0, a->c1, H);
+  p.wstages = S;
+  p.axis = a->axis; p.nf = a->nf; p.nt = a->nt;
+  int tiles;
+  if (a->axis == FNSSL_ALONG_FREQ) {
+    p.rows = (long long)a->nb * a->nt; p.steps = a->nf; p.tiles_per_b = 0;
+    tiles = (int)((p.rows + kRows - 1) / kRows);
+  } else {
+    p.rows = (long long)a->nb * a->nf; p.steps = a->nt; p.tiles_per_b = (a->nf + kRows - 1) / kRows;
+    tiles = a->nb * p.tiles_per_b;
+  }
+  p.bias = reinterpret_cast<const float*>(reinterpret_cast<const char*>(a->weights) + wbytes);
+  p.out0 = (__half*)a->out0; p.out0_ld = a->out0_ld; p.out0_off = a->out0_off;
+  p.addend = (const __half*)a->addend; p.addend_ld = a->addend_ld;
+  p.out1 = (__half*)a->out1; p.out1_ld = a->out1_ld;
+  // 16-byte vector stores / loads in the epilogue
+  FNSSL_REQUIRE(!a->out0 || ((reinterpret_cast<uintptr_t>(a->out0) & 15) == 0 && a->out0_ld % 8 == 0 && a->out0_off % 8 == 0),
+                "lstm(tcgen05): out0 must be 16-byte aligned (ld, offset multiples of 8)");
+  FNSSL_REQUIRE(!a->out1 || ((reinterpret_cast<uintptr_t>(a->out1) & 15) == 0 && a->out1_ld % 8 == 0 &&
+                             (reinterpret_cast<uintptr_t>(a->addend) & 15) == 0 && a->addend_ld % 8 == 0),
+                "lstm(tcgen05): out1/addend must be 16-byte aligned");
+  p.error_flag = tc_error_flag();
+
+  CUtensorMap m0, m1, mw;
+  if (make_grid_map(&m0, a->src0, a->c0, a->ld0, a->nb, a->nt, a->nf, a->axis)) return 1;
+  if (a->c1 > 0) { if (make_grid_map(&m1, a->src1, a->c1, a->ld1, a->nb, a->nt, a->nf, a->axis)) return 1; }
+  else m1 = m0;
+  {
+    const uint64_t dims[4] = {(uint64_t)nslabs * kSlabK, (uint64_t)a->num_dirs * NCH * kChunkN, 1, 1};
+    const uint64_t str[3] = {(uint64_t)nslabs * kSlabK * 2, (uint64_t)nslabs * kSlabK * 2 * a->num_dirs * NCH * kChunkN,
+                             (uint64_t)nslabs * kSlabK * 2 * a->num_dirs * NCH * kChunkN};
+    auto enc = get_encode();
+    FNSSL_REQUIRE(enc, "lstm(tcgen05): cuTensorMapEncodeTiled is unavailable in this driver");
+    const uint32_t box[2] = {kSlabK, kChunkN};
+    const uint32_t estr[2] = {1, 1};
+    CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a->weights), dims, str, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FNSSL_REQUIRE(r == CUDA_SUCCESS, "lstm(tcgen05): weight tensor map failed (%d)", (int)r);
+  }
+  const size_t smem = (size_t)fixed + (size_t)S * kSlabBytes;
+  FNSSL_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(tiles, a->num_dirs);
+  lstm_tc_kernel<H><<<grid, kTcThreads, smem, st>>>(m0, m1, mw, p);
+  FNSSL_LAUNCH_CHECK("lstm_tc_kernel");
+  return 0;
+}
+
+int lstm_forward_tc(const fnssl_lstm_args* a, cudaStream_t st) {
+  FNSSL_REQUIRE(a->dtype == FNSSL_F16, "lstm(tcgen05): grids must be fp16");
+  FNSSL_REQUIRE(a->c0 % 16 == 0 && a->c1 % 16 == 0, "lstm(tcgen05): channel counts must be multiples of 16 (got %d, %d); pad the grid",
+                a->c0, a->c1);
+  FNSSL_REQUIRE((a->c0 + 63) / 64 + (a->c1 + 63) / 64 <= kMaxXSlabs, "lstm(tcgen05): too many input channels (%d + %d)", a->c0, a->c1);
+  switch (a->hidden) {
+    case 64: return launch_tc<64>(a, st);
+    case 128: return launch_tc<128>(a, st);
+    default: FNSSL_FAIL("lstm(tcgen05): hidden size %d is not built (64, 128)", a->hidden);
+  }
+}
+
 }  // namespace fnssl
+
+extern "C" int fnssl_lstm_tc_supported(int hidden, int c0, int c1) {
+  fnssl_lstm_args a{};
+  a.dtype = FNSSL_F16; a.hidden = hidden; a.c0 = c0; a.c1 = c1;
+  return fnssl::lstm_tc_supports(&a) ? 1 : 0;
+}
+
+extern "C" int fnssl_lstm_tc_error_site(void) {
+  // site code recorded by a timed-out mbarrier wait (0 = none); resets the flag
+  if (!fnssl::g_flag_host) return 0;
+  const int v = *reinterpret_cast<volatile int*>(fnssl::g_flag_host);
+  *fnssl::g_flag_host = 0;
+  return v;
+}

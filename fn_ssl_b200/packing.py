@@ -81,4 +81,59 @@ def pack_lstm_simt(dirs: Sequence[Tuple[Tensor, Tensor, Tensor, Tensor]]) -> Ten
 
 
 def pack_lstm_tc(dirs, splits) -> Tensor:
-    raise RuntimeError("tcgen05 weight packing is not available in this build")
+    """tcgen05 engine, fp16.  splits = ((c_real, c_padded), ...) per input source (c_padded % 16 == 0).
+
+    K is cut into 64-column slabs: ceil(c_padded/64) slabs per source (zero columns beyond c_real), then H/64
+    slabs for h_{t-1}.  Rows are grouped per accumulator chunk of 32 hidden units in column order
+    [chunk][gate i,f,g,o][unit]:   W[d][chunk*128 + gate*32 + u][kcol] = weight[gate*H + chunk*32 + u][k].
+    Buffer = fp16 W [dirs][4H][nslabs*64]  ++  fp32 bias (b_ih + b_hh) [dirs][4H] in the same row order."""
+    w_ih0, w_hh0 = dirs[0][0], dirs[0][1]
+    H = w_hh0.shape[1]
+    nch = H // 32
+    dev = w_ih0.device
+    ws, bs = [], []
+    for (wi, wh, bi, bh) in dirs:
+        cols, off = [], 0
+        for (c_real, c_pad) in splits:
+            width = (c_pad + 63) // 64 * 64
+            blk = torch.zeros((4 * H, width), dtype=torch.float32, device=dev)
+            blk[:, :c_real] = wi[:, off:off + c_real]
+            cols.append(blk)
+            off += c_real
+        assert off == wi.shape[1], "splits do not cover the LSTM input size"
+        hw = (H + 63) // 64 * 64
+        blk = torch.zeros((4 * H, hw), dtype=torch.float32, device=dev)
+        blk[:, :H] = wh
+        cols.append(blk)
+        wcat = torch.cat(cols, dim=1)                                             # (4H, Kpad), rows gate-major
+        kpad = wcat.shape[1]
+        wcat = wcat.reshape(4, nch, 32, kpad).permute(1, 0, 2, 3).reshape(4 * H, kpad)
+        ws.append(wcat.to(torch.float16).contiguous())
+        bs.append((bi + bh).reshape(4, nch, 32).permute(1, 0, 2).reshape(4 * H).float().contiguous())
+    wbytes = torch.stack(ws).contiguous().view(torch.uint8).reshape(-1)
+    bbytes = torch.stack(bs).contiguous().view(torch.uint8).reshape(-1)
+    return torch.cat((wbytes, bbytes)).contiguous()
+
+
+def _pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+def run_lstm(params: "LSTMParams", eng: str, axis: int, src0: Tensor, c0: int, src1, c1: int,
+             addend=None, want_h: bool = True):
+    """Run one LSTM layer with the model-level engine `eng` ("tcgen05" | "simt").  In tcgen05 mode the layer
+    uses the tensor-core kernel when it is built for this shape (fnssl_lstm_tc_supported) and the fp32
+    CUDA-core kernel (on the same fp16 grids) otherwise.  c0/c1 are the REAL channel counts; fp16 grids are
+    zero-padded to multiples of 16 channels, which is what the tensor-core kernel consumes."""
+    from . import _lib, ops
+    H = params.hidden_size
+    if eng == "tcgen05":
+        p0, p1 = _pad16(c0), _pad16(c1) if src1 is not None else 0
+        ok = (src0.dtype == torch.float16 and src0.shape[-1] >= p0 and (src1 is None or src1.shape[-1] >= p1)
+              and _lib.load().fnssl_lstm_tc_supported(H, p0, p1))
+        if ok:
+            splits = ((c0, p0),) + (((c1, p1),) if src1 is not None else ())
+            w = params.packed(ops.ENGINE_TCGEN05, splits)
+            return ops.lstm(ops.ENGINE_TCGEN05, axis, src0, p0, src1, p1, w, H, params.num_dirs, addend=addend, want_h=want_h)
+    w = params.packed(ops.ENGINE_SIMT, (c0, c1))
+    return ops.lstm(ops.ENGINE_SIMT, axis, src0, c0, src1, c1, w, H, params.num_dirs, addend=addend, want_h=want_h)

@@ -133,6 +133,11 @@ typedef struct fnssl_lstm_args {
 
 int fnssl_lstm_forward(const fnssl_lstm_args* args, void* stream);
 
+/* 1 if the tcgen05 engine is built for this layer shape (fp16 grids; hidden, c0, c1 as in fnssl_lstm_args) */
+int fnssl_lstm_tc_supported(int hidden, int c0, int c1);
+/* diagnostic: site code written by a timed-out pipeline wait inside the tcgen05 kernel (0 = none) */
+int fnssl_lstm_tc_error_site(void);
+
 /* ---- heads ---------------------------------------------------------------------------------- */
 
 /* FN_SSL head (Model.py:79-87): AvgPool over 12 frames -> Linear(C,2) -> tanh -> [ch0 over f | ch1 over f].

@@ -125,7 +125,7 @@ def test_feature_grid_layout(dtype):
 
 def _lstm_case(engine, axis, nb, nt, nf, c0, c1, H, bidir, use_addend, seed=0):
     from fn_ssl_b200 import config, ops
-    from fn_ssl_b200.packing import LSTMParams
+    from fn_ssl_b200.packing import LSTMParams, run_lstm
     dt = config.grid_dtype(engine)
     torch.manual_seed(seed)
     p = LSTMParams(c0 + c1, H, bidirectional=bidir).to(DEV)
@@ -136,8 +136,12 @@ def _lstm_case(engine, axis, nb, nt, nf, c0, c1, H, bidir, use_addend, seed=0):
     g0 = ops.grid_copy(x0.to(DEV), c0, dt)
     g1 = ops.grid_copy(x1.to(DEV), c1, dt) if c1 else None
     ga = ops.grid_copy(add.to(DEV), oc, dt) if use_addend else None
-    w = p.packed(config.engine_code(engine), (c0, c1) if c1 else (c0,))
-    h, hs = ops.lstm(config.engine_code(engine), axis, g0, c0, g1, c1, w, H, 2 if bidir else 1, addend=ga)
+    before = ops.LAUNCHES
+    h, hs = run_lstm(p, engine, axis, g0, c0, g1, c1, addend=ga)
+    assert ops.LAUNCHES == before + 1
+    if engine == "tcgen05":   # the layer really ran on the tensor-core kernel, not the CUDA-core fallback
+        from fn_ssl_b200 import _lib
+        assert _lib.load().fnssl_lstm_tc_supported(H, (c0 + 15) // 16 * 16, (c1 + 15) // 16 * 16) == 1
     # oracle on the same (dtype-rounded) inputs
     x = torch.cat([t for t in (g0[..., :c0].float().cpu(), g1[..., :c1].float().cpu() if c1 else None) if t is not None], -1)
     sd = {"l." + k: v.detach().cpu() for k, v in p.state_dict().items()}
@@ -162,8 +166,8 @@ def test_lstm_layer_simt(axis, H, bidir, c0, c1, addend):
 
 @pytest.mark.parametrize("axis", [0, 1])
 @pytest.mark.parametrize("H,bidir,c0,c1,addend", [
-    (128, True, 4, 0, False), (128, True, 256, 0, True), (256, False, 256, 4, True), (256, False, 256, 0, False),
-    (128, True, 256, 4, False), (64, True, 8, 0, False), (128, False, 128, 8, False), (64, True, 128, 8, False)])
+    (128, True, 4, 0, False), (128, True, 256, 0, True), (128, True, 256, 4, True), (128, False, 256, 0, False),
+    (128, True, 256, 8, False), (64, True, 8, 0, False), (128, False, 128, 8, False), (64, True, 128, 8, True)])
 def test_lstm_layer_tcgen05(axis, H, bidir, c0, c1, addend):
     from fn_ssl_b200 import config
     if not config.TC_AVAILABLE:
