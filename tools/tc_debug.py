@@ -15,6 +15,8 @@ CASES = [
     ("freq_c256_H128_bi_add", 0, 1, 200, 6, 256, 0, 128, True, True),
     ("time_c256+16_H128_bi_add", 1, 2, 9, 256, 256, 4, 128, True, True),
     ("freq_c4_H128_bi_ragged", 0, 2, 70, 40, 4, 0, 128, True, False),
+    ("time_c256+4_H256_uni_add", 1, 1, 7, 256, 256, 4, 256, False, True),
+    ("freq_c64_H256_uni", 0, 1, 100, 5, 64, 0, 256, False, False),
 ]
 
 
@@ -72,8 +74,14 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         run_case(int(sys.argv[1]))
     else:
-        for i in range(len(CASES)):
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), str(i)], capture_output=True, text=True, timeout=300)
-            print(r.stdout.strip())
-            if r.returncode != 0:
-                print(f"[{CASES[i][0]}] exit code {r.returncode}: {r.stderr.strip()[-600:]}")
+        for rows in ("64", "128"):
+            print(f"==== FNSSL_TC_ROWS={rows}")
+            for i in range(len(CASES)):
+                if rows == "128" and CASES[i][7] == 256:
+                    continue
+                env = dict(os.environ, FNSSL_TC_ROWS=rows)
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), str(i)], capture_output=True, text=True,
+                                   timeout=300, env=env)
+                print(r.stdout.strip())
+                if r.returncode != 0:
+                    print(f"[{CASES[i][0]}] exit code {r.returncode}: {r.stderr.strip()[-600:]}")
