@@ -60,6 +60,7 @@ struct TcParams {
   const __half* addend; int addend_ld;
   __half* out1; int out1_ld;
   int* error_flag;
+  int debug;                      // timing experiments only (FNSSL_TC_DEBUG): 1 = skip gate math, 2 = skip MMA issue
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -334,9 +335,11 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_consta
               tc_fence_after();
               const uint64_t a_desc = make_sw128_desc(a_tile);
               const uint64_t b_desc = make_sw128_desc(ws_base + ws * kWSlabBytes);
-              for (int k = 0; k < nk16; ++k) {
-                umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accumulate);  // +32 B per K=16 step
-                accumulate = 1;
+              if (!(p.debug & 2)) {
+                for (int k = 0; k < nk16; ++k) {
+                  umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accumulate);  // +32 B per K=16 step
+                  accumulate = 1;
+                }
               }
               umma_commit(W_EMPTY(ws));                               // weight stage free once these MMAs retire
               if (c == NCH - 1 && j < nxs) umma_commit(X_EMPTY(xb, j));   // x_t slab free for a later step
@@ -400,6 +403,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_consta
           tmem_ld_dep(gti); tmem_ld_dep(gtf); tmem_ld_dep(gtg); tmem_ld_dep(gto); tmem_ld_dep(cs);
           const float* bs = bias_s + c * kChunkN + u0;
           float hv[8];
+          if (p.debug & 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) hv[e] = gti[e] + gtf[e] + gtg[e] + gto[e] + cs[e];
+          } else
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             // sigmoid(x) = 1/(1+2^(-x log2 e)) needs no clamp (2^big = inf -> 1/inf = 0); tanh(g) and tanh(c') are
@@ -575,6 +582,7 @@ static int launch_tc(const fnssl_lstm_args* a, cudaStream_t st) {
                              (reinterpret_cast<uintptr_t>(a->addend) & 15) == 0 && a->addend_ld % 8 == 0),
                 "lstm(tcgen05): out1/addend must be 16-byte aligned");
   p.error_flag = tc_error_flag();
+  if (const char* e = getenv("FNSSL_TC_DEBUG")) p.debug = atoi(e);
 
   CUtensorMap m0, m1, mw;
   if (make_grid_map(&m0, a->src0, a->c0, a->ld0, a->nb, a->nt, a->nf, a->axis, MR)) return 1;
