@@ -31,6 +31,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace fnssl {
 
@@ -63,122 +64,6 @@ struct TcParams {
   int debug;                      // timing experiments only (FNSSL_TC_DEBUG): 1 = skip gate math, 2 = skip MMA issue
 };
 
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait: ~1 s of SM clock, then record the site and trap (fails the launch, never hangs the box)
-__device__ __noinline__ void mbar_timeout(int* flag, int site) {
-  if (flag) { *reinterpret_cast<volatile int*>(flag) = site; }   // host-mapped: survives the trap
-  __threadfence_system();
-  __trap();
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* flag, int site) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 2000000000LL) mbar_timeout(flag, site);
-  }
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-          dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem] * B[smem]^T, fp16 operands, fp32 accumulate; issued by ONE thread
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// mbarrier arrives when every MMA issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// tcgen05.ld is asynchronous: its destination registers are valid only after tcgen05.wait::ld.  Threading the
-// registers through an (empty) volatile asm placed after the wait gives the compiler a true dependency, so no
-// consumer can be scheduled above the wait.
-__device__ __forceinline__ void tmem_ld_dep(float (&v)[8]) {
-  asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])::"memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// K-major, 128B-swizzled operand tile descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
-//   start address >> 4 | LBO (unused for swizzled K-major, =1) << 16 | SBO = 1024 B (8 rows x 128 B) >> 4 << 32
-//   | version 1 << 46 | layout SWIZZLE_128B (2) << 61
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
-  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 // instruction descriptor, kind::f16: D = f32 (bit 4), A = B = f16 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 template <int MR>
 constexpr uint32_t make_idesc() { return (1u << 4) | ((uint32_t)(kChunkN >> 3) << 17) | ((uint32_t)(MR >> 4) << 24); }
@@ -496,7 +381,7 @@ static int make_map4(CUtensorMap* m, const void* base, const uint64_t dims[4], c
   return 0;
 }
 
-static int make_grid_map(CUtensorMap* m, const void* base, int c, int ld, int nb, int nt, int nf, int axis, int mr) {
+int make_grid_map(CUtensorMap* m, const void* base, int c, int ld, int nb, int nt, int nf, int axis, int mr) {
   FNSSL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld % 8) == 0, "lstm(tcgen05): grid base / channel stride not 16-byte aligned");
   if (axis == FNSSL_ALONG_FREQ) {
     const uint64_t dims[4] = {(uint64_t)c, (uint64_t)nf, (uint64_t)nb * nt, 1};
@@ -510,8 +395,23 @@ static int make_grid_map(CUtensorMap* m, const void* base, int c, int ld, int nb
   return make_map4(m, base, dims, str, box);
 }
 
-static int* g_flag_host = nullptr;
-static int* tc_error_flag() {   // one host-mapped int per process; written by mbar_timeout, readable after a trap
+// 2-D fp16 map over the packed weights [nchunks_total * 128 rows][nslabs * 64], box = one [128 x 64] slab
+int make_weight_map(CUtensorMap* m, const void* weights, int nslabs, int nchunks_total) {
+  auto enc = get_encode();
+  FNSSL_REQUIRE(enc, "lstm(tcgen05): cuTensorMapEncodeTiled is unavailable in this driver");
+  const uint64_t dims[2] = {(uint64_t)nslabs * kSlabK, (uint64_t)nchunks_total * kChunkN};
+  const uint64_t str[1] = {(uint64_t)nslabs * kSlabK * 2};
+  const uint32_t box[2] = {kSlabK, kChunkN};
+  const uint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(weights), dims, str, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FNSSL_REQUIRE(r == CUDA_SUCCESS, "lstm(tcgen05): weight tensor map failed (%d)", (int)r);
+  return 0;
+}
+
+int* g_flag_host = nullptr;
+int* tc_error_flag() {   // one host-mapped int per process; written by mbar_timeout, readable after a trap
   static int* flag_dev = nullptr;
   if (!flag_dev) {
     if (cudaHostAlloc(&g_flag_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return nullptr;
@@ -588,19 +488,7 @@ static int launch_tc(const fnssl_lstm_args* a, cudaStream_t st) {
   if (make_grid_map(&m0, a->src0, a->c0, a->ld0, a->nb, a->nt, a->nf, a->axis, MR)) return 1;
   if (a->c1 > 0) { if (make_grid_map(&m1, a->src1, a->c1, a->ld1, a->nb, a->nt, a->nf, a->axis, MR)) return 1; }
   else m1 = m0;
-  {
-    const uint64_t dims[4] = {(uint64_t)nslabs * kSlabK, (uint64_t)a->num_dirs * NCH * kChunkN, 1, 1};
-    const uint64_t str[3] = {(uint64_t)nslabs * kSlabK * 2, (uint64_t)nslabs * kSlabK * 2 * a->num_dirs * NCH * kChunkN,
-                             (uint64_t)nslabs * kSlabK * 2 * a->num_dirs * NCH * kChunkN};
-    auto enc = get_encode();
-    FNSSL_REQUIRE(enc, "lstm(tcgen05): cuTensorMapEncodeTiled is unavailable in this driver");
-    const uint32_t box[2] = {kSlabK, kChunkN};
-    const uint32_t estr[2] = {1, 1};
-    CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a->weights), dims, str, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    FNSSL_REQUIRE(r == CUDA_SUCCESS, "lstm(tcgen05): weight tensor map failed (%d)", (int)r);
-  }
+  if (make_weight_map(&mw, a->weights, nslabs, a->num_dirs * NCH)) return 1;
   const size_t smem = (size_t)fixed + (size_t)S * kWSlabBytes;
   FNSSL_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<H, MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(tiles, a->num_dirs);
@@ -609,8 +497,19 @@ static int launch_tc(const fnssl_lstm_args* a, cudaStream_t st) {
   return 0;
 }
 
+bool lstm_tc2_supports(int hidden, int c0, int c1);
+int lstm_forward_tc2(const fnssl_lstm_args* a, cudaStream_t st);
+
 int lstm_forward_tc(const fnssl_lstm_args* a, cudaStream_t st) {
   FNSSL_REQUIRE(a->dtype == FNSSL_F16, "lstm(tcgen05): grids must be fp16");
+  {
+    // Kernel generation: 2 = cluster-resident weights (lstm_tc2.cu, default whenever the layer fits),
+    // 1 = weight-streaming kernel below.  FNSSL_TC_KERNEL overrides (tests / profiling).
+    const char* e = getenv("FNSSL_TC_KERNEL");
+    const int want = e ? atoi(e) : 2;
+    if (want != 1 && a->c0 % 16 == 0 && a->c1 % 16 == 0 && lstm_tc2_supports(a->hidden, a->c0, a->c1))
+      return lstm_forward_tc2(a, st);
+  }
   FNSSL_REQUIRE(a->c0 % 16 == 0 && a->c1 % 16 == 0, "lstm(tcgen05): channel counts must be multiples of 16 (got %d, %d); pad the grid",
                 a->c0, a->c1);
   FNSSL_REQUIRE((a->c0 + 63) / 64 + (a->c1 + 63) / 64 <= kMaxXSlabs, "lstm(tcgen05): too many input channels (%d + %d)", a->c0, a->c1);

@@ -1,0 +1,410 @@
+// Cluster-resident tcgen05 LSTM kernel (second generation of FNSSL_ENGINE_TCGEN05) for sm_100a.
+//
+// Why: the first kernel (lstm_tc.cu) lets one CTA compute all 4H gate columns of its row tile, so the layer's whole
+// weight matrix (400-600 KB, more than one SM's shared memory) is re-streamed from L2 through a small TMA ring every
+// time step; measured on B200 that stream -- not the MMA, not the gate math -- bounds the step (profiles/r1_*).
+//
+// Here the 4H gate columns are split across a thread-block cluster: CTA k of a cluster of C = H/32 CTAs owns hidden
+// units [32k, 32k+32) (N = 128 gate columns i,f,g,o) of a shared tile of MR sequences, and keeps its 1/C slice of the
+// weights RESIDENT in shared memory for the whole launch (loaded once by TMA).  Per step and CTA:
+//     x-part   G  = x_t . W_x^T      x_t slabs are TMA-multicast to the whole cluster through a small ring; issued a
+//                                    step ahead into the other accumulator buffer, off the critical path
+//     h-part   G += h_{t-1} . W_h^T  needs all of h_{t-1}: every CTA's epilogue writes its 32-unit slice of h_t into the
+//                                    operand buffer of ALL CTAs of the cluster (st.shared::cluster, DSMEM) and signals
+//                                    their "h_t complete" mbarriers (release/acquire at cluster scope)
+//     epilogue 16 warps: tcgen05.ld gates -> sigmoid/tanh -> c (fp32, resident in TMEM) -> h_t (fp16) -> DSMEM + HBM
+// The serial chain of a step is: h-part MMA (K = H) -> gate math of 32 units -> DSMEM exchange; weights never move.
+//
+// Replaces nn.LSTM at FN-SSL/Lightning/Model.py:38,46 and IPDnet/FixedAarryIPDnet.py:32,36 (+ glue :35-37,41-45,49).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace fnssl {
+namespace tc2 {
+
+constexpr int kThreads = 576;          // producer warp + MMA warp + 16 epilogue warps
+constexpr int kEpiThreads = 512;
+constexpr int kEpiWarps = 16;
+constexpr int kSlabK = 64;
+constexpr int kWSlab = 128 * 128;      // [128 gate columns x 64] fp16
+constexpr int kChunkUnits = 32;
+constexpr int kChunkN = 128;
+constexpr int kMaxXSlabs = 6;
+constexpr int kMaxXStages = 6;
+constexpr int kSmemLimit = 232448;
+
+struct Params {
+  int nxs;
+  int xs_src[kMaxXSlabs];
+  int xs_k0[kMaxXSlabs];
+  int xs_nk16[kMaxXSlabs];
+  int xstages;
+  int steps, axis, nf, nt;
+  long long rows;
+  int tiles_per_b;
+  const float* bias;               // [dirs][4H], accumulator column order [chunk][gate][unit]
+  __half* out0; int out0_ld; int out0_off;
+  const __half* addend; int addend_ld;
+  __half* out1; int out1_ld;
+  int* error_flag;
+};
+
+template <int MR>
+constexpr uint32_t make_idesc() { return (1u << 4) | ((uint32_t)(kChunkN >> 3) << 17) | ((uint32_t)(MR >> 4) << 24); }
+
+template <int H, int MR>
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_constant__ CUtensorMap map_src1,
+                const __grid_constant__ CUtensorMap map_w, const Params p) {
+  constexpr int C = H / kChunkUnits;      // cluster size == number of 32-unit chunks
+  constexpr int NHS = H / kSlabK;         // K slabs of h
+  constexpr int kASlab = MR * 128;        // one [MR x 64] fp16 A tile
+  static_assert(H == 64 || H == 128 || H == 256, "H in {64,128,256}");
+  static_assert(MR == 64 || MR == 128, "MR in {64,128}");
+
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) unsigned long long bars[1 + 2 * kMaxXStages + 6];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.y;
+  const uint32_t rank = cluster_ctarank();          // == chunk owned by this CTA
+  const int tile = blockIdx.x / C;
+  const uint16_t mask = (uint16_t)((1u << C) - 1u);
+  const int nxs = p.nxs, XS = p.xstages, L = p.steps;
+  const int nslabs = nxs + NHS;
+
+  const uint32_t dyn0 = (smem_addr(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t w_base = dyn0;                                     // resident weights: nslabs tiles
+  const uint32_t hs_base = w_base + (uint32_t)nslabs * kWSlab;      // h operand: 2 buffers x NHS tiles
+  const uint32_t xr_base = hs_base + 2u * NHS * kASlab;             // x ring: XS tiles
+  const uint32_t bias_base = xr_base + (uint32_t)XS * kASlab;       // 128 floats
+  float* bias_s = reinterpret_cast<float*>(smem_dyn + (bias_base - smem_addr(smem_dyn)));
+
+  const uint32_t bar0 = smem_addr(bars);
+  const uint32_t W_FULL = bar0;
+  auto X_FULL = [&](int i) { return bar0 + 8u * (1 + i); };
+  auto X_EMPTY = [&](int i) { return bar0 + 8u * (1 + kMaxXStages + i); };
+  auto ACC_FULL = [&](int i) { return bar0 + 8u * (1 + 2 * kMaxXStages + i); };
+  auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (1 + 2 * kMaxXStages + 2 + i); };
+  auto H_FULL = [&](int i) { return bar0 + 8u * (1 + 2 * kMaxXStages + 4 + i); };
+
+  if (tid == 0) {
+    mbar_init(W_FULL, 1);
+    for (int i = 0; i < kMaxXStages; ++i) { mbar_init(X_FULL(i), 1); mbar_init(X_EMPTY(i), C); }
+    for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), kEpiThreads); mbar_init(H_FULL(i), C * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&map_src0); prefetch_tmap(&map_src1); prefetch_tmap(&map_w); }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < kChunkN; i += kThreads) bias_s[i] = p.bias[dir * 4 * H + rank * kChunkN + i];
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // every CTA's barriers are initialised before any multicast / remote arrive can reach them
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tmem_c = tmem;             // cell state of this CTA's 32 units: columns [0, 32)
+  const uint32_t tmem_acc = tmem + 128;     // 2 accumulator buffers x 128 columns
+
+  int coord_b = 0, coord_r0 = 0;
+  long long row0;
+  int valid_rows;
+  if (p.axis == FNSSL_ALONG_FREQ) {
+    row0 = (long long)tile * MR;
+    coord_r0 = (int)row0;
+    valid_rows = (int)min((long long)MR, p.rows - row0);
+  } else {
+    coord_b = tile / p.tiles_per_b;
+    coord_r0 = (tile % p.tiles_per_b) * MR;
+    row0 = (long long)coord_b * p.nf + coord_r0;
+    valid_rows = min(MR, p.nf - coord_r0);
+  }
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      mbar_expect_tx(W_FULL, (uint32_t)nslabs * kWSlab);
+      for (int j = 0; j < nslabs; ++j)
+        tma_load_2d(w_base + j * kWSlab, &map_w, W_FULL, j * kSlabK, (dir * C + (int)rank) * kChunkN);
+      int n = 0;
+      for (int t = 0; t < L; ++t) {
+        const int s = dir ? (L - 1 - t) : t;
+        for (int j = 0; j < nxs; ++j, ++n) {
+          const int stage = n % XS, use = n / XS;
+          if (use > 0) mbar_wait(X_EMPTY(stage), (uint32_t)((use - 1) & 1), p.error_flag, 100 + stage);
+          mbar_expect_tx(X_FULL(stage), kASlab);
+          if ((uint32_t)(n % C) == rank) {   // one CTA fetches the slab for the whole cluster
+            const CUtensorMap* m = p.xs_src[j] ? &map_src1 : &map_src0;
+            const uint32_t dst = xr_base + (uint32_t)stage * kASlab;
+            if (p.axis == FNSSL_ALONG_FREQ) tma_load_4d_mc(dst, m, X_FULL(stage), p.xs_k0[j], s, coord_r0, 0, mask);
+            else tma_load_4d_mc(dst, m, X_FULL(stage), p.xs_k0[j], coord_r0, s, coord_b, mask);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<MR>();
+      mbar_wait(W_FULL, 0, p.error_flag, 200);
+      int n = 0;
+      for (int t = 0; t < L; ++t) {
+        const int b = t & 1, use = t >> 1;
+        if (use > 0) mbar_wait(ACC_EMPTY(b), (uint32_t)((use - 1) & 1), p.error_flag, 201 + b);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_acc + (uint32_t)b * kChunkN;
+        uint32_t accumulate = 0;
+        for (int j = 0; j < nxs; ++j, ++n) {
+          const int stage = n % XS;
+          mbar_wait(X_FULL(stage), (uint32_t)((n / XS) & 1), p.error_flag, 210 + stage);
+          tc_fence_after();
+          const uint64_t a_desc = make_sw128_desc(xr_base + (uint32_t)stage * kASlab);
+          const uint64_t b_desc = make_sw128_desc(w_base + (uint32_t)j * kWSlab);
+          const int nk16 = p.xs_nk16[j];
+          for (int k = 0; k < nk16; ++k) {
+            umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit_mc(X_EMPTY(stage), mask);    // this CTA is done with the slab: tell every CTA's ring
+        }
+        if (t > 0) {
+          // h_{t-1}: 32-unit slices written by all CTAs of the cluster (generic proxy, DSMEM)
+          mbar_wait_cluster(H_FULL((t - 1) & 1), (uint32_t)(((t - 1) >> 1) & 1), p.error_flag, 220);
+          fence_async_smem();
+          tc_fence_after();
+#pragma unroll
+          for (int hs = 0; hs < NHS; ++hs) {
+            const uint64_t a_desc = make_sw128_desc(hs_base + (uint32_t)(((t - 1) & 1) * NHS + hs) * kASlab);
+            const uint64_t b_desc = make_sw128_desc(w_base + (uint32_t)(nxs + hs) * kWSlab);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, 1u);
+          }
+        }
+        umma_commit(ACC_FULL(b));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== epilogue warps ==============================
+    const int q = warp & 3;                    // TMEM lane quadrant of this warp
+    const int sub = (warp - 2) >> 2;           // 8-unit group of the CTA's 32 units
+    const bool active = (MR == 128) || (lane < 16);   // M = 64: rows live in lanes 0-15 of each quadrant
+    const int r = (MR == 128) ? (q * 32 + lane) : (q * 16 + (lane & 15));
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const bool valid = active && r < valid_rows;
+    const int u0 = sub * 8;
+    const int ua = (int)rank * kChunkUnits + u0;      // absolute hidden unit of this thread's first element
+    long long base, sstride;
+    if (p.axis == FNSSL_ALONG_FREQ) { base = (row0 + r) * p.nf; sstride = 1; }
+    else { base = (long long)coord_b * p.nt * p.nf + coord_r0 + r; sstride = p.nf; }
+    // destination of this thread's 16-byte h piece inside an h operand buffer (128B swizzle)
+    const uint32_t hpiece = (uint32_t)(ua >> 6) * kASlab + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+                            (uint32_t)((((ua & 63) >> 3) ^ (r & 7)) << 4);
+    {
+      float z[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z[i] = 0.0f;
+      tmem_st8(tmem_c + lane_off + u0, z);
+      tmem_wait_st();
+    }
+    const float kL2E = 1.4426950408889634f;
+    float bsv[4][8];
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bsv[gq][e] = bias_s[gq * kChunkUnits + u0 + e];
+
+    for (int t = 0; t < L; ++t) {
+      const int b = t & 1;
+      const int s = dir ? (L - 1 - t) : t;
+      const long long pos = base + (long long)s * sstride;
+      uint4 addv = make_uint4(0, 0, 0, 0);
+      if (p.out1 && valid) addv = __ldg(reinterpret_cast<const uint4*>(p.addend + pos * p.addend_ld + dir * H + ua));
+      mbar_wait(ACC_FULL(b), (uint32_t)((t >> 1) & 1), p.error_flag, 300 + b);
+      tc_fence_after();
+      const uint32_t acc = tmem_acc + (uint32_t)b * kChunkN + lane_off + u0;
+      float gti[8], gtf[8], gtg[8], gto[8], cs[8];
+      tmem_ld8(acc + 0 * kChunkUnits, gti);
+      tmem_ld8(acc + 1 * kChunkUnits, gtf);
+      tmem_ld8(acc + 2 * kChunkUnits, gtg);
+      tmem_ld8(acc + 3 * kChunkUnits, gto);
+      tmem_ld8(tmem_c + lane_off + u0, cs);
+      tmem_wait_ld();
+      tmem_ld_dep(gti); tmem_ld_dep(gtf); tmem_ld_dep(gtg); tmem_ld_dep(gto); tmem_ld_dep(cs);
+      tc_fence_before();
+      mbar_arrive(ACC_EMPTY(b));      // accumulator drained: the MMA warp may start the x-part of step t+2 into it
+      float hv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        // sigmoid(x) = 1/(1+2^(-x log2 e)) (no clamp needed: 2^big = inf -> 0); tanh as (1-E)/(1+E) shares a
+        // reciprocal with a sigmoid, so E must stay finite: clamp its argument to +-15
+        const float xg = fminf(fmaxf(gtg[e] + bsv[2][e], -15.f), 15.f);
+        const float ei = ex2_approx(-kL2E * (gti[e] + bsv[0][e]));
+        const float ef = ex2_approx(-kL2E * (gtf[e] + bsv[1][e]));
+        const float eg = ex2_approx(-2.0f * kL2E * xg);
+        const float eo = ex2_approx(-kL2E * (gto[e] + bsv[3][e]));
+        const float cn = cs[e] * rcp_approx(1.0f + ef) + (1.0f - eg) * rcp_approx((1.0f + ei) * (1.0f + eg));
+        cs[e] = cn;
+        const float ec = ex2_approx(-2.0f * kL2E * fminf(fmaxf(cn, -15.f), 15.f));
+        hv[e] = (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
+      }
+      tmem_st8(tmem_c + lane_off + u0, cs);
+      __half2 h01 = __floats2half2_rn(hv[0], hv[1]), h23 = __floats2half2_rn(hv[2], hv[3]);
+      __half2 h45 = __floats2half2_rn(hv[4], hv[5]), h67 = __floats2half2_rn(hv[6], hv[7]);
+      uint4 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
+      pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
+      if (active) {
+        // h_t slice -> the operand buffer of every CTA in the cluster (including this one)
+        const uint32_t local = hs_base + (uint32_t)(b * NHS) * kASlab + hpiece;
+#pragma unroll
+        for (int d = 0; d < C; ++d) st_cluster_v4(mapa_shared(local, (uint32_t)d), pk);
+      }
+      if (valid) {
+        if (p.out0) *reinterpret_cast<uint4*>(p.out0 + pos * p.out0_ld + p.out0_off + dir * H + ua) = pk;
+        if (p.out1) {
+          const __half2* av = reinterpret_cast<const __half2*>(&addv);
+          __half2 o0 = __floats2half2_rn(hv[0] + __low2float(av[0]), hv[1] + __high2float(av[0]));
+          __half2 o1 = __floats2half2_rn(hv[2] + __low2float(av[1]), hv[3] + __high2float(av[1]));
+          __half2 o2 = __floats2half2_rn(hv[4] + __low2float(av[2]), hv[5] + __high2float(av[2]));
+          __half2 o3 = __floats2half2_rn(hv[6] + __low2float(av[3]), hv[7] + __high2float(av[3]));
+          uint4 ok;
+          ok.x = *reinterpret_cast<uint32_t*>(&o0); ok.y = *reinterpret_cast<uint32_t*>(&o1);
+          ok.z = *reinterpret_cast<uint32_t*>(&o2); ok.w = *reinterpret_cast<uint32_t*>(&o3);
+          *reinterpret_cast<uint4*>(p.out1 + pos * p.out1_ld + dir * H + ua) = ok;
+        }
+      }
+      tmem_wait_st();
+      // publish: every lane's DSMEM stores are ordered before lane 0's release-arrives at cluster scope
+      asm volatile("fence.acq_rel.cluster;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t hb = H_FULL(b);
+#pragma unroll
+        for (int d = 0; d < C; ++d) mbar_arrive_remote(mapa_shared(hb, (uint32_t)d));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // no CTA leaves while a peer may still write into its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+
+struct Plan { bool ok; int mr; int xstages; int nxs; size_t smem; };
+
+static Plan make_plan(int H, int c0, int c1) {
+  Plan pl{false, 0, 0, 0, 0};
+  if (H != 64 && H != 128 && H != 256) return pl;
+  if (c0 % 16 || c1 % 16 || c0 <= 0) return pl;
+  const int nxs = (c0 + 63) / 64 + (c1 + 63) / 64;
+  if (nxs > kMaxXSlabs) return pl;
+  const int NHS = H / 64, nslabs = nxs + NHS;
+  int mr_first = 128;
+  if (const char* e = getenv("FNSSL_TC_ROWS")) { if (atoi(e) == 64) mr_first = 64; }   // tests / profiling
+  for (int mr = mr_first; mr >= 64; mr -= 64) {
+    const int aslab = mr * 128;
+    const long fixed = (long)nslabs * kWSlab + 2L * NHS * aslab + kChunkN * 4 + 1024;
+    long xs = (kSmemLimit - 1024 - fixed) / aslab;
+    if (xs > kMaxXStages) xs = kMaxXStages;
+    if (xs >= 2) {
+      pl.ok = true; pl.mr = mr; pl.xstages = (int)xs; pl.nxs = nxs;
+      pl.smem = (size_t)fixed + (size_t)xs * aslab;
+      return pl;
+    }
+  }
+  return pl;
+}
+
+template <int H, int MR>
+static int launch(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
+  constexpr int C = H / kChunkUnits, NHS = H / kSlabK;
+  Params p{};
+  int nxs = 0;
+  for (int src = 0; src < 2; ++src) {
+    const int c = src ? a->c1 : a->c0;
+    for (int k0 = 0; k0 < c; k0 += kSlabK) {
+      p.xs_src[nxs] = src; p.xs_k0[nxs] = k0;
+      p.xs_nk16[nxs] = (((c - k0) < kSlabK ? (c - k0) : kSlabK) + 15) / 16;
+      ++nxs;
+    }
+  }
+  p.nxs = nxs;
+  p.xstages = pl.xstages;
+  const int nslabs = nxs + NHS;
+  const int64_t wbytes = (int64_t)a->num_dirs * C * kChunkN * nslabs * kSlabK * 2;
+  const int64_t need = wbytes + (int64_t)a->num_dirs * 4 * H * 4;
+  FNSSL_REQUIRE(a->weights_bytes == need, "lstm(tcgen05): packed weight buffer is %lld bytes, expected %lld",
+                (long long)a->weights_bytes, (long long)need);
+  FNSSL_REQUIRE((reinterpret_cast<uintptr_t>(a->weights) & 15) == 0, "lstm(tcgen05): weights not 16-byte aligned");
+  p.axis = a->axis; p.nf = a->nf; p.nt = a->nt;
+  int tiles;
+  if (a->axis == FNSSL_ALONG_FREQ) {
+    p.rows = (long long)a->nb * a->nt; p.steps = a->nf; p.tiles_per_b = 0;
+    tiles = (int)((p.rows + MR - 1) / MR);
+  } else {
+    p.rows = (long long)a->nb * a->nf; p.steps = a->nt; p.tiles_per_b = (a->nf + MR - 1) / MR;
+    tiles = a->nb * p.tiles_per_b;
+  }
+  p.bias = reinterpret_cast<const float*>(reinterpret_cast<const char*>(a->weights) + wbytes);
+  p.out0 = (__half*)a->out0; p.out0_ld = a->out0_ld; p.out0_off = a->out0_off;
+  p.addend = (const __half*)a->addend; p.addend_ld = a->addend_ld;
+  p.out1 = (__half*)a->out1; p.out1_ld = a->out1_ld;
+  FNSSL_REQUIRE(!a->out0 || ((reinterpret_cast<uintptr_t>(a->out0) & 15) == 0 && a->out0_ld % 8 == 0 && a->out0_off % 8 == 0),
+                "lstm(tcgen05): out0 must be 16-byte aligned (ld, offset multiples of 8)");
+  FNSSL_REQUIRE(!a->out1 || ((reinterpret_cast<uintptr_t>(a->out1) & 15) == 0 && a->out1_ld % 8 == 0 &&
+                             (reinterpret_cast<uintptr_t>(a->addend) & 15) == 0 && a->addend_ld % 8 == 0),
+                "lstm(tcgen05): out1/addend must be 16-byte aligned");
+  p.error_flag = tc_error_flag();
+
+  CUtensorMap m0, m1, mw;
+  if (make_grid_map(&m0, a->src0, a->c0, a->ld0, a->nb, a->nt, a->nf, a->axis, MR)) return 1;
+  if (a->c1 > 0) { if (make_grid_map(&m1, a->src1, a->c1, a->ld1, a->nb, a->nt, a->nf, a->axis, MR)) return 1; }
+  else m1 = m0;
+  if (make_weight_map(&mw, a->weights, nslabs, a->num_dirs * C)) return 1;
+
+  auto kern = lstm_tc2_kernel<H, MR>;
+  FNSSL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)tiles * C, (unsigned)a->num_dirs, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  FNSSL_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, mw, p));
+  FNSSL_LAUNCH_CHECK("lstm_tc2_kernel");
+  return 0;
+}
+
+}  // namespace tc2
+
+bool lstm_tc2_supports(int hidden, int c0, int c1) { return tc2::make_plan(hidden, c0, c1).ok; }
+
+int lstm_forward_tc2(const fnssl_lstm_args* a, cudaStream_t st) {
+  const tc2::Plan pl = tc2::make_plan(a->hidden, a->c0, a->c1);
+  FNSSL_REQUIRE(pl.ok, "lstm(tcgen05 cluster kernel): unsupported layer (H=%d c0=%d c1=%d)", a->hidden, a->c0, a->c1);
+  if (a->hidden == 64) return pl.mr == 128 ? tc2::launch<64, 128>(a, pl, st) : tc2::launch<64, 64>(a, pl, st);
+  if (a->hidden == 128) return pl.mr == 128 ? tc2::launch<128, 128>(a, pl, st) : tc2::launch<128, 64>(a, pl, st);
+  return pl.mr == 128 ? tc2::launch<256, 128>(a, pl, st) : tc2::launch<256, 64>(a, pl, st);
+}
+
+}  // namespace fnssl

@@ -164,21 +164,24 @@ def test_lstm_layer_simt(axis, H, bidir, c0, c1, addend):
     assert _lstm_case("simt", axis, 2, 7, 19, c0, c1, H, bidir, addend) <= 2e-5
 
 
+@pytest.mark.parametrize("kernel", ["2", "1"])
 @pytest.mark.parametrize("rows", ["64", "128"])
 @pytest.mark.parametrize("axis", [0, 1])
 @pytest.mark.parametrize("H,bidir,c0,c1,addend", [
     (128, True, 4, 0, False), (128, True, 256, 0, True), (128, True, 256, 4, True), (128, False, 256, 0, False),
     (128, True, 256, 8, False), (64, True, 8, 0, False), (128, False, 128, 8, False), (64, True, 128, 8, True),
     (256, False, 256, 4, True), (256, False, 256, 0, False), (256, False, 256, 8, False)])
-def test_lstm_layer_tcgen05(monkeypatch, rows, axis, H, bidir, c0, c1, addend):
-    """Both row-tile shapes of the tensor-core kernel (128-row and 64-row CTAs), ragged tiles (70 frames / 40 bins
-    are not multiples of the tile), two-source inputs and the fused residual output."""
+def test_lstm_layer_tcgen05(monkeypatch, kernel, rows, axis, H, bidir, c0, c1, addend):
+    """Both tensor-core kernels (2 = cluster-resident weights, 1 = weight streaming), both row-tile shapes (128 / 64
+    sequences per tile), ragged tiles (70 frames / 40 bins are not multiples of the tile), two-source inputs and
+    the fused residual output."""
     from fn_ssl_b200 import config
     if not config.TC_AVAILABLE:
         pytest.skip("tcgen05 engine not built")
     if H == 256 and rows == "128":
         pytest.skip("H = 256 only exists with 64-row tiles")
     monkeypatch.setenv("FNSSL_TC_ROWS", rows)
+    monkeypatch.setenv("FNSSL_TC_KERNEL", kernel)
     nb, nt, nf = (2, 70, 256) if axis == 1 else (2, 70, 40)
     assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, H, bidir, addend) <= 1e-3
 

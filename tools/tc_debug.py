@@ -74,12 +74,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         run_case(int(sys.argv[1]))
     else:
-        for rows in ("64", "128"):
-            print(f"==== FNSSL_TC_ROWS={rows}")
+        kernels = os.environ.get("TC_DEBUG_KERNELS", "2,1").split(",")
+        for kern, rows in [(k, r) for k in kernels for r in ("128", "64")]:
+            print(f"==== FNSSL_TC_KERNEL={kern} FNSSL_TC_ROWS={rows}")
             for i in range(len(CASES)):
                 if rows == "128" and CASES[i][7] == 256:
                     continue
-                env = dict(os.environ, FNSSL_TC_ROWS=rows)
+                env = dict(os.environ, FNSSL_TC_ROWS=rows, FNSSL_TC_KERNEL=kern)
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), str(i)], capture_output=True, text=True,
                                    timeout=300, env=env)
                 print(r.stdout.strip())
