@@ -10,8 +10,8 @@
 //     x-part   G  = x_t . W_x^T      x_t slabs are TMA-multicast to the whole cluster through a small ring; issued a
 //                                    step ahead into the other accumulator buffer, off the critical path
 //     h-part   G += h_{t-1} . W_h^T  needs all of h_{t-1}: every CTA's epilogue writes its 32-unit slice of h_t into the
-//                                    operand buffer of ALL CTAs of the cluster (st.shared::cluster, DSMEM) and signals
-//                                    their "h_t complete" mbarriers (release/acquire at cluster scope)
+//                                    operand buffer of ALL CTAs of the cluster with st.async (DSMEM); every 16-byte
+//                                    store completes tx bytes on the destination's "h_t complete" mbarrier
 //     epilogue 16 warps: tcgen05.ld gates -> sigmoid/tanh -> c (fp32, resident in TMEM) -> h_t (fp16) -> DSMEM + HBM
 // The serial chain of a step is: h-part MMA (K = H) -> gate math of 32 units -> DSMEM exchange; weights never move.
 //
@@ -51,6 +51,7 @@ struct Params {
   const __half* addend; int addend_ld;
   __half* out1; int out1_ld;
   int* error_flag;
+  int debug;                       // timing experiments only (FNSSL_TC_DEBUG): 1 = skip gate math, 2 = skip MMA issue
 };
 
 template <int MR>
@@ -96,7 +97,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   if (tid == 0) {
     mbar_init(W_FULL, 1);
     for (int i = 0; i < kMaxXStages; ++i) { mbar_init(X_FULL(i), 1); mbar_init(X_EMPTY(i), C); }
-    for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), kEpiThreads); mbar_init(H_FULL(i), C * kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), kEpiThreads); mbar_init(H_FULL(i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&map_src0); prefetch_tmap(&map_src1); prefetch_tmap(&map_w); }
@@ -169,14 +170,17 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           const uint64_t a_desc = make_sw128_desc(xr_base + (uint32_t)stage * kASlab);
           const uint64_t b_desc = make_sw128_desc(w_base + (uint32_t)j * kWSlab);
           const int nk16 = p.xs_nk16[j];
-          for (int k = 0; k < nk16; ++k) {
-            umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accumulate);
-            accumulate = 1;
+          if (!(p.debug & 2)) {
+            for (int k = 0; k < nk16; ++k) {
+              umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accumulate);
+              accumulate = 1;
+            }
           }
           umma_commit_mc(X_EMPTY(stage), mask);    // this CTA is done with the slab: tell every CTA's ring
         }
         if (t > 0) {
-          // h_{t-1}: 32-unit slices written by all CTAs of the cluster (generic proxy, DSMEM)
+          // h_{t-1}: 32-unit slices st.async'ed by all CTAs of the cluster; each 16-byte store completes 16 tx bytes
+          mbar_expect_tx(H_FULL((t - 1) & 1), (uint32_t)(MR * H * 2));
           mbar_wait_cluster(H_FULL((t - 1) & 1), (uint32_t)(((t - 1) >> 1) & 1), p.error_flag, 220);
           fence_async_smem();
           tc_fence_after();
@@ -185,7 +189,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
             const uint64_t a_desc = make_sw128_desc(hs_base + (uint32_t)(((t - 1) & 1) * NHS + hs) * kASlab);
             const uint64_t b_desc = make_sw128_desc(w_base + (uint32_t)(nxs + hs) * kWSlab);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, 1u);
+            for (int k = 0; k < 4; ++k) if (!(p.debug & 2)) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, 1u);
           }
         }
         umma_commit(ACC_FULL(b));
@@ -242,6 +246,10 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       tc_fence_before();
       mbar_arrive(ACC_EMPTY(b));      // accumulator drained: the MMA warp may start the x-part of step t+2 into it
       float hv[8];
+      if (p.debug & 1) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) hv[e] = gti[e] + gtf[e] + gtg[e] + gto[e] + cs[e];
+      } else
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         // sigmoid(x) = 1/(1+2^(-x log2 e)) (no clamp needed: 2^big = inf -> 0); tanh as (1-E)/(1+E) shares a
@@ -256,18 +264,20 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         const float ec = ex2_approx(-2.0f * kL2E * fminf(fmaxf(cn, -15.f), 15.f));
         hv[e] = (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
       }
-      tmem_st8(tmem_c + lane_off + u0, cs);
       __half2 h01 = __floats2half2_rn(hv[0], hv[1]), h23 = __floats2half2_rn(hv[2], hv[3]);
       __half2 h45 = __floats2half2_rn(hv[4], hv[5]), h67 = __floats2half2_rn(hv[6], hv[7]);
       uint4 pk;
       pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
       pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
-      if (active) {
-        // h_t slice -> the operand buffer of every CTA in the cluster (including this one)
+      if (active && t + 1 < L) {
+        // h_t slice -> the operand buffer of every CTA in the cluster (including this one): asynchronous DSMEM stores
+        // that complete on the destination's "h_t complete" mbarrier.  Issued before anything else of the tail.
         const uint32_t local = hs_base + (uint32_t)(b * NHS) * kASlab + hpiece;
+        const uint32_t hb = H_FULL(b);
 #pragma unroll
-        for (int d = 0; d < C; ++d) st_cluster_v4(mapa_shared(local, (uint32_t)d), pk);
+        for (int d = 0; d < C; ++d) st_async_v4(mapa_shared(local, (uint32_t)d), pk, mapa_shared(hb, (uint32_t)d));
       }
+      tmem_st8(tmem_c + lane_off + u0, cs);
       if (valid) {
         if (p.out0) *reinterpret_cast<uint4*>(p.out0 + pos * p.out0_ld + p.out0_off + dir * H + ua) = pk;
         if (p.out1) {
@@ -283,14 +293,6 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         }
       }
       tmem_wait_st();
-      // publish: every lane's DSMEM stores are ordered before lane 0's release-arrives at cluster scope
-      asm volatile("fence.acq_rel.cluster;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) {
-        const uint32_t hb = H_FULL(b);
-#pragma unroll
-        for (int d = 0; d < C; ++d) mbar_arrive_remote(mapa_shared(hb, (uint32_t)d));
-      }
     }
   }
 
@@ -372,6 +374,7 @@ static int launch(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
                              (reinterpret_cast<uintptr_t>(a->addend) & 15) == 0 && a->addend_ld % 8 == 0),
                 "lstm(tcgen05): out1/addend must be 16-byte aligned");
   p.error_flag = tc_error_flag();
+  if (const char* e = getenv("FNSSL_TC_DEBUG")) p.debug = atoi(e);
 
   CUtensorMap m0, m1, mw;
   if (make_grid_map(&m0, a->src0, a->c0, a->ld0, a->nb, a->nt, a->nf, a->axis, MR)) return 1;

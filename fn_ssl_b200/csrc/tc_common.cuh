@@ -147,6 +147,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void st_cluster_v4(uint32_t caddr, const uint4& v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(caddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// asynchronous 16-byte store into (possibly remote) shared memory of the cluster; on completion the store performs
+// complete_tx(16) on the mbarrier `cbar` (cluster address, same CTA as the destination) -- no fences, no arrives
+__device__ __forceinline__ void st_async_v4(uint32_t caddr, const uint4& v, uint32_t cbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(caddr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cbar)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t caddr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
 }
