@@ -51,6 +51,7 @@ struct Params {
   const __half* addend; int addend_ld;
   __half* out1; int out1_ld;
   int* error_flag;
+  long long* trace;                // FNSSL_TC_TRACE: clock64 stamps of cluster 0 / CTA 0, steps [8, 16): [step][16 events]
   int debug;                       // timing experiments only (FNSSL_TC_DEBUG): 1 = skip gate math, 2 = skip MMA issue
 };
 
@@ -157,8 +158,11 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       constexpr uint32_t idesc = make_idesc<MR>();
       mbar_wait(W_FULL, 0, p.error_flag, 200);
       int n = 0;
+      const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
       for (int t = 0; t < L; ++t) {
         const int b = t & 1, use = t >> 1;
+        long long* tp = (tr && t >= 8 && t < 16) ? p.trace + (t - 8) * 16 : nullptr;
+        if (tp) tp[0] = clock64();
         if (use > 0) mbar_wait(ACC_EMPTY(b), (uint32_t)((use - 1) & 1), p.error_flag, 201 + b);
         tc_fence_after();
         const uint32_t d_tmem = tmem_acc + (uint32_t)b * kChunkN;
@@ -178,12 +182,15 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           }
           umma_commit_mc(X_EMPTY(stage), mask);    // this CTA is done with the slab: tell every CTA's ring
         }
+        if (tp) tp[1] = clock64();
         if (t > 0) {
           // h_{t-1}: 32-unit slices st.async'ed by all CTAs of the cluster; each 16-byte store completes 16 tx bytes
           mbar_expect_tx(H_FULL((t - 1) & 1), (uint32_t)(MR * H * 2));
           mbar_wait_cluster(H_FULL((t - 1) & 1), (uint32_t)(((t - 1) >> 1) & 1), p.error_flag, 220);
+          if (tp) tp[2] = clock64();
           fence_async_smem();
           tc_fence_after();
+          if (tp) tp[3] = clock64();
 #pragma unroll
           for (int hs = 0; hs < NHS; ++hs) {
             const uint64_t a_desc = make_sw128_desc(hs_base + (uint32_t)(((t - 1) & 1) * NHS + hs) * kASlab);
@@ -193,6 +200,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           }
         }
         umma_commit(ACC_FULL(b));
+        if (tp) tp[4] = clock64();
       }
     }
     __syncwarp();
@@ -226,13 +234,17 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
 #pragma unroll
       for (int e = 0; e < 8; ++e) bsv[gq][e] = bias_s[gq * kChunkUnits + u0 + e];
 
+    const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0;
     for (int t = 0; t < L; ++t) {
       const int b = t & 1;
       const int s = dir ? (L - 1 - t) : t;
       const long long pos = base + (long long)s * sstride;
+      long long* tp = (tr && t >= 8 && t < 16) ? p.trace + (t - 8) * 16 : nullptr;
+      if (tp) tp[8] = clock64();
       uint4 addv = make_uint4(0, 0, 0, 0);
       if (p.out1 && valid) addv = __ldg(reinterpret_cast<const uint4*>(p.addend + pos * p.addend_ld + dir * H + ua));
       mbar_wait(ACC_FULL(b), (uint32_t)((t >> 1) & 1), p.error_flag, 300 + b);
+      if (tp) tp[9] = clock64();
       tc_fence_after();
       const uint32_t acc = tmem_acc + (uint32_t)b * kChunkN + lane_off + u0;
       float gti[8], gtf[8], gtg[8], gto[8], cs[8];
@@ -243,6 +255,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       tmem_ld8(tmem_c + lane_off + u0, cs);
       tmem_wait_ld();
       tmem_ld_dep(gti); tmem_ld_dep(gtf); tmem_ld_dep(gtg); tmem_ld_dep(gto); tmem_ld_dep(cs);
+      if (tp) tp[10] = clock64();
       tc_fence_before();
       mbar_arrive(ACC_EMPTY(b));      // accumulator drained: the MMA warp may start the x-part of step t+2 into it
       float hv[8];
@@ -269,6 +282,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       uint4 pk;
       pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
       pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
+      if (tp) tp[11] = clock64();
       if (active && t + 1 < L) {
         // h_t slice -> the operand buffer of every CTA in the cluster (including this one): asynchronous DSMEM stores
         // that complete on the destination's "h_t complete" mbarrier.  Issued before anything else of the tail.
@@ -277,6 +291,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
 #pragma unroll
         for (int d = 0; d < C; ++d) st_async_v4(mapa_shared(local, (uint32_t)d), pk, mapa_shared(hb, (uint32_t)d));
       }
+      if (tp) tp[12] = clock64();
       tmem_st8(tmem_c + lane_off + u0, cs);
       if (valid) {
         if (p.out0) *reinterpret_cast<uint4*>(p.out0 + pos * p.out0_ld + p.out0_off + dir * H + ua) = pk;
@@ -293,6 +308,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         }
       }
       tmem_wait_st();
+      if (tp) tp[13] = clock64();
     }
   }
 
@@ -332,6 +348,17 @@ static Plan make_plan(int H, int c0, int c1) {
     }
   }
   return pl;
+}
+
+long long* g_trace_host = nullptr;
+static long long* tc2_trace_buffer() {
+  static long long* dev = nullptr;
+  if (!dev) {
+    if (cudaHostAlloc(&g_trace_host, 8 * 16 * sizeof(long long), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    for (int i = 0; i < 128; ++i) g_trace_host[i] = 0;
+    if (cudaHostGetDevicePointer(&dev, g_trace_host, 0) != cudaSuccess) dev = nullptr;
+  }
+  return dev;
 }
 
 template <int H, int MR>
@@ -375,6 +402,7 @@ static int launch(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
                 "lstm(tcgen05): out1/addend must be 16-byte aligned");
   p.error_flag = tc_error_flag();
   if (const char* e = getenv("FNSSL_TC_DEBUG")) p.debug = atoi(e);
+  if (getenv("FNSSL_TC_TRACE")) p.trace = tc2_trace_buffer();
 
   CUtensorMap m0, m1, mw;
   if (make_grid_map(&m0, a->src0, a->c0, a->ld0, a->nb, a->nt, a->nf, a->axis, MR)) return 1;
@@ -399,6 +427,13 @@ static int launch(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
 }
 
 }  // namespace tc2
+
+// diagnostic: copy the last trace (8 steps x 16 clock64 stamps) recorded with FNSSL_TC_TRACE=1
+extern "C" int fnssl_lstm_tc_trace(long long* out128) {
+  if (!tc2::g_trace_host) return 0;
+  for (int i = 0; i < 128; ++i) out128[i] = tc2::g_trace_host[i];
+  return 1;
+}
 
 bool lstm_tc2_supports(int hidden, int c0, int c1) { return tc2::make_plan(hidden, c0, c1).ok; }
 
