@@ -185,7 +185,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         if (tp) tp[1] = clock64();
         if (t > 0) {
           // h_{t-1}: 32-unit slices st.async'ed by all CTAs of the cluster; each 16-byte store completes 16 tx bytes
-          mbar_expect_tx(H_FULL((t - 1) & 1), (uint32_t)(MR * H * 2));
+          mbar_expect_tx(H_FULL((t - 1) & 1), (uint32_t)(MR * H * 2) >> ((p.debug & 4) ? 2 : 0));
           mbar_wait_cluster(H_FULL((t - 1) & 1), (uint32_t)(((t - 1) >> 1) & 1), p.error_flag, 220);
           if (tp) tp[2] = clock64();
           fence_async_smem();
@@ -235,14 +235,24 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       for (int e = 0; e < 8; ++e) bsv[gq][e] = bias_s[gq * kChunkUnits + u0 + e];
 
     const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0;
+    // residual operand of the next layer (h + addend): fetched one whole step ahead so its HBM latency never sits
+    // between the gate math and the h exchange
+    uint4 addv_next = make_uint4(0, 0, 0, 0);
+    if (p.out1 && valid) {
+      const long long pos0 = base + (long long)(dir ? (L - 1) : 0) * sstride;
+      addv_next = __ldg(reinterpret_cast<const uint4*>(p.addend + pos0 * p.addend_ld + dir * H + ua));
+    }
     for (int t = 0; t < L; ++t) {
       const int b = t & 1;
       const int s = dir ? (L - 1 - t) : t;
       const long long pos = base + (long long)s * sstride;
       long long* tp = (tr && t >= 8 && t < 16) ? p.trace + (t - 8) * 16 : nullptr;
       if (tp) tp[8] = clock64();
-      uint4 addv = make_uint4(0, 0, 0, 0);
-      if (p.out1 && valid) addv = __ldg(reinterpret_cast<const uint4*>(p.addend + pos * p.addend_ld + dir * H + ua));
+      const uint4 addv = addv_next;
+      if (p.out1 && valid && t + 1 < L) {
+        const long long posn = base + (long long)(dir ? (L - 2 - t) : (t + 1)) * sstride;
+        addv_next = __ldg(reinterpret_cast<const uint4*>(p.addend + posn * p.addend_ld + dir * H + ua));
+      }
       mbar_wait(ACC_FULL(b), (uint32_t)((t >> 1) & 1), p.error_flag, 300 + b);
       if (tp) tp[9] = clock64();
       tc_fence_after();
@@ -283,7 +293,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
       pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
       if (tp) tp[11] = clock64();
-      if (active && t + 1 < L) {
+      if (active && t + 1 < L && (!(p.debug & 4) || (lane & 3) == 0)) {
         // h_t slice -> the operand buffer of every CTA in the cluster (including this one): asynchronous DSMEM stores
         // that complete on the destination's "h_t complete" mbarrier.  Issued before anything else of the tail.
         const uint32_t local = hs_base + (uint32_t)(b * NHS) * kASlab + hpiece;
@@ -292,6 +302,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         for (int d = 0; d < C; ++d) st_async_v4(mapa_shared(local, (uint32_t)d), pk, mapa_shared(hb, (uint32_t)d));
       }
       if (tp) tp[12] = clock64();
+      if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && t == 12) p.trace[128 + warp] = clock64();
       tmem_st8(tmem_c + lane_off + u0, cs);
       if (valid) {
         if (p.out0) *reinterpret_cast<uint4*>(p.out0 + pos * p.out0_ld + p.out0_off + dir * H + ua) = pk;
@@ -354,8 +365,8 @@ long long* g_trace_host = nullptr;
 static long long* tc2_trace_buffer() {
   static long long* dev = nullptr;
   if (!dev) {
-    if (cudaHostAlloc(&g_trace_host, 8 * 16 * sizeof(long long), cudaHostAllocMapped) != cudaSuccess) return nullptr;
-    for (int i = 0; i < 128; ++i) g_trace_host[i] = 0;
+    if (cudaHostAlloc(&g_trace_host, 160 * sizeof(long long), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    for (int i = 0; i < 160; ++i) g_trace_host[i] = 0;
     if (cudaHostGetDevicePointer(&dev, g_trace_host, 0) != cudaSuccess) dev = nullptr;
   }
   return dev;
@@ -429,9 +440,9 @@ static int launch(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
 }  // namespace tc2
 
 // diagnostic: copy the last trace (8 steps x 16 clock64 stamps) recorded with FNSSL_TC_TRACE=1
-extern "C" int fnssl_lstm_tc_trace(long long* out128) {
+extern "C" int fnssl_lstm_tc_trace(long long* out160) {
   if (!tc2::g_trace_host) return 0;
-  for (int i = 0; i < 128; ++i) out128[i] = tc2::g_trace_host[i];
+  for (int i = 0; i < 160; ++i) out160[i] = tc2::g_trace_host[i];
   return 1;
 }
 

@@ -137,8 +137,8 @@ int fnssl_lstm_forward(const fnssl_lstm_args* args, void* stream);
 int fnssl_lstm_tc_supported(int hidden, int c0, int c1);
 /* diagnostic: site code written by a timed-out pipeline wait inside the tcgen05 kernel (0 = none) */
 int fnssl_lstm_tc_error_site(void);
-/* diagnostic: last in-kernel timeline (8 steps x 16 SM-clock stamps) recorded when FNSSL_TC_TRACE is set; 0 if none */
-int fnssl_lstm_tc_trace(long long* out128);
+/* diagnostic: last in-kernel timeline (8 steps x 16 SM-clock stamps + 32 per-warp stamps) recorded when FNSSL_TC_TRACE is set; 0 if none */
+int fnssl_lstm_tc_trace(long long* out160);
 
 /* ---- heads ---------------------------------------------------------------------------------- */
 

@@ -26,12 +26,13 @@ for name, axis, nb, nt, nf, c0, c1, H, bidir, add in cfgs:
     for _ in range(2):
         run_lstm(p, "tcgen05", axis, g0, c0, g1, c1, addend=ga)
     torch.cuda.synchronize()
-    buf = (C.c_longlong * 128)()
+    buf = (C.c_longlong * 160)()
     if not _lib.load().fnssl_lstm_tc_trace(buf):
         print("no trace"); continue
     tr = [[buf[s * 16 + k] for k in range(16)] for s in range(8)]
     print(f"== {name}: period (epi iter start to next) = {[tr[s+1][8]-tr[s][8] for s in range(7)]}")
     s = 4
-    t0 = tr[s][9]   # reference: epilogue passes ACC_FULL of step s
+    t0 = tr[s][9]
+    print("   per-warp st.async issue (step 12, rel.):", [buf[128 + w] - t0 for w in range(2, 18)])   # reference: epilogue passes ACC_FULL of step s
     for k in (0, 1, 2, 3, 4, 8, 9, 10, 11, 12, 13):
         print(f"   {names[k]:28s} step{s + 8}: {tr[s][k] - t0:7d}    step{s + 9}: {tr[s + 1][k] - t0:7d}")
