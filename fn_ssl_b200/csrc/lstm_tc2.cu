@@ -228,11 +228,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       tmem_wait_st();
     }
     const float kL2E = 1.4426950408889634f;
-    float bsv[4][8];
-#pragma unroll
-    for (int gq = 0; gq < 4; ++gq)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) bsv[gq][e] = bias_s[gq * kChunkUnits + u0 + e];
+    const float* bsp = bias_s + u0;      // bias of (gate, unit) at bsp[gate * 32 + e] (broadcast shared-memory reads)
 
     const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0;
     // residual operand of the next layer (h + addend): fetched one whole step ahead so its HBM latency never sits
@@ -269,37 +265,63 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       tc_fence_before();
       mbar_arrive(ACC_EMPTY(b));      // accumulator drained: the MMA warp may start the x-part of step t+2 into it
       float hv[8];
-      if (p.debug & 1) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) hv[e] = gti[e] + gtf[e] + gtg[e] + gto[e] + cs[e];
-      } else
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
+      const uint32_t local = hs_base + (uint32_t)(b * NHS) * kASlab + hpiece;
+      const uint32_t hb = H_FULL(b);
+      const bool send = active && t + 1 < L && (!(p.debug & 4) || (lane & 3) == 0);
+      auto gate_math = [&](int e) {
         // sigmoid(x) = 1/(1+2^(-x log2 e)) (no clamp needed: 2^big = inf -> 0); tanh as (1-E)/(1+E) shares a
         // reciprocal with a sigmoid, so E must stay finite: clamp its argument to +-15
-        const float xg = fminf(fmaxf(gtg[e] + bsv[2][e], -15.f), 15.f);
-        const float ei = ex2_approx(-kL2E * (gti[e] + bsv[0][e]));
-        const float ef = ex2_approx(-kL2E * (gtf[e] + bsv[1][e]));
+        const float xg = fminf(fmaxf(gtg[e] + bsp[2 * kChunkUnits + e], -15.f), 15.f);
+        const float ei = ex2_approx(-kL2E * (gti[e] + bsp[e]));
+        const float ef = ex2_approx(-kL2E * (gtf[e] + bsp[kChunkUnits + e]));
         const float eg = ex2_approx(-2.0f * kL2E * xg);
-        const float eo = ex2_approx(-kL2E * (gto[e] + bsv[3][e]));
+        const float eo = ex2_approx(-kL2E * (gto[e] + bsp[3 * kChunkUnits + e]));
         const float cn = cs[e] * rcp_approx(1.0f + ef) + (1.0f - eg) * rcp_approx((1.0f + ei) * (1.0f + eg));
         cs[e] = cn;
         const float ec = ex2_approx(-2.0f * kL2E * fminf(fmaxf(cn, -15.f), 15.f));
         hv[e] = (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
-      }
-      __half2 h01 = __floats2half2_rn(hv[0], hv[1]), h23 = __floats2half2_rn(hv[2], hv[3]);
-      __half2 h45 = __floats2half2_rn(hv[4], hv[5]), h67 = __floats2half2_rn(hv[6], hv[7]);
+      };
       uint4 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
-      pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
-      if (tp) tp[11] = clock64();
-      if (active && t + 1 < L && (!(p.debug & 4) || (lane & 3) == 0)) {
-        // h_t slice -> the operand buffer of every CTA in the cluster (including this one): asynchronous DSMEM stores
-        // that complete on the destination's "h_t complete" mbarrier.  Issued before anything else of the tail.
-        const uint32_t local = hs_base + (uint32_t)(b * NHS) * kASlab + hpiece;
-        const uint32_t hb = H_FULL(b);
+      if (p.debug & 1) {
 #pragma unroll
-        for (int d = 0; d < C; ++d) st_async_v4(mapa_shared(local, (uint32_t)d), pk, mapa_shared(hb, (uint32_t)d));
+        for (int e = 0; e < 8; ++e) hv[e] = gti[e] + gtf[e] + gtg[e] + gto[e] + cs[e];
+      }
+      if (p.debug & 8) {
+        // experiment: exchange in two 8-byte halves so the first stores overlap the second half of the gate math
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          if (!(p.debug & 1)) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) gate_math(hf * 4 + e);
+          }
+          __half2 a0 = __floats2half2_rn(hv[hf * 4 + 0], hv[hf * 4 + 1]), a1 = __floats2half2_rn(hv[hf * 4 + 2], hv[hf * 4 + 3]);
+          const uint32_t x0 = *reinterpret_cast<uint32_t*>(&a0), x1 = *reinterpret_cast<uint32_t*>(&a1);
+          if (hf == 0) { pk.x = x0; pk.y = x1; } else { pk.z = x0; pk.w = x1; }
+          if (send) {
+#pragma unroll
+            for (int d = 0; d < C; ++d)
+              st_async_v2(mapa_shared(local + 8u * hf, (uint32_t)d), x0, x1, mapa_shared(hb, (uint32_t)d));
+          }
+        }
+      } else {
+        if (!(p.debug & 1)) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) gate_math(e);
+        }
+        __half2 h01 = __floats2half2_rn(hv[0], hv[1]), h23 = __floats2half2_rn(hv[2], hv[3]);
+        __half2 h45 = __floats2half2_rn(hv[4], hv[5]), h67 = __floats2half2_rn(hv[6], hv[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
+        pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
+        if (tp) tp[11] = clock64();
+        if (send) {
+          // h_t slice -> the operand buffer of every CTA of the cluster: asynchronous DSMEM stores that complete tx
+          // bytes on the destination's "h_t complete" mbarrier; remote peers first, own copy last
+#pragma unroll
+          for (int dd = 1; dd <= C; ++dd) {
+            const uint32_t d = (rank + (uint32_t)dd) % C;
+            st_async_v4(mapa_shared(local, d), pk, mapa_shared(hb, d));
+          }
+        }
       }
       if (tp) tp[12] = clock64();
       if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && t == 12) p.trace[128 + warp] = clock64();

@@ -154,6 +154,11 @@ __device__ __forceinline__ void st_async_v4(uint32_t caddr, const uint4& v, uint
                "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cbar)
                : "memory");
 }
+__device__ __forceinline__ void st_async_v2(uint32_t caddr, uint32_t x, uint32_t y, uint32_t cbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(caddr), "r"(x),
+               "r"(y), "r"(cbar)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t caddr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
 }
