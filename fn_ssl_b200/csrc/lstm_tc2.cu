@@ -9,9 +9,10 @@
 // weights RESIDENT in shared memory for the whole launch (loaded once by TMA).  Per step and CTA:
 //     x-part   G  = x_t . W_x^T      x_t slabs are TMA-multicast to the whole cluster through a small ring; issued a
 //                                    step ahead into the other accumulator buffer, off the critical path
-//     h-part   G += h_{t-1} . W_h^T  needs all of h_{t-1}: every CTA's epilogue writes its 32-unit slice of h_t into the
-//                                    operand buffer of ALL CTAs of the cluster with st.async (DSMEM); every 16-byte
-//                                    store completes tx bytes on the destination's "h_t complete" mbarrier
+//     h-part   G += h_{t-1} . W_h^T  needs all of h_{t-1}: h lives as C tiles [MR x 32 units] (64B-swizzled K-major); a
+//                                    CTA's epilogue writes its own tile locally and each 32-row quadrant is pushed to
+//                                    every peer with one DSMEM bulk copy (cp.async.bulk shared::cta -> shared::cluster)
+//                                    that completes tx bytes on the peer's "h_t complete" mbarrier
 //     epilogue 16 warps: tcgen05.ld gates -> sigmoid/tanh -> c (fp32, resident in TMEM) -> h_t (fp16) -> DSMEM + HBM
 // The serial chain of a step is: h-part MMA (K = H) -> gate math of 32 units -> DSMEM exchange; weights never move.
 //
@@ -64,7 +65,8 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
                 const __grid_constant__ CUtensorMap map_w, const Params p) {
   constexpr int C = H / kChunkUnits;      // cluster size == number of 32-unit chunks
   constexpr int NHS = H / kSlabK;         // K slabs of h
-  constexpr int kASlab = MR * 128;        // one [MR x 64] fp16 A tile
+  constexpr int kASlab = MR * 128;        // one [MR x 64] fp16 A tile (x slabs, 128B swizzle)
+  constexpr int kHTile = MR * 64;         // one [MR x 32] fp16 h tile (one chunk, 64B swizzle)
   static_assert(H == 64 || H == 128 || H == 256, "H in {64,128,256}");
   static_assert(MR == 64 || MR == 128, "MR in {64,128}");
 
@@ -83,7 +85,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   const uint32_t dyn0 = (smem_addr(smem_dyn) + 1023u) & ~1023u;
   const uint32_t w_base = dyn0;                                     // resident weights: nslabs tiles
   const uint32_t hs_base = w_base + (uint32_t)nslabs * kWSlab;      // h operand: 2 buffers x NHS tiles
-  const uint32_t xr_base = hs_base + 2u * NHS * kASlab;             // x ring: XS tiles
+  const uint32_t xr_base = hs_base + 2u * C * kHTile;               // x ring: XS tiles (2*C*kHTile == 2*NHS*kASlab)
   const uint32_t bias_base = xr_base + (uint32_t)XS * kASlab;       // 128 floats
   float* bias_s = reinterpret_cast<float*>(smem_dyn + (bias_base - smem_addr(smem_dyn)));
 
@@ -98,7 +100,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   if (tid == 0) {
     mbar_init(W_FULL, 1);
     for (int i = 0; i < kMaxXStages; ++i) { mbar_init(X_FULL(i), 1); mbar_init(X_EMPTY(i), C); }
-    for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), kEpiThreads); mbar_init(H_FULL(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), kEpiThreads); mbar_init(H_FULL(i), 5); }   // MMA thread's expect_tx + 4 local quadrants
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&map_src0); prefetch_tmap(&map_src1); prefetch_tmap(&map_w); }
@@ -184,19 +186,19 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         }
         if (tp) tp[1] = clock64();
         if (t > 0) {
-          // h_{t-1}: 32-unit slices st.async'ed by all CTAs of the cluster; each 16-byte store completes 16 tx bytes
-          mbar_expect_tx(H_FULL((t - 1) & 1), (uint32_t)(MR * H * 2) >> ((p.debug & 4) ? 2 : 0));
+          // h_{t-1}: the C-1 remote tiles arrive as DSMEM bulk copies (tx bytes), the local tile by plain arrives
+          mbar_expect_tx(H_FULL((t - 1) & 1), (uint32_t)((C - 1) * kHTile));
           mbar_wait_cluster(H_FULL((t - 1) & 1), (uint32_t)(((t - 1) >> 1) & 1), p.error_flag, 220);
           if (tp) tp[2] = clock64();
           fence_async_smem();
           tc_fence_after();
           if (tp) tp[3] = clock64();
 #pragma unroll
-          for (int hs = 0; hs < NHS; ++hs) {
-            const uint64_t a_desc = make_sw128_desc(hs_base + (uint32_t)(((t - 1) & 1) * NHS + hs) * kASlab);
-            const uint64_t b_desc = make_sw128_desc(w_base + (uint32_t)(nxs + hs) * kWSlab);
+          for (int kc = 0; kc < C; ++kc) {   // K = 32 units of chunk kc: two K=16 steps; W columns inside 128B-swizzled slab kc/2
+            const uint64_t a_desc = make_sw64_desc(hs_base + (uint32_t)(((t - 1) & 1) * C + kc) * kHTile);
+            const uint64_t b_desc = make_sw128_desc(w_base + (uint32_t)(nxs + (kc >> 1)) * kWSlab) + 4u * (kc & 1);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) if (!(p.debug & 2)) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, 1u);
+            for (int k = 0; k < 2; ++k) if (!(p.debug & 2)) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, 1u);
           }
         }
         umma_commit(ACC_FULL(b));
@@ -217,9 +219,12 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
     long long base, sstride;
     if (p.axis == FNSSL_ALONG_FREQ) { base = (row0 + r) * p.nf; sstride = 1; }
     else { base = (long long)coord_b * p.nt * p.nf + coord_r0 + r; sstride = p.nf; }
-    // destination of this thread's 16-byte h piece inside an h operand buffer (128B swizzle)
-    const uint32_t hpiece = (uint32_t)(ua >> 6) * kASlab + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
-                            (uint32_t)((((ua & 63) >> 3) ^ (r & 7)) << 4);
+    // this thread's 16-byte h piece inside the CTA's own [MR x 32] tile (64B swizzle: chunk ^= (row >> 1) & 3)
+    const uint32_t hpiece = (uint32_t)rank * kHTile + (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u +
+                            (uint32_t)((sub ^ ((r >> 1) & 3)) << 4);
+    // the quadrant's rows form one contiguous region of that tile: 32 rows (MR = 128) or 16 rows (MR = 64) x 64 B
+    constexpr uint32_t kQuadBytes = (MR == 128) ? 2048u : 1024u;
+    const uint32_t hquad = (uint32_t)rank * kHTile + (uint32_t)q * kQuadBytes;
     {
       float z[8];
 #pragma unroll
@@ -265,62 +270,46 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       tc_fence_before();
       mbar_arrive(ACC_EMPTY(b));      // accumulator drained: the MMA warp may start the x-part of step t+2 into it
       float hv[8];
-      const uint32_t local = hs_base + (uint32_t)(b * NHS) * kASlab + hpiece;
-      const uint32_t hb = H_FULL(b);
-      const bool send = active && t + 1 < L && (!(p.debug & 4) || (lane & 3) == 0);
-      auto gate_math = [&](int e) {
-        // sigmoid(x) = 1/(1+2^(-x log2 e)) (no clamp needed: 2^big = inf -> 0); tanh as (1-E)/(1+E) shares a
-        // reciprocal with a sigmoid, so E must stay finite: clamp its argument to +-15
-        const float xg = fminf(fmaxf(gtg[e] + bsp[2 * kChunkUnits + e], -15.f), 15.f);
-        const float ei = ex2_approx(-kL2E * (gti[e] + bsp[e]));
-        const float ef = ex2_approx(-kL2E * (gtf[e] + bsp[kChunkUnits + e]));
-        const float eg = ex2_approx(-2.0f * kL2E * xg);
-        const float eo = ex2_approx(-kL2E * (gto[e] + bsp[3 * kChunkUnits + e]));
-        const float cn = cs[e] * rcp_approx(1.0f + ef) + (1.0f - eg) * rcp_approx((1.0f + ei) * (1.0f + eg));
-        cs[e] = cn;
-        const float ec = ex2_approx(-2.0f * kL2E * fminf(fmaxf(cn, -15.f), 15.f));
-        hv[e] = (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
-      };
-      uint4 pk;
       if (p.debug & 1) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) hv[e] = gti[e] + gtf[e] + gtg[e] + gto[e] + cs[e];
-      }
-      if (p.debug & 8) {
-        // experiment: exchange in two 8-byte halves so the first stores overlap the second half of the gate math
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          if (!(p.debug & 1)) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) gate_math(hf * 4 + e);
-          }
-          __half2 a0 = __floats2half2_rn(hv[hf * 4 + 0], hv[hf * 4 + 1]), a1 = __floats2half2_rn(hv[hf * 4 + 2], hv[hf * 4 + 3]);
-          const uint32_t x0 = *reinterpret_cast<uint32_t*>(&a0), x1 = *reinterpret_cast<uint32_t*>(&a1);
-          if (hf == 0) { pk.x = x0; pk.y = x1; } else { pk.z = x0; pk.w = x1; }
-          if (send) {
-#pragma unroll
-            for (int d = 0; d < C; ++d)
-              st_async_v2(mapa_shared(local + 8u * hf, (uint32_t)d), x0, x1, mapa_shared(hb, (uint32_t)d));
-          }
-        }
       } else {
-        if (!(p.debug & 1)) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) gate_math(e);
+        for (int e = 0; e < 8; ++e) {
+          // sigmoid(x) = 1/(1+2^(-x log2 e)) (no clamp needed: 2^big = inf -> 0); tanh as (1-E)/(1+E) shares a
+          // reciprocal with a sigmoid, so E must stay finite: clamp its argument to +-15
+          const float xg = fminf(fmaxf(gtg[e] + bsp[2 * kChunkUnits + e], -15.f), 15.f);
+          const float ei = ex2_approx(-kL2E * (gti[e] + bsp[e]));
+          const float ef = ex2_approx(-kL2E * (gtf[e] + bsp[kChunkUnits + e]));
+          const float eg = ex2_approx(-2.0f * kL2E * xg);
+          const float eo = ex2_approx(-kL2E * (gto[e] + bsp[3 * kChunkUnits + e]));
+          const float cn = cs[e] * rcp_approx(1.0f + ef) + (1.0f - eg) * rcp_approx((1.0f + ei) * (1.0f + eg));
+          cs[e] = cn;
+          const float ec = ex2_approx(-2.0f * kL2E * fminf(fmaxf(cn, -15.f), 15.f));
+          hv[e] = (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
         }
-        __half2 h01 = __floats2half2_rn(hv[0], hv[1]), h23 = __floats2half2_rn(hv[2], hv[3]);
-        __half2 h45 = __floats2half2_rn(hv[4], hv[5]), h67 = __floats2half2_rn(hv[6], hv[7]);
-        pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
-        pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
-        if (tp) tp[11] = clock64();
-        if (send) {
-          // h_t slice -> the operand buffer of every CTA of the cluster: asynchronous DSMEM stores that complete tx
-          // bytes on the destination's "h_t complete" mbarrier; remote peers first, own copy last
+      }
+      __half2 h01 = __floats2half2_rn(hv[0], hv[1]), h23 = __floats2half2_rn(hv[2], hv[3]);
+      __half2 h45 = __floats2half2_rn(hv[4], hv[5]), h67 = __floats2half2_rn(hv[6], hv[7]);
+      uint4 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
+      pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
+      if (tp) tp[11] = clock64();
+      if (t + 1 < L) {
+        // publish h_t: own tile locally (generic stores -> proxy fence), then the 4 warps of this quadrant meet and one
+        // thread pushes the quadrant's contiguous region to every peer with a DSMEM bulk copy
+        const uint32_t buf = hs_base + (uint32_t)(b * C) * kHTile;
+        if (active) st_shared_v4(buf + hpiece, pk);
+        fence_async_smem();
+        named_bar_sync(1 + q, 128);
+        if (sub == 0 && lane == 0) {
+          const uint32_t hb = H_FULL(b);
 #pragma unroll
-          for (int dd = 1; dd <= C; ++dd) {
+          for (int dd = 1; dd < C; ++dd) {
             const uint32_t d = (rank + (uint32_t)dd) % C;
-            st_async_v4(mapa_shared(local, d), pk, mapa_shared(hb, d));
+            bulk_copy_s2c(mapa_shared(buf + hquad, d), buf + hquad, kQuadBytes, mapa_shared(hb, d));
           }
+          mbar_arrive(hb);     // the local copy of this quadrant is in place
         }
       }
       if (tp) tp[12] = clock64();

@@ -123,6 +123,28 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   return d;
 }
 
+// K-major, 64B-swizzled operand tile (rows of 64 B = 32 fp16; 8-row groups of 512 B; 16-byte chunk ^= (row >> 1) & 3)
+__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;   // UMMA::LayoutType::SWIZZLE_64B
+  return d;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// bulk copy shared::cta -> shared memory of a cluster peer; completes `bytes` of tx on the peer's mbarrier
+__device__ __forceinline__ void bulk_copy_s2c(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+
 // ---- host-side helpers implemented in lstm_tc.cu ----------------------------------------------------
 int make_grid_map(CUtensorMap* m, const void* base, int c, int ld, int nb, int nt, int nf, int axis, int mr);
 int make_weight_map(CUtensorMap* m, const void* weights, int nslabs, int nchunks_total);
