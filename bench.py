@@ -250,8 +250,15 @@ def main():
         # SIMT engine: fp32 CUDA cores; its roof is the FP32 FMA pipe (148 SMs x 128 lanes x 2 x clock), not the tensor pipe
         fp32_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
         peak = tf_peak if tensor_bound else fp32_peak
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this layer
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json"))).get(top["kernel"])
+            if tr and args.batch == PER_GPU_BATCH:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["tflops"], "peak": round(peak, 1), "unit": "TFLOP/s",
-                "frac": round(top["tflops"] / peak, 4), "traffic": None,
+                "frac": round(top["tflops"] / peak, 4), "traffic": traffic,
                 "peak_source": (peak_src + ", bf16/fp16 dense sustained") if tensor_bound else "FP32 FMA pipe, 148 SMs x 128 x 2 x max clock",
                 "hbm_achieved_gbs": top["hbm_gbs"], "hbm_peak_gbs": hbm_peak, "hbm_frac": round(top["hbm_gbs"] / hbm_peak, 4),
                 "note": "LSTM layers are tensor-pipe bound (AI 260-512 FLOP/B); hbm_frac is the figure BASELINE.json names"}

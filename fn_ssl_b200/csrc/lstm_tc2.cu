@@ -96,13 +96,11 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   auto ACC_FULL = [&](int i) { return bar0 + 8u * (1 + 2 * kMaxXStages + i); };
   auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (1 + 2 * kMaxXStages + 2 + i); };
   auto H_FULL = [&](int i) { return bar0 + 8u * (1 + 2 * kMaxXStages + 4 + i); };
-  const uint32_t ACCH_EMPTY = bar0 + 8u * (1 + 2 * kMaxXStages + 6);
 
   if (tid == 0) {
     mbar_init(W_FULL, 1);
     for (int i = 0; i < kMaxXStages; ++i) { mbar_init(X_FULL(i), 1); mbar_init(X_EMPTY(i), C); }
     for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), kEpiThreads); mbar_init(H_FULL(i), 5); }   // MMA thread's expect_tx + 4 local quadrants
-    mbar_init(ACCH_EMPTY, kEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&map_src0); prefetch_tmap(&map_src1); prefetch_tmap(&map_w); }
@@ -117,8 +115,8 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
   const uint32_t tmem_c = tmem;             // cell state of this CTA's 32 units: columns [0, 32)
-  const uint32_t tmem_acch = tmem + 128;    // h-part accumulator (x_t-independent critical path), 128 columns
-  const uint32_t tmem_accx = tmem + 256;    // x-part accumulators, 2 buffers x 128 columns (filled one step ahead)
+  const uint32_t tmem_acc = tmem + 128;     // gate accumulators, 2 buffers x 128 columns (G_x of step t+1 is produced
+                                            // into the other buffer while step t is being finished)
 
   int coord_b = 0, coord_r0 = 0;
   long long row0;
@@ -159,9 +157,9 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
     __syncwarp();
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    // Two accumulators per step: G_x = x_t W_x^T (buffer t&1, issued one step ahead, paced by the x ring) and
-    // G_h = h_{t-1} W_h^T (single buffer, the serial chain); the epilogue adds them.  Per iteration the thread issues
-    // the h-part of step t first and only then the x-part of step t+1, so x-ring latency never delays the recurrence.
+    // Per iteration the thread first issues the h-part of step t (accumulating onto G_x(t), which it produced during
+    // the previous iteration) and only then the x-part of step t+1 into the other buffer, so the pacing of the x ring
+    // stays off the recurrence's critical path.
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc<MR>();
       const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
@@ -171,7 +169,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         const int b = s & 1;
         if (s >= 2) mbar_wait(ACC_EMPTY(b), (uint32_t)(((s >> 1) - 1) & 1), p.error_flag, 201 + b);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_accx + (uint32_t)b * kChunkN;
+        const uint32_t d_tmem = tmem_acc + (uint32_t)b * kChunkN;
         uint32_t accumulate = 0;
         for (int j = 0; j < nxs; ++j, ++n) {
           const int stage = n % XS;
@@ -194,7 +192,6 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         long long* tp = (tr && t >= 8 && t < 16) ? p.trace + (t - 8) * 16 : nullptr;
         if (tp) tp[0] = clock64();
         if (t > 0) {
-          mbar_wait(ACCH_EMPTY, (uint32_t)((t - 1) & 1), p.error_flag, 205);   // epilogue(t-1) has read G_h
           // h_{t-1}: the C-1 remote tiles arrive as DSMEM bulk copies (tx bytes), the local tile by plain arrives
           mbar_expect_tx(H_FULL((t - 1) & 1), (uint32_t)((C - 1) * kHTile));
           if (tp) tp[1] = clock64();
@@ -207,10 +204,10 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
             const uint64_t b_desc = make_sw128_desc(w_base + (uint32_t)(nxs + (kc >> 1)) * kWSlab) + 4u * (kc & 1);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-              if (!(p.debug & 2)) umma_f16(tmem_acch, a_desc + 2u * k, b_desc + 2u * k, idesc, (kc | k) ? 1u : 0u);
+              if (!(p.debug & 2)) umma_f16(tmem_acc + (uint32_t)(t & 1) * kChunkN, a_desc + 2u * k, b_desc + 2u * k, idesc, 1u);
           }
         }
-        umma_commit(ACC_FULL(t & 1));     // fires when G_h(t) -- and G_x(t), issued earlier by this thread -- are complete
+        umma_commit(ACC_FULL(t & 1));     // fires when the h-part -- and G_x(t), issued earlier by this thread -- are complete
         if (tp) tp[4] = clock64();
         if (t + 1 < L) x_part(t + 1);
         if (tp) tp[3] = clock64();
@@ -268,36 +265,18 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       mbar_wait(ACC_FULL(b), (uint32_t)((t >> 1) & 1), p.error_flag, 300 + b);
       if (tp) tp[9] = clock64();
       tc_fence_after();
-      const uint32_t accx = tmem_accx + (uint32_t)b * kChunkN + lane_off + u0;
-      const uint32_t acch = tmem_acch + lane_off + u0;
+      const uint32_t acc = tmem_acc + (uint32_t)b * kChunkN + lane_off + u0;
       float gti[8], gtf[8], gtg[8], gto[8], cs[8];
-      tmem_ld8(accx + 0 * kChunkUnits, gti);
-      tmem_ld8(accx + 1 * kChunkUnits, gtf);
-      tmem_ld8(accx + 2 * kChunkUnits, gtg);
-      tmem_ld8(accx + 3 * kChunkUnits, gto);
+      tmem_ld8(acc + 0 * kChunkUnits, gti);
+      tmem_ld8(acc + 1 * kChunkUnits, gtf);
+      tmem_ld8(acc + 2 * kChunkUnits, gtg);
+      tmem_ld8(acc + 3 * kChunkUnits, gto);
       tmem_ld8(tmem_c + lane_off + u0, cs);
-      if (t > 0) {   // + G_h (no recurrent term at the first step: h_{-1} = 0)
-        float hi[8], hf[8];
-        tmem_ld8(acch + 0 * kChunkUnits, hi);
-        tmem_ld8(acch + 1 * kChunkUnits, hf);
-        tmem_wait_ld();
-        tmem_ld_dep(gti); tmem_ld_dep(gtf); tmem_ld_dep(hi); tmem_ld_dep(hf);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { gti[e] += hi[e]; gtf[e] += hf[e]; }
-        tmem_ld8(acch + 2 * kChunkUnits, hi);
-        tmem_ld8(acch + 3 * kChunkUnits, hf);
-        tmem_wait_ld();
-        tmem_ld_dep(gtg); tmem_ld_dep(gto); tmem_ld_dep(cs); tmem_ld_dep(hi); tmem_ld_dep(hf);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { gtg[e] += hi[e]; gto[e] += hf[e]; }
-      } else {
-        tmem_wait_ld();
-        tmem_ld_dep(gti); tmem_ld_dep(gtf); tmem_ld_dep(gtg); tmem_ld_dep(gto); tmem_ld_dep(cs);
-      }
+      tmem_wait_ld();
+      tmem_ld_dep(gti); tmem_ld_dep(gtf); tmem_ld_dep(gtg); tmem_ld_dep(gto); tmem_ld_dep(cs);
       if (tp) tp[10] = clock64();
       tc_fence_before();
-      mbar_arrive(ACC_EMPTY(b));      // G_x buffer drained: the MMA warp may fill it for step t+2
-      mbar_arrive(ACCH_EMPTY);        // G_h drained: the MMA warp may issue the h-part of step t+1
+      mbar_arrive(ACC_EMPTY(b));      // accumulator drained: the MMA warp may produce G_x of step t+2 into it
       float hv[8];
       if (p.debug & 1) {
 #pragma unroll

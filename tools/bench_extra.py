@@ -1,0 +1,59 @@
+"""Secondary measurements (not the contract bench): IPDnet cfg3 (4-mic, hidden 256, online, batch 32x4s) and FN-SSL at
+other batch sizes, on one GPU.  Prints one JSON object per workload."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import fn_ssl_b200 as F  # noqa: E402
+from fn_ssl_b200 import ops  # noqa: E402
+from oracle import fnssl_oracle as orc  # noqa: E402
+
+
+def timed(fn, steps=5, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ops.profile_start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    rec = ops.profile_stop()
+    by = {}
+    for label, flops, nbytes, a, b in rec:
+        d = by.setdefault(label, [0.0, 0])
+        d[0] += a.elapsed_time(b); d[1] += 1
+    return e0.elapsed_time(e1) / steps, {k: round(v[0] / v[1], 3) for k, v in by.items()}
+
+
+def main():
+    dev = "cuda"
+    which = sys.argv[1:] or ["ipdnet", "fnssl_b64"]
+    if "ipdnet" in which:
+        kw = dict(input_size=8, hidden_size=256, max_track=2, is_online=True)
+        net = F.IPDnet(**kw).eval()
+        net.load_state_dict(orc.seeded_ipdnet_state_dict(0, **kw))
+        pipe = F.IPDnetPipeline(net.to(dev))
+        sig = orc.white_noise(32, 64000, 4).to(dev)
+        ms, layers = timed(lambda: pipe(sig))
+        print(json.dumps({"workload": "IPDnet 4-mic hidden 256 online, batch 32x4s (cfg3)", "ms_per_step": round(ms, 3),
+                          "frames_per_s": round(32 * 249 / ms * 1e3, 1), "lstm_ms": layers}))
+    for tag, B, online in (("fnssl_b64", 64, False), ("fnssl_b64_online", 64, True), ("fnssl_b4", 4, False)):
+        if tag not in which:
+            continue
+        net = F.FN_SSL(is_online=online).eval()
+        net.load_state_dict(orc.seeded_fnssl_state_dict(0, is_online=online))
+        pipe = F.FNSSLPipeline(net.to(dev))
+        sig = orc.white_noise(B, 64000, 2).to(dev)
+        ms, layers = timed(lambda: pipe(sig))
+        print(json.dumps({"workload": f"FN-SSL {'online' if online else 'offline'} batch {B}x4s", "ms_per_step": round(ms, 3),
+                          "frames_per_s": round(B * 249 / ms * 1e3, 1), "lstm_ms": layers}))
+
+
+if __name__ == "__main__":
+    main()
