@@ -218,131 +218,220 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
     // ============================== epilogue warps ==============================
     const int q = warp & 3;                    // TMEM lane quadrant of this warp
     const int sub = (warp - 2) >> 2;           // 8-unit group of the CTA's 32 units
-    const bool active = (MR == 128) || (lane < 16);   // M = 64: rows live in lanes 0-15 of each quadrant
-    const int r = (MR == 128) ? (q * 32 + lane) : (q * 16 + (lane & 15));
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const bool valid = active && r < valid_rows;
     const int u0 = sub * 8;
-    const int ua = (int)rank * kChunkUnits + u0;      // absolute hidden unit of this thread's first element
-    long long base, sstride;
-    if (p.axis == FNSSL_ALONG_FREQ) { base = (row0 + r) * p.nf; sstride = 1; }
-    else { base = (long long)coord_b * p.nt * p.nf + coord_r0 + r; sstride = p.nf; }
-    // this thread's 16-byte h piece inside the CTA's own [MR x 32] tile (64B swizzle: chunk ^= (row >> 1) & 3)
-    const uint32_t hpiece = (uint32_t)rank * kHTile + (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u +
-                            (uint32_t)((sub ^ ((r >> 1) & 3)) << 4);
-    // the quadrant's rows form one contiguous region of that tile: 32 rows (MR = 128) or 16 rows (MR = 64) x 64 B
-    constexpr uint32_t kQuadBytes = (MR == 128) ? 2048u : 1024u;
-    const uint32_t hquad = (uint32_t)rank * kHTile + (uint32_t)q * kQuadBytes;
-    {
-      float z[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) z[i] = 0.0f;
-      tmem_st8(tmem_c + lane_off + u0, z);
-      tmem_wait_st();
-    }
     const float kL2E = 1.4426950408889634f;
-    const float* bsp = bias_s + u0;      // bias of (gate, unit) at bsp[gate * 32 + e] (broadcast shared-memory reads)
-
-    const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0;
-    // residual operand of the next layer (h + addend): fetched one whole step ahead so its HBM latency never sits
-    // between the gate math and the h exchange
-    uint4 addv_next = make_uint4(0, 0, 0, 0);
-    if (p.out1 && valid) {
-      const long long pos0 = base + (long long)(dir ? (L - 1) : 0) * sstride;
-      addv_next = __ldg(reinterpret_cast<const uint4*>(p.addend + pos0 * p.addend_ld + dir * H + ua));
-    }
-    for (int t = 0; t < L; ++t) {
-      const int b = t & 1;
-      const int s = dir ? (L - 1 - t) : t;
-      const long long pos = base + (long long)s * sstride;
-      long long* tp = (tr && t >= 8 && t < 16) ? p.trace + (t - 8) * 16 : nullptr;
-      if (tp) tp[8] = clock64();
-      const uint4 addv = addv_next;
-      if (p.out1 && valid && t + 1 < L) {
-        const long long posn = base + (long long)(dir ? (L - 2 - t) : (t + 1)) * sstride;
-        addv_next = __ldg(reinterpret_cast<const uint4*>(p.addend + posn * p.addend_ld + dir * H + ua));
-      }
-      mbar_wait(ACC_FULL(b), (uint32_t)((t >> 1) & 1), p.error_flag, 300 + b);
-      if (tp) tp[9] = clock64();
-      tc_fence_after();
-      const uint32_t acc = tmem_acc + (uint32_t)b * kChunkN + lane_off + u0;
-      float gti[8], gtf[8], gtg[8], gto[8], cs[8];
-      tmem_ld8(acc + 0 * kChunkUnits, gti);
-      tmem_ld8(acc + 1 * kChunkUnits, gtf);
-      tmem_ld8(acc + 2 * kChunkUnits, gtg);
-      tmem_ld8(acc + 3 * kChunkUnits, gto);
-      tmem_ld8(tmem_c + lane_off + u0, cs);
-      tmem_wait_ld();
-      tmem_ld_dep(gti); tmem_ld_dep(gtf); tmem_ld_dep(gtg); tmem_ld_dep(gto); tmem_ld_dep(cs);
-      if (tp) tp[10] = clock64();
-      tc_fence_before();
-      mbar_arrive(ACC_EMPTY(b));      // accumulator drained: the MMA warp may produce G_x of step t+2 into it
-      float hv[8];
-      if (p.debug & 1) {
+    const float* bsp = bias_s + u0;            // bias of (gate, unit) at bsp[gate * 32 + e] (broadcast shared-memory reads)
+    // One (row, unit): c' = sigmoid(f) c + sigmoid(i) tanh(g), h = sigmoid(o) tanh(c').  sigmoid(x) = 1/(1+2^(-x log2 e)),
+    // tanh as (1-E)/(1+E); the cell update runs over ONE reciprocal: [c A B + (1-Eg) F] / (F A B), A = 1+Ei, B = 1+Eg,
+    // F = 1+Ef (5 ex2 + 2 rcp per element).  Clamps keep the products finite: sigmoid(-20) = 2e-9, tanh(15) = 1 - 2e-13.
+    auto lstm_cell = [&](float gi, float gf, float gg, float go, float& c) -> float {
+      const float xg = fminf(fmaxf(gg, -15.f), 15.f);
+      const float ei = ex2_approx(-kL2E * fmaxf(gi, -20.f));
+      const float ef = ex2_approx(-kL2E * fmaxf(gf, -20.f));
+      const float eg = ex2_approx(-2.0f * kL2E * xg);
+      const float eo = ex2_approx(-kL2E * go);
+      const float ab = (1.0f + ei) * (1.0f + eg);
+      const float ff = 1.0f + ef;
+      const float cn = fmaf(c, ab, (1.0f - eg) * ff) * rcp_approx(ff * ab);
+      c = cn;
+      const float ec = ex2_approx(-2.0f * kL2E * fminf(fmaxf(cn, -15.f), 15.f));
+      return (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
+    };
+    // publish the quadrant's region of the CTA's own h tile: 4 warps meet, one thread pushes it to every peer
+    auto publish_quadrant = [&](uint32_t buf, uint32_t hquad, uint32_t nbytes, int b) {
+      fence_async_smem();
+      named_bar_sync(1 + q, 128);
+      if (sub == 0 && lane == 0) {
+        const uint32_t hb = H_FULL(b);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) hv[e] = gti[e] + gtf[e] + gtg[e] + gto[e] + cs[e];
-      } else {
+        for (int dd = 1; dd < C; ++dd) {
+          const uint32_t d = (rank + (uint32_t)dd) % C;
+          bulk_copy_s2c(mapa_shared(buf + hquad, d), buf + hquad, nbytes, mapa_shared(hb, d));
+        }
+        mbar_arrive(hb);     // the local copy of this quadrant is in place
+      }
+    };
+
+    if constexpr (MR == 64) {
+      // ---- M = 64: the accumulator occupies lanes 0-15 of each quadrant.  16x256b TMEM accesses keep all 32 threads
+      // busy: thread T owns rows {T/4, T/4+8} of the quadrant's 16 rows and units {2(T%4), 2(T%4)+1} of the 8-unit group.
+      const int uo = 2 * (lane & 3);                       // unit offset inside the 8-unit group
+      const int ua = (int)rank * kChunkUnits + u0 + uo;    // absolute hidden unit of the thread's first column
+      long long base[2];
+      long long sstride = 1;
+      bool valid[2];
+      uint32_t hpiece[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = q * 16 + (lane >> 2) + 8 * i;
+        valid[i] = r < valid_rows;
+        if (p.axis == FNSSL_ALONG_FREQ) { base[i] = (row0 + r) * p.nf; sstride = 1; }
+        else { base[i] = (long long)coord_b * p.nt * p.nf + coord_r0 + r; sstride = p.nf; }
+        hpiece[i] = (uint32_t)rank * kHTile + (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u +
+                    (uint32_t)((sub ^ ((r >> 1) & 3)) << 4) + (uint32_t)uo * 2u;
+      }
+      const uint32_t hquad = (uint32_t)rank * kHTile + (uint32_t)q * 1024u;   // 16 rows x 64 B
+      {
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        tmem_st4_16x256(tmem_c + lane_off + u0, z);
+        tmem_wait_st();
+      }
+      uint32_t addn[2] = {0u, 0u};
+      if (p.out1) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          if (valid[i]) {
+            const long long pos0 = base[i] + (long long)(dir ? (L - 1) : 0) * sstride;
+            addn[i] = __ldg(reinterpret_cast<const unsigned int*>(p.addend + pos0 * p.addend_ld + dir * H + ua));
+          }
+      }
+      for (int t = 0; t < L; ++t) {
+        const int b = t & 1;
+        const int s = dir ? (L - 1 - t) : t;
+        const uint32_t addc[2] = {addn[0], addn[1]};
+        if (p.out1 && t + 1 < L) {     // residual operand of the next layer, fetched one step ahead
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            if (valid[i]) {
+              const long long posn = base[i] + (long long)(dir ? (L - 2 - t) : (t + 1)) * sstride;
+              addn[i] = __ldg(reinterpret_cast<const unsigned int*>(p.addend + posn * p.addend_ld + dir * H + ua));
+            }
+        }
+        mbar_wait(ACC_FULL(b), (uint32_t)((t >> 1) & 1), p.error_flag, 300 + b);
+        tc_fence_after();
+        const uint32_t acc = tmem_acc + (uint32_t)b * kChunkN + lane_off + u0;
+        float gi[4], gf[4], gg[4], go[4], cs[4];
+        tmem_ld4_16x256(acc + 0 * kChunkUnits, gi);
+        tmem_ld4_16x256(acc + 1 * kChunkUnits, gf);
+        tmem_ld4_16x256(acc + 2 * kChunkUnits, gg);
+        tmem_ld4_16x256(acc + 3 * kChunkUnits, go);
+        tmem_ld4_16x256(tmem_c + lane_off + u0, cs);
+        tmem_wait_ld();
+        tmem_ld_dep4(gi); tmem_ld_dep4(gf); tmem_ld_dep4(gg); tmem_ld_dep4(go); tmem_ld_dep4(cs);
+        tc_fence_before();
+        mbar_arrive(ACC_EMPTY(b));      // accumulator drained: the MMA warp may produce G_x of step t+2 into it
+        float hv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int uu = uo + (e & 1);
+          if (p.debug & 1) hv[e] = gi[e] + gf[e] + gg[e] + go[e] + cs[e];
+          else hv[e] = lstm_cell(gi[e] + bsp[uu], gf[e] + bsp[kChunkUnits + uu], gg[e] + bsp[2 * kChunkUnits + uu],
+                                 go[e] + bsp[3 * kChunkUnits + uu], cs[e]);
+        }
+        __half2 hp[2] = {__floats2half2_rn(hv[0], hv[1]), __floats2half2_rn(hv[2], hv[3])};
+        if (t + 1 < L) {
+          const uint32_t buf = hs_base + (uint32_t)(b * C) * kHTile;
+          st_shared_b32(buf + hpiece[0], *reinterpret_cast<uint32_t*>(&hp[0]));
+          st_shared_b32(buf + hpiece[1], *reinterpret_cast<uint32_t*>(&hp[1]));
+          publish_quadrant(buf, hquad, 1024u, b);
+        }
+        tmem_st4_16x256(tmem_c + lane_off + u0, cs);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (!valid[i]) continue;
+          const long long pos = base[i] + (long long)s * sstride;
+          if (p.out0) *reinterpret_cast<__half2*>(p.out0 + pos * p.out0_ld + p.out0_off + dir * H + ua) = hp[i];
+          if (p.out1) {
+            const __half2 av = *reinterpret_cast<const __half2*>(&addc[i]);
+            *reinterpret_cast<__half2*>(p.out1 + pos * p.out1_ld + dir * H + ua) =
+                __floats2half2_rn(hv[2 * i] + __low2float(av), hv[2 * i + 1] + __high2float(av));
+          }
+        }
+        tmem_wait_st();
+      }
+    } else {
+      // ---- M = 128: TMEM lane == row; thread = (row, 8 hidden units)
+      const int r = q * 32 + lane;
+      const bool valid = r < valid_rows;
+      const int ua = (int)rank * kChunkUnits + u0;      // absolute hidden unit of this thread's first element
+      long long base, sstride;
+      if (p.axis == FNSSL_ALONG_FREQ) { base = (row0 + r) * p.nf; sstride = 1; }
+      else { base = (long long)coord_b * p.nt * p.nf + coord_r0 + r; sstride = p.nf; }
+      // this thread's 16-byte h piece inside the CTA's own [128 x 32] tile (64B swizzle: chunk ^= (row >> 1) & 3)
+      const uint32_t hpiece = (uint32_t)rank * kHTile + (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u +
+                              (uint32_t)((sub ^ ((r >> 1) & 3)) << 4);
+      const uint32_t hquad = (uint32_t)rank * kHTile + (uint32_t)q * 2048u;   // the quadrant's 32 rows x 64 B
+      {
+        float z[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = 0.0f;
+        tmem_st8(tmem_c + lane_off + u0, z);
+        tmem_wait_st();
+      }
+      const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0;
+      // residual operand of the next layer (h + addend): fetched one whole step ahead so its HBM latency never sits
+      // between the gate math and the h exchange
+      uint4 addv_next = make_uint4(0, 0, 0, 0);
+      if (p.out1 && valid) {
+        const long long pos0 = base + (long long)(dir ? (L - 1) : 0) * sstride;
+        addv_next = __ldg(reinterpret_cast<const uint4*>(p.addend + pos0 * p.addend_ld + dir * H + ua));
+      }
+      for (int t = 0; t < L; ++t) {
+        const int b = t & 1;
+        const int s = dir ? (L - 1 - t) : t;
+        const long long pos = base + (long long)s * sstride;
+        long long* tp = (tr && t >= 8 && t < 16) ? p.trace + (t - 8) * 16 : nullptr;
+        if (tp) tp[8] = clock64();
+        const uint4 addv = addv_next;
+        if (p.out1 && valid && t + 1 < L) {
+          const long long posn = base + (long long)(dir ? (L - 2 - t) : (t + 1)) * sstride;
+          addv_next = __ldg(reinterpret_cast<const uint4*>(p.addend + posn * p.addend_ld + dir * H + ua));
+        }
+        mbar_wait(ACC_FULL(b), (uint32_t)((t >> 1) & 1), p.error_flag, 300 + b);
+        if (tp) tp[9] = clock64();
+        tc_fence_after();
+        const uint32_t acc = tmem_acc + (uint32_t)b * kChunkN + lane_off + u0;
+        float gti[8], gtf[8], gtg[8], gto[8], cs[8];
+        tmem_ld8(acc + 0 * kChunkUnits, gti);
+        tmem_ld8(acc + 1 * kChunkUnits, gtf);
+        tmem_ld8(acc + 2 * kChunkUnits, gtg);
+        tmem_ld8(acc + 3 * kChunkUnits, gto);
+        tmem_ld8(tmem_c + lane_off + u0, cs);
+        tmem_wait_ld();
+        tmem_ld_dep(gti); tmem_ld_dep(gtf); tmem_ld_dep(gtg); tmem_ld_dep(gto); tmem_ld_dep(cs);
+        if (tp) tp[10] = clock64();
+        tc_fence_before();
+        mbar_arrive(ACC_EMPTY(b));      // accumulator drained: the MMA warp may produce G_x of step t+2 into it
+        float hv[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          // sigmoid(x) = 1/(1+2^(-x log2 e)) (no clamp needed: 2^big = inf -> 0); tanh as (1-E)/(1+E) shares a
-          // reciprocal with a sigmoid, so E must stay finite: clamp its argument to +-15
-          // c' = sigmoid(f) c + sigmoid(i) tanh(g) over ONE reciprocal: [c A B + (1-Eg) F] / (F A B) with A = 1+Ei,
-          // B = 1+Eg, F = 1+Ef.  Clamps keep the triple product finite (E <= e^20, e^30): sigmoid(-20) = 2e-9.
-          const float xg = fminf(fmaxf(gtg[e] + bsp[2 * kChunkUnits + e], -15.f), 15.f);
-          const float ei = ex2_approx(-kL2E * fmaxf(gti[e] + bsp[e], -20.f));
-          const float ef = ex2_approx(-kL2E * fmaxf(gtf[e] + bsp[kChunkUnits + e], -20.f));
-          const float eg = ex2_approx(-2.0f * kL2E * xg);
-          const float eo = ex2_approx(-kL2E * (gto[e] + bsp[3 * kChunkUnits + e]));
-          const float ab = (1.0f + ei) * (1.0f + eg);
-          const float ff = 1.0f + ef;
-          const float cn = fmaf(cs[e], ab, (1.0f - eg) * ff) * rcp_approx(ff * ab);
-          cs[e] = cn;
-          const float ec = ex2_approx(-2.0f * kL2E * fminf(fmaxf(cn, -15.f), 15.f));
-          hv[e] = (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
+          if (p.debug & 1) hv[e] = gti[e] + gtf[e] + gtg[e] + gto[e] + cs[e];
+          else hv[e] = lstm_cell(gti[e] + bsp[e], gtf[e] + bsp[kChunkUnits + e], gtg[e] + bsp[2 * kChunkUnits + e],
+                                 gto[e] + bsp[3 * kChunkUnits + e], cs[e]);
         }
-      }
-      __half2 h01 = __floats2half2_rn(hv[0], hv[1]), h23 = __floats2half2_rn(hv[2], hv[3]);
-      __half2 h45 = __floats2half2_rn(hv[4], hv[5]), h67 = __floats2half2_rn(hv[6], hv[7]);
-      uint4 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
-      pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
-      if (tp) tp[11] = clock64();
-      if (t + 1 < L) {
-        // publish h_t: own tile locally (generic stores -> proxy fence), then the 4 warps of this quadrant meet and one
-        // thread pushes the quadrant's contiguous region to every peer with a DSMEM bulk copy
-        const uint32_t buf = hs_base + (uint32_t)(b * C) * kHTile;
-        if (active) st_shared_v4(buf + hpiece, pk);
-        fence_async_smem();
-        named_bar_sync(1 + q, 128);
-        if (sub == 0 && lane == 0) {
-          const uint32_t hb = H_FULL(b);
-#pragma unroll
-          for (int dd = 1; dd < C; ++dd) {
-            const uint32_t d = (rank + (uint32_t)dd) % C;
-            bulk_copy_s2c(mapa_shared(buf + hquad, d), buf + hquad, kQuadBytes, mapa_shared(hb, d));
+        __half2 h01 = __floats2half2_rn(hv[0], hv[1]), h23 = __floats2half2_rn(hv[2], hv[3]);
+        __half2 h45 = __floats2half2_rn(hv[4], hv[5]), h67 = __floats2half2_rn(hv[6], hv[7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
+        pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
+        if (tp) tp[11] = clock64();
+        if (t + 1 < L) {
+          // publish h_t: own tile locally (generic stores -> proxy fence), then one DSMEM bulk copy per peer and quadrant
+          const uint32_t buf = hs_base + (uint32_t)(b * C) * kHTile;
+          st_shared_v4(buf + hpiece, pk);
+          publish_quadrant(buf, hquad, 2048u, b);
+        }
+        if (tp) tp[12] = clock64();
+        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && t == 12) p.trace[128 + warp] = clock64();
+        tmem_st8(tmem_c + lane_off + u0, cs);
+        if (valid) {
+          if (p.out0) *reinterpret_cast<uint4*>(p.out0 + pos * p.out0_ld + p.out0_off + dir * H + ua) = pk;
+          if (p.out1) {
+            const __half2* av = reinterpret_cast<const __half2*>(&addv);
+            __half2 o0 = __floats2half2_rn(hv[0] + __low2float(av[0]), hv[1] + __high2float(av[0]));
+            __half2 o1 = __floats2half2_rn(hv[2] + __low2float(av[1]), hv[3] + __high2float(av[1]));
+            __half2 o2 = __floats2half2_rn(hv[4] + __low2float(av[2]), hv[5] + __high2float(av[2]));
+            __half2 o3 = __floats2half2_rn(hv[6] + __low2float(av[3]), hv[7] + __high2float(av[3]));
+            uint4 ok;
+            ok.x = *reinterpret_cast<uint32_t*>(&o0); ok.y = *reinterpret_cast<uint32_t*>(&o1);
+            ok.z = *reinterpret_cast<uint32_t*>(&o2); ok.w = *reinterpret_cast<uint32_t*>(&o3);
+            *reinterpret_cast<uint4*>(p.out1 + pos * p.out1_ld + dir * H + ua) = ok;
           }
-          mbar_arrive(hb);     // the local copy of this quadrant is in place
         }
+        tmem_wait_st();
+        if (tp) tp[13] = clock64();
       }
-      if (tp) tp[12] = clock64();
-      if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && t == 12) p.trace[128 + warp] = clock64();
-      tmem_st8(tmem_c + lane_off + u0, cs);
-      if (valid) {
-        if (p.out0) *reinterpret_cast<uint4*>(p.out0 + pos * p.out0_ld + p.out0_off + dir * H + ua) = pk;
-        if (p.out1) {
-          const __half2* av = reinterpret_cast<const __half2*>(&addv);
-          __half2 o0 = __floats2half2_rn(hv[0] + __low2float(av[0]), hv[1] + __high2float(av[0]));
-          __half2 o1 = __floats2half2_rn(hv[2] + __low2float(av[1]), hv[3] + __high2float(av[1]));
-          __half2 o2 = __floats2half2_rn(hv[4] + __low2float(av[2]), hv[5] + __high2float(av[2]));
-          __half2 o3 = __floats2half2_rn(hv[6] + __low2float(av[3]), hv[7] + __high2float(av[3]));
-          uint4 ok;
-          ok.x = *reinterpret_cast<uint32_t*>(&o0); ok.y = *reinterpret_cast<uint32_t*>(&o1);
-          ok.z = *reinterpret_cast<uint32_t*>(&o2); ok.w = *reinterpret_cast<uint32_t*>(&o3);
-          *reinterpret_cast<uint4*>(p.out1 + pos * p.out1_ld + dir * H + ua) = ok;
-        }
-      }
-      tmem_wait_st();
-      if (tp) tp[13] = clock64();
     }
   }
 

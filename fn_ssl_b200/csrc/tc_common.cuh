@@ -91,6 +91,27 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                : "memory");
 }
+// 16 lanes x 256 bits: thread t holds (row t/4, columns 2(t%4), 2(t%4)+1) in v[0], v[1] and (row t/4 + 8, same columns)
+// in v[2], v[3] -- the access shape for M = 64 accumulators (16 lanes per quadrant) that keeps all 32 threads busy
+__device__ __forceinline__ void tmem_ld4_16x256(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st4_16x256(uint32_t taddr, const float (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_dep4(float (&v)[4]) {
+  asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3])::"memory");
+}
+__device__ __forceinline__ void st_shared_b32(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // tcgen05.ld is asynchronous: its destination registers are valid only after tcgen05.wait::ld.  Threading the
 // registers through an (empty) volatile asm placed after the wait gives the compiler a true dependency, so no
