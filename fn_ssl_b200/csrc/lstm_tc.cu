@@ -499,16 +499,20 @@ static int launch_tc(const fnssl_lstm_args* a, cudaStream_t st) {
 
 bool lstm_tc2_supports(int hidden, int c0, int c1);
 int lstm_forward_tc2(const fnssl_lstm_args* a, cudaStream_t st);
+bool lstm_tc3_supports(int hidden, int c0, int c1);
+int lstm_forward_tc3(const fnssl_lstm_args* a, cudaStream_t st);
 
 int lstm_forward_tc(const fnssl_lstm_args* a, cudaStream_t st) {
   FNSSL_REQUIRE(a->dtype == FNSSL_F16, "lstm(tcgen05): grids must be fp16");
   {
-    // Kernel generation: 2 = cluster-resident weights (lstm_tc2.cu, default whenever the layer fits),
-    // 1 = weight-streaming kernel below.  FNSSL_TC_KERNEL overrides (tests / profiling).
+    // Kernel generation: 3 = cluster-resident weights with two interleaved 64-row sub-tiles (lstm_tc3.cu; H <= 128),
+    // 2 = cluster-resident weights, one tile (lstm_tc2.cu; also H = 256), 1 = weight-streaming kernel below.
+    // Default: the highest generation that supports the layer.  FNSSL_TC_KERNEL caps it (tests / profiling).
     const char* e = getenv("FNSSL_TC_KERNEL");
-    const int want = e ? atoi(e) : 2;
-    if (want != 1 && a->c0 % 16 == 0 && a->c1 % 16 == 0 && lstm_tc2_supports(a->hidden, a->c0, a->c1))
-      return lstm_forward_tc2(a, st);
+    const int want = e ? atoi(e) : 3;
+    const bool aligned = a->c0 % 16 == 0 && a->c1 % 16 == 0;
+    if (want >= 3 && aligned && lstm_tc3_supports(a->hidden, a->c0, a->c1)) return lstm_forward_tc3(a, st);
+    if (want >= 2 && aligned && lstm_tc2_supports(a->hidden, a->c0, a->c1)) return lstm_forward_tc2(a, st);
   }
   FNSSL_REQUIRE(a->c0 % 16 == 0 && a->c1 % 16 == 0, "lstm(tcgen05): channel counts must be multiples of 16 (got %d, %d); pad the grid",
                 a->c0, a->c1);
