@@ -139,8 +139,21 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       for (int j = 0; j < nslabs; ++j)
         tma_load_2d(w_base + j * kWSlab, &map_w, W_FULL, j * kSlabK, (dir * C + (int)rank) * kChunkN);
       int n = 0;
+      // x_t comes from HBM (~3.4 k cycles per TMA round trip, far more than the ring can cover): every CTA pulls its
+      // share of the slabs of step t+2 into L2 while the ring works on step t / t+1, so the real loads are L2 hits
+      auto prefetch_step = [&](int tt) {
+        const int ss = dir ? (L - 1 - tt) : tt;
+        for (int j = 0; j < nxs; ++j) {
+          if ((uint32_t)((tt * nxs + j) % C) != rank) continue;
+          const CUtensorMap* m = p.xs_src[j] ? &map_src1 : &map_src0;
+          if (p.axis == FNSSL_ALONG_FREQ) tma_prefetch_l2_4d(m, p.xs_k0[j], ss, coord_r0, 0);
+          else tma_prefetch_l2_4d(m, p.xs_k0[j], coord_r0, ss, coord_b);
+        }
+      };
+      if (!(p.debug & 16)) { if (L > 1) prefetch_step(1); }
       for (int t = 0; t < L; ++t) {
         const int s = dir ? (L - 1 - t) : t;
+        if (!(p.debug & 16) && t + 2 < L) prefetch_step(t + 2);
         for (int j = 0; j < nxs; ++j, ++n) {
           const int stage = n % XS, use = n / XS;
           if (use > 0) mbar_wait(X_EMPTY(stage), (uint32_t)((use - 1) & 1), p.error_flag, 100 + stage);

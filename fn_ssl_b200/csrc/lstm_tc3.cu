@@ -138,8 +138,22 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       for (int j = 0; j < nslabs; ++j)
         tma_load_2d(w_base + j * kWSlab, &map_w, W_FULL, j * kSlabK, (dir * C + (int)rank) * kChunkN);
       int n = 0;
+      // L2 prefetch of step t+2's slabs (see lstm_tc2.cu): the ring's real loads then hit L2
+      auto prefetch_step = [&](int tt) {
+        const int ss = dir ? (L - 1 - tt) : tt;
+        for (int sub = 0; sub < 2; ++sub)
+          for (int j = 0; j < nxs; ++j) {
+            if ((uint32_t)(((tt * 2 + sub) * nxs + j) % C) != rank) continue;
+            const CUtensorMap* m = p.xs_src[j] ? &map_src1 : &map_src0;
+            const int r0 = coord_r0 + sub * kSubRows;
+            if (p.axis == FNSSL_ALONG_FREQ) tma_prefetch_l2_4d(m, p.xs_k0[j], ss, r0, 0);
+            else tma_prefetch_l2_4d(m, p.xs_k0[j], r0, ss, coord_b);
+          }
+      };
+      if (!(p.debug & 16)) { if (L > 1) prefetch_step(1); }
       for (int t = 0; t < L; ++t) {
         const int s = dir ? (L - 1 - t) : t;
+        if (!(p.debug & 16) && t + 2 < L) prefetch_step(t + 2);
         for (int sub = 0; sub < 2; ++sub) {
           for (int j = 0; j < nxs; ++j, ++n) {
             const int stage = n % XS, use = n / XS;
