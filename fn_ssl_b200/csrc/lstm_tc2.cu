@@ -99,7 +99,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
 
   if (tid == 0) {
     mbar_init(W_FULL, 1);
-    for (int i = 0; i < kMaxXStages; ++i) { mbar_init(X_FULL(i), 1); mbar_init(X_EMPTY(i), C); }
+    for (int i = 0; i < kMaxXStages; ++i) { mbar_init(X_FULL(i), 1); mbar_init(X_EMPTY(i), (p.debug & 32) ? 1 : C); }
     for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), kEpiThreads); mbar_init(H_FULL(i), 5); }   // MMA thread's expect_tx + 4 local quadrants
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -197,7 +197,8 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
               accumulate = 1;
             }
           }
-          umma_commit_mc(X_EMPTY(stage), mask);    // this CTA is done with the slab: tell every CTA's ring
+          if (p.debug & 32) umma_commit(X_EMPTY(stage));   // timing experiment only: local release (racy)
+          else umma_commit_mc(X_EMPTY(stage), mask);    // this CTA is done with the slab: tell every CTA's ring
         }
       };
       x_part(0);
