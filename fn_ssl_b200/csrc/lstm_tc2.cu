@@ -99,7 +99,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
 
   if (tid == 0) {
     mbar_init(W_FULL, 1);
-    for (int i = 0; i < kMaxXStages; ++i) { mbar_init(X_FULL(i), 1); mbar_init(X_EMPTY(i), (p.debug & 32) ? 1 : C); }
+    for (int i = 0; i < kMaxXStages; ++i) { mbar_init(X_FULL(i), 1); mbar_init(X_EMPTY(i), C); }
     for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), kEpiThreads); mbar_init(H_FULL(i), 5); }   // MMA thread's expect_tx + 4 local quadrants
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -184,9 +184,13 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         tc_fence_after();
         const uint32_t d_tmem = tmem_acc + (uint32_t)b * kChunkN;
         uint32_t accumulate = 0;
+        long long w_acc = 0, i_acc = 0;
         for (int j = 0; j < nxs; ++j, ++n) {
           const int stage = n % XS;
+          const long long c0 = tr ? clock64() : 0;
           mbar_wait(X_FULL(stage), (uint32_t)((n / XS) & 1), p.error_flag, 210 + stage);
+          const long long c1 = tr ? clock64() : 0;
+          w_acc += c1 - c0;
           tc_fence_after();
           const uint64_t a_desc = make_sw128_desc(xr_base + (uint32_t)stage * kASlab);
           const uint64_t b_desc = make_sw128_desc(w_base + (uint32_t)j * kWSlab);
@@ -197,9 +201,10 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
               accumulate = 1;
             }
           }
-          if (p.debug & 32) umma_commit(X_EMPTY(stage));   // timing experiment only: local release (racy)
-          else umma_commit_mc(X_EMPTY(stage), mask);    // this CTA is done with the slab: tell every CTA's ring
+          umma_commit_mc(X_EMPTY(stage), mask);    // this CTA is done with the slab: tell every CTA's ring
+          if (tr) i_acc += clock64() - c1;
         }
+        if (tr && s >= 8 && s < 16) { p.trace[(s - 8) * 16 + 5] = w_acc; p.trace[(s - 8) * 16 + 6] = i_acc; }
       };
       x_part(0);
       for (int t = 0; t < L; ++t) {

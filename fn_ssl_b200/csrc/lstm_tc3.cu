@@ -94,7 +94,7 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
 
   if (tid == 0) {
     mbar_init(W_FULL, 1);
-    for (int i = 0; i < kMaxXStages; ++i) { mbar_init(X_FULL(i), 1); mbar_init(X_EMPTY(i), (p.debug & 32) ? 1 : C); }
+    for (int i = 0; i < kMaxXStages; ++i) { mbar_init(X_FULL(i), 1); mbar_init(X_EMPTY(i), C); }
     for (int sub = 0; sub < 2; ++sub)
       for (int i = 0; i < 2; ++i) {
         mbar_init(ACC_FULL(sub, i), 1);
@@ -195,8 +195,7 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
               accumulate = 1;
             }
           }
-          if (p.debug & 32) umma_commit(X_EMPTY(stage));   // timing experiment only: local release (racy)
-          else umma_commit_mc(X_EMPTY(stage), mask);    // this CTA is done with the slab: tell every CTA's ring
+          umma_commit_mc(X_EMPTY(stage), mask);    // this CTA is done with the slab: tell every CTA's ring
         }
       };
       auto h_part = [&](int sub, int t) {   // += h_{t-1} W_h^T, then hand the accumulator to the epilogue
