@@ -11,7 +11,8 @@
 //     state live in lanes 16-31 of the SAME columns (D address lane offset 16).
 //   * all 16 epilogue warps serve A, then B, then A ... with 16x256b TMEM accesses (thread T owns rows {T/4, T/4+8} of
 //     the quadrant's 16 rows and two adjacent hidden units), so every lane is busy on either sub-tile.
-//   * one x ring, one MMA thread; issue order per step:  h-part A(t), x-part A(t+1), h-part B(t), x-part B(t+1).
+//   * one x ring; one MMA-issuing thread per sub-tile (warps 1 and 18), each running  h-part(t), x-part(t+1)  for its
+//     own chain, so the issue back-pressure and the multicast commits of one chain never delay the other.
 //
 // Replaces nn.LSTM at FN-SSL/Lightning/Model.py:38,46 and IPDnet/FixedAarryIPDnet.py:32,36 (+ glue :35-37,41-45,49).
 #include <cuda.h>
@@ -24,7 +25,7 @@
 namespace fnssl {
 namespace tc3 {
 
-constexpr int kThreads = 576;          // producer warp + MMA warp + 16 epilogue warps
+constexpr int kThreads = 608;          // producer warp + MMA warp (sub-tile A) + 16 epilogue warps + MMA warp (sub-tile B)
 constexpr int kEpiThreads = 512;
 constexpr int kSlabK = 64;
 constexpr int kWSlab = 128 * 128;      // [128 gate columns x 64] fp16
@@ -171,18 +172,19 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
+  } else if (warp == 1 || warp == 18) {
+    // ============================== MMA issuers (warp 1: sub-tile A, warp 18: sub-tile B) ==============================
     if (lane == 0) {
+      const int sub = (warp == 1) ? 0 : 1;
       mbar_wait(W_FULL, 0, p.error_flag, 200);
-      int n = 0;
-      auto x_part = [&](int sub, int s) {   // G_x of step s of sub-tile `sub` -> accumulator buffer s & 1
+      auto x_part = [&](int s) {   // G_x of step s of this sub-tile -> accumulator buffer s & 1
         const int b = s & 1;
         if (s >= 2) mbar_wait(ACC_EMPTY(sub, b), (uint32_t)(((s >> 1) - 1) & 1), p.error_flag, 201 + sub * 2 + b);
         tc_fence_after();
         const uint32_t d_tmem = tmem_acc + (uint32_t)b * kChunkN + ((uint32_t)(sub * 16) << 16);
         uint32_t accumulate = 0;
-        for (int j = 0; j < nxs; ++j, ++n) {
+        for (int j = 0; j < nxs; ++j) {
+          const int n = (2 * s + sub) * nxs + j;           // position of the slab in the ring's sequence
           const int stage = n % XS;
           mbar_wait(X_FULL(stage), (uint32_t)((n / XS) & 1), p.error_flag, 210 + stage);
           tc_fence_after();
@@ -198,7 +200,7 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           umma_commit_mc(X_EMPTY(stage), mask);    // this CTA is done with the slab: tell every CTA's ring
         }
       };
-      auto h_part = [&](int sub, int t) {   // += h_{t-1} W_h^T, then hand the accumulator to the epilogue
+      auto h_part = [&](int t) {   // += h_{t-1} W_h^T, then hand the accumulator to the epilogue
         if (t > 0) {
           const int pb = (t - 1) & 1;
           mbar_expect_tx(H_FULL(sub, pb), (uint32_t)((C - 1) * kHTile));   // C-1 remote tiles (tx) + 4 local arrives
@@ -216,13 +218,10 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         }
         umma_commit(ACC_FULL(sub, t & 1));
       };
-      x_part(0, 0);
-      x_part(1, 0);
+      x_part(0);
       for (int t = 0; t < L; ++t) {
-        h_part(0, t);
-        if (t + 1 < L) x_part(0, t + 1);
-        h_part(1, t);
-        if (t + 1 < L) x_part(1, t + 1);
+        h_part(t);
+        if (t + 1 < L) x_part(t + 1);
       }
     }
     __syncwarp();
