@@ -158,9 +158,13 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         for (int sub = 0; sub < 2; ++sub) {
           for (int j = 0; j < nxs; ++j, ++n) {
             const int stage = n % XS, use = n / XS;
-            if (use > 0) mbar_wait(X_EMPTY(stage), (uint32_t)((use - 1) & 1), p.error_flag, 100 + stage);
+            const bool issuer = (uint32_t)(n % C) == rank;
+            if (use > 0) {   // see lstm_tc2.cu: only the fetching CTA waits for the consumers' releases
+              if (issuer) mbar_wait(X_EMPTY(stage), (uint32_t)((use - 1) & 1), p.error_flag, 100 + stage);
+              else mbar_wait(X_FULL(stage), (uint32_t)((use - 1) & 1), p.error_flag, 110 + stage);
+            }
             mbar_expect_tx(X_FULL(stage), kXSlab);
-            if ((uint32_t)(n % C) == rank) {   // one CTA fetches the slab for the whole cluster
+            if (issuer) {   // one CTA fetches the slab for the whole cluster
               const CUtensorMap* m = p.xs_src[j] ? &map_src1 : &map_src0;
               const uint32_t dst = xr_base + (uint32_t)stage * kXSlab;
               const int r0 = coord_r0 + sub * kSubRows;
@@ -197,7 +201,8 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
               accumulate = 1;
             }
           }
-          umma_commit_mc(X_EMPTY(stage), mask);    // this CTA is done with the slab: tell every CTA's ring
+          // this CTA is done with the slab: tell the CTA that will refill the slot (slab n + XS)
+          umma_commit_mc(X_EMPTY(stage), (uint16_t)(1u << ((n + XS) % C)));
         }
       };
       auto h_part = [&](int t) {   // += h_{t-1} W_h^T, then hand the accumulator to the epilogue
