@@ -139,6 +139,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       for (int j = 0; j < nslabs; ++j)
         tma_load_2d(w_base + j * kWSlab, &map_w, W_FULL, j * kSlabK, (dir * C + (int)rank) * kChunkN);
       int n = 0;
+      uint32_t xe_phase = 0;   // per-stage phase parity of THIS CTA's X_EMPTY barriers (it only sees the uses it refills)
       // x_t comes from HBM (~3.4 k cycles per TMA round trip, far more than the ring can cover): every CTA pulls its
       // share of the slabs of step t+2 into L2 while the ring works on step t / t+1, so the real loads are L2 hits
       auto prefetch_step = [&](int tt) {
@@ -160,7 +161,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           if (use > 0) {
             // the fetching CTA needs every consumer's release of the slot (X_EMPTY, C arrivals sent to it alone); the
             // others only re-arm their "full" barrier, which they may do once the previous fill has landed
-            if (issuer) mbar_wait(X_EMPTY(stage), (uint32_t)((use - 1) & 1), p.error_flag, 100 + stage);
+            if (issuer) { mbar_wait(X_EMPTY(stage), (xe_phase >> stage) & 1u, p.error_flag, 100 + stage); xe_phase ^= 1u << stage; }
             else mbar_wait(X_FULL(stage), (uint32_t)((use - 1) & 1), p.error_flag, 110 + stage);
           }
           mbar_expect_tx(X_FULL(stage), kASlab);

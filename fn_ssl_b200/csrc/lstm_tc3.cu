@@ -139,6 +139,7 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       for (int j = 0; j < nslabs; ++j)
         tma_load_2d(w_base + j * kWSlab, &map_w, W_FULL, j * kSlabK, (dir * C + (int)rank) * kChunkN);
       int n = 0;
+      uint32_t xe_phase = 0;   // per-stage phase parity of THIS CTA's X_EMPTY barriers (it only sees the uses it refills)
       // L2 prefetch of step t+2's slabs (see lstm_tc2.cu): the ring's real loads then hit L2
       auto prefetch_step = [&](int tt) {
         const int ss = dir ? (L - 1 - tt) : tt;
@@ -160,7 +161,7 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
             const int stage = n % XS, use = n / XS;
             const bool issuer = (uint32_t)(n % C) == rank;
             if (use > 0) {   // see lstm_tc2.cu: only the fetching CTA waits for the consumers' releases
-              if (issuer) mbar_wait(X_EMPTY(stage), (uint32_t)((use - 1) & 1), p.error_flag, 100 + stage);
+              if (issuer) { mbar_wait(X_EMPTY(stage), (xe_phase >> stage) & 1u, p.error_flag, 100 + stage); xe_phase ^= 1u << stage; }
               else mbar_wait(X_FULL(stage), (uint32_t)((use - 1) & 1), p.error_flag, 110 + stage);
             }
             mbar_expect_tx(X_FULL(stage), kXSlab);
