@@ -511,7 +511,12 @@ int lstm_forward_tc(const fnssl_lstm_args* a, cudaStream_t st) {
     const char* e = getenv("FNSSL_TC_KERNEL");
     const int want = e ? atoi(e) : 3;
     const bool aligned = a->c0 % 16 == 0 && a->c1 % 16 == 0;
-    if (want >= 3 && aligned && lstm_tc3_supports(a->hidden, a->c0, a->c1)) return lstm_forward_tc3(a, st);
+    // Generation 3 issues its x-part as M = 64 MMAs (twice the tensor-pipe time and twice the x-ring hand-shakes of
+    // generation 2), which only pays off when the input projection is small: measured on cfg2 it is 1.06 vs 1.46 ms
+    // for the 16-channel first layer but 1.80 vs 1.59 ms for the 256-channel layers -> use it for <= 2 input slabs.
+    const int nxs = (a->c0 + 63) / 64 + (a->c1 + 63) / 64;
+    const bool force3 = e && atoi(e) == 3;
+    if (want >= 3 && aligned && (nxs <= 2 || force3) && lstm_tc3_supports(a->hidden, a->c0, a->c1)) return lstm_forward_tc3(a, st);
     if (want >= 2 && aligned && lstm_tc2_supports(a->hidden, a->c0, a->c1)) return lstm_forward_tc2(a, st);
   }
   FNSSL_REQUIRE(a->c0 % 16 == 0 && a->c1 % 16 == 0, "lstm(tcgen05): channel counts must be multiples of 16 (got %d, %d); pad the grid",

@@ -139,7 +139,6 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       for (int j = 0; j < nslabs; ++j)
         tma_load_2d(w_base + j * kWSlab, &map_w, W_FULL, j * kSlabK, (dir * C + (int)rank) * kChunkN);
       int n = 0;
-      uint32_t xe_phase = 0;   // per-stage phase parity of THIS CTA's X_EMPTY barriers (it only sees the uses it refills)
       // x_t comes from HBM (~3.4 k cycles per TMA round trip, far more than the ring can cover): every CTA pulls its
       // share of the slabs of step t+2 into L2 while the ring works on step t / t+1, so the real loads are L2 hits
       auto prefetch_step = [&](int tt) {
@@ -157,15 +156,9 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         if (!(p.debug & 16) && t + 2 < L) prefetch_step(t + 2);
         for (int j = 0; j < nxs; ++j, ++n) {
           const int stage = n % XS, use = n / XS;
-          const bool issuer = (uint32_t)(n % C) == rank;
-          if (use > 0) {
-            // the fetching CTA needs every consumer's release of the slot (X_EMPTY, C arrivals sent to it alone); the
-            // others only re-arm their "full" barrier, which they may do once the previous fill has landed
-            if (issuer) { mbar_wait(X_EMPTY(stage), (xe_phase >> stage) & 1u, p.error_flag, 100 + stage); xe_phase ^= 1u << stage; }
-            else mbar_wait(X_FULL(stage), (uint32_t)((use - 1) & 1), p.error_flag, 110 + stage);
-          }
+          if (use > 0) mbar_wait(X_EMPTY(stage), (uint32_t)((use - 1) & 1), p.error_flag, 100 + stage);
           mbar_expect_tx(X_FULL(stage), kASlab);
-          if (issuer) {   // one CTA fetches the slab for the whole cluster
+          if ((uint32_t)(n % C) == rank) {   // one CTA fetches the slab for the whole cluster
             const CUtensorMap* m = p.xs_src[j] ? &map_src1 : &map_src0;
             const uint32_t dst = xr_base + (uint32_t)stage * kASlab;
             if (p.axis == FNSSL_ALONG_FREQ) tma_load_4d_mc(dst, m, X_FULL(stage), p.xs_k0[j], s, coord_r0, 0, mask);
@@ -208,8 +201,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
               accumulate = 1;
             }
           }
-          // this CTA is done with the slab: tell the CTA that will refill the slot (slab n + XS)
-          umma_commit_mc(X_EMPTY(stage), (uint16_t)(1u << ((n + XS) % C)));
+          umma_commit_mc(X_EMPTY(stage), mask);    // this CTA is done with the slab: tell every CTA's ring
           if (tr) i_acc += clock64() - c1;
         }
         if (tr && s >= 8 && s < 16) { p.trace[(s - 8) * 16 + 5] = w_acc; p.trace[(s - 8) * 16 + 6] = i_acc; }

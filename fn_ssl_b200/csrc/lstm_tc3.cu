@@ -139,7 +139,6 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       for (int j = 0; j < nslabs; ++j)
         tma_load_2d(w_base + j * kWSlab, &map_w, W_FULL, j * kSlabK, (dir * C + (int)rank) * kChunkN);
       int n = 0;
-      uint32_t xe_phase = 0;   // per-stage phase parity of THIS CTA's X_EMPTY barriers (it only sees the uses it refills)
       // L2 prefetch of step t+2's slabs (see lstm_tc2.cu): the ring's real loads then hit L2
       auto prefetch_step = [&](int tt) {
         const int ss = dir ? (L - 1 - tt) : tt;
@@ -159,13 +158,9 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         for (int sub = 0; sub < 2; ++sub) {
           for (int j = 0; j < nxs; ++j, ++n) {
             const int stage = n % XS, use = n / XS;
-            const bool issuer = (uint32_t)(n % C) == rank;
-            if (use > 0) {   // see lstm_tc2.cu: only the fetching CTA waits for the consumers' releases
-              if (issuer) { mbar_wait(X_EMPTY(stage), (xe_phase >> stage) & 1u, p.error_flag, 100 + stage); xe_phase ^= 1u << stage; }
-              else mbar_wait(X_FULL(stage), (uint32_t)((use - 1) & 1), p.error_flag, 110 + stage);
-            }
+            if (use > 0) mbar_wait(X_EMPTY(stage), (uint32_t)((use - 1) & 1), p.error_flag, 100 + stage);
             mbar_expect_tx(X_FULL(stage), kXSlab);
-            if (issuer) {   // one CTA fetches the slab for the whole cluster
+            if ((uint32_t)(n % C) == rank) {   // one CTA fetches the slab for the whole cluster
               const CUtensorMap* m = p.xs_src[j] ? &map_src1 : &map_src0;
               const uint32_t dst = xr_base + (uint32_t)stage * kXSlab;
               const int r0 = coord_r0 + sub * kSubRows;
@@ -202,8 +197,7 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
               accumulate = 1;
             }
           }
-          // this CTA is done with the slab: tell the CTA that will refill the slot (slab n + XS)
-          umma_commit_mc(X_EMPTY(stage), (uint16_t)(1u << ((n + XS) % C)));
+          umma_commit_mc(X_EMPTY(stage), mask);    // this CTA is done with the slab: tell every CTA's ring
         }
       };
       auto h_part = [&](int t) {   // += h_{t-1} W_h^T, then hand the accumulator to the epilogue
