@@ -151,7 +151,7 @@ stft512_kernel(const float* __restrict__ signal, int nsample, int nch, int hop, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// normaliser: one thread per feature row, sequential over frames (utils_.py:27-44)
+// normaliser: one warp per feature row (utils_.py:27-44)
 // ------------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ void row_channels(int r, int nch, int pairing, int& b, int& ci, int& cj) {
@@ -165,15 +165,20 @@ __device__ __forceinline__ void row_channels(int r, int nch, int pairing, int& b
   ci = i; cj = i + 1 + p;
 }
 
-__global__ void norm_scan_kernel(const float* __restrict__ magsum, int R, int nt, int nch, int nbins, int pairing, int norm,
-                                 int sample_length, float* __restrict__ mu_out) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per feature row: the per-frame means are gathered in parallel into shared memory, lane 0 runs the
+// T-sequential recursion out of shared memory (no dependent global loads), the result is written back coalesced.
+__global__ void __launch_bounds__(32)
+norm_scan_kernel(const float* __restrict__ magsum, int R, int nt, int nch, int nbins, int pairing, int norm,
+                 int sample_length, float* __restrict__ mu_out) {
+  extern __shared__ float fm[];   // [nt] frame means, overwritten by mu
+  const int r = blockIdx.x;
+  const int lane = threadIdx.x;
   if (r >= R) return;
   int b, ci, cj;
   row_channels(r, nch, pairing, b, ci, cj);
   const int C = (pairing == FNSSL_PAIRS_ALL) ? nch : 2;
   const float cnt = (float)(C * nbins);
-  auto frame_mean = [&](int t) {
+  for (int t = lane; t < nt; t += 32) {
     float s;
     if (pairing == FNSSL_PAIRS_ALL) {
       s = 0.0f;
@@ -181,30 +186,34 @@ __global__ void norm_scan_kernel(const float* __restrict__ magsum, int R, int nt
     } else {
       s = magsum[((size_t)b * nch + ci) * nt + t] + magsum[((size_t)b * nch + cj) * nt + t];
     }
-    return s / cnt;
-  };
-  float* mu_row = mu_out + (size_t)r * nt;
-  if (norm == FNSSL_NORM_GLOBAL) {
-    float s = 0.0f;
-    for (int t = 0; t < nt; ++t) s += frame_mean(t);
-    const float m = s / (float)nt;
-    for (int t = 0; t < nt; ++t) mu_row[t] = m;
-    return;
+    fm[t] = s / cnt;
   }
-  const double alpha = (double)(sample_length - 1) / (double)(sample_length + 1);
-  float mu = 0.0f;
-  for (int t = 0; t < nt; ++t) {
-    float a, om;
-    if (t < sample_length) {
-      a = (float)fmin((double)(t - 1) / (double)(t + 1), alpha);  // fp32 tensor in the reference (:31)
-      om = 1.0f - a;
+  __syncwarp();
+  if (lane == 0) {
+    if (norm == FNSSL_NORM_GLOBAL) {
+      float s = 0.0f;
+      for (int t = 0; t < nt; ++t) s += fm[t];
+      const float m = s / (float)nt;
+      for (int t = 0; t < nt; ++t) fm[t] = m;
     } else {
-      a = (float)alpha;
-      om = (float)(1.0 - alpha);
+      const double alpha = (double)(sample_length - 1) / (double)(sample_length + 1);
+      float mu = 0.0f;
+      for (int t = 0; t < nt; ++t) {
+        float a, om;
+        if (t < sample_length) {
+          a = (float)fmin((double)(t - 1) / (double)(t + 1), alpha);  // fp32 tensor in the reference (:31)
+          om = 1.0f - a;
+        } else {
+          a = (float)alpha;
+          om = (float)(1.0 - alpha);
+        }
+        mu = a * mu + om * fm[t];
+        fm[t] = mu;
+      }
     }
-    mu = a * mu + om * frame_mean(t);
-    mu_row[t] = mu;
   }
+  __syncwarp();
+  for (int t = lane; t < nt; t += 32) mu_out[(size_t)r * nt + t] = fm[t];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -379,7 +388,9 @@ int fnssl_norm_forward(const float* magsum, int nb, int nch, int nt, int nbins, 
   FNSSL_REQUIRE(norm == FNSSL_NORM_FORGETTING || norm == FNSSL_NORM_GLOBAL, "norm: bad norm %d", norm);
   FNSSL_REQUIRE(pairing == FNSSL_PAIRS_ALL || nch >= 2, "norm: pair modes need >= 2 channels");
   const int R = fnssl_feature_rows(nb, nch, pairing);
-  norm_scan_kernel<<<(R + 127) / 128, 128, 0, (cudaStream_t)stream>>>(magsum, R, nt, nch, nbins, pairing, norm, sample_length, mu);
+  FNSSL_REQUIRE((size_t)nt * 4 <= 200 * 1024, "norm: too many frames (%d)", nt);
+  FNSSL_CUDA(cudaFuncSetAttribute(norm_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nt * 4));
+  norm_scan_kernel<<<R, 32, (size_t)nt * 4, (cudaStream_t)stream>>>(magsum, R, nt, nch, nbins, pairing, norm, sample_length, mu);
   FNSSL_LAUNCH_CHECK("norm_scan_kernel");
   return 0;
 }
