@@ -6,6 +6,8 @@
 // "pad 2 then crop 2" along time makes every conv causal: out[f,t] = sum_{kf,kt} W[o,c,kf,kt] * in[f+kf-1, t+kt-2].
 // ReLU and the average pooling are fused into the conv epilogue (pooling window = POOL consecutive frames
 // computed by the same thread), so each intermediate is written once, already pooled.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fnssl {
@@ -92,7 +94,8 @@ conv3x3_pool_relu_kernel(const T* __restrict__ src0, int c0, int ld0, const T* _
 }
 
 // last conv: tiny cout, one thread per output element, output in the reference layout (nb, cout, nf, nt)
-__global__ void conv3x3_tanh_kernel(const float* __restrict__ in, int C, int nb, int nt, int nf,
+template <typename T>
+__global__ void conv3x3_tanh_kernel(const T* __restrict__ in, int C, int nb, int nt, int nf,
                                     const float* __restrict__ wr, int O, float* __restrict__ out) {
   const int64_t total = (int64_t)nb * nt * nf * O;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -107,27 +110,36 @@ __global__ void conv3x3_tanh_kernel(const float* __restrict__ in, int C, int nb,
       for (int kt = 0; kt < 3; ++kt) {
         const int tt = t + kt - 2;
         if (tt < 0) continue;
-        const float* a = in + (((int64_t)b * nt + tt) * nf + ff) * C;
+        const T* a = in + (((int64_t)b * nt + tt) * nf + ff) * C;
         const float* w = wr + (size_t)(kf * 3 + kt) * C * O + o;
-        for (int c = 0; c < C; ++c) acc = fmaf(a[c], __ldg(w + (size_t)c * O), acc);
+        for (int c = 0; c < C; ++c) acc = fmaf(ld_act<T>(a + c), __ldg(w + (size_t)c * O), acc);
       }
     }
     out[(((int64_t)b * O + o) * nf + f) * nt + t] = tanhf(acc);
   }
 }
 
+// tcgen05 implicit-GEMM path (conv_tc.cu)
+bool causcnn_tc_supports(int c0, int c1, int hid, int dtype);
+size_t causcnn_tc_workspace_bytes(int nb, int nt, int nf, int c0, int c1, int cout);
+int causcnn_forward_tc(const void* src0, int c0, int c0_real, int ld0, const void* src1, int c1, int c1_real, int ld1, int nb, int nt,
+                       int nf, const float* w1, const float* w2, void* work, __half** y2_out, float** w3r_out, cudaStream_t st);
+
 }  // namespace fnssl
 
 using namespace fnssl;
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static int pad16(int c) { return (c + 15) / 16 * 16; }
 
 extern "C" {
 
 size_t fnssl_causcnn_workspace_bytes(int nb, int nt, int nf, int cin, int hid, int cout) {
   const size_t nt1 = nt / 3, nt2 = nt1 / 4;
-  return align256((size_t)nb * nt1 * nf * hid * 4) + align256((size_t)nb * nt2 * nf * hid * 4) +
-         align256((size_t)9 * cin * hid * 4) + align256((size_t)9 * hid * hid * 4) + align256((size_t)9 * hid * cout * 4);
+  const size_t simt = align256((size_t)nb * nt1 * nf * hid * 4) + align256((size_t)nb * nt2 * nf * hid * 4) +
+                      align256((size_t)9 * cin * hid * 4) + align256((size_t)9 * hid * hid * 4) + align256((size_t)9 * hid * cout * 4);
+  const size_t tc = causcnn_tc_workspace_bytes(nb, nt, nf, pad16(cin), 64, cout);   // upper bound on the slab count
+  return simt > tc ? simt : tc;
 }
 
 int fnssl_causcnn_forward(const void* src0, int c0, int ld0, const void* src1, int c1, int ld1, int dtype, int nb, int nt,
@@ -141,6 +153,24 @@ int fnssl_causcnn_forward(const void* src0, int c0, int ld0, const void* src1, i
   const int nt1 = nt / 3, nt2 = nt1 / 4;
   if (nt2 == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // tensor-core path: fp16 grids, 128 hidden channels, sources zero-padded to multiples of 16 channels.
+    // FNSSL_CONV_ENGINE=simt forces the CUDA-core path below (tests).
+    const int c0p = pad16(c0), c1p = c1 > 0 ? pad16(c1) : 0;
+    const char* e = getenv("FNSSL_CONV_ENGINE");
+    const bool want_tc = !(e && e[0] == 's');
+    if (want_tc && ld0 >= c0p && (c1 == 0 || ld1 >= c1p) && causcnn_tc_supports(c0p, c1p, hid, dtype)) {
+      __half* y2h = nullptr;
+      float* w3r = nullptr;
+      if (causcnn_forward_tc(src0, c0p, c0, ld0, src1, c1p, c1, ld1, nb, nt, nf, w1, w2, work, &y2h, &w3r, st)) return 1;
+      repack_conv_weight_kernel<<<16, 256, 0, st>>>(w3, cout, hid, w3r);
+      const int64_t total = (int64_t)nb * nt2 * nf * cout;
+      const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+      conv3x3_tanh_kernel<__half><<<blocks, 256, 0, st>>>(y2h, hid, nb, nt2, nf, w3r, cout, out);
+      FNSSL_LAUNCH_CHECK("conv3x3_tanh_kernel");
+      return 0;
+    }
+  }
   char* wsp = (char*)work;
   float* y1 = (float*)wsp; wsp += align256((size_t)nb * nt1 * nf * hid * 4);
   float* y2 = (float*)wsp; wsp += align256((size_t)nb * nt2 * nf * hid * 4);
@@ -177,7 +207,7 @@ int fnssl_causcnn_forward(const void* src0, int c0, int ld0, const void* src1, i
   {
     const int64_t total = (int64_t)nb * nt2 * nf * cout;
     const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-    conv3x3_tanh_kernel<<<blocks, 256, 0, st>>>(y2, hid, nb, nt2, nf, w3r, cout, out);
+    conv3x3_tanh_kernel<float><<<blocks, 256, 0, st>>>(y2, hid, nb, nt2, nf, w3r, cout, out);
     FNSSL_LAUNCH_CHECK("conv3x3_tanh_kernel");
   }
   return 0;

@@ -244,6 +244,29 @@ def test_causcnn_matches_reference_golden(golden_ipdnet):
     assert _relerr(y, g["cnn_y"]) <= 2e-5
 
 
+@pytest.mark.parametrize("cin0,cin1", [(32, 0), (256, 8), (128, 4)])
+def test_causcnn_tensor_core_path(monkeypatch, cin0, cin1):
+    """CausCnnBlock on fp16 grids: tcgen05 implicit-GEMM conv1/conv2 (two-source input, ragged bins/frames) against the
+    oracle, and bit-for-bit agreement of its dispatch with the CUDA-core kernels' semantics (same input grids)."""
+    import fn_ssl_b200 as F
+    from fn_ssl_b200 import ops
+    cin = cin0 + cin1
+    torch.manual_seed(21)
+    cnn = F.CausCnnBlock(inp_dim=cin, out_dim=6, cnn_hidden_dim=128).eval().to(DEV)
+    x = _randn((2, cin, 150, 38), 24)                      # 150 bins: two 128-bin tiles, the second ragged
+    g0 = ops.cfirst_to_grid(x[:, :cin0].to(DEV), torch.float16)
+    g1 = ops.cfirst_to_grid(x[:, cin0:].to(DEV), torch.float16) if cin1 else None
+    xq = torch.cat([g0[..., :cin0].float().cpu()] + ([g1[..., :cin1].float().cpu()] if cin1 else []), -1).permute(0, 3, 2, 1)
+    ref = orc.causcnn(xq, {"conv." + k: v.detach().cpu() for k, v in cnn.state_dict().items()})
+    y_tc = cnn.forward_grid(g0, cin0, g1, cin1)
+    assert y_tc.shape == ref.shape == (2, 6, 150, 3)
+    assert _relerr(y_tc, ref) <= 1e-3
+    monkeypatch.setenv("FNSSL_CONV_ENGINE", "simt")
+    y_simt = cnn.forward_grid(g0, cin0, g1, cin1)
+    assert _relerr(y_simt, ref) <= 2e-5
+    assert _relerr(y_tc, y_simt) <= 1e-3
+
+
 # ---------------------------------------------------------------------------------------------
 # end to end at BASELINE sizes (4 s @ 16 kHz): oracle on a small batch + size-independent properties
 # ---------------------------------------------------------------------------------------------
