@@ -305,9 +305,12 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
             addn[i] = __ldg(reinterpret_cast<const unsigned int*>(p.addend + pos0 * p.addend_ld + dir * H + ua));
           }
       }
+      const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0;
       for (int t = 0; t < L; ++t) {
         const int b = t & 1;
         const int s = dir ? (L - 1 - t) : t;
+        long long* tp = (tr && t >= 8 && t < 16) ? p.trace + (t - 8) * 16 : nullptr;
+        if (tp) tp[8] = clock64();
         const uint32_t addc[2] = {addn[0], addn[1]};
         if (p.out1 && t + 1 < L) {     // residual operand of the next layer, fetched one step ahead
 #pragma unroll
@@ -318,6 +321,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
             }
         }
         mbar_wait(ACC_FULL(b), (uint32_t)((t >> 1) & 1), p.error_flag, 300 + b);
+        if (tp) tp[9] = clock64();
         tc_fence_after();
         const uint32_t acc = tmem_acc + (uint32_t)b * kChunkN + lane_off + u0;
         float gi[4], gf[4], gg[4], go[4], cs[4];
@@ -328,6 +332,7 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         tmem_ld4_16x256(tmem_c + lane_off + u0, cs);
         tmem_wait_ld();
         tmem_ld_dep4(gi); tmem_ld_dep4(gf); tmem_ld_dep4(gg); tmem_ld_dep4(go); tmem_ld_dep4(cs);
+        if (tp) tp[10] = clock64();
         tc_fence_before();
         mbar_arrive(ACC_EMPTY(b));      // accumulator drained: the MMA warp may produce G_x of step t+2 into it
         float hv[4];
@@ -339,12 +344,15 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
                                  go[e] + bsp[3 * kChunkUnits + uu], cs[e]);
         }
         __half2 hp[2] = {__floats2half2_rn(hv[0], hv[1]), __floats2half2_rn(hv[2], hv[3])};
+        if (tp) tp[11] = clock64();
         if (t + 1 < L) {
           const uint32_t buf = hs_base + (uint32_t)(b * C) * kHTile;
           st_shared_b32(buf + hpiece[0], *reinterpret_cast<uint32_t*>(&hp[0]));
           st_shared_b32(buf + hpiece[1], *reinterpret_cast<uint32_t*>(&hp[1]));
           publish_quadrant(buf, hquad, 1024u, b);
         }
+        if (tp) tp[12] = clock64();
+        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && t == 12) p.trace[128 + warp] = clock64();
         tmem_st4_16x256(tmem_c + lane_off + u0, cs);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
