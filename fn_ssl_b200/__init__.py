@@ -10,7 +10,8 @@ All arithmetic runs in libfnssl_b200.so (hand-written CUDA, C ABI in include/fns
 from . import config  # noqa: F401
 from .FixedAarryIPDnet import CausalConv1dBlock, CausCnnBlock, FixedArrayIPDnet, IPDnet  # noqa: F401
 from .Model import FN_SSL, FN_lightning, FNblock, FullNarrowBlock  # noqa: F401
-from .Module import STFT, AddChToBatch, RemoveChFromBatch, forgetting_norm  # noqa: F401
+from .Module import (DPIPD, STFT, AddChToBatch, RemoveChFromBatch, SourceDetectLocalize, forgetting_norm,  # noqa: F401
+                     pred_ipd_to_doa)
 from .pipeline import FNSSLPipeline, IPDnetPipeline, data_preprocess_fnssl, data_preprocess_ipdnet  # noqa: F401
 
 __version__ = "0.1.0"

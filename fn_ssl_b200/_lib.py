@@ -53,6 +53,7 @@ SIGNATURES = {
     "fnssl_lstm_tc_trace": (_i, [C.POINTER(C.c_longlong)]),
     "fnssl_ipd_head_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "fnssl_linear_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "fnssl_doa_decode_idl": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fnssl_causcnn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "fnssl_causcnn_forward": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
 }

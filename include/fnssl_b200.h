@@ -164,6 +164,18 @@ int fnssl_causcnn_forward(const void* src0, int c0, int ld0, const void* src1, i
                           int nb, int nt, int nf, const float* w1, const float* w2, const float* w3, int hid,
                           int cout, void* work, float* out, void* stream);
 
+/* ---- IPD -> DOA decoding ("next" row of the scope contract) ------------------------------------- */
+
+/* SourceDetectLocalize.forward, meth_mode 'IDL' (FN-SSL/Lightning/Module.py:525-581): max_sources rounds of
+ * spatial spectrum (pred_ipd . templates / (K/2)) -> first-maximum argmax -> projection ratio -> residual update.
+ *   pred_ipd : (R, K) f32, R = nb*nt, K = 2nf*npairs in (2nf, pair) order       templ : (ncand, K), templ_t : (K, ncand)
+ *   cur, map : workspaces (R, K) and (R, ncand)      ss : (R, ncand) spectrum of the first round
+ *   idx_out : (R, max_sources) int32 candidate index (ele*nazi + azi)            vad_out : (R, max_sources)
+ *   vad_mode : 0 -> 0, 1 -> 1 ('kNum'), 2 -> projection ratio ('unkNum') */
+int fnssl_doa_decode_idl(const float* pred_ipd, const float* templ, const float* templ_t, int R, int K, int ncand,
+                         int max_sources, int vad_mode, float* cur, float* map, float* ss, int* idx_out,
+                         float* vad_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

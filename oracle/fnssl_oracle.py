@@ -357,3 +357,83 @@ def white_noise(nb: int, nsample: int, nch: int, seed: int = 1234) -> Tensor:
     """Synthetic input of SURVEY.md §8d: torch.randn(B, nsample, M) from Generator(seed)."""
     g = torch.Generator().manual_seed(seed)
     return torch.randn(nb, nsample, nch, generator=g, dtype=torch.float32)
+
+
+# --------------------------------------------------------------------------------------
+# "Next" row #1 (SURVEY.md section 8f): DP-IPD templates and IPD -> DOA decoding
+# --------------------------------------------------------------------------------------
+
+
+def _pair_select(data, ch_mode: str):
+    """``DPIPD.data_adjust`` FN-SSL/Lightning/Module.py:500-514: (..., nmic, nmic) -> (..., npairs)."""
+    import numpy as np
+    nmic = data.shape[-1]
+    if ch_mode == "M":
+        return data[..., 0, 1:]
+    if ch_mode == "MM":
+        cols = [data[..., i, j] for i in range(nmic - 1) for j in range(i + 1, nmic)]
+        return np.stack(cols, axis=-1).astype(np.complex64)
+    raise Exception("Microphone channel mode unrecognised")
+
+
+def dpipd_template(ndoa_candidate, mic_location, nf: int = 257, fre_max: float = 8000, ch_mode: str = "M",
+                   speed: float = 343.0):
+    """Far-field direct-path IPD templates, ``DPIPD.__init__`` FN-SSL/Lightning/Module.py:428-462.
+    Returns (template (nele, nazi, nf, npairs) complex, [ele_candidate, azi_candidate])."""
+    import numpy as np
+    nele, nazi = ndoa_candidate
+    ele = np.linspace(0, np.pi, nele)
+    azi = np.linspace(-np.pi, np.pi, nazi)
+    nmic = mic_location.shape[-2]
+    r = np.stack([np.outer(np.sin(ele), np.cos(azi)), np.outer(np.sin(ele), np.sin(azi)),
+                  np.tile(np.cos(ele), [nazi, 1]).transpose()], axis=2)                    # (nele, nazi, 3) unit vectors
+    fre = np.linspace(0.0, fre_max, nf)
+    ipd = np.empty((nele, nazi, nf, nmic, nmic))
+    for m1 in range(nmic):
+        for m2 in range(nmic):
+            itd = np.dot(r, mic_location[m2, :] - mic_location[m1, :]) / speed            # :449
+            ipd[:, :, :, m1, m2] = -2 * np.pi * fre[None, None, :] * itd[:, :, None]      # :450-451
+    return _pair_select(np.exp(1j * ipd), ch_mode), [ele, azi]
+
+
+def doa_templates_for_decode(template, fre_range_used=range(1, 257)):
+    """``PredDOA.predgt2DOA`` FN-SSL/Lightning/Module.py:701-716: [re | im] over the used bins, elevation fixed to the
+    horizontal plane, azimuths 0..pi.  (nele,nazi,nf,P) complex -> ((1, nazi_half, 2*len(bins), P) f32, [ele, azi])."""
+    import numpy as np
+    t = np.concatenate((template.real[:, :, fre_range_used, :], template.imag[:, :, fre_range_used, :]), axis=2).astype(np.float32)
+    nele, nazi = t.shape[:2]
+    t = t[int((nele - 1) / 2):int((nele - 1) / 2) + 1, int((nazi - 1) / 2):nazi, :, :]
+    return t, [np.linspace(np.pi / 2, np.pi / 2, 1), np.linspace(0, np.pi, 37)]
+
+
+def source_detect_localize_idl(pred_ipd: Tensor, template: Tensor, doa_candidate, max_num_sources: int = 1,
+                               source_num_mode: str = "kNum"):
+    """Iterative detection/localisation, ``SourceDetectLocalize.forward`` (meth_mode 'IDL')
+    FN-SSL/Lightning/Module.py:525-577.  pred_ipd (nb, nt, 2nf, P), template (nele, nazi, 2nf, P) ->
+    (DOAs (nb,nt,2,ns) [ele, azi] radians, VADs (nb,nt,ns), spatial spectrum (nb,nt,nele,nazi))."""
+    import numpy as np
+    nb, nt, nf2, P = pred_ipd.shape
+    nele, nazi = template.shape[:2]
+    tmat = template.reshape(nele * nazi, nf2 * P)                       # (cand, K): same (2nf, P) flattening as :537
+    cur = pred_ipd.reshape(nb * nt, nf2 * P).clone()
+    scale = P * nf2 / 2
+    doas = torch.zeros(nb * nt, 2, max_num_sources)
+    vads = torch.zeros(nb * nt, max_num_sources)
+    ss0 = None
+    for sidx in range(max_num_sources):
+        smap = cur @ tmat.t() / scale                                   # :553-556
+        if ss0 is None:
+            ss0 = smap.clone()
+        idx = smap.argmax(dim=1)                                        # :558
+        e_idx, a_idx = np.unravel_index(idx.numpy(), (nele, nazi))
+        doas[:, 0, sidx] = torch.from_numpy(np.asarray(doa_candidate[0])[e_idx]).float()
+        doas[:, 1, sidx] = torch.from_numpy(np.asarray(doa_candidate[1])[a_idx]).float()
+        best = tmat[idx]                                                # (R, K)
+        ratio = (best * cur).sum(1) / (best * best).sum(1)              # :571-574
+        if source_num_mode == "kNum":
+            vads[:, sidx] = 1
+        elif source_num_mode == "unkNum":
+            vads[:, sidx] = ratio
+        cur = cur - ratio[:, None] * best                               # :575,:580
+    return (doas.reshape(nb, nt, 2, max_num_sources), vads.reshape(nb, nt, max_num_sources),
+            ss0.reshape(nb, nt, nele, nazi))

@@ -88,6 +88,31 @@ def gen_fnssl():
     out["blk_next_y"], out["blk_next_fb"], out["blk_next_nb"] = y2.numpy(), fb2.numpy(), nbs2.numpy()
     for k, v in blk2.state_dict().items():
         out["blk_next_sd." + k] = v.numpy()
+    # ---- "next" row: DPIPD templates + SourceDetectLocalize (IDL) + PredDOA.predgt2DOA
+    mic3 = np.array(((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0), (0.0, 0.05, 0.01)))
+    for mode in ("M", "MM"):
+        d = ref_module.DPIPD(ndoa_candidate=[7, 13], mic_location=mic3, nf=33, fre_max=8000, ch_mode=mode, speed=340)
+        tpl, _, cand = d()
+        out[f"dec_template_{mode}_re"], out[f"dec_template_{mode}_im"] = tpl.real.astype(np.float32), tpl.imag.astype(np.float32)
+        _, ipd_gt, _ = d(source_doa=np.array([[[[1.2, 0.7], [0.4, -2.0]]]]))      # (nb=1, nt=1, 2, nsource=2)
+        out[f"dec_gt_{mode}_re"], out[f"dec_gt_{mode}_im"] = ipd_gt.real.astype(np.float32), ipd_gt.imag.astype(np.float32)
+    d2 = ref_module.DPIPD(ndoa_candidate=[37, 73], mic_location=np.array(((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0))), nf=257,
+                          fre_max=8000, ch_mode="MM", speed=340)
+    tpl2, _, _ = d2()
+    t2 = np.concatenate((tpl2.real[:, :, range(1, 257), :], tpl2.imag[:, :, range(1, 257), :]), axis=2).astype(np.float32)
+    t2 = torch.from_numpy(t2[18:19, 36:73])                                       # horizontal plane, azimuth 0..pi (:708)
+    cand2 = [np.linspace(np.pi / 2, np.pi / 2, 1), np.linspace(0, np.pi, 37)]
+    pred = 0.7 * t2[0, 5][None, None] + 0.4 * t2[0, 30][None, None] + 0.05 * _randn((2, 6, 512, 1), 15)
+    out["dec_pred_ipd"] = pred.numpy()
+    for snm in ("kNum", "unkNum", "KNum"):
+        sdl = ref_module.SourceDetectLocalize(max_num_sources=2, source_num_mode=snm, meth_mode="IDL")
+        doa, vad, ss = sdl(pred.clone(), t2, cand2)
+        out[f"dec_doa_{snm}"], out[f"dec_vad_{snm}"] = doa.numpy(), vad.numpy()
+    out["dec_ss"] = ss.numpy()
+    pd = ref_module.PredDOA(device="cpu")
+    netout = _randn((3, 4, 512), 16).tanh()                                       # a fake (nb*P, nt//12, 2nf) network output
+    pb, _ = pd.predgt2DOA(pred_batch=netout)
+    out["dec_preddoa_doa"], out["dec_preddoa_vad"], out["dec_preddoa_ss"] = pb["doa"].numpy(), pb["vad_sources"].numpy(), pb["spatial_spectrum"].numpy()
     # FN_lightning wrapper key names (FN-SSL/Model.py:92-99, loaded with expandtabs because of the TabError at :61)
     src = open(os.path.join(REF, "FN-SSL", "Model.py")).read().expandtabs(8)
     ns = {"__name__": "ref_fnssl_model"}

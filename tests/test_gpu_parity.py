@@ -319,3 +319,68 @@ def test_ipdnet_end_to_end_4mic():
         out = F.IPDnetPipeline(net)(sig.to(DEV))
         assert out.shape == (1, 20, 512, 3, 2)
         assert _relerr(out, ref) <= TOL[eng], eng
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" row: IPD -> DOA decoding
+# ---------------------------------------------------------------------------------------------
+
+def test_dpipd_templates_match_reference_golden(golden_fnssl):
+    import fn_ssl_b200 as F
+    g = golden_fnssl
+    mic3 = np.array(((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0), (0.0, 0.05, 0.01)))
+    for mode in ("M", "MM"):
+        d = F.DPIPD(ndoa_candidate=[7, 13], mic_location=mic3, nf=33, fre_max=8000, ch_mode=mode, speed=340)
+        tpl, gt, cand = d(source_doa=np.array([[[[1.2, 0.7], [0.4, -2.0]]]]))
+        assert _relerr(tpl.real.astype(np.float32), g[f"dec_template_{mode}_re"]) <= 1e-6
+        assert _relerr(tpl.imag.astype(np.float32), g[f"dec_template_{mode}_im"]) <= 1e-6
+        assert _relerr(gt.real.astype(np.float32), g[f"dec_gt_{mode}_re"]) <= 1e-6
+        assert _relerr(gt.imag.astype(np.float32), g[f"dec_gt_{mode}_im"]) <= 1e-6
+        assert len(cand[0]) == 7 and len(cand[1]) == 13
+
+
+@pytest.mark.parametrize("snm", ["kNum", "unkNum", "KNum"])
+def test_source_detect_localize_matches_reference_golden(golden_fnssl, snm):
+    import fn_ssl_b200 as F
+    g = golden_fnssl
+    d = F.DPIPD(ndoa_candidate=[37, 73], mic_location=np.array(((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0))), nf=257, fre_max=8000,
+                ch_mode="MM", speed=340)
+    t2, cand2 = orc.doa_templates_for_decode(d.dpipd_template)      # the slicing PredDOA.predgt2DOA applies
+    sdl = F.SourceDetectLocalize(max_num_sources=2, source_num_mode=snm, meth_mode="IDL")
+    doa, vad, ss = sdl(torch.from_numpy(g["dec_pred_ipd"]).to(DEV), torch.from_numpy(t2), cand2)
+    assert np.array_equal(doa.cpu().numpy(), g[f"dec_doa_{snm}"])          # identical candidates picked (index work: exact)
+    assert _relerr(ss, g["dec_ss"]) <= 1e-5
+    if snm == "unkNum":
+        assert _relerr(vad, g[f"dec_vad_{snm}"]) <= 1e-5
+    else:
+        assert np.array_equal(vad.cpu().numpy(), g[f"dec_vad_{snm}"])      # 'KNum' (main.py's spelling) leaves the VADs at 0
+
+
+def test_pred_ipd_to_doa_matches_reference_golden(golden_fnssl):
+    import fn_ssl_b200 as F
+    g = golden_fnssl
+    gd = F.DPIPD(ndoa_candidate=[37, 73], mic_location=np.array(((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0))), nf=257, fre_max=8000,
+                 ch_mode="MM", speed=340)
+    sdl = F.SourceDetectLocalize(max_num_sources=1, source_num_mode="kNum", meth_mode="IDL")
+    netout = _randn((3, 4, 512), 16).tanh().to(DEV)
+    out = F.pred_ipd_to_doa(netout, gd, sdl, ch_mode="MM")
+    assert np.array_equal(out["doa"].cpu().numpy(), g["dec_preddoa_doa"])
+    assert np.array_equal(out["vad_sources"].cpu().numpy(), g["dec_preddoa_vad"])
+    assert _relerr(out["spatial_spectrum"], g["dec_preddoa_ss"]) <= 1e-5
+
+
+def test_decode_many_pairs_and_sources():
+    """8-mic 'MM' (28 pairs, K = 14336 > one shared-memory chunk) and 3 sources against the oracle."""
+    import fn_ssl_b200 as F
+    rng = np.random.RandomState(3)
+    mics = rng.uniform(-0.1, 0.1, size=(8, 3))
+    d = F.DPIPD(ndoa_candidate=[9, 19], mic_location=mics, nf=257, fre_max=8000, ch_mode="MM", speed=343.0)
+    tpl = d.dpipd_template
+    t = np.concatenate((tpl.real[:, :, 1:257, :], tpl.imag[:, :, 1:257, :]), axis=2).astype(np.float32)
+    T = torch.from_numpy(t)
+    pred = 0.6 * T[2, 3][None, None] + 0.5 * T[6, 15][None, None] + 0.3 * T[4, 9][None, None] + 0.02 * _randn((2, 5, 512, 28), 8)
+    ref = orc.source_detect_localize_idl(pred, T, d.doa_candidate, 3, "unkNum")
+    sdl = F.SourceDetectLocalize(max_num_sources=3, source_num_mode="unkNum", meth_mode="IDL")
+    doa, vad, ss = sdl(pred.to(DEV), T, d.doa_candidate)
+    assert np.array_equal(doa.cpu().numpy(), ref[0].numpy())
+    assert _relerr(vad, ref[1]) <= 1e-4 and _relerr(ss, ref[2]) <= 1e-4

@@ -82,3 +82,21 @@ def test_causcnn_matches_reference(golden_ipdnet):
     sd = {"conv." + k[len("cnn_sd."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("cnn_sd.")}
     xc = _randn((2, 20, 12, 37), 23)
     _close(orc.causcnn(xc, sd), g["cnn_y"], 1e-5)
+
+
+def test_decode_oracle_matches_reference(golden_fnssl):
+    """'next' row: DPIPD templates / targets and SourceDetectLocalize (IDL) against the reference's outputs."""
+    g = golden_fnssl
+    mic3 = np.array(((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0), (0.0, 0.05, 0.01)))
+    for mode in ("M", "MM"):
+        tpl, cand = orc.dpipd_template([7, 13], mic3, 33, 8000, mode, 340)
+        _close(tpl.real.astype(np.float32), g[f"dec_template_{mode}_re"], 1e-6)
+        _close(tpl.imag.astype(np.float32), g[f"dec_template_{mode}_im"], 1e-6)
+    tpl2, _ = orc.dpipd_template([37, 73], np.array(((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0))), 257, 8000, "MM", 340)
+    t2, cand2 = orc.doa_templates_for_decode(tpl2)
+    pred = torch.from_numpy(g["dec_pred_ipd"])
+    for snm in ("kNum", "unkNum", "KNum"):
+        doa, vad, ss = orc.source_detect_localize_idl(pred, torch.from_numpy(t2), cand2, 2, snm)
+        assert np.array_equal(doa.numpy(), g[f"dec_doa_{snm}"])
+        _close(vad, g[f"dec_vad_{snm}"], 1e-5) if snm == "unkNum" else np.testing.assert_array_equal(vad.numpy(), g[f"dec_vad_{snm}"])
+    _close(ss, g["dec_ss"], 1e-5)
