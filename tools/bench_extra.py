@@ -43,6 +43,14 @@ def main():
         ms, layers = timed(lambda: pipe(sig))
         print(json.dumps({"workload": "IPDnet 4-mic hidden 256 online, batch 32x4s (cfg3)", "ms_per_step": round(ms, 3),
                           "frames_per_s": round(32 * 249 / ms * 1e3, 1), "lstm_ms": layers}))
+    if "decode" in which:
+        import numpy as np
+        gd = F.DPIPD(ndoa_candidate=[37, 73], mic_location=np.array(((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0))), nf=257,
+                     fre_max=8000, ch_mode="MM", speed=340)
+        sdl = F.SourceDetectLocalize(max_num_sources=1, source_num_mode="kNum", meth_mode="IDL")
+        netout = torch.randn(16, 20, 512, device=dev).tanh()
+        ms, _ = timed(lambda: F.pred_ipd_to_doa(netout, gd, sdl, ch_mode="MM"))
+        print(json.dumps({"workload": "IPD->DOA decode (IDL, 37 candidates), 16 utterances x 20 frames", "ms_per_step": round(ms, 4)}))
     for tag, B, online in (("fnssl_b64", 64, False), ("fnssl_b64_online", 64, True), ("fnssl_b4", 4, False)):
         if tag not in which:
             continue
