@@ -150,7 +150,7 @@ def main():
     import fn_ssl_b200 as F
     from fn_ssl_b200 import config, ops
     from fn_ssl_b200 import distributed as D
-    from oracle import fnssl_oracle as orc   # synthetic-input generator + seeded weights + cpu_baseline only
+    # (oracle/ is imported only inside cpu_reference_run -- the cpu_baseline / reference-arm legs)
 
     rank, world, local = D.init_from_env("nccl")
     if world != args.gpus and rank == 0 and world > 1:
@@ -158,9 +158,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
 
+    # weights: PyTorch default init under torch.manual_seed(0) -- the module reproduces the reference's init stream,
+    # so this equals `torch.manual_seed(0); FN_SSL(...)` of the reference; rank 0's copy is broadcast
+    torch.manual_seed(0 if rank == 0 else 1000 + rank)
     net = F.FN_SSL(is_online=online).eval()
-    if rank == 0:
-        net.load_state_dict(orc.seeded_fnssl_state_dict(0, is_online=online))
     net.to(dev)
     wbytes = D.broadcast_weights(net, src=0)               # thin weight broadcast (NCCL)
     net.engine = args.engine
@@ -168,7 +169,8 @@ def main():
     pipe = F.FNSSLPipeline(net)
 
     B = args.batch
-    sig_host = orc.white_noise(B, NSAMPLE, NCH, seed=1234 + rank).pin_memory()
+    gen = torch.Generator().manual_seed(1234 + rank)        # white noise, sigma = 1
+    sig_host = torch.randn(B, NSAMPLE, NCH, generator=gen, dtype=torch.float32).pin_memory()
     sig_dev = sig_host.to(dev)
     counts = [B] * world
     out_host = torch.empty((B * world, NT // 12, 512), dtype=torch.float32).pin_memory()
