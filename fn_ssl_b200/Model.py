@@ -50,21 +50,22 @@ class FNblock(nn.Module):
 
     # -- grid-level forward used by FN_SSL (everything stays channels-last on the device) ----------------
     def _run(self, eng: str, x_full_in: Tensor, c_in: int, raw: Optional[Tensor], narr_addend: Optional[Tensor],
-             next_full_addend: bool, need_fb: bool):
+             next_full_addend: bool, need_fb: bool, state=None):
         """x_full_in: operand grid of the full-band pass (block input, or block input + fb_skip).
         raw: first block only -- the raw feature grid concatenated to the narrow-band input.
         narr_addend: non-first blocks -- the block input (narrow-band residual, :44-45).
+        state: optional (h, c) of the narrow-band LSTM carried across chunks of a stream (online blocks only).
         Returns (N, N + F [if next_full_addend], F)."""
         fh = self.full_hidden_size
         if self.is_first:
             F_, _ = run_lstm(self.fullLstm, eng, ops.ALONG_FREQ, x_full_in, c_in, None, 0)
             N_, S_ = run_lstm(self.narrLstm, eng, ops.ALONG_TIME, F_, 2 * fh, raw, c_in,
-                              addend=F_ if next_full_addend else None)
+                              addend=F_ if next_full_addend else None, state=state)
         else:
             F_, U_ = run_lstm(self.fullLstm, eng, ops.ALONG_FREQ, x_full_in, c_in, None, 0, addend=narr_addend,
                               want_h=need_fb)
             N_, S_ = run_lstm(self.narrLstm, eng, ops.ALONG_TIME, U_, 2 * fh, None, 0,
-                              addend=F_ if next_full_addend else None)
+                              addend=F_ if next_full_addend else None, state=state)
         return N_, S_, F_
 
     def forward(self, x: Tensor, nb_skip: Optional[Tensor] = None, fb_skip: Optional[Tensor] = None
@@ -113,14 +114,16 @@ class FN_SSL(nn.Module):
         b = self.block_1
         return config.resolve(self.engine, (b.full_hidden_size, b.narr_hidden_size))
 
-    def forward_grid(self, g0: Tensor, eng: Optional[str] = None) -> Tensor:
-        """g0: feature grid (nb, nt, nf, ld) already in the engine's dtype (fused front-end path)."""
+    def forward_grid(self, g0: Tensor, eng: Optional[str] = None, states=None) -> Tensor:
+        """g0: feature grid (nb, nt, nf, ld) already in the engine's dtype (fused front-end path).
+        states: optional list of three (h, c) pairs -- the narrow-band LSTM states of a stream (fn_ssl_b200.streaming)."""
         _require_eval(self)
         eng = eng or self._engine()
         ci = self.input_size
-        N1, S1, _ = self.block_1._run(eng, g0, ci, g0, None, True, True)
-        N2, S2, _ = self.block_2._run(eng, S1, self.hidden_size, None, N1, True, True)
-        N3, _, _ = self.block_3._run(eng, S2, self.hidden_size, None, N2, False, False)
+        st = states or (None, None, None)
+        N1, S1, _ = self.block_1._run(eng, g0, ci, g0, None, True, True, state=st[0])
+        N2, S2, _ = self.block_2._run(eng, S1, self.hidden_size, None, N1, True, True, state=st[1])
+        N3, _, _ = self.block_3._run(eng, S2, self.hidden_size, None, N2, False, False, state=st[2])
         out = ops.ipd_head(N3, N3.shape[-1], self.emb2ipd.weight, self.emb2ipd.bias)
         if self.is_doa:
             out = ops.linear(out, self.ipd2doa.weight, self.ipd2doa.bias)

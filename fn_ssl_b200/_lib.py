@@ -29,6 +29,7 @@ class LstmArgs(C.Structure):
         ("out0", C.c_void_p), ("out0_ld", C.c_int32), ("out0_off", C.c_int32),
         ("addend", C.c_void_p), ("addend_ld", C.c_int32),
         ("out1", C.c_void_p), ("out1_ld", C.c_int32),
+        ("h_state", C.c_void_p), ("c_state", C.c_void_p), ("state_flags", C.c_int32),
     ]
 
 
@@ -40,6 +41,7 @@ SIGNATURES = {
     "fnssl_stft_num_frames": (_i, [_i, _i, _i]),
     "fnssl_stft_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "fnssl_norm_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "fnssl_norm_stream_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.c_longlong, _vp, _vp, _vp]),
     "fnssl_feature_rows": (_i, [_i, _i, _i]),
     "fnssl_feature_channels": (_i, [_i, _i]),
     "fnssl_features_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _i, _i, _vp, _vp]),
@@ -75,7 +77,7 @@ def load(build_if_missing: bool = True):
             fn = getattr(lib, name)   # AttributeError if the header and the library disagree
             fn.restype = res
             fn.argtypes = args
-        if lib.fnssl_abi_version() != 1:
+        if lib.fnssl_abi_version() != 2:
             raise RuntimeError("libfnssl_b200.so: ABI version mismatch, rebuild it")
         _lib = lib
         return lib

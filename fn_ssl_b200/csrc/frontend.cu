@@ -169,7 +169,7 @@ __device__ __forceinline__ void row_channels(int r, int nch, int pairing, int& b
 // T-sequential recursion out of shared memory (no dependent global loads), the result is written back coalesced.
 __global__ void __launch_bounds__(32)
 norm_scan_kernel(const float* __restrict__ magsum, int R, int nt, int nch, int nbins, int pairing, int norm,
-                 int sample_length, float* __restrict__ mu_out) {
+                 int sample_length, float* __restrict__ mu_out, long long t0, float* __restrict__ mu_state) {
   extern __shared__ float fm[];   // [nt] frame means, overwritten by mu
   const int r = blockIdx.x;
   const int lane = threadIdx.x;
@@ -197,11 +197,12 @@ norm_scan_kernel(const float* __restrict__ magsum, int R, int nt, int nch, int n
       for (int t = 0; t < nt; ++t) fm[t] = m;
     } else {
       const double alpha = (double)(sample_length - 1) / (double)(sample_length + 1);
-      float mu = 0.0f;
+      float mu = (t0 > 0 && mu_state) ? mu_state[r] : 0.0f;   // a chunk of a longer stream resumes the recursion
       for (int t = 0; t < nt; ++t) {
         float a, om;
-        if (t < sample_length) {
-          a = (float)fmin((double)(t - 1) / (double)(t + 1), alpha);  // fp32 tensor in the reference (:31)
+        const long long tt = t0 + t;
+        if (tt < sample_length) {
+          a = (float)fmin((double)(tt - 1) / (double)(tt + 1), alpha);  // fp32 tensor in the reference (:31)
           om = 1.0f - a;
         } else {
           a = (float)alpha;
@@ -210,6 +211,7 @@ norm_scan_kernel(const float* __restrict__ magsum, int R, int nt, int nch, int n
         mu = a * mu + om * fm[t];
         fm[t] = mu;
       }
+      if (mu_state) mu_state[r] = mu;
     }
   }
   __syncwarp();
@@ -390,7 +392,22 @@ int fnssl_norm_forward(const float* magsum, int nb, int nch, int nt, int nbins, 
   const int R = fnssl_feature_rows(nb, nch, pairing);
   FNSSL_REQUIRE((size_t)nt * 4 <= 200 * 1024, "norm: too many frames (%d)", nt);
   FNSSL_CUDA(cudaFuncSetAttribute(norm_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nt * 4));
-  norm_scan_kernel<<<R, 32, (size_t)nt * 4, (cudaStream_t)stream>>>(magsum, R, nt, nch, nbins, pairing, norm, sample_length, mu);
+  norm_scan_kernel<<<R, 32, (size_t)nt * 4, (cudaStream_t)stream>>>(magsum, R, nt, nch, nbins, pairing, norm, sample_length, mu,
+                                                                    0, nullptr);
+  FNSSL_LAUNCH_CHECK("norm_scan_kernel");
+  return 0;
+}
+
+int fnssl_norm_stream_forward(const float* magsum, int nb, int nch, int nt, int nbins, int pairing, int sample_length,
+                              long long t0, float* mu_state, float* mu, void* stream) {
+  FNSSL_REQUIRE(magsum && mu && mu_state && nb > 0 && nch > 0 && nt > 0 && nbins > 0 && t0 >= 0, "norm(stream): bad arguments");
+  FNSSL_REQUIRE(pairing >= 0 && pairing <= 2, "norm(stream): bad pairing %d", pairing);
+  FNSSL_REQUIRE(pairing == FNSSL_PAIRS_ALL || nch >= 2, "norm(stream): pair modes need >= 2 channels");
+  const int R = fnssl_feature_rows(nb, nch, pairing);
+  FNSSL_REQUIRE((size_t)nt * 4 <= 200 * 1024, "norm(stream): too many frames (%d)", nt);
+  FNSSL_CUDA(cudaFuncSetAttribute(norm_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nt * 4));
+  norm_scan_kernel<<<R, 32, (size_t)nt * 4, (cudaStream_t)stream>>>(magsum, R, nt, nch, nbins, pairing, FNSSL_NORM_FORGETTING,
+                                                                    sample_length, mu, t0, mu_state);
   FNSSL_LAUNCH_CHECK("norm_scan_kernel");
   return 0;
 }
@@ -399,15 +416,15 @@ int fnssl_features_forward(const float* spec, const float* magsum, int nb, int n
                            int sample_length, float eps, float* mu, void* feat, int dtype, int ld, float* feat_cfirst,
                            void* stream) {
   FNSSL_REQUIRE(pairing >= 0 && pairing <= 2, "features: bad pairing %d", pairing);
-  FNSSL_REQUIRE(norm >= 0 && norm <= 2, "features: bad norm %d", norm);
+  FNSSL_REQUIRE(norm >= 0 && norm <= 3, "features: bad norm %d", norm);
   FNSSL_REQUIRE(pairing == FNSSL_PAIRS_ALL || nch >= 2, "features: pair modes need >= 2 channels");
   FNSSL_REQUIRE(dtype == FNSSL_F32 || dtype == FNSSL_F16, "features: bad dtype %d", dtype);
   const int C = fnssl_feature_channels(nch, pairing);
   const int R = fnssl_feature_rows(nb, nch, pairing);
   FNSSL_REQUIRE(ld >= C, "features: ld (%d) < channels (%d)", ld, C);
-  FNSSL_REQUIRE(spec && feat && (norm == FNSSL_NORM_NONE || (magsum && mu)), "features: null pointer");
+  FNSSL_REQUIRE(spec && feat && (norm == FNSSL_NORM_NONE || (norm == FNSSL_NORM_GIVEN && mu) || (magsum && mu)), "features: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (norm != FNSSL_NORM_NONE) {
+  if (norm == FNSSL_NORM_FORGETTING || norm == FNSSL_NORM_GLOBAL) {
     if (fnssl_norm_forward(magsum, nb, nch, nt, kBins, pairing, norm, sample_length, mu, stream)) return 1;
   }
   dim3 grid((nt + kAsmTT - 1) / kAsmTT, 256 / kAsmTF, nb);

@@ -21,6 +21,11 @@ extern "C" int fnssl_lstm_forward(const fnssl_lstm_args* a, void* stream) {
   FNSSL_REQUIRE(!a->out0 || (a->out0_off >= 0 && a->out0_ld >= a->out0_off + oc), "lstm: out0 window (off %d + %d channels) exceeds ld %d",
                 a->out0_off, oc, a->out0_ld);
   FNSSL_REQUIRE(!a->out1 || (a->addend && a->addend_ld >= oc && a->out1_ld >= oc), "lstm: bad out1/addend");
+  if (a->state_flags) {
+    FNSSL_REQUIRE((a->state_flags & ~3) == 0, "lstm: bad state_flags %d", a->state_flags);
+    FNSSL_REQUIRE(a->num_dirs == 1, "lstm: recurrent state is carried for uni-directional layers only");
+    FNSSL_REQUIRE(a->h_state && a->c_state, "lstm: state_flags set but h_state/c_state is null");
+  }
   if (a->engine == FNSSL_ENGINE_SIMT) return lstm_forward_simt(a, (cudaStream_t)stream);
   if (a->engine == FNSSL_ENGINE_TCGEN05) return lstm_forward_tc(a, (cudaStream_t)stream);
   FNSSL_FAIL("lstm: unknown engine %d", a->engine);

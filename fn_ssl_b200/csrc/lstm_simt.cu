@@ -25,6 +25,7 @@ struct SimtParams {
   void* out1; int out1_ld;
   int64_t rows; int steps; int nf; int nt; int axis;
   int I, K, Kp;
+  float* h_state; float* c_state; int state_flags;   // optional carried state, fp32 (rows, H)
 };
 
 template <typename T, int H>
@@ -63,6 +64,17 @@ lstm_simt_kernel(const SimtParams p) {
   float c[kRowsPerThread];
 #pragma unroll
   for (int i = 0; i < kRowsPerThread; ++i) c[i] = 0.0f;
+  if (p.state_flags & 1) {   // resume from a carried (h, c)
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) {
+      const int lr = rg * kRowsPerThread + i;
+      if (row0 + lr < p.rows) {
+        c[i] = p.c_state[(row0 + lr) * H + j];
+        smem_a[lr * Kp + I + j] = p.h_state[(row0 + lr) * H + j];
+      }
+    }
+    __syncthreads();
+  }
 
   for (int step = 0; step < p.steps; ++step) {
     const int s = dir ? (p.steps - 1 - step) : step;
@@ -127,6 +139,16 @@ lstm_simt_kernel(const SimtParams p) {
     }
     // (the x_t load of the next step touches columns [0, I) only; the barrier after it also orders these h writes)
   }
+  if (p.state_flags & 2) {
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) {
+      const int lr = rg * kRowsPerThread + i;
+      if (row0 + lr < p.rows) {
+        p.c_state[(row0 + lr) * H + j] = c[i];
+        p.h_state[(row0 + lr) * H + j] = smem_a[lr * Kp + I + j];   // written by this thread in the last step
+      }
+    }
+  }
 }
 
 template <typename T, int H>
@@ -156,6 +178,7 @@ int lstm_forward_simt(const fnssl_lstm_args* a, cudaStream_t st) {
   p.out0 = a->out0; p.out0_ld = a->out0_ld; p.out0_off = a->out0_off;
   p.addend = a->addend; p.addend_ld = a->addend_ld; p.out1 = a->out1; p.out1_ld = a->out1_ld;
   p.nf = a->nf; p.nt = a->nt; p.axis = a->axis;
+  p.h_state = a->h_state; p.c_state = a->c_state; p.state_flags = a->state_flags;
   if (a->axis == FNSSL_ALONG_FREQ) { p.rows = (int64_t)a->nb * a->nt; p.steps = a->nf; }
   else { p.rows = (int64_t)a->nb * a->nf; p.steps = a->nt; }
 #define FNSSL_SIMT_CASE(HH)                                                         \

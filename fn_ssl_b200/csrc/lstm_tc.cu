@@ -516,6 +516,11 @@ int lstm_forward_tc(const fnssl_lstm_args* a, cudaStream_t st) {
     // for the 16-channel first layer but 1.80 vs 1.59 ms for the 256-channel layers -> use it for <= 2 input slabs.
     const int nxs = (a->c0 + 63) / 64 + (a->c1 + 63) / 64;
     const bool force3 = e && atoi(e) == 3;
+    if (a->state_flags) {   // carried (h, c): implemented by the cluster kernel of generation 2
+      FNSSL_REQUIRE(aligned && lstm_tc2_supports(a->hidden, a->c0, a->c1),
+                    "lstm(tcgen05): recurrent state needs the cluster kernel, which does not support H=%d c0=%d c1=%d", a->hidden, a->c0, a->c1);
+      return lstm_forward_tc2(a, st);
+    }
     if (want >= 3 && aligned && (nxs <= 2 || force3) && lstm_tc3_supports(a->hidden, a->c0, a->c1)) return lstm_forward_tc3(a, st);
     if (want >= 2 && aligned && lstm_tc2_supports(a->hidden, a->c0, a->c1)) return lstm_forward_tc2(a, st);
   }

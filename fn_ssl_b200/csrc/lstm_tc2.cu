@@ -51,6 +51,7 @@ struct Params {
   __half* out0; int out0_ld; int out0_off;
   const __half* addend; int addend_ld;
   __half* out1; int out1_ld;
+  float* h_state; float* c_state; int state_flags;   // optional carried state, fp32 (rows, H); dirs == 1
   int* error_flag;
   long long* trace;                // FNSSL_TC_TRACE: clock64 stamps of cluster 0 / CTA 0, steps [8, 16): [step][16 events]
   int debug;                       // timing experiments only (FNSSL_TC_DEBUG): 1 = skip gate math, 2 = skip MMA issue
@@ -132,6 +133,29 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
     valid_rows = min(MR, p.nf - coord_r0);
   }
 
+  if (p.state_flags & 1) {
+    // Resume from a carried state: h_{-1} takes the place step -1 would have written, i.e. all C tiles of buffer 1
+    // (every CTA needs the whole h vector of its rows); c_{-1} is loaded by the epilogue warps below.
+    constexpr int PPR = H / 8;                 // 16-byte pieces (8 units) per row
+    for (int idx = tid; idx < MR * PPR; idx += kThreads) {
+      const int r = idx / PPR, pc = idx % PPR, kc = pc >> 2, sb = pc & 3;
+      uint4 pk = make_uint4(0, 0, 0, 0);
+      if (r < valid_rows) {
+        const float4* g = reinterpret_cast<const float4*>(p.h_state + (row0 + r) * H + pc * 8);
+        const float4 a = __ldg(g), b = __ldg(g + 1);
+        __half2 h01 = __floats2half2_rn(a.x, a.y), h23 = __floats2half2_rn(a.z, a.w);
+        __half2 h45 = __floats2half2_rn(b.x, b.y), h67 = __floats2half2_rn(b.z, b.w);
+        pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
+        pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
+      }
+      st_shared_v4(hs_base + (uint32_t)(C + kc) * kHTile + (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u +
+                       (uint32_t)((sb ^ ((r >> 1) & 3)) << 4), pk);
+    }
+    fence_async_smem();
+    __syncthreads();
+    cluster_sync_all();   // all peers have read the old state before anyone's last step overwrites it (steps == 1)
+  }
+
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
@@ -210,12 +234,14 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       for (int t = 0; t < L; ++t) {
         long long* tp = (tr && t >= 8 && t < 16) ? p.trace + (t - 8) * 16 : nullptr;
         if (tp) tp[0] = clock64();
-        if (t > 0) {
-          // h_{t-1}: the C-1 remote tiles arrive as DSMEM bulk copies (tx bytes), the local tile by plain arrives
-          mbar_expect_tx(H_FULL((t - 1) & 1), (uint32_t)((C - 1) * kHTile));
-          if (tp) tp[1] = clock64();
-          mbar_wait_cluster(H_FULL((t - 1) & 1), (uint32_t)(((t - 1) >> 1) & 1), p.error_flag, 220);
-          if (tp) tp[2] = clock64();
+        if (t > 0 || (p.state_flags & 1)) {
+          if (t > 0) {
+            // h_{t-1}: the C-1 remote tiles arrive as DSMEM bulk copies (tx bytes), the local tile by plain arrives
+            mbar_expect_tx(H_FULL((t - 1) & 1), (uint32_t)((C - 1) * kHTile));
+            if (tp) tp[1] = clock64();
+            mbar_wait_cluster(H_FULL((t - 1) & 1), (uint32_t)(((t - 1) >> 1) & 1), p.error_flag, 220);
+            if (tp) tp[2] = clock64();
+          }   // t == 0 with a carried state: h_{-1} was placed in buffer 1 before the roles split
           tc_fence_after();
 #pragma unroll
           for (int kc = 0; kc < C; ++kc) {   // K = 32 units of chunk kc: two K=16 steps; W columns inside 128B-swizzled slab kc/2
@@ -293,6 +319,11 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       const uint32_t hquad = (uint32_t)rank * kHTile + (uint32_t)q * 1024u;   // 16 rows x 64 B
       {
         float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.state_flags & 1) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (valid[e >> 1]) z[e] = __ldg(p.c_state + (row0 + q * 16 + (lane >> 2) + 8 * (e >> 1)) * H + ua + (e & 1));
+        }
         tmem_st4_16x256(tmem_c + lane_off + u0, z);
         tmem_wait_st();
       }
@@ -354,6 +385,15 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         if (tp) tp[12] = clock64();
         if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && t == 12) p.trace[128 + warp] = clock64();
         tmem_st4_16x256(tmem_c + lane_off + u0, cs);
+        if ((p.state_flags & 2) && t + 1 == L) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (valid[e >> 1]) {
+              const long long so = (row0 + q * 16 + (lane >> 2) + 8 * (e >> 1)) * H + ua + (e & 1);
+              p.c_state[so] = cs[e];
+              p.h_state[so] = __half2float(__float2half_rn(hv[e]));   // the fp16 value the next step would have read
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           if (!valid[i]) continue;
@@ -383,6 +423,10 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         float z[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) z[i] = 0.0f;
+        if ((p.state_flags & 1) && valid) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) z[i] = __ldg(p.c_state + (row0 + r) * H + ua + i);
+        }
         tmem_st8(tmem_c + lane_off + u0, z);
         tmem_wait_st();
       }
@@ -442,6 +486,13 @@ lstm_tc2_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         if (tp) tp[12] = clock64();
         if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && t == 12) p.trace[128 + warp] = clock64();
         tmem_st8(tmem_c + lane_off + u0, cs);
+        if ((p.state_flags & 2) && t + 1 == L && valid) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            p.c_state[(row0 + r) * H + ua + i] = cs[i];
+            p.h_state[(row0 + r) * H + ua + i] = __half2float(__float2half_rn(hv[i]));
+          }
+        }
         if (valid) {
           if (p.out0) *reinterpret_cast<uint4*>(p.out0 + pos * p.out0_ld + p.out0_off + dir * H + ua) = pk;
           if (p.out1) {
@@ -550,6 +601,8 @@ static int launch(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
   FNSSL_REQUIRE(!a->out1 || ((reinterpret_cast<uintptr_t>(a->out1) & 15) == 0 && a->out1_ld % 8 == 0 &&
                              (reinterpret_cast<uintptr_t>(a->addend) & 15) == 0 && a->addend_ld % 8 == 0),
                 "lstm(tcgen05): out1/addend must be 16-byte aligned");
+  p.h_state = a->h_state; p.c_state = a->c_state; p.state_flags = a->state_flags;
+  FNSSL_REQUIRE(!a->state_flags || (reinterpret_cast<uintptr_t>(a->h_state) & 15) == 0, "lstm(tcgen05): h_state not 16-byte aligned");
   p.error_flag = tc_error_flag();
   if (const char* e = getenv("FNSSL_TC_DEBUG")) p.debug = atoi(e);
   if (getenv("FNSSL_TC_TRACE")) p.trace = tc2_trace_buffer();

@@ -98,9 +98,30 @@ def stft(signal: Tensor, win_len: int = 512, hop: int = 256, nfft: int = 512,
     return torch.view_as_complex(spec), magsum
 
 
+NORM_GIVEN = 3   # FNSSL_NORM_GIVEN: mu is an input of features() (streaming)
+
+
+def norm_stream(magsum: Tensor, pairing: str, sample_length: int, t0: int, mu_state: Tensor) -> Tensor:
+    """forgetting_norm for frames [t0, t0+nt) of a stream; mu_state (R,) f32 is read (t0 > 0) and updated in place."""
+    _need_cuda(magsum, mu_state)
+    lib = _lib.load()
+    nb, nch, nt = magsum.shape
+    pm = PAIRING[pairing]
+    R = lib.fnssl_feature_rows(nb, nch, pm)
+    if mu_state.shape != (R,) or mu_state.dtype != torch.float32 or not mu_state.is_contiguous():
+        raise RuntimeError(f"norm_stream: mu_state must be a contiguous float32 tensor of shape ({R},)")
+    mu = torch.empty((R, nt), dtype=torch.float32, device=magsum.device)
+    _count(1)
+    _lib.check(lib.fnssl_norm_stream_forward(magsum.contiguous().data_ptr(), nb, nch, nt, 257, pm, sample_length, int(t0),
+                                             mu_state.data_ptr(), mu.data_ptr(), _stream()))
+    return mu
+
+
 def features(spec: Tensor, magsum: Optional[Tensor], pairing: str, norm: int, sample_length: int, eps: float,
-             dtype: torch.dtype, want_cfirst: bool = False) -> Tuple[Tensor, Optional[Tensor], Optional[Tensor]]:
-    """spec (nb,257,nt,nch) complex64 -> grid (R, nt, 256, ld) of dtype, mu (R, nt), [(R, C, 256, nt) f32]."""
+             dtype: torch.dtype, want_cfirst: bool = False, mu: Optional[Tensor] = None
+             ) -> Tuple[Tensor, Optional[Tensor], Optional[Tensor]]:
+    """spec (nb,257,nt,nch) complex64 -> grid (R, nt, 256, ld) of dtype, mu (R, nt), [(R, C, 256, nt) f32].
+    norm = NORM_GIVEN takes the normaliser `mu` (R, nt) from the caller (norm_stream)."""
     _need_cuda(spec)
     lib = _lib.load()
     nb, nbins, nt, nch = spec.shape
@@ -112,9 +133,13 @@ def features(spec: Tensor, magsum: Optional[Tensor], pairing: str, norm: int, sa
     ld = pad_channels(Cc, dtype)
     sp = torch.view_as_real(spec.contiguous())
     feat = torch.empty((R, nt, 256, ld), dtype=dtype, device=spec.device)
-    mu = torch.empty((R, nt), dtype=torch.float32, device=spec.device)
+    if norm == NORM_GIVEN:
+        if mu is None or mu.shape != (R, nt) or mu.dtype != torch.float32 or not mu.is_contiguous():
+            raise RuntimeError("features: NORM_GIVEN needs a contiguous float32 mu of shape (R, nt)")
+    else:
+        mu = torch.empty((R, nt), dtype=torch.float32, device=spec.device)
     cf = torch.empty((R, Cc, 256, nt), dtype=torch.float32, device=spec.device) if want_cfirst else None
-    _count(2 if norm != NORM_NONE else 1)
+    _count(2 if norm in (NORM_FORGETTING, NORM_GLOBAL) else 1)
     _lib.check(lib.fnssl_features_forward(sp.data_ptr(), _ptr(magsum), nb, nt, nch, pm, norm, sample_length, float(eps),
                                           mu.data_ptr(), feat.data_ptr(), code_of(dtype), ld, _ptr(cf), _stream()))
     return feat, mu, cf
@@ -184,8 +209,11 @@ def grid_add(a: Tensor, b: Tensor) -> Tensor:
 
 def lstm(engine: int, axis: int, src0: Tensor, c0: int, src1: Optional[Tensor], c1: int, weights: Tensor, hidden: int,
          num_dirs: int, addend: Optional[Tensor] = None, want_h: bool = True,
-         out0: Optional[Tensor] = None, out0_off: int = 0) -> Tuple[Optional[Tensor], Optional[Tensor]]:
-    """One LSTM layer over a grid (see fnssl_lstm_forward).  Returns (h grid, h + addend grid)."""
+         out0: Optional[Tensor] = None, out0_off: int = 0,
+         state: Optional[Tuple[Tensor, Tensor]] = None) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    """One LSTM layer over a grid (see fnssl_lstm_forward).  Returns (h grid, h + addend grid).
+    state = (h, c): float32 (rows, hidden) tensors the layer starts from and overwrites with its final state
+    (nn.LSTM's (h_0, c_0) -> (h_n, c_n); uni-directional layers only)."""
     _need_cuda(src0, src1, weights, addend)
     lib = _lib.load()
     nb, nt, nf, ld0 = src0.shape
@@ -211,6 +239,12 @@ def lstm(engine: int, axis: int, src0: Tensor, c0: int, src1: Optional[Tensor], 
     a.addend_ld = addend.shape[-1] if addend is not None else 0
     a.out1 = _ptr(out1)
     a.out1_ld = oc if out1 is not None else 0
+    if state is not None:
+        rows = nb * nt if axis == ALONG_FREQ else nb * nf
+        for s_ in state:
+            if s_.shape != (rows, hidden) or s_.dtype != torch.float32 or not s_.is_contiguous() or s_.device != dev:
+                raise RuntimeError(f"lstm: state tensors must be contiguous float32 ({rows}, {hidden}) on {dev}")
+        a.h_state, a.c_state, a.state_flags = state[0].data_ptr(), state[1].data_ptr(), 3
     _count(1)
     if _PROFILE is not None:
         rows, steps = (nb * nt, nf) if axis == ALONG_FREQ else (nb * nf, nt)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FNSSL_ABI_VERSION 1
+#define FNSSL_ABI_VERSION 2
 
 /* element types of grid tensors */
 #define FNSSL_F32 0
@@ -49,6 +49,7 @@ extern "C" {
 #define FNSSL_NORM_NONE 0
 #define FNSSL_NORM_FORGETTING 1 /* utils_.py:9-55  */
 #define FNSSL_NORM_GLOBAL 2     /* runIPDnetOff.py:248-251 */
+#define FNSSL_NORM_GIVEN 3      /* fnssl_features_forward only: mu is an INPUT (e.g. from fnssl_norm_stream_forward) */
 
 int fnssl_abi_version(void);
 const char* fnssl_last_error(void);
@@ -70,6 +71,12 @@ int fnssl_stft_forward(const float* signal, int nb, int nsample, int nch, int wi
  *   magsum : (nb, nch, nt) f32 sums of |X| over `nbins` bins;  mu : (R, nt) f32, R = fnssl_feature_rows() */
 int fnssl_norm_forward(const float* magsum, int nb, int nch, int nt, int nbins, int pairing, int norm,
                        int sample_length, float* mu, void* stream);
+
+/* forgetting_norm continued across chunks of one stream (chunked inference; the reference runs whole clips):
+ * frames [t0, t0+nt) of the recursion utils_.py:27-44.  mu_state : (R) f32, read as mu_{t0-1} when t0 > 0 and
+ * always written with mu_{t0+nt-1}; mu : (R, nt) f32.  Feed mu to fnssl_features_forward(norm = FNSSL_NORM_GIVEN). */
+int fnssl_norm_stream_forward(const float* magsum, int nb, int nch, int nt, int nbins, int pairing, int sample_length,
+                              long long t0, float* mu_state, float* mu, void* stream);
 
 /* rows of the feature tensor for a pairing mode: nb*(nch-1), nb*nch*(nch-1)/2 or nb */
 int fnssl_feature_rows(int nb, int nch, int pairing);
@@ -129,6 +136,12 @@ typedef struct fnssl_lstm_args {
   void* out0; int32_t out0_ld; int32_t out0_off;
   const void* addend; int32_t addend_ld;
   void* out1; int32_t out1_ld;
+  /* Optional recurrent state for chunked (streaming) inference -- nn.LSTM's (h_0, c_0) argument / (h_n, c_n)
+   * result, which the reference leaves at zero / discards (Model.py:38,46) because it runs whole clips.
+   * fp32 (rows, hidden), rows = nb*nf for FNSSL_ALONG_TIME, nb*nt for FNSSL_ALONG_FREQ; num_dirs == 1 only.
+   * state_flags bit 0: start from h_state/c_state instead of zeros; bit 1: write the state after the last
+   * step back into the same buffers.  0 / NULL = the reference's behaviour. */
+  float* h_state; float* c_state; int32_t state_flags;
 } fnssl_lstm_args;
 
 int fnssl_lstm_forward(const fnssl_lstm_args* args, void* stream);

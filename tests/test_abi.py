@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in include/fnssl_b200.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(syms)
-    assert lib.fnssl_abi_version() == 1
+    assert lib.fnssl_abi_version() == 2
 
 
 def test_host_only_entry_points():

@@ -384,3 +384,115 @@ def test_decode_many_pairs_and_sources():
     doa, vad, ss = sdl(pred.to(DEV), T, d.doa_candidate)
     assert np.array_equal(doa.cpu().numpy(), ref[0].numpy())
     assert _relerr(vad, ref[1]) <= 1e-4 and _relerr(ss, ref[2]) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# "next" row: stateful (streaming) API -- carried LSTM state, forgetting-norm state, STFT overlap
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("rows", ["64", "128"])
+@pytest.mark.parametrize("engine,H,c0,c1", [("simt", 64, 20, 0), ("simt", 256, 256, 4), ("tcgen05", 64, 64, 0),
+                                            ("tcgen05", 128, 256, 16), ("tcgen05", 256, 256, 0), ("tcgen05", 256, 128, 16)])
+def test_lstm_carried_state_equals_whole_sequence(monkeypatch, rows, engine, H, c0, c1):
+    """nn.LSTM semantics of (h_0, c_0) -> (h_n, c_n): running a narrow-band layer over 3 chunks with the state carried
+    gives bit-identical outputs to one run over the whole sequence, and the final state matches the oracle."""
+    from fn_ssl_b200 import config, ops
+    from fn_ssl_b200.packing import LSTMParams, run_lstm
+    monkeypatch.setenv("FNSSL_TC_ROWS", rows)
+    monkeypatch.setenv("FNSSL_TC_KERNEL", "2")      # whole-sequence run on the same kernel generation the state path uses
+    dt = config.grid_dtype(engine)
+    nb, nt, nf = 2, 21, 75                           # 150 rows: ragged against both tile sizes
+    torch.manual_seed(7)
+    p = LSTMParams(c0 + c1, H, bidirectional=False).to(DEV)
+    g0 = ops.grid_copy(_randn((nb, nt, nf, c0), 70).to(DEV), c0, dt)
+    g1 = ops.grid_copy(_randn((nb, nt, nf, c1), 71).to(DEV), c1, dt) if c1 else None
+    ga = ops.grid_copy(_randn((nb, nt, nf, H), 72).to(DEV), H, dt)
+    whole_h, whole_s = run_lstm(p, engine, ops.ALONG_TIME, g0, c0, g1, c1, addend=ga)
+    state = (torch.zeros(nb * nf, H, device=DEV), torch.zeros(nb * nf, H, device=DEV))
+    hs, ss = [], []
+    for a, b in ((0, 1), (1, 9), (9, 21)):          # a one-step chunk exercises the steps == 1 path
+        h, s = run_lstm(p, engine, ops.ALONG_TIME, g0[:, a:b].contiguous(), c0, g1[:, a:b].contiguous() if c1 else None, c1,
+                        addend=ga[:, a:b].contiguous(), state=state)
+        hs.append(h); ss.append(s)
+    assert torch.equal(torch.cat(hs, 1), whole_h)
+    assert torch.equal(torch.cat(ss, 1), whole_s)
+    # final state against the oracle (h_n is the last output; c_n from the fp32 recursion)
+    x = torch.cat([t for t in (g0[..., :c0].float().cpu(), g1[..., :c1].float().cpu() if c1 else None) if t is not None], -1)
+    sd = {"l." + k: v.detach().cpu() for k, v in p.state_dict().items()}
+    xs = x.permute(0, 2, 1, 3).reshape(nb * nf, nt, -1)
+    lstm = torch.nn.LSTM(c0 + c1, H, batch_first=True)
+    lstm.load_state_dict({k[2:]: v for k, v in sd.items()})
+    with torch.no_grad():
+        ref_y, (ref_h, ref_c) = lstm(xs)
+    assert _relerr(orc.lstm(xs, sd, "l."), ref_y) <= 1e-6      # the torch module and the oracle agree (oracle is the checker)
+    tol = 2e-5 if engine == "simt" else 1e-3
+    assert _relerr(state[0], ref_h[0]) <= tol
+    assert _relerr(state[1], ref_c[0]) <= tol
+    assert torch.equal(state[0].to(whole_h.dtype), whole_h[:, -1].reshape(nb * nf, -1)[:, :H])
+
+
+def test_lstm_state_rejects_bidirectional():
+    from fn_ssl_b200 import ops
+    from fn_ssl_b200.packing import LSTMParams, run_lstm
+    p = LSTMParams(8, 32, bidirectional=True).to(DEV)
+    g = ops.grid_copy(_randn((1, 4, 6, 8), 1).to(DEV), 8, torch.float32)
+    st = (torch.zeros(6, 32, device=DEV), torch.zeros(6, 32, device=DEV))
+    with pytest.raises(RuntimeError, match="uni-directional"):
+        run_lstm(p, "simt", ops.ALONG_TIME, g, 8, None, 0, state=st)
+
+
+def test_norm_stream_continues_the_recursion():
+    """forgetting_norm over frames [0, nt) in three pieces == one pass (bit-exact), across the t < L / t >= L switch."""
+    from fn_ssl_b200 import ops
+    sig = _randn((2, 512 + 256 * 39, 3), 81).to(DEV)
+    spec, magsum = ops.stft(sig, want_magsum=True)
+    _, mu_whole, _ = ops.features(spec, magsum, "MM", ops.NORM_FORGETTING, 16, 1e-6, torch.float32)
+    state = torch.zeros(6, device=DEV)
+    parts, t0 = [], 0
+    for a, b in ((0, 5), (5, 17), (17, 40)):
+        parts.append(ops.norm_stream(magsum[:, :, a:b].contiguous(), "MM", 16, t0, state))
+        t0 = b
+    mu = torch.cat(parts, 1)
+    assert torch.equal(mu, mu_whole)
+    assert torch.equal(state, mu_whole[:, -1])
+    g_whole, _, _ = ops.features(spec, magsum, "MM", ops.NORM_FORGETTING, 16, 1e-6, torch.float32)
+    g_given, _, _ = ops.features(spec, None, "MM", ops.NORM_GIVEN, 16, 1e-6, torch.float32, mu=mu)
+    assert torch.equal(g_whole, g_given)
+
+
+@pytest.mark.parametrize("engine", ["tcgen05", "simt"])
+def test_fnssl_stream_equals_whole_clip(engine):
+    """Feeding a clip to FNSSLStream in uneven pieces reproduces the whole-clip pipeline output exactly."""
+    import fn_ssl_b200 as F
+    from fn_ssl_b200.streaming import FNSSLStream
+    torch.manual_seed(11)
+    net = F.FN_SSL(is_online=True).eval().to(DEV)
+    net.engine = engine
+    nb, nsample = 2, 512 + 256 * 40 + 100            # 41 frames -> 3 output frames, 5 frames + 100 samples left over
+    sig = _randn((nb, nsample, 2), 82).to(DEV)
+    whole = F.FNSSLPipeline(net)(sig)                # (2, 3, 512)
+    st = FNSSLStream(net, nb=nb, nch=2)
+    outs, pos = [], 0
+    for n in (300, 3000, 3072, 1, 2500, nsample):    # last piece: whatever is left
+        piece = sig[:, pos:pos + n]
+        pos = min(nsample, pos + n)
+        o = st.push(piece)
+        if o is not None:
+            outs.append(o)
+    got = torch.cat(outs, 1)
+    assert got.shape == whole.shape
+    assert torch.equal(got, whole)
+    assert st.frames_done == 36 and st.pending_samples == nsample - 36 * 256
+    # oracle check of the streamed result (the whole-clip pipeline is itself checked against the oracle elsewhere)
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    ref = orc.fnssl_forward(orc.preprocess_fnssl(sig.cpu(), "MM"), sd, fast=True)
+    assert _relerr(got, ref) <= (2e-5 if engine == "simt" else 1e-3)
+    st.reset()
+    assert st.push(sig[:, :512 + 256 * 11]).shape == (nb, 1, 512)
+
+
+def test_fnssl_stream_rejects_offline_model():
+    import fn_ssl_b200 as F
+    from fn_ssl_b200.streaming import FNSSLStream
+    with pytest.raises(RuntimeError, match="offline"):
+        FNSSLStream(F.FN_SSL(is_online=False).eval().to(DEV), nb=1)
