@@ -39,15 +39,16 @@ class FNblock(nn.Module):
                                    bidirectional=not is_online)
         self.engine = None
 
-    def _run(self, eng: str, x: Tensor, cx: int, raw: Tensor, craw: int) -> Tensor:
+    def _run(self, eng: str, x: Tensor, cx: int, raw: Tensor, craw: int, state=None) -> Tensor:
         """x: grid with cx channels (block 1: the raw grid itself; block 2: previous narrow output), raw: raw grid.
+        state: optional (h, c) of the narrow-band LSTM carried across chunks of a stream (online blocks only).
         Returns the narrow-band output grid N (hidden channels); the [N | raw] concat stays virtual."""
         fh = self.full_hidden_size
         if self.is_first:
             F_, _ = run_lstm(self.fullLstm, eng, ops.ALONG_FREQ, x, cx, None, 0)
         else:
             F_, _ = run_lstm(self.fullLstm, eng, ops.ALONG_FREQ, x, cx, raw, craw)
-        N_, _ = run_lstm(self.narrLstm, eng, ops.ALONG_TIME, F_, 2 * fh, raw, craw)
+        N_, _ = run_lstm(self.narrLstm, eng, ops.ALONG_TIME, F_, 2 * fh, raw, craw, state=state)
         return N_
 
     def forward(self, x: Tensor, fb_skip: Tensor, nb_skip: Tensor) -> Tensor:
@@ -114,8 +115,13 @@ class IPDnet(nn.Module):
         b = self.block_1
         return config.resolve(self.engine, (b.full_hidden_size, b.narr_hidden_size))
 
-    def forward_grid(self, g0: Tensor, eng: str, nt_real: int, chunked: bool) -> Tensor:
-        """g0: raw feature grid (nb, nt, nf, ld); for chunked offline inference nt is already padded to a multiple of n_seg."""
+    CONV_HISTORY = 36   # frames of conv input a stream keeps: 3 causal 3x3 layers behind pools of 3 and 4 frames
+
+    def forward_grid(self, g0: Tensor, eng: str, nt_real: int, chunked: bool, stream: Optional[dict] = None) -> Tensor:
+        """g0: raw feature grid (nb, nt, nf, ld); for chunked offline inference nt is already padded to a multiple of n_seg.
+        stream: state of a chunked run of the online model (fn_ssl_b200.streaming.IPDnetStream): "lstm" = two (h, c)
+        pairs, "conv" = the last CONV_HISTORY frames of the conv block's two input grids (None at the start of a clip:
+        the block is bias-free with ReLU, so an all-zero history is exactly its zero padding)."""
         _require_eval(self)
         nb, nt, nf, _ = g0.shape
         ci = self.input_size
@@ -124,9 +130,19 @@ class IPDnet(nn.Module):
         if chunked:                                   # fold ceil(T/n) zero-padded chunks into the batch (:97-101) -- a view
             nseg = nt // self.n
             g0 = g0.reshape(nb * nseg, self.n, nf, g0.shape[-1])
-        N1 = self.block_1._run(eng, g0, ci, g0, ci)
-        N2 = self.block_2._run(eng, N1, self.hidden_size, g0, ci)
-        y = self.conv.forward_grid(N2, self.hidden_size, g0, ci)                    # (nb', cout, nf, nt2)
+        st = stream["lstm"] if stream is not None else (None, None)
+        N1 = self.block_1._run(eng, g0, ci, g0, ci, state=st[0])
+        N2 = self.block_2._run(eng, N1, self.hidden_size, g0, ci, state=st[1])
+        if stream is not None:
+            # conv3's frame q needs pool4 frames q-2..q, each built from 4 pool3 frames that look 2 more frames back:
+            # 36 frames (3 output frames) of history make the first NEW output frame exact; the 3 recomputed ones are dropped
+            Hh = self.CONV_HISTORY
+            hist = stream.get("conv") or [N2.new_zeros((nb, Hh) + tuple(N2.shape[2:])), g0.new_zeros((nb, Hh) + tuple(g0.shape[2:]))]
+            N2c, g0c = torch.cat((hist[0], N2), dim=1), torch.cat((hist[1], g0), dim=1)
+            stream["conv"] = [N2c[:, -Hh:].contiguous(), g0c[:, -Hh:].contiguous()]
+            y = self.conv.forward_grid(N2c, self.hidden_size, g0c, ci)[..., Hh // 12:]
+        else:
+            y = self.conv.forward_grid(N2, self.hidden_size, g0, ci)                # (nb', cout, nf, nt2)
         nbp, nt2 = y.shape[0], y.shape[3]
         x = y.permute(0, 3, 2, 1).reshape(nbp, nt2, nf, 2, -1).permute(0, 1, 3, 2, 4)   # :114 (tiny output tensor)
         if chunked:

@@ -13,6 +13,6 @@ from .Model import FN_SSL, FN_lightning, FNblock, FullNarrowBlock  # noqa: F401
 from .Module import (DPIPD, STFT, AddChToBatch, RemoveChFromBatch, SourceDetectLocalize, forgetting_norm,  # noqa: F401
                      pred_ipd_to_doa)
 from .pipeline import FNSSLPipeline, IPDnetPipeline, data_preprocess_fnssl, data_preprocess_ipdnet  # noqa: F401
-from .streaming import FNSSLStream  # noqa: F401
+from .streaming import FNSSLStream, IPDnetStream  # noqa: F401
 
 __version__ = "0.1.0"

@@ -496,3 +496,28 @@ def test_fnssl_stream_rejects_offline_model():
     from fn_ssl_b200.streaming import FNSSLStream
     with pytest.raises(RuntimeError, match="offline"):
         FNSSLStream(F.FN_SSL(is_online=False).eval().to(DEV), nb=1)
+
+
+@pytest.mark.parametrize("kw,nch", [(dict(input_size=4, hidden_size=128, max_track=2, is_online=True), 2),
+                                    (dict(input_size=8, hidden_size=256, max_track=2, is_online=True), 4)])
+def test_ipdnet_stream_equals_whole_clip(kw, nch):
+    """IPDnetStream (carried LSTM state + 36 frames of conv history) reproduces the whole-clip output exactly."""
+    import fn_ssl_b200 as F
+    torch.manual_seed(12)
+    net = F.IPDnet(**kw).eval().to(DEV)
+    nb, nsample = 2, 512 + 256 * 63 + 17             # 64 frames -> 5 output frames (4 frames left over)
+    sig = _randn((nb, nsample, nch), 83).to(DEV)
+    whole = F.IPDnetPipeline(net)(sig)               # (2, 5, 512, nch-1, 2)
+    st = F.IPDnetStream(net, nb=nb)
+    outs, pos = [], 0
+    for n in (3328, 3072, 100, 6144, 2972, nsample):
+        o = st.push(sig[:, pos:pos + n])
+        pos = min(nsample, pos + n)
+        if o is not None:
+            outs.append(o)
+    got = torch.cat(outs, 1)
+    assert got.shape == whole.shape == (nb, 5, 512, nch - 1, 2)
+    assert torch.equal(got, whole)
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    ref = orc.ipdnet_forward(orc.preprocess_ipdnet(sig.cpu()), sd)
+    assert _relerr(got, ref) <= 1e-3
