@@ -53,6 +53,7 @@ SIGNATURES = {
     "fnssl_lstm_tc_supported": (_i, [_i, _i, _i]),
     "fnssl_lstm_tc_error_site": (_i, []),
     "fnssl_lstm_tc_trace": (_i, [C.POINTER(C.c_longlong)]),
+    "fnssl_lstm_tc4_trace": (_i, [C.POINTER(C.c_longlong)]),
     "fnssl_ipd_head_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "fnssl_linear_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "fnssl_doa_decode_idl": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -501,15 +501,18 @@ bool lstm_tc2_supports(int hidden, int c0, int c1);
 int lstm_forward_tc2(const fnssl_lstm_args* a, cudaStream_t st);
 bool lstm_tc3_supports(int hidden, int c0, int c1);
 int lstm_forward_tc3(const fnssl_lstm_args* a, cudaStream_t st);
+bool lstm_tc4_supports(int hidden, int c0, int c1);
+int lstm_forward_tc4(const fnssl_lstm_args* a, cudaStream_t st);
 
 int lstm_forward_tc(const fnssl_lstm_args* a, cudaStream_t st) {
   FNSSL_REQUIRE(a->dtype == FNSSL_F16, "lstm(tcgen05): grids must be fp16");
   {
-    // Kernel generation: 3 = cluster-resident weights with two interleaved 64-row sub-tiles (lstm_tc3.cu; H <= 128),
+    // Kernel generation: 4 = cluster-resident weights, two independent row tiles per cluster run half a step apart
+    // (lstm_tc4.cu; every H), 3 = cluster-resident weights with two interleaved 64-row sub-tiles (lstm_tc3.cu; H <= 128),
     // 2 = cluster-resident weights, one tile (lstm_tc2.cu; also H = 256), 1 = weight-streaming kernel below.
     // Default: the highest generation that supports the layer.  FNSSL_TC_KERNEL caps it (tests / profiling).
     const char* e = getenv("FNSSL_TC_KERNEL");
-    const int want = e ? atoi(e) : 3;
+    const int want = e ? atoi(e) : 4;
     const bool aligned = a->c0 % 16 == 0 && a->c1 % 16 == 0;
     // Generation 3 issues its x-part as M = 64 MMAs (twice the tensor-pipe time and twice the x-ring hand-shakes of
     // generation 2), which only pays off when the input projection is small: measured on cfg2 it is 1.06 vs 1.46 ms
@@ -521,6 +524,7 @@ int lstm_forward_tc(const fnssl_lstm_args* a, cudaStream_t st) {
                     "lstm(tcgen05): recurrent state needs the cluster kernel, which does not support H=%d c0=%d c1=%d", a->hidden, a->c0, a->c1);
       return lstm_forward_tc2(a, st);
     }
+    if (want >= 4 && aligned && lstm_tc4_supports(a->hidden, a->c0, a->c1)) return lstm_forward_tc4(a, st);
     if (want >= 3 && aligned && (nxs <= 2 || force3) && lstm_tc3_supports(a->hidden, a->c0, a->c1)) return lstm_forward_tc3(a, st);
     if (want >= 2 && aligned && lstm_tc2_supports(a->hidden, a->c0, a->c1)) return lstm_forward_tc2(a, st);
   }

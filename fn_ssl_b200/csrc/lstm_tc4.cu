@@ -1,0 +1,706 @@
+// Two-chain cluster-resident tcgen05 LSTM kernel (fourth generation of FNSSL_ENGINE_TCGEN05), H in {64, 128, 256}.
+//
+// Same decomposition as lstm_tc2.cu -- the 4H gate columns are split over a cluster of C = H/32 CTAs, each keeping its
+// weight slice resident in shared memory, x_t slabs TMA-multicast to the cluster, h_t exchanged by DSMEM bulk copies --
+// but a cluster now owns TWO full row tiles (sub-tiles A and B, SUB = 128 rows each; 64 for H = 256) whose recurrences
+// are independent and run half a step apart.  Generation 2's step is a serial chain (h-part MMA -> gate math -> DSMEM
+// exchange -> barrier hand-offs, ~6 k cycles measured) that leaves the MUFU pipe, the tensor pipe and the DSMEM fabric
+// idle most of the time; here the 16 epilogue warps alternate A, B, A, B ... so that one chain's gate math covers the
+// other chain's exchange + MMA.  Unlike generation 3 (two 64-row halves of ONE tile) every MMA is a full-rate M = 128
+// instruction, the same resident weights serve twice the rows (half the clusters, one wave on cfg2), and:
+//
+//   * h is SINGLE-buffered (that is what makes two 128-row tiles fit beside the weights).  The write-after-read hazard
+//     on h_{t-1} is closed by an explicit hand-shake: the MMA thread of every CTA multicasts a tcgen05.commit arrive
+//     ("my h-part of step t has finished reading h_{t-1}") to the H_FREE barrier of all CTAs; the epilogue waits for
+//     that phase -- one whole gate-math time old by then -- before it overwrites / pushes h_t.
+//   * three accumulator buffers rotate over the slot sequence (A,0) (B,0) (A,1) (B,1) ...; the x-part of slot n+2 is
+//     issued right behind the h-part of slot n, so the input projection never sits on a recurrence's critical path.
+//
+// TMEM: columns [0,64) cell state (32 per sub-tile), [128,512) three gate accumulators of 128 columns.
+// Replaces nn.LSTM at FN-SSL/Lightning/Model.py:38,46 and IPDnet/FixedAarryIPDnet.py:32,36 (+ glue :35-37,41-45,49).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace fnssl {
+namespace tc4 {
+
+constexpr int kThreads = 608;          // producer warp + h-part MMA warp + 16 epilogue warps + x-part MMA warp
+constexpr int kXWarp = 18;
+constexpr int kEpiThreads = 512;
+constexpr int kSlabK = 64;
+constexpr int kWSlab = 128 * 128;      // [128 gate columns x 64] fp16
+constexpr int kChunkUnits = 32;
+constexpr int kChunkN = 128;
+constexpr int kMaxXSlabs = 6;
+constexpr int kMaxXStages = 6;
+constexpr int kAccBufs = 3;
+constexpr int kSmemLimit = 232448;
+constexpr int kNumBars = 1 + 2 * kMaxXStages + 3 * kAccBufs + 4;
+
+struct Params {
+  int nxs;
+  uint32_t xs_srcmask;             // bit j: slab j comes from src1
+  unsigned long long xs_k0pack;    // byte j: first channel of slab j / 16
+  uint32_t xs_nkpack;              // nibble j: K=16 steps of slab j (1..4)
+  int xstages;
+  int steps, axis, nf, nt;
+  long long rows;
+  int tiles_per_b;
+  const float* bias;               // [dirs][4H], accumulator column order [chunk][gate][unit]
+  __half* out0; int out0_ld; int out0_off;
+  const __half* addend; int addend_ld;
+  __half* out1; int out1_ld;
+  int* error_flag;
+  long long* trace;                // FNSSL_TC_TRACE: clock64 stamps of CTA (0,0): [slot 16..31][16 events]
+  int debug;                       // experiments only (FNSSL_TC_DEBUG): 1 = skip gate math, 2 = skip MMA issue, 32 = ex2/rcp gates instead of tanh.approx, 64 = no L2 prefetch
+};
+
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// One (row, unit): c' = sigmoid(f) c + sigmoid(i) tanh(g), h = sigmoid(o) tanh(c').  sigmoid(x) = 1/(1+2^(-x log2 e)),
+// tanh as (1-E)/(1+E); the cell update runs over ONE reciprocal (5 ex2 + 2 rcp per element, see lstm_tc2.cu).
+__device__ __forceinline__ float lstm_cell(float gi, float gf, float gg, float go, float& c) {
+  const float kL2E = 1.4426950408889634f;
+  const float xg = fminf(fmaxf(gg, -15.f), 15.f);
+  const float ei = ex2_approx(-kL2E * fmaxf(gi, -20.f));
+  const float ef = ex2_approx(-kL2E * fmaxf(gf, -20.f));
+  const float eg = ex2_approx(-2.0f * kL2E * xg);
+  const float eo = ex2_approx(-kL2E * go);
+  const float ab = (1.0f + ei) * (1.0f + eg);
+  const float ff = 1.0f + ef;
+  const float cn = fmaf(c, ab, (1.0f - eg) * ff) * rcp_approx(ff * ab);
+  c = cn;
+  const float ec = ex2_approx(-2.0f * kL2E * fminf(fmaxf(cn, -15.f), 15.f));
+  return (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
+}
+// experiment (FNSSL_TC_DEBUG & 32): 5 MUFU.TANH per element instead of 5 EX2 + 2 RCP (2^-11 relative error per tanh)
+__device__ __forceinline__ float lstm_cell_tanh(float gi, float gf, float gg, float go, float& c) {
+  const float si = fmaf(0.5f, tanh_approx(0.5f * gi), 0.5f);
+  const float sf = fmaf(0.5f, tanh_approx(0.5f * gf), 0.5f);
+  const float so = fmaf(0.5f, tanh_approx(0.5f * go), 0.5f);
+  const float cn = fmaf(sf, c, si * tanh_approx(gg));
+  c = cn;
+  return so * tanh_approx(cn);
+}
+
+template <int H, int SUB, bool TRACE>
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_constant__ CUtensorMap map_src1,
+                const __grid_constant__ CUtensorMap map_w, const Params p) {
+  constexpr int C = H / kChunkUnits;      // cluster size == number of 32-unit chunks
+  constexpr int NHS = H / kSlabK;         // K slabs of h in the weight layout
+  constexpr int kXSlab = SUB * 128;       // one [SUB x 64] fp16 x slab (128B swizzle)
+  constexpr int kHTile = SUB * 64;        // one [SUB x 32] fp16 h tile (one chunk, 64B swizzle)
+  constexpr int kTileRows = 2 * SUB;      // rows of a cluster tile (two sub-tiles)
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kChunkN >> 3) << 17) | ((uint32_t)(SUB >> 4) << 24);
+  static_assert(H == 64 || H == 128 || H == 256, "H in {64,128,256}");
+  static_assert(SUB == 64 || SUB == 128, "SUB in {64,128}");
+
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) unsigned long long bars[kNumBars];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.y;
+  const uint32_t rank = cluster_ctarank();          // == chunk owned by this CTA
+  const int tile = blockIdx.x / C;
+  const uint16_t mask = (uint16_t)((1u << C) - 1u);
+  const int nxs = p.nxs, XS = p.xstages, L = p.steps;
+  const int nslabs = nxs + NHS;
+  const int nslots = 2 * L;
+
+  const uint32_t dyn0 = (smem_addr(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t w_base = dyn0;                                     // resident weights: nslabs tiles
+  const uint32_t hs_base = w_base + (uint32_t)nslabs * kWSlab;      // h operand: [sub][chunk] tiles (single buffer)
+  const uint32_t xr_base = hs_base + 2u * C * kHTile;               // x ring: XS slabs
+  const uint32_t bias_base = xr_base + (uint32_t)XS * kXSlab;       // 128 floats
+  float* bias_s = reinterpret_cast<float*>(smem_dyn + (bias_base - smem_addr(smem_dyn)));
+
+  const uint32_t bar0 = smem_addr(bars);
+  const uint32_t W_FULL = bar0;
+  auto X_FULL = [&](int i) { return bar0 + 8u * (1 + i); };
+  auto X_EMPTY = [&](int i) { return bar0 + 8u * (1 + kMaxXStages + i); };
+  auto ACC_FULL = [&](int i) { return bar0 + 8u * (1 + 2 * kMaxXStages + i); };
+  auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (1 + 2 * kMaxXStages + kAccBufs + i); };
+  auto H_FULL = [&](int sub) { return bar0 + 8u * (1 + 2 * kMaxXStages + 2 * kAccBufs + sub); };
+  auto H_FREE = [&](int sub) { return bar0 + 8u * (1 + 2 * kMaxXStages + 2 * kAccBufs + 2 + sub); };
+  auto XP_DONE = [&](int i) { return bar0 + 8u * (1 + 2 * kMaxXStages + 2 * kAccBufs + 4 + i); };
+
+  if (tid == 0) {
+    mbar_init(W_FULL, 1);
+    for (int i = 0; i < kMaxXStages; ++i) { mbar_init(X_FULL(i), 1); mbar_init(X_EMPTY(i), C); }
+    for (int i = 0; i < kAccBufs; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), kEpiThreads); mbar_init(XP_DONE(i), 1); }
+    for (int sub = 0; sub < 2; ++sub) {
+      mbar_init(H_FULL(sub), 5);    // MMA thread's expect_tx + 4 local quadrants (+ tx bytes of the C-1 remote tiles)
+      mbar_init(H_FREE(sub), C);    // one multicast commit per CTA of the cluster
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&map_src0); prefetch_tmap(&map_src1); prefetch_tmap(&map_w); }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < kChunkN; i += kThreads) bias_s[i] = p.bias[dir * 4 * H + rank * kChunkN + i];
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // every CTA's barriers are initialised before any multicast / remote traffic can reach them
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tmem_c = tmem;             // cell state: columns [32 sub, 32 sub + 32)
+  const uint32_t tmem_acc = tmem + 128;     // gate accumulators: kAccBufs buffers x 128 columns
+
+  int coord_b = 0, coord_r0 = 0;
+  long long row0;
+  int valid_rows;
+  if (p.axis == FNSSL_ALONG_FREQ) {
+    row0 = (long long)tile * kTileRows;
+    coord_r0 = (int)row0;
+    valid_rows = (int)min((long long)kTileRows, p.rows - row0);
+  } else {
+    coord_b = tile / p.tiles_per_b;
+    coord_r0 = (tile % p.tiles_per_b) * kTileRows;
+    row0 = (long long)coord_b * p.nf + coord_r0;
+    valid_rows = min(kTileRows, p.nf - coord_r0);
+  }
+  const bool tr_cta = TRACE && p.trace && blockIdx.x == 0 && blockIdx.y == 0;
+
+  // The three single-lane roles below are instruction-latency bound (one warp executing a serial program at ~8 cycles
+  // per instruction; ncu: 560 warp instructions per slot in the first version of this loop = 5 k cycles, more than the
+  // tensor pipe's 1.5 k), so they are kept lean: the elected lane runs the whole loop (ptxas emits tcgen05 / TMA
+  // instructions straight-line behind an elect.sync predicate), descriptors are base + offset adds, and the x-part and
+  // the h-part are issued by two different warps.
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (elect_one()) {
+      mbar_expect_tx(W_FULL, (uint32_t)nslabs * kWSlab);
+      for (int j = 0; j < nslabs; ++j)
+        tma_load_2d(w_base + j * kWSlab, &map_w, W_FULL, j * kSlabK, (dir * C + (int)rank) * kChunkN);
+      int stage = 0, fetcher = 0;
+      uint32_t phase = 0;                 // parity of the X_EMPTY wait; the first pass over the ring does not wait
+      bool wrapped = false;
+      const bool along_f = p.axis == FNSSL_ALONG_FREQ;
+      // x_t comes from HBM (~3.4 k cycles per TMA round trip, the whole ring holds one slot): the CTA that will fetch a
+      // slab pulls it into L2 kAhead slots earlier, so the ring's real loads are L2 hits
+      const int ahead = (p.debug & 64) ? 0 : ((p.debug >> 8) & 15 ? (p.debug >> 8) & 15 : 4);
+      auto prefetch_slot = [&](int nn) {
+        const int tt = nn >> 1;
+        const int ss = dir ? (L - 1 - tt) : tt;
+        const int rr0 = coord_r0 + (nn & 1) * SUB;
+        int f = (nn * nxs) % C;
+        for (int j = 0; j < nxs; ++j) {
+          if ((uint32_t)f == rank) {
+            const CUtensorMap* m = ((p.xs_srcmask >> j) & 1) ? &map_src1 : &map_src0;
+            const int k0 = (int)((p.xs_k0pack >> (8 * j)) & 0xff) * 16;
+            if (along_f) tma_prefetch_l2_4d(m, k0, ss, rr0, 0);
+            else tma_prefetch_l2_4d(m, k0, rr0, ss, coord_b);
+          }
+          if (++f == C) f = 0;
+        }
+      };
+      for (int nn = 1; nn < ahead && nn < nslots; ++nn) prefetch_slot(nn);
+      for (int n = 0; n < nslots; ++n) {
+        const int t = n >> 1, sub = n & 1;
+        const int s = dir ? (L - 1 - t) : t;
+        const int r0 = coord_r0 + sub * SUB;
+        if (ahead && n + ahead < nslots) prefetch_slot(n + ahead);
+        for (int j = 0; j < nxs; ++j) {
+          if (wrapped) mbar_wait(X_EMPTY(stage), phase, p.error_flag, 100 + stage);
+          mbar_expect_tx(X_FULL(stage), kXSlab);
+          if ((uint32_t)fetcher == rank) {   // one CTA fetches the slab for the whole cluster
+            const CUtensorMap* m = ((p.xs_srcmask >> j) & 1) ? &map_src1 : &map_src0;
+            const uint32_t dst = xr_base + (uint32_t)stage * kXSlab;
+            const int k0 = (int)((p.xs_k0pack >> (8 * j)) & 0xff) * 16;
+            if (along_f) tma_load_4d_mc(dst, m, X_FULL(stage), k0, s, r0, 0, mask);
+            else tma_load_4d_mc(dst, m, X_FULL(stage), k0, r0, s, coord_b, mask);
+          }
+          if (++fetcher == C) fetcher = 0;
+          if (++stage == XS) { stage = 0; phase ^= wrapped ? 1u : 0u; wrapped = true; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kXWarp) {
+    // ============================== x-part MMA issuer ==============================
+    // G_x of slot n -> accumulator buffer n % 3, up to three slots ahead of the recurrences (bounded by ACC_EMPTY and
+    // the x ring); XP_DONE tells the h-part issuer that the buffer holds the complete input projection.
+    if (elect_one()) {
+      mbar_wait(W_FULL, 0, p.error_flag, 200);
+      const uint64_t a_desc0 = make_sw128_desc(xr_base);
+      const uint64_t b_desc0 = make_sw128_desc(w_base);
+      int xstage = 0, a = 0;
+      uint32_t xphase = 0, empty_par = 0;
+      for (int n = 0; n < nslots; ++n) {
+        long long* tp = (TRACE && tr_cta && n >= 16 && n < 32) ? p.trace + (n - 16) * 16 : nullptr;
+        long long w_acc = 0, e_acc = 0;
+        if (TRACE && tp) { tp[8] = clock64(); e_acc = clock64(); }
+        if (n >= kAccBufs) {
+          mbar_wait(ACC_EMPTY(a), (empty_par >> a) & 1u, p.error_flag, 201 + a);
+          empty_par ^= 1u << a;
+        }
+        if (TRACE && tp) e_acc = clock64() - e_acc;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_acc + (uint32_t)a * kChunkN;
+        uint32_t nkp = p.xs_nkpack;
+        for (int j = 0; j < nxs; ++j, nkp >>= 4) {
+          const long long c1 = (TRACE && tp) ? clock64() : 0;
+          mbar_wait(X_FULL(xstage), xphase, p.error_flag, 210 + xstage);
+          if (TRACE && tp) w_acc += clock64() - c1;
+          tc_fence_after();
+          const uint64_t a_desc = a_desc0 + (uint64_t)(xstage * (kXSlab >> 4));
+          const uint64_t b_desc = b_desc0 + (uint64_t)(j * (kWSlab >> 4));
+          const uint32_t nk = nkp & 15u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if ((uint32_t)k < nk) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (uint32_t)(j | k));
+          umma_commit_mc(X_EMPTY(xstage), mask);    // this CTA is done with the slab: tell every CTA's ring
+          if (++xstage == XS) { xstage = 0; xphase ^= 1u; }
+        }
+        umma_commit(XP_DONE(a));
+        if (TRACE && tp) { tp[9] = clock64(); tp[11] = e_acc; tp[12] = w_acc; }
+        a = (a == kAccBufs - 1) ? 0 : a + 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================== h-part MMA issuer (the recurrences' critical path) ==============================
+    if (elect_one()) {
+      mbar_wait(W_FULL, 0, p.error_flag, 230);
+      const uint64_t h_desc0 = make_sw64_desc(hs_base);
+      const uint64_t wh_desc0 = make_sw128_desc(w_base + (uint32_t)nxs * kWSlab);
+      int a = 0;
+      uint32_t xp_par = 0;
+      for (int n = 0; n < nslots; ++n) {
+        const int t = n >> 1, sub = n & 1;
+        long long* tp = (TRACE && tr_cta && n >= 16 && n < 32) ? p.trace + (n - 16) * 16 : nullptr;
+        if (TRACE && tp) tp[0] = clock64();
+        mbar_wait(XP_DONE(a), (xp_par >> a) & 1u, p.error_flag, 240 + a);     // G_x of this slot is complete
+        xp_par ^= 1u << a;
+        if (t > 0) {
+          // h_{t-1} of this sub-tile: C-1 remote tiles arrive as DSMEM bulk copies (tx bytes), the local one by arrives
+          mbar_expect_tx(H_FULL(sub), (uint32_t)((C - 1) * kHTile));
+          mbar_wait_cluster(H_FULL(sub), (uint32_t)((t - 1) & 1), p.error_flag, 220 + sub);
+          if (TRACE && tp) tp[1] = clock64();
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_acc + (uint32_t)a * kChunkN;
+          const uint64_t a_sub = h_desc0 + (uint64_t)(sub * C * (kHTile >> 4));
+#pragma unroll
+          for (int kc = 0; kc < C; ++kc) {   // K = 32 units of chunk kc: two K=16 steps; W columns inside 128B-swizzled slab kc/2
+            const uint64_t a_desc = a_sub + (uint64_t)(kc * (kHTile >> 4));
+            const uint64_t b_desc = wh_desc0 + (uint64_t)((kc >> 1) * (kWSlab >> 4) + 4 * (kc & 1));
+#pragma unroll
+            for (int k = 0; k < 2; ++k) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+          }
+          // h_{t-1} has been read once these MMAs retire: every CTA may then overwrite its copy with h_t
+          if (t + 1 < L) umma_commit_mc(H_FREE(sub), mask);
+        } else {
+          tc_fence_after();
+        }
+        umma_commit(ACC_FULL(a));            // fires when the h-part (and G_x, complete since XP_DONE) is done
+        if (TRACE && tp) tp[2] = clock64();
+        a = (a == kAccBufs - 1) ? 0 : a + 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== epilogue warps ==============================
+    const int q = warp & 3;                    // TMEM lane quadrant of this warp
+    const int sg = (warp - 2) >> 2;            // 8-unit group of the CTA's 32 units
+    const int u0 = sg * 8;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const float* bsp = bias_s + u0;            // bias of (gate, unit) at bsp[gate * 32 + e] (broadcast shared-memory reads)
+    const long long sstride = (p.axis == FNSSL_ALONG_FREQ) ? 1 : p.nf;
+    const bool fast = !(p.debug & 32);
+    const bool tr = tr_cta && warp == 2 && lane == 0;
+    constexpr uint32_t kQuadBytes = (SUB == 128) ? 2048u : 1024u;   // a quadrant's rows x 64 B of the CTA's own h tile
+    const uint32_t hquad = (uint32_t)rank * kHTile + (uint32_t)q * kQuadBytes;
+
+    // publish the quadrant's region of the CTA's own h tile: 4 warps meet, one thread pushes it to every peer
+    auto publish_quadrant = [&](uint32_t buf, int sub) {
+      fence_async_smem();
+      named_bar_sync(1 + q, 128);
+      if (sg == 0) {
+        if (elect_one()) {
+          const uint32_t hb = H_FULL(sub);
+#pragma unroll
+          for (int dd = 1; dd < C; ++dd) {
+            const uint32_t d = (rank + (uint32_t)dd) % C;
+            bulk_copy_s2c(mapa_shared(buf + hquad, d), buf + hquad, kQuadBytes, mapa_shared(hb, d));
+          }
+          mbar_arrive(hb);     // the local copy of this quadrant is in place
+        }
+      }
+    };
+
+    int a = 0;
+    uint32_t full_par = 0;
+
+    if constexpr (SUB == 128) {
+      // ---- M = 128: TMEM lane == row of the sub-tile; thread = (row, 8 hidden units)
+      const int r = q * 32 + lane;
+      const int ua = (int)rank * kChunkUnits + u0;      // absolute hidden unit of this thread's first element
+      bool valid[2];
+      long long base[2];
+      uint4 addv_next[2];
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const int R = sub * SUB + r;
+        valid[sub] = R < valid_rows;
+        base[sub] = (p.axis == FNSSL_ALONG_FREQ) ? (row0 + R) * p.nf : ((long long)coord_b * p.nt * p.nf + coord_r0 + R);
+        addv_next[sub] = make_uint4(0, 0, 0, 0);
+        if (p.out1 && valid[sub]) {
+          const long long pos0 = base[sub] + (long long)(dir ? (L - 1) : 0) * sstride;
+          addv_next[sub] = __ldg(reinterpret_cast<const uint4*>(p.addend + pos0 * p.addend_ld + dir * H + ua));
+        }
+      }
+      // this thread's 16-byte h piece inside the CTA's own [128 x 32] tile (64B swizzle: chunk ^= (row >> 1) & 3)
+      const uint32_t hpiece = (uint32_t)rank * kHTile + (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u +
+                              (uint32_t)((sg ^ ((r >> 1) & 3)) << 4);
+      {
+        float z[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = 0.0f;
+        tmem_st8(tmem_c + lane_off + u0, z);
+        tmem_st8(tmem_c + 32 + lane_off + u0, z);
+        tmem_wait_st();
+      }
+#pragma unroll 1
+      for (int t = 0; t < L; ++t) {
+        const int s = dir ? (L - 1 - t) : t;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          long long* tp = (tr && t >= 8 && t < 16) ? p.trace + ((t - 8) * 2 + sub) * 16 : nullptr;
+          const long long pos = base[sub] + (long long)s * sstride;
+          const uint4 addv = addv_next[sub];
+          if (p.out1 && valid[sub] && t + 1 < L) {     // residual operand of the next layer, fetched one step ahead
+            const long long posn = base[sub] + (long long)(dir ? (L - 2 - t) : (t + 1)) * sstride;
+            addv_next[sub] = __ldg(reinterpret_cast<const uint4*>(p.addend + posn * p.addend_ld + dir * H + ua));
+          }
+          if (TRACE && tp) tp[4] = clock64();
+          mbar_wait(ACC_FULL(a), (full_par >> a) & 1u, p.error_flag, 300 + a);
+          full_par ^= 1u << a;
+          if (TRACE && tp) tp[5] = clock64();
+          tc_fence_after();
+          const uint32_t acc = tmem_acc + (uint32_t)a * kChunkN + lane_off + u0;
+          const uint32_t cad = tmem_c + (uint32_t)(sub * 32) + lane_off + u0;
+          float gti[8], gtf[8], gtg[8], gto[8], cs[8];
+          tmem_ld8(acc + 0 * kChunkUnits, gti);
+          tmem_ld8(acc + 1 * kChunkUnits, gtf);
+          tmem_ld8(acc + 2 * kChunkUnits, gtg);
+          tmem_ld8(acc + 3 * kChunkUnits, gto);
+          tmem_ld8(cad, cs);
+          tmem_wait_ld();
+          tmem_ld_dep(gti); tmem_ld_dep(gtf); tmem_ld_dep(gtg); tmem_ld_dep(gto); tmem_ld_dep(cs);
+          tc_fence_before();
+          mbar_arrive(ACC_EMPTY(a));      // accumulator drained: the MMA thread may produce G_x of slot n+3 into it
+          a = (a == kAccBufs - 1) ? 0 : a + 1;
+          float hv[8];
+          if (p.debug & 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) hv[e] = gti[e] + gtf[e] + gtg[e] + gto[e] + cs[e];
+          } else if (fast) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              hv[e] = lstm_cell_tanh(gti[e] + bsp[e], gtf[e] + bsp[kChunkUnits + e], gtg[e] + bsp[2 * kChunkUnits + e],
+                                     gto[e] + bsp[3 * kChunkUnits + e], cs[e]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              hv[e] = lstm_cell(gti[e] + bsp[e], gtf[e] + bsp[kChunkUnits + e], gtg[e] + bsp[2 * kChunkUnits + e],
+                                gto[e] + bsp[3 * kChunkUnits + e], cs[e]);
+          }
+          __half2 h01 = __floats2half2_rn(hv[0], hv[1]), h23 = __floats2half2_rn(hv[2], hv[3]);
+          __half2 h45 = __floats2half2_rn(hv[4], hv[5]), h67 = __floats2half2_rn(hv[6], hv[7]);
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
+          pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
+          if (TRACE && tp) tp[6] = clock64();
+          if (t + 1 < L) {
+            // every CTA's h-part of step t has finished reading h_{t-1} (and with it all pushes of h_{t-1} have landed)
+            const long long c2 = (TRACE && tp) ? clock64() : 0;
+            if (t > 0) mbar_wait_cluster(H_FREE(sub), (uint32_t)((t - 1) & 1), p.error_flag, 320 + sub);
+            if (TRACE && tp) tp[10] = clock64() - c2;
+            const uint32_t buf = hs_base + (uint32_t)(sub * C) * kHTile;
+            st_shared_v4(buf + hpiece, pk);
+            publish_quadrant(buf, sub);
+          }
+          if (TRACE && tp) tp[7] = clock64();
+          tmem_st8(cad, cs);
+          if (valid[sub]) {
+            if (p.out0) *reinterpret_cast<uint4*>(p.out0 + pos * p.out0_ld + p.out0_off + dir * H + ua) = pk;
+            if (p.out1) {
+              const __half2* av = reinterpret_cast<const __half2*>(&addv);
+              __half2 o0 = __floats2half2_rn(hv[0] + __low2float(av[0]), hv[1] + __high2float(av[0]));
+              __half2 o1 = __floats2half2_rn(hv[2] + __low2float(av[1]), hv[3] + __high2float(av[1]));
+              __half2 o2 = __floats2half2_rn(hv[4] + __low2float(av[2]), hv[5] + __high2float(av[2]));
+              __half2 o3 = __floats2half2_rn(hv[6] + __low2float(av[3]), hv[7] + __high2float(av[3]));
+              uint4 ok;
+              ok.x = *reinterpret_cast<uint32_t*>(&o0); ok.y = *reinterpret_cast<uint32_t*>(&o1);
+              ok.z = *reinterpret_cast<uint32_t*>(&o2); ok.w = *reinterpret_cast<uint32_t*>(&o3);
+              *reinterpret_cast<uint4*>(p.out1 + pos * p.out1_ld + dir * H + ua) = ok;
+            }
+          }
+          tmem_wait_st();
+        }
+      }
+    } else {
+      // ---- M = 64: the accumulator occupies lanes 0-15 of each quadrant.  16x256b TMEM accesses keep all 32 threads
+      // busy: thread T owns rows {T/4, T/4+8} of the quadrant's 16 rows and units {2(T%4), 2(T%4)+1} of the 8-unit group.
+      const int uo = 2 * (lane & 3);                       // unit offset inside the 8-unit group
+      const int ua = (int)rank * kChunkUnits + u0 + uo;    // absolute hidden unit of the thread's first column
+      const float bias_i[2] = {bsp[uo], bsp[uo + 1]};
+      const float bias_f[2] = {bsp[kChunkUnits + uo], bsp[kChunkUnits + uo + 1]};
+      const float bias_g[2] = {bsp[2 * kChunkUnits + uo], bsp[2 * kChunkUnits + uo + 1]};
+      const float bias_o[2] = {bsp[3 * kChunkUnits + uo], bsp[3 * kChunkUnits + uo + 1]};
+      long long base[2][2];
+      bool valid[2][2];
+      uint32_t hpiece[2];
+      uint32_t addn[2][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int rs = q * 16 + (lane >> 2) + 8 * i;       // row inside the sub-tile
+        hpiece[i] = (uint32_t)rank * kHTile + (uint32_t)(rs >> 3) * 512u + (uint32_t)(rs & 7) * 64u +
+                    (uint32_t)((sg ^ ((rs >> 1) & 3)) << 4) + (uint32_t)uo * 2u;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const int R = sub * SUB + rs;                    // row inside the cluster tile
+          valid[sub][i] = R < valid_rows;
+          base[sub][i] = (p.axis == FNSSL_ALONG_FREQ) ? (row0 + R) * p.nf : ((long long)coord_b * p.nt * p.nf + coord_r0 + R);
+          addn[sub][i] = 0u;
+          if (p.out1 && valid[sub][i]) {
+            const long long pos0 = base[sub][i] + (long long)(dir ? (L - 1) : 0) * sstride;
+            addn[sub][i] = __ldg(reinterpret_cast<const unsigned int*>(p.addend + pos0 * p.addend_ld + dir * H + ua));
+          }
+        }
+      }
+      {
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        tmem_st4_16x256(tmem_c + lane_off + u0, z);
+        tmem_st4_16x256(tmem_c + 32 + lane_off + u0, z);
+        tmem_wait_st();
+      }
+#pragma unroll 1
+      for (int t = 0; t < L; ++t) {
+        const int s = dir ? (L - 1 - t) : t;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          long long* tp = (tr && t >= 8 && t < 16) ? p.trace + ((t - 8) * 2 + sub) * 16 : nullptr;
+          const uint32_t addc[2] = {addn[sub][0], addn[sub][1]};
+          if (p.out1 && t + 1 < L) {     // residual operand of the next layer, fetched one step ahead
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              if (valid[sub][i]) {
+                const long long posn = base[sub][i] + (long long)(dir ? (L - 2 - t) : (t + 1)) * sstride;
+                addn[sub][i] = __ldg(reinterpret_cast<const unsigned int*>(p.addend + posn * p.addend_ld + dir * H + ua));
+              }
+          }
+          if (TRACE && tp) tp[4] = clock64();
+          mbar_wait(ACC_FULL(a), (full_par >> a) & 1u, p.error_flag, 300 + a);
+          full_par ^= 1u << a;
+          if (TRACE && tp) tp[5] = clock64();
+          tc_fence_after();
+          const uint32_t acc = tmem_acc + (uint32_t)a * kChunkN + lane_off + u0;
+          const uint32_t cad = tmem_c + (uint32_t)(sub * 32) + lane_off + u0;
+          float gi[4], gf[4], gg[4], go[4], cs[4];
+          tmem_ld4_16x256(acc + 0 * kChunkUnits, gi);
+          tmem_ld4_16x256(acc + 1 * kChunkUnits, gf);
+          tmem_ld4_16x256(acc + 2 * kChunkUnits, gg);
+          tmem_ld4_16x256(acc + 3 * kChunkUnits, go);
+          tmem_ld4_16x256(cad, cs);
+          tmem_wait_ld();
+          tmem_ld_dep4(gi); tmem_ld_dep4(gf); tmem_ld_dep4(gg); tmem_ld_dep4(go); tmem_ld_dep4(cs);
+          tc_fence_before();
+          mbar_arrive(ACC_EMPTY(a));
+          a = (a == kAccBufs - 1) ? 0 : a + 1;
+          float hv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int w = e & 1;
+            if (p.debug & 1) hv[e] = gi[e] + gf[e] + gg[e] + go[e] + cs[e];
+            else if (fast) hv[e] = lstm_cell_tanh(gi[e] + bias_i[w], gf[e] + bias_f[w], gg[e] + bias_g[w], go[e] + bias_o[w], cs[e]);
+            else hv[e] = lstm_cell(gi[e] + bias_i[w], gf[e] + bias_f[w], gg[e] + bias_g[w], go[e] + bias_o[w], cs[e]);
+          }
+          __half2 hp[2] = {__floats2half2_rn(hv[0], hv[1]), __floats2half2_rn(hv[2], hv[3])};
+          if (TRACE && tp) tp[6] = clock64();
+          if (t + 1 < L) {
+            if (t > 0) mbar_wait_cluster(H_FREE(sub), (uint32_t)((t - 1) & 1), p.error_flag, 320 + sub);
+            const uint32_t buf = hs_base + (uint32_t)(sub * C) * kHTile;
+            st_shared_b32(buf + hpiece[0], *reinterpret_cast<uint32_t*>(&hp[0]));
+            st_shared_b32(buf + hpiece[1], *reinterpret_cast<uint32_t*>(&hp[1]));
+            publish_quadrant(buf, sub);
+          }
+          if (TRACE && tp) tp[7] = clock64();
+          tmem_st4_16x256(cad, cs);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (!valid[sub][i]) continue;
+            const long long pos = base[sub][i] + (long long)s * sstride;
+            if (p.out0) *reinterpret_cast<__half2*>(p.out0 + pos * p.out0_ld + p.out0_off + dir * H + ua) = hp[i];
+            if (p.out1) {
+              const __half2 av = *reinterpret_cast<const __half2*>(&addc[i]);
+              *reinterpret_cast<__half2*>(p.out1 + pos * p.out1_ld + dir * H + ua) =
+                  __floats2half2_rn(hv[2 * i] + __low2float(av), hv[2 * i + 1] + __high2float(av));
+            }
+          }
+          tmem_wait_st();
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // no CTA leaves while a peer may still write into its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+
+struct Plan { bool ok; int sub; int xstages; int nxs; size_t smem; };
+
+static Plan make_plan(int H, int c0, int c1) {
+  Plan pl{false, 0, 0, 0, 0};
+  if (H != 64 && H != 128 && H != 256) return pl;
+  if (c0 % 16 || c1 % 16 || c0 <= 0) return pl;
+  const int nxs = (c0 + 63) / 64 + (c1 + 63) / 64;
+  if (nxs > kMaxXSlabs) return pl;
+  const int C = H / kChunkUnits, NHS = H / 64, nslabs = nxs + NHS;
+  int sub_first = 128;
+  if (const char* e = getenv("FNSSL_TC_ROWS")) { if (atoi(e) == 64) sub_first = 64; }   // tests / profiling
+  for (int sub = sub_first; sub >= 64; sub -= 64) {
+    const long xslab = sub * 128L, htile = sub * 64L;
+    const long fixed = (long)nslabs * kWSlab + 2L * C * htile + kChunkN * 4 + 1024;
+    long xs = (kSmemLimit - 1024 - fixed) / xslab;
+    if (xs > kMaxXStages) xs = kMaxXStages;
+    if (xs >= 2) {
+      pl.ok = true; pl.sub = sub; pl.xstages = (int)xs; pl.nxs = nxs;
+      pl.smem = (size_t)fixed + (size_t)xs * xslab;
+      return pl;
+    }
+  }
+  return pl;
+}
+
+long long* g_trace_dev = nullptr;   // device memory: stores into host-mapped memory stall the traced threads for ~2 k cycles per slot
+static long long* trace_buffer() {
+  if (!g_trace_dev) {
+    if (cudaMalloc(&g_trace_dev, 256 * sizeof(long long)) != cudaSuccess) { g_trace_dev = nullptr; return nullptr; }
+    cudaMemset(g_trace_dev, 0, 256 * sizeof(long long));
+  }
+  return g_trace_dev;
+}
+
+template <int H, int SUB, bool TRACE>
+static int launch_t(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
+  constexpr int C = H / kChunkUnits, NHS = H / kSlabK;
+  constexpr int kTileRows = 2 * SUB;
+  Params p{};
+  int nxs = 0;
+  for (int src = 0; src < 2; ++src) {
+    const int c = src ? a->c1 : a->c0;
+    for (int k0 = 0; k0 < c; k0 += kSlabK) {
+      p.xs_srcmask |= (uint32_t)src << nxs;
+      p.xs_k0pack |= (unsigned long long)(k0 / 16) << (8 * nxs);
+      p.xs_nkpack |= (uint32_t)((((c - k0) < kSlabK ? (c - k0) : kSlabK) + 15) / 16) << (4 * nxs);
+      ++nxs;
+    }
+  }
+  p.nxs = nxs;
+  p.xstages = pl.xstages;
+  const int nslabs = nxs + NHS;
+  const int64_t wbytes = (int64_t)a->num_dirs * C * kChunkN * nslabs * kSlabK * 2;
+  const int64_t need = wbytes + (int64_t)a->num_dirs * 4 * H * 4;
+  FNSSL_REQUIRE(a->weights_bytes == need, "lstm(tcgen05): packed weight buffer is %lld bytes, expected %lld",
+                (long long)a->weights_bytes, (long long)need);
+  FNSSL_REQUIRE((reinterpret_cast<uintptr_t>(a->weights) & 15) == 0, "lstm(tcgen05): weights not 16-byte aligned");
+  FNSSL_REQUIRE(!a->state_flags, "lstm(tcgen05 two-chain kernel): carried state is implemented by the generation-2 kernel");
+  p.axis = a->axis; p.nf = a->nf; p.nt = a->nt;
+  int tiles;
+  if (a->axis == FNSSL_ALONG_FREQ) {
+    p.rows = (long long)a->nb * a->nt; p.steps = a->nf; p.tiles_per_b = 0;
+    tiles = (int)((p.rows + kTileRows - 1) / kTileRows);
+  } else {
+    p.rows = (long long)a->nb * a->nf; p.steps = a->nt; p.tiles_per_b = (a->nf + kTileRows - 1) / kTileRows;
+    tiles = a->nb * p.tiles_per_b;
+  }
+  p.bias = reinterpret_cast<const float*>(reinterpret_cast<const char*>(a->weights) + wbytes);
+  p.out0 = (__half*)a->out0; p.out0_ld = a->out0_ld; p.out0_off = a->out0_off;
+  p.addend = (const __half*)a->addend; p.addend_ld = a->addend_ld;
+  p.out1 = (__half*)a->out1; p.out1_ld = a->out1_ld;
+  if (SUB == 128) {   // 16-byte epilogue accesses
+    FNSSL_REQUIRE(!a->out0 || ((reinterpret_cast<uintptr_t>(a->out0) & 15) == 0 && a->out0_ld % 8 == 0 && a->out0_off % 8 == 0),
+                  "lstm(tcgen05): out0 must be 16-byte aligned (ld, offset multiples of 8)");
+    FNSSL_REQUIRE(!a->out1 || ((reinterpret_cast<uintptr_t>(a->out1) & 15) == 0 && a->out1_ld % 8 == 0 &&
+                               (reinterpret_cast<uintptr_t>(a->addend) & 15) == 0 && a->addend_ld % 8 == 0),
+                  "lstm(tcgen05): out1/addend must be 16-byte aligned");
+  } else {            // 4-byte (half2) epilogue accesses
+    FNSSL_REQUIRE(!a->out0 || ((reinterpret_cast<uintptr_t>(a->out0) & 3) == 0 && a->out0_ld % 2 == 0 && a->out0_off % 2 == 0),
+                  "lstm(tcgen05): out0 must be 4-byte aligned (even ld / offset)");
+    FNSSL_REQUIRE(!a->out1 || ((reinterpret_cast<uintptr_t>(a->out1) & 3) == 0 && a->out1_ld % 2 == 0 &&
+                               (reinterpret_cast<uintptr_t>(a->addend) & 3) == 0 && a->addend_ld % 2 == 0),
+                  "lstm(tcgen05): out1/addend must be 4-byte aligned");
+  }
+  p.error_flag = tc_error_flag();
+  if (const char* e = getenv("FNSSL_TC_DEBUG")) p.debug = atoi(e);
+  if (getenv("FNSSL_TC_TRACE")) p.trace = trace_buffer();
+
+  CUtensorMap m0, m1, mw;
+  if (make_grid_map(&m0, a->src0, a->c0, a->ld0, a->nb, a->nt, a->nf, a->axis, SUB)) return 1;
+  if (a->c1 > 0) { if (make_grid_map(&m1, a->src1, a->c1, a->ld1, a->nb, a->nt, a->nf, a->axis, SUB)) return 1; }
+  else m1 = m0;
+  if (make_weight_map(&mw, a->weights, nslabs, a->num_dirs * C)) return 1;
+
+  auto kern = lstm_tc4_kernel<H, SUB, TRACE>;
+  FNSSL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)tiles * C, (unsigned)a->num_dirs, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  FNSSL_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, mw, p));
+  FNSSL_LAUNCH_CHECK("lstm_tc4_kernel");
+  return 0;
+}
+
+template <int H, int SUB>
+static int launch(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
+  return getenv("FNSSL_TC_TRACE") ? launch_t<H, SUB, true>(a, pl, st) : launch_t<H, SUB, false>(a, pl, st);
+}
+
+}  // namespace tc4
+
+// diagnostic: copy the last trace (16 slots x 16 clock64 stamps) recorded with FNSSL_TC_TRACE=1
+extern "C" int fnssl_lstm_tc4_trace(long long* out256) {
+  if (!tc4::g_trace_dev) return 0;
+  return cudaMemcpy(out256, tc4::g_trace_dev, 256 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 1 : 0;
+}
+
+bool lstm_tc4_supports(int hidden, int c0, int c1) { return tc4::make_plan(hidden, c0, c1).ok; }
+
+int lstm_forward_tc4(const fnssl_lstm_args* a, cudaStream_t st) {
+  const tc4::Plan pl = tc4::make_plan(a->hidden, a->c0, a->c1);
+  FNSSL_REQUIRE(pl.ok, "lstm(tcgen05 two-chain kernel): unsupported layer (H=%d c0=%d c1=%d)", a->hidden, a->c0, a->c1);
+  if (a->hidden == 64) return pl.sub == 128 ? tc4::launch<64, 128>(a, pl, st) : tc4::launch<64, 64>(a, pl, st);
+  if (a->hidden == 128) return pl.sub == 128 ? tc4::launch<128, 128>(a, pl, st) : tc4::launch<128, 64>(a, pl, st);
+  FNSSL_REQUIRE(pl.sub == 64, "lstm(tcgen05 two-chain kernel): H = 256 needs 64-row sub-tiles");
+  return tc4::launch<256, 64>(a, pl, st);
+}
+
+}  // namespace fnssl

@@ -172,6 +172,15 @@ __device__ __forceinline__ void bulk_copy_s2c(uint32_t dst_cluster, uint32_t src
                : "memory");
 }
 
+// One lane of a fully converged warp.  ptxas recognises a predicate that comes from elect.sync as "single thread", so
+// tcgen05.mma / tcgen05.commit / TMA instructions guarded by it are emitted straight-line; behind an `if (lane == 0)`
+// each of them is wrapped in an ELECT + BRA.U.ANY loop that costs ~64 cycles of issue time (tools/micro/mma_rate.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred q;\n elect.sync _|q, 0xffffffff;\n selp.u32 %0, 1, 0, q;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- host-side helpers implemented in lstm_tc.cu ----------------------------------------------------
 int make_grid_map(CUtensorMap* m, const void* base, int c, int ld, int nb, int nt, int nf, int axis, int mr);
 int make_weight_map(CUtensorMap* m, const void* weights, int nslabs, int nchunks_total);

@@ -152,6 +152,8 @@ int fnssl_lstm_tc_supported(int hidden, int c0, int c1);
 int fnssl_lstm_tc_error_site(void);
 /* diagnostic: last in-kernel timeline (8 steps x 16 SM-clock stamps + 32 per-warp stamps) recorded when FNSSL_TC_TRACE is set; 0 if none */
 int fnssl_lstm_tc_trace(long long* out160);
+/* same for the two-chain kernel (lstm_tc4.cu): 16 slots x 16 stamps */
+int fnssl_lstm_tc4_trace(long long* out256);
 
 /* ---- heads ---------------------------------------------------------------------------------- */
 

@@ -74,7 +74,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         run_case(int(sys.argv[1]))
     else:
-        kernels = os.environ.get("TC_DEBUG_KERNELS", "3,2,1").split(",")
+        kernels = os.environ.get("TC_DEBUG_KERNELS", "4,3,2,1").split(",")
         for kern, rows in [(k, r) for k in kernels for r in ("128", "64")]:
             print(f"==== FNSSL_TC_KERNEL={kern} FNSSL_TC_ROWS={rows}")
             for i in range(len(CASES)):

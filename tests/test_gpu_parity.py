@@ -164,7 +164,7 @@ def test_lstm_layer_simt(axis, H, bidir, c0, c1, addend):
     assert _lstm_case("simt", axis, 2, 7, 19, c0, c1, H, bidir, addend) <= 2e-5
 
 
-@pytest.mark.parametrize("kernel", ["3", "2", "1"])
+@pytest.mark.parametrize("kernel", ["4", "3", "2", "1"])
 @pytest.mark.parametrize("rows", ["64", "128"])
 @pytest.mark.parametrize("axis", [0, 1])
 @pytest.mark.parametrize("H,bidir,c0,c1,addend", [
@@ -172,7 +172,8 @@ def test_lstm_layer_simt(axis, H, bidir, c0, c1, addend):
     (128, True, 256, 8, False), (64, True, 8, 0, False), (128, False, 128, 8, False), (64, True, 128, 8, True),
     (256, False, 256, 4, True), (256, False, 256, 0, False), (256, False, 256, 8, False)])
 def test_lstm_layer_tcgen05(monkeypatch, kernel, rows, axis, H, bidir, c0, c1, addend):
-    """All tensor-core kernel generations (3 = cluster-resident + interleaved sub-tiles, 2 = cluster-resident,
+    """All tensor-core kernel generations (4 = cluster-resident, two row tiles per cluster half a step apart,
+    3 = cluster-resident + interleaved sub-tiles, 2 = cluster-resident,
     1 = weight streaming; a generation that does not support a shape hands it to the next lower one), both row-tile shapes (128 / 64
     sequences per tile), ragged tiles (70 frames / 40 bins are not multiples of the tile), two-source inputs and
     the fused residual output."""
