@@ -53,7 +53,8 @@ class FNblock(nn.Module):
              next_full_addend: bool, need_fb: bool, state=None):
         """x_full_in: operand grid of the full-band pass (block input, or block input + fb_skip).
         raw: first block only -- the raw feature grid concatenated to the narrow-band input.
-        narr_addend: non-first blocks -- the block input (narrow-band residual, :44-45).
+        narr_addend: non-first blocks -- the block input (narrow-band residual, :44-45); CONSUMED (overwritten with
+            full-band output + residual when the tensor-core engine runs the layer).
         state: optional (h, c) of the narrow-band LSTM carried across chunks of a stream (online blocks only).
         Returns (N, N + F [if next_full_addend], F)."""
         fh = self.full_hidden_size
@@ -62,10 +63,15 @@ class FNblock(nn.Module):
             N_, S_ = run_lstm(self.narrLstm, eng, ops.ALONG_TIME, F_, 2 * fh, raw, c_in,
                               addend=F_ if next_full_addend else None, state=state)
         else:
+            # Both residual sums are accumulated in place (TMA reduce-add in the tensor-core kernel): narr_addend is dead
+            # after the full-band layer and F_ after the narrow-band one, and neither is an input of the layer that
+            # overwrites it.  (The first block's narrow-band layer reads F_ as its input, so its sum is a new grid.)
             F_, U_ = run_lstm(self.fullLstm, eng, ops.ALONG_FREQ, x_full_in, c_in, None, 0, addend=narr_addend,
-                              want_h=need_fb)
+                              want_h=need_fb, inplace_addend=True)
             N_, S_ = run_lstm(self.narrLstm, eng, ops.ALONG_TIME, U_, 2 * fh, None, 0,
-                              addend=F_ if next_full_addend else None, state=state)
+                              addend=F_ if next_full_addend else None, state=state, inplace_addend=True)
+            if next_full_addend:
+                F_ = None        # overwritten by S_
         return N_, S_, F_
 
     def forward(self, x: Tensor, nb_skip: Optional[Tensor] = None, fb_skip: Optional[Tensor] = None

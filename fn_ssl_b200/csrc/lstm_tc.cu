@@ -395,6 +395,29 @@ int make_grid_map(CUtensorMap* m, const void* base, int c, int ld, int nb, int n
   return make_map4(m, base, dims, str, box);
 }
 
+int make_out_map(CUtensorMap* m, const void* base, int ld, int nb, int nt, int nf, int axis, int rows) {
+  auto enc = get_encode();
+  FNSSL_REQUIRE(enc, "lstm(tcgen05): cuTensorMapEncodeTiled is unavailable in this driver");
+  FNSSL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld % 8) == 0, "lstm(tcgen05): output grid base / channel stride not 16-byte aligned");
+  uint64_t dims[4], str[3];
+  uint32_t box[4];
+  if (axis == FNSSL_ALONG_FREQ) {
+    dims[0] = (uint64_t)ld; dims[1] = (uint64_t)nf; dims[2] = (uint64_t)nb * nt; dims[3] = 1;
+    str[0] = (uint64_t)ld * 2; str[1] = (uint64_t)nf * ld * 2; str[2] = (uint64_t)nb * nt * nf * ld * 2;
+    box[0] = 32; box[1] = 1; box[2] = (uint32_t)rows; box[3] = 1;
+  } else {
+    dims[0] = (uint64_t)ld; dims[1] = (uint64_t)nf; dims[2] = (uint64_t)nt; dims[3] = (uint64_t)nb;
+    str[0] = (uint64_t)ld * 2; str[1] = (uint64_t)nf * ld * 2; str[2] = (uint64_t)nt * nf * ld * 2;
+    box[0] = 32; box[1] = (uint32_t)rows; box[2] = 1; box[3] = 1;
+  }
+  const uint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, str, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FNSSL_REQUIRE(r == CUDA_SUCCESS, "lstm(tcgen05): output tensor map failed (%d)", (int)r);
+  return 0;
+}
+
 // 2-D fp16 map over the packed weights [nchunks_total * 128 rows][nslabs * 64], box = one [128 x 64] slab
 int make_weight_map(CUtensorMap* m, const void* weights, int nslabs, int nchunks_total) {
   auto enc = get_encode();
@@ -519,12 +542,12 @@ int lstm_forward_tc(const fnssl_lstm_args* a, cudaStream_t st) {
     // for the 16-channel first layer but 1.80 vs 1.59 ms for the 256-channel layers -> use it for <= 2 input slabs.
     const int nxs = (a->c0 + 63) / 64 + (a->c1 + 63) / 64;
     const bool force3 = e && atoi(e) == 3;
-    if (a->state_flags) {   // carried (h, c): implemented by the cluster kernel of generation 2
+    if (want >= 4 && aligned && lstm_tc4_supports(a->hidden, a->c0, a->c1)) return lstm_forward_tc4(a, st);
+    if (a->state_flags) {   // carried (h, c): generations 4 (above) and 2
       FNSSL_REQUIRE(aligned && lstm_tc2_supports(a->hidden, a->c0, a->c1),
                     "lstm(tcgen05): recurrent state needs the cluster kernel, which does not support H=%d c0=%d c1=%d", a->hidden, a->c0, a->c1);
       return lstm_forward_tc2(a, st);
     }
-    if (want >= 4 && aligned && lstm_tc4_supports(a->hidden, a->c0, a->c1)) return lstm_forward_tc4(a, st);
     if (want >= 3 && aligned && (nxs <= 2 || force3) && lstm_tc3_supports(a->hidden, a->c0, a->c1)) return lstm_forward_tc3(a, st);
     if (want >= 2 && aligned && lstm_tc2_supports(a->hidden, a->c0, a->c1)) return lstm_forward_tc2(a, st);
   }

@@ -54,6 +54,9 @@ struct Params {
   __half* out0; int out0_ld; int out0_off;
   const __half* addend; int addend_ld;
   __half* out1; int out1_ld;
+  float* h_state; float* c_state; int state_flags;   // optional carried state, fp32 (rows, H); dirs == 1 (see lstm_tc2.cu)
+  int tma_out;                     // bit 0: out0 is written by TMA tile stores out of the h exchange tiles; bit 1: out1 aliases
+                                   // addend and is produced in place by TMA reduce-add (global += h)
   int* error_flag;
   long long* trace;                // FNSSL_TC_TRACE: clock64 stamps of CTA (0,0): [slot 16..31][16 events]
   int debug;                       // experiments only (FNSSL_TC_DEBUG): 1 = skip gate math, 2 = skip MMA issue, 32 = ex2/rcp gates instead of tanh.approx, 64 = no L2 prefetch
@@ -94,7 +97,8 @@ __device__ __forceinline__ float lstm_cell_tanh(float gi, float gf, float gg, fl
 template <int H, int SUB, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_constant__ CUtensorMap map_src1,
-                const __grid_constant__ CUtensorMap map_w, const Params p) {
+                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out0,
+                const __grid_constant__ CUtensorMap map_out1, const Params p) {
   constexpr int C = H / kChunkUnits;      // cluster size == number of 32-unit chunks
   constexpr int NHS = H / kSlabK;         // K slabs of h in the weight layout
   constexpr int kXSlab = SUB * 128;       // one [SUB x 64] fp16 x slab (128B swizzle)
@@ -172,6 +176,30 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
     valid_rows = min(kTileRows, p.nf - coord_r0);
   }
   const bool tr_cta = TRACE && p.trace && blockIdx.x == 0 && blockIdx.y == 0;
+  const int hoff = (p.state_flags & 1) ? 1 : 0;    // a carried state adds an h-part (and an H_FREE phase) at step 0
+
+  if (hoff) {
+    // Resume from a carried state: h_{-1} takes the place step -1 would have written, i.e. all C tiles of both sub-tiles
+    // (every CTA needs the whole h vector of its rows); c_{-1} is loaded by the epilogue warps below.
+    constexpr int PPR = H / 8;                 // 16-byte pieces (8 units) per row
+    for (int idx = tid; idx < kTileRows * PPR; idx += kThreads) {
+      const int R = idx / PPR, pc = idx % PPR, kc = pc >> 2, sb = pc & 3;
+      const int sub = R / SUB, r = R % SUB;
+      uint4 pk = make_uint4(0, 0, 0, 0);
+      if (R < valid_rows) {
+        const float4* g = reinterpret_cast<const float4*>(p.h_state + (row0 + R) * H + pc * 8);
+        const float4 a = __ldg(g), b = __ldg(g + 1);
+        __half2 h01 = __floats2half2_rn(a.x, a.y), h23 = __floats2half2_rn(a.z, a.w);
+        __half2 h45 = __floats2half2_rn(b.x, b.y), h67 = __floats2half2_rn(b.z, b.w);
+        pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
+        pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
+      }
+      st_shared_v4(hs_base + (uint32_t)(sub * C + kc) * kHTile + (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u +
+                       (uint32_t)((sb ^ ((r >> 1) & 3)) << 4), pk);
+    }
+    fence_async_smem();
+    __syncthreads();
+  }
 
   // The three single-lane roles below are instruction-latency bound (one warp executing a serial program at ~8 cycles
   // per instruction; ncu: 560 warp instructions per slot in the first version of this loop = 5 k cycles, more than the
@@ -284,10 +312,12 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         if (TRACE && tp) tp[0] = clock64();
         mbar_wait(XP_DONE(a), (xp_par >> a) & 1u, p.error_flag, 240 + a);     // G_x of this slot is complete
         xp_par ^= 1u << a;
-        if (t > 0) {
-          // h_{t-1} of this sub-tile: C-1 remote tiles arrive as DSMEM bulk copies (tx bytes), the local one by arrives
-          mbar_expect_tx(H_FULL(sub), (uint32_t)((C - 1) * kHTile));
-          mbar_wait_cluster(H_FULL(sub), (uint32_t)((t - 1) & 1), p.error_flag, 220 + sub);
+        if (t > 0 || hoff) {
+          if (t > 0) {
+            // h_{t-1} of this sub-tile: C-1 remote tiles arrive as DSMEM bulk copies (tx bytes), the local one by arrives
+            mbar_expect_tx(H_FULL(sub), (uint32_t)((C - 1) * kHTile));
+            mbar_wait_cluster(H_FULL(sub), (uint32_t)((t - 1) & 1), p.error_flag, 220 + sub);
+          }   // t == 0 with a carried state: h_{-1} was placed in the tiles before the roles split
           if (TRACE && tp) tp[1] = clock64();
           tc_fence_after();
           const uint32_t d_tmem = tmem_acc + (uint32_t)a * kChunkN;
@@ -300,7 +330,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
             for (int k = 0; k < 2; ++k) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, 1u);
           }
           // h_{t-1} has been read once these MMAs retire: every CTA may then overwrite its copy with h_t
-          if (t + 1 < L) umma_commit_mc(H_FREE(sub), mask);
+          umma_commit_mc(H_FREE(sub), mask);
         } else {
           tc_fence_after();
         }
@@ -324,21 +354,47 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
     const uint32_t hquad = (uint32_t)rank * kHTile + (uint32_t)q * kQuadBytes;
 
     // publish the quadrant's region of the CTA's own h tile: 4 warps meet, one thread pushes it to every peer
-    auto publish_quadrant = [&](uint32_t buf, int sub) {
+    // The same shared-memory tile feeds the HBM outputs: one TMA tile store per quadrant writes h_t (out0), one TMA
+    // reduce-add accumulates it onto the residual operand in place (out1 == addend).  Per-thread global accesses of this
+    // epilogue are 16-byte pieces of 32 different rows per warp instruction (32 LSU wavefronts each, ~1.5 k cycles of LSU
+    // time per slot for addend + out0 + out1); the bulk copies cost no issue slots at all.
+    constexpr int kQuadRows = SUB / 4;
+    const bool pusher = elect_one() && sg == 0;      // one fixed lane per quadrant: issues the pushes and owns the bulk groups
+    const int out_c = p.out0_off + dir * H + (int)rank * kChunkUnits;    // first channel of this CTA's tile in out0
+    const int out1_c = dir * H + (int)rank * kChunkUnits;
+    const bool along_f = p.axis == FNSSL_ALONG_FREQ;
+    auto publish_quadrant = [&](uint32_t buf, int sub, int s, bool push) {
       fence_async_smem();
       named_bar_sync(1 + q, 128);
-      if (sg == 0) {
-        if (elect_one()) {
-          const uint32_t hb = H_FULL(sub);
+      {
+        if (pusher) {
+          if (push) {
+            const uint32_t hb = H_FULL(sub);
 #pragma unroll
-          for (int dd = 1; dd < C; ++dd) {
-            const uint32_t d = (rank + (uint32_t)dd) % C;
-            bulk_copy_s2c(mapa_shared(buf + hquad, d), buf + hquad, kQuadBytes, mapa_shared(hb, d));
+            for (int dd = 1; dd < C; ++dd) {
+              const uint32_t d = (rank + (uint32_t)dd) % C;
+              bulk_copy_s2c(mapa_shared(buf + hquad, d), buf + hquad, kQuadBytes, mapa_shared(hb, d));
+            }
+            mbar_arrive(hb);     // the local copy of this quadrant is in place
           }
-          mbar_arrive(hb);     // the local copy of this quadrant is in place
+          if (p.tma_out) {
+            const int r0 = coord_r0 + sub * SUB + q * kQuadRows;
+            if (p.tma_out & 1) {
+              if (along_f) tma_store_4d(&map_out0, buf + hquad, out_c, s, r0, 0);
+              else tma_store_4d(&map_out0, buf + hquad, out_c, r0, s, coord_b);
+            }
+            if (p.tma_out & 2) {
+              if (along_f) tma_reduce_add_4d(&map_out1, buf + hquad, out1_c, s, r0, 0);
+              else tma_reduce_add_4d(&map_out1, buf + hquad, out1_c, r0, s, coord_b);
+            }
+            bulk_commit_group();
+          }
         }
       }
     };
+    const bool thr_out0 = p.out0 && !(p.tma_out & 1);     // per-thread stores (fallback paths)
+    const bool thr_out1 = p.out1 && !(p.tma_out & 2);
+    const bool tma_any = p.tma_out != 0;
 
     int a = 0;
     uint32_t full_par = 0;
@@ -356,7 +412,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         valid[sub] = R < valid_rows;
         base[sub] = (p.axis == FNSSL_ALONG_FREQ) ? (row0 + R) * p.nf : ((long long)coord_b * p.nt * p.nf + coord_r0 + R);
         addv_next[sub] = make_uint4(0, 0, 0, 0);
-        if (p.out1 && valid[sub]) {
+        if (thr_out1 && valid[sub]) {
           const long long pos0 = base[sub] + (long long)(dir ? (L - 1) : 0) * sstride;
           addv_next[sub] = __ldg(reinterpret_cast<const uint4*>(p.addend + pos0 * p.addend_ld + dir * H + ua));
         }
@@ -364,14 +420,18 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       // this thread's 16-byte h piece inside the CTA's own [128 x 32] tile (64B swizzle: chunk ^= (row >> 1) & 3)
       const uint32_t hpiece = (uint32_t)rank * kHTile + (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u +
                               (uint32_t)((sg ^ ((r >> 1) & 3)) << 4);
-      {
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
         float z[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) z[i] = 0.0f;
-        tmem_st8(tmem_c + lane_off + u0, z);
-        tmem_st8(tmem_c + 32 + lane_off + u0, z);
-        tmem_wait_st();
+        if (hoff && valid[sub]) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) z[i] = __ldg(p.c_state + (row0 + sub * SUB + r) * H + ua + i);
+        }
+        tmem_st8(tmem_c + (uint32_t)(sub * 32) + lane_off + u0, z);
       }
+      tmem_wait_st();
 #pragma unroll 1
       for (int t = 0; t < L; ++t) {
         const int s = dir ? (L - 1 - t) : t;
@@ -380,10 +440,11 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           long long* tp = (tr && t >= 8 && t < 16) ? p.trace + ((t - 8) * 2 + sub) * 16 : nullptr;
           const long long pos = base[sub] + (long long)s * sstride;
           const uint4 addv = addv_next[sub];
-          if (p.out1 && valid[sub] && t + 1 < L) {     // residual operand of the next layer, fetched one step ahead
+          if (thr_out1 && valid[sub] && t + 1 < L) {     // residual operand of the next layer, fetched one step ahead
             const long long posn = base[sub] + (long long)(dir ? (L - 2 - t) : (t + 1)) * sstride;
             addv_next[sub] = __ldg(reinterpret_cast<const uint4*>(p.addend + posn * p.addend_ld + dir * H + ua));
           }
+          if (tma_any && pusher) bulk_wait_read_all();   // the tile stores of the previous slot have read their source
           if (TRACE && tp) tp[4] = clock64();
           mbar_wait(ACC_FULL(a), (full_par >> a) & 1u, p.error_flag, 300 + a);
           full_par ^= 1u << a;
@@ -423,20 +484,27 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
           pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
           if (TRACE && tp) tp[6] = clock64();
-          if (t + 1 < L) {
+          if (t + 1 < L || tma_any) {
             // every CTA's h-part of step t has finished reading h_{t-1} (and with it all pushes of h_{t-1} have landed)
             const long long c2 = (TRACE && tp) ? clock64() : 0;
-            if (t > 0) mbar_wait_cluster(H_FREE(sub), (uint32_t)((t - 1) & 1), p.error_flag, 320 + sub);
+            if (t + hoff > 0) mbar_wait_cluster(H_FREE(sub), (uint32_t)((t - 1 + hoff) & 1), p.error_flag, 320 + sub);
             if (TRACE && tp) tp[10] = clock64() - c2;
             const uint32_t buf = hs_base + (uint32_t)(sub * C) * kHTile;
             st_shared_v4(buf + hpiece, pk);
-            publish_quadrant(buf, sub);
+            publish_quadrant(buf, sub, s, t + 1 < L);
           }
           if (TRACE && tp) tp[7] = clock64();
           tmem_st8(cad, cs);
+          if ((p.state_flags & 2) && t + 1 == L && valid[sub]) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              p.c_state[(row0 + sub * SUB + r) * H + ua + i] = cs[i];
+              p.h_state[(row0 + sub * SUB + r) * H + ua + i] = __half2float(__float2half_rn(hv[i]));   // the fp16 value the next step would read
+            }
+          }
           if (valid[sub]) {
-            if (p.out0) *reinterpret_cast<uint4*>(p.out0 + pos * p.out0_ld + p.out0_off + dir * H + ua) = pk;
-            if (p.out1) {
+            if (thr_out0) *reinterpret_cast<uint4*>(p.out0 + pos * p.out0_ld + p.out0_off + dir * H + ua) = pk;
+            if (thr_out1) {
               const __half2* av = reinterpret_cast<const __half2*>(&addv);
               __half2 o0 = __floats2half2_rn(hv[0] + __low2float(av[0]), hv[1] + __high2float(av[0]));
               __half2 o1 = __floats2half2_rn(hv[2] + __low2float(av[1]), hv[3] + __high2float(av[1]));
@@ -475,18 +543,24 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           valid[sub][i] = R < valid_rows;
           base[sub][i] = (p.axis == FNSSL_ALONG_FREQ) ? (row0 + R) * p.nf : ((long long)coord_b * p.nt * p.nf + coord_r0 + R);
           addn[sub][i] = 0u;
-          if (p.out1 && valid[sub][i]) {
+          if (thr_out1 && valid[sub][i]) {
             const long long pos0 = base[sub][i] + (long long)(dir ? (L - 1) : 0) * sstride;
             addn[sub][i] = __ldg(reinterpret_cast<const unsigned int*>(p.addend + pos0 * p.addend_ld + dir * H + ua));
           }
         }
       }
-      {
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
         float z[4] = {0.f, 0.f, 0.f, 0.f};
-        tmem_st4_16x256(tmem_c + lane_off + u0, z);
-        tmem_st4_16x256(tmem_c + 32 + lane_off + u0, z);
-        tmem_wait_st();
+        if (hoff) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (valid[sub][e >> 1])
+              z[e] = __ldg(p.c_state + (row0 + sub * SUB + q * 16 + (lane >> 2) + 8 * (e >> 1)) * H + ua + (e & 1));
+        }
+        tmem_st4_16x256(tmem_c + (uint32_t)(sub * 32) + lane_off + u0, z);
       }
+      tmem_wait_st();
 #pragma unroll 1
       for (int t = 0; t < L; ++t) {
         const int s = dir ? (L - 1 - t) : t;
@@ -494,7 +568,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         for (int sub = 0; sub < 2; ++sub) {
           long long* tp = (tr && t >= 8 && t < 16) ? p.trace + ((t - 8) * 2 + sub) * 16 : nullptr;
           const uint32_t addc[2] = {addn[sub][0], addn[sub][1]};
-          if (p.out1 && t + 1 < L) {     // residual operand of the next layer, fetched one step ahead
+          if (thr_out1 && t + 1 < L) {     // residual operand of the next layer, fetched one step ahead
 #pragma unroll
             for (int i = 0; i < 2; ++i)
               if (valid[sub][i]) {
@@ -502,6 +576,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
                 addn[sub][i] = __ldg(reinterpret_cast<const unsigned int*>(p.addend + posn * p.addend_ld + dir * H + ua));
               }
           }
+          if (tma_any && pusher) bulk_wait_read_all();
           if (TRACE && tp) tp[4] = clock64();
           mbar_wait(ACC_FULL(a), (full_par >> a) & 1u, p.error_flag, 300 + a);
           full_par ^= 1u << a;
@@ -530,21 +605,30 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           }
           __half2 hp[2] = {__floats2half2_rn(hv[0], hv[1]), __floats2half2_rn(hv[2], hv[3])};
           if (TRACE && tp) tp[6] = clock64();
-          if (t + 1 < L) {
-            if (t > 0) mbar_wait_cluster(H_FREE(sub), (uint32_t)((t - 1) & 1), p.error_flag, 320 + sub);
+          if (t + 1 < L || tma_any) {
+            if (t + hoff > 0) mbar_wait_cluster(H_FREE(sub), (uint32_t)((t - 1 + hoff) & 1), p.error_flag, 320 + sub);
             const uint32_t buf = hs_base + (uint32_t)(sub * C) * kHTile;
             st_shared_b32(buf + hpiece[0], *reinterpret_cast<uint32_t*>(&hp[0]));
             st_shared_b32(buf + hpiece[1], *reinterpret_cast<uint32_t*>(&hp[1]));
-            publish_quadrant(buf, sub);
+            publish_quadrant(buf, sub, s, t + 1 < L);
           }
           if (TRACE && tp) tp[7] = clock64();
           tmem_st4_16x256(cad, cs);
+          if ((p.state_flags & 2) && t + 1 == L) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (valid[sub][e >> 1]) {
+                const long long so = (row0 + sub * SUB + q * 16 + (lane >> 2) + 8 * (e >> 1)) * H + ua + (e & 1);
+                p.c_state[so] = cs[e];
+                p.h_state[so] = __half2float(__float2half_rn(hv[e]));
+              }
+          }
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             if (!valid[sub][i]) continue;
             const long long pos = base[sub][i] + (long long)s * sstride;
-            if (p.out0) *reinterpret_cast<__half2*>(p.out0 + pos * p.out0_ld + p.out0_off + dir * H + ua) = hp[i];
-            if (p.out1) {
+            if (thr_out0) *reinterpret_cast<__half2*>(p.out0 + pos * p.out0_ld + p.out0_off + dir * H + ua) = hp[i];
+            if (thr_out1) {
               const __half2 av = *reinterpret_cast<const __half2*>(&addc[i]);
               *reinterpret_cast<__half2*>(p.out1 + pos * p.out1_ld + dir * H + ua) =
                   __floats2half2_rn(hv[2 * i] + __low2float(av), hv[2 * i + 1] + __high2float(av));
@@ -556,6 +640,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
     }
   }
 
+  bulk_wait_all();         // TMA tile stores of this thread (if any) are complete before the CTA may exit
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();      // no CTA leaves while a peer may still write into its shared memory
@@ -626,7 +711,8 @@ static int launch_t(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
   FNSSL_REQUIRE(a->weights_bytes == need, "lstm(tcgen05): packed weight buffer is %lld bytes, expected %lld",
                 (long long)a->weights_bytes, (long long)need);
   FNSSL_REQUIRE((reinterpret_cast<uintptr_t>(a->weights) & 15) == 0, "lstm(tcgen05): weights not 16-byte aligned");
-  FNSSL_REQUIRE(!a->state_flags, "lstm(tcgen05 two-chain kernel): carried state is implemented by the generation-2 kernel");
+  p.h_state = a->h_state; p.c_state = a->c_state; p.state_flags = a->state_flags;
+  FNSSL_REQUIRE(!a->state_flags || (reinterpret_cast<uintptr_t>(a->h_state) & 15) == 0, "lstm(tcgen05): h_state not 16-byte aligned");
   p.axis = a->axis; p.nf = a->nf; p.nt = a->nt;
   int tiles;
   if (a->axis == FNSSL_ALONG_FREQ) {
@@ -662,6 +748,17 @@ static int launch_t(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
   if (a->c1 > 0) { if (make_grid_map(&m1, a->src1, a->c1, a->ld1, a->nb, a->nt, a->nf, a->axis, SUB)) return 1; }
   else m1 = m0;
   if (make_weight_map(&mw, a->weights, nslabs, a->num_dirs * C)) return 1;
+  // outputs through TMA: out0 as tile stores, out1 as an in-place reduce-add when it aliases the residual operand
+  CUtensorMap mo0 = m0, mo1 = m0;
+  const bool no_tma_out = getenv("FNSSL_TC_NO_TMA_OUT") != nullptr;
+  if (a->out0 && !no_tma_out && a->out0_off % 8 == 0) {
+    if (make_out_map(&mo0, a->out0, a->out0_ld, a->nb, a->nt, a->nf, a->axis, SUB / 4)) return 1;
+    p.tma_out |= 1;
+  }
+  if (a->out1 && a->out1 == a->addend && a->out1_ld == a->addend_ld && !no_tma_out) {
+    if (make_out_map(&mo1, a->out1, a->out1_ld, a->nb, a->nt, a->nf, a->axis, SUB / 4)) return 1;
+    p.tma_out |= 2;
+  }
 
   auto kern = lstm_tc4_kernel<H, SUB, TRACE>;
   FNSSL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
@@ -674,7 +771,7 @@ static int launch_t(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  FNSSL_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, mw, p));
+  FNSSL_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, mw, mo0, mo1, p));
   FNSSL_LAUNCH_CHECK("lstm_tc4_kernel");
   return 0;
 }

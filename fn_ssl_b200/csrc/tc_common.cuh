@@ -172,6 +172,26 @@ __device__ __forceinline__ void bulk_copy_s2c(uint32_t dst_cluster, uint32_t src
                : "memory");
 }
 
+// TMA tile stores: shared::cta -> global through a 4-D tensor map, tracked by the thread's bulk async-group
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// global[tile] += shared tile (element-wise add performed by the memory system; fp16 per the tensor map)
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk groups have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... and have completed (writes performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // One lane of a fully converged warp.  ptxas recognises a predicate that comes from elect.sync as "single thread", so
 // tcgen05.mma / tcgen05.commit / TMA instructions guarded by it are emitted straight-line; behind an `if (lane == 0)`
 // each of them is wrapped in an ELECT + BRA.U.ANY loop that costs ~64 cycles of issue time (tools/micro/mma_rate.cu).
@@ -183,6 +203,8 @@ __device__ __forceinline__ bool elect_one() {
 
 // ---- host-side helpers implemented in lstm_tc.cu ----------------------------------------------------
 int make_grid_map(CUtensorMap* m, const void* base, int c, int ld, int nb, int nt, int nf, int axis, int mr);
+// output grid map: box = [rows x 32 channels] in the 64B-swizzled layout of an h tile (TMA stores out of the exchange tiles)
+int make_out_map(CUtensorMap* m, const void* base, int ld, int nb, int nt, int nf, int axis, int rows);
 int make_weight_map(CUtensorMap* m, const void* weights, int nslabs, int nchunks_total);
 int* tc_error_flag();
 

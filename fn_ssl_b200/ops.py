@@ -210,8 +210,11 @@ def grid_add(a: Tensor, b: Tensor) -> Tensor:
 def lstm(engine: int, axis: int, src0: Tensor, c0: int, src1: Optional[Tensor], c1: int, weights: Tensor, hidden: int,
          num_dirs: int, addend: Optional[Tensor] = None, want_h: bool = True,
          out0: Optional[Tensor] = None, out0_off: int = 0,
-         state: Optional[Tuple[Tensor, Tensor]] = None) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+         state: Optional[Tuple[Tensor, Tensor]] = None, inplace_addend: bool = False
+         ) -> Tuple[Optional[Tensor], Optional[Tensor]]:
     """One LSTM layer over a grid (see fnssl_lstm_forward).  Returns (h grid, h + addend grid).
+    inplace_addend: the sum is accumulated into `addend` itself (out1 aliases addend; tensor-core engine only) -- the
+    caller must not need the residual operand afterwards and it must not be one of the layer's inputs.
     state = (h, c): float32 (rows, hidden) tensors the layer starts from and overwrites with its final state
     (nn.LSTM's (h_0, c_0) -> (h_n, c_n); uni-directional layers only)."""
     _need_cuda(src0, src1, weights, addend)
@@ -224,7 +227,14 @@ def lstm(engine: int, axis: int, src0: Tensor, c0: int, src1: Optional[Tensor], 
         raise RuntimeError("lstm: grids must be contiguous")
     if out0 is None and want_h:
         out0 = torch.empty((nb, nt, nf, oc), dtype=dt, device=dev)
-    out1 = torch.empty((nb, nt, nf, oc), dtype=dt, device=dev) if addend is not None else None
+    if addend is not None and inplace_addend and engine == ENGINE_TCGEN05:
+        if addend.data_ptr() in (src0.data_ptr(), src1.data_ptr() if src1 is not None else 0):
+            raise RuntimeError("lstm: an in-place residual operand must not be an input of the same layer")
+        if not addend.is_contiguous() or addend.shape != (nb, nt, nf, oc):
+            raise RuntimeError("lstm: in-place residual operand must be a contiguous (nb, nt, nf, dirs*hidden) grid")
+        out1 = addend
+    else:
+        out1 = torch.empty((nb, nt, nf, oc), dtype=dt, device=dev) if addend is not None else None
     a = _lib.LstmArgs()
     a.engine, a.axis = engine, axis
     a.nb, a.nt, a.nf = nb, nt, nf

@@ -123,7 +123,7 @@ def test_feature_grid_layout(dtype):
 # LSTM layer, both axes, both engines
 # ---------------------------------------------------------------------------------------------
 
-def _lstm_case(engine, axis, nb, nt, nf, c0, c1, H, bidir, use_addend, seed=0):
+def _lstm_case(engine, axis, nb, nt, nf, c0, c1, H, bidir, use_addend, seed=0, inplace=False):
     from fn_ssl_b200 import config, ops
     from fn_ssl_b200.packing import LSTMParams, run_lstm
     dt = config.grid_dtype(engine)
@@ -137,8 +137,11 @@ def _lstm_case(engine, axis, nb, nt, nf, c0, c1, H, bidir, use_addend, seed=0):
     g1 = ops.grid_copy(x1.to(DEV), c1, dt) if c1 else None
     ga = ops.grid_copy(add.to(DEV), oc, dt) if use_addend else None
     before = ops.LAUNCHES
-    h, hs = run_lstm(p, engine, axis, g0, c0, g1, c1, addend=ga)
+    ga_ref = ga.float().cpu() if use_addend else None
+    h, hs = run_lstm(p, engine, axis, g0, c0, g1, c1, addend=ga, inplace_addend=inplace)
     assert ops.LAUNCHES == before + 1
+    if inplace and use_addend and engine == "tcgen05":
+        assert hs.data_ptr() == ga.data_ptr()      # the sum really was accumulated into the residual operand
     if engine == "tcgen05":   # the layer really ran on the tensor-core kernel, not the CUDA-core fallback
         from fn_ssl_b200 import _lib
         assert _lib.load().fnssl_lstm_tc_supported(H, (c0 + 15) // 16 * 16, (c1 + 15) // 16 * 16) == 1
@@ -151,7 +154,7 @@ def _lstm_case(engine, axis, nb, nt, nf, c0, c1, H, bidir, use_addend, seed=0):
         ref = orc.lstm(x.permute(0, 2, 1, 3).reshape(nb * nf, nt, -1), sd, "l.").reshape(nb, nf, nt, oc).permute(0, 2, 1, 3)
     e = _relerr(h, ref)
     if use_addend:
-        e = max(e, _relerr(hs, ref + ga.float().cpu()))
+        e = max(e, _relerr(hs, ref + ga_ref))
     return e
 
 
@@ -186,6 +189,22 @@ def test_lstm_layer_tcgen05(monkeypatch, kernel, rows, axis, H, bidir, c0, c1, a
     monkeypatch.setenv("FNSSL_TC_KERNEL", kernel)
     nb, nt, nf = (2, 70, 256) if axis == 1 else (2, 70, 40)
     assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, H, bidir, addend) <= 1e-3
+    if addend:   # residual sum accumulated in place (generation 4: TMA reduce-add; older generations: same threads)
+        assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, H, bidir, addend, inplace=True) <= 1e-3
+
+
+@pytest.mark.parametrize("axis,nb,nt,nf", [(0, 3, 100, 7), (1, 1, 6, 300), (1, 2, 5, 515)])
+def test_lstm_layer_tcgen05_multi_tile(monkeypatch, axis, nb, nt, nf):
+    """Generation 4 with more than one cluster tile and ragged last tiles on both sub-tiles (300 rows = 256 + 44,
+    515 bins = 2 x 256 + 3), outputs through TMA tile stores / in-place reduce-add."""
+    from fn_ssl_b200 import config
+    if not config.TC_AVAILABLE:
+        pytest.skip("tcgen05 engine not built")
+    monkeypatch.setenv("FNSSL_TC_KERNEL", "4")
+    for rows in ("128", "64"):
+        monkeypatch.setenv("FNSSL_TC_ROWS", rows)
+        assert _lstm_case("tcgen05", axis, nb, nt, nf, 64, 4, 128, True, True, inplace=True) <= 1e-3
+        assert _lstm_case("tcgen05", axis, nb, nt, nf, 16, 0, 64, False, False) <= 1e-3
 
 
 # ---------------------------------------------------------------------------------------------
@@ -391,16 +410,19 @@ def test_decode_many_pairs_and_sources():
 # "next" row: stateful (streaming) API -- carried LSTM state, forgetting-norm state, STFT overlap
 # ------------------------------------------------------------------------------------------------
 
+@pytest.mark.parametrize("kernel", ["4", "2"])
 @pytest.mark.parametrize("rows", ["64", "128"])
 @pytest.mark.parametrize("engine,H,c0,c1", [("simt", 64, 20, 0), ("simt", 256, 256, 4), ("tcgen05", 64, 64, 0),
                                             ("tcgen05", 128, 256, 16), ("tcgen05", 256, 256, 0), ("tcgen05", 256, 128, 16)])
-def test_lstm_carried_state_equals_whole_sequence(monkeypatch, rows, engine, H, c0, c1):
+def test_lstm_carried_state_equals_whole_sequence(monkeypatch, kernel, rows, engine, H, c0, c1):
     """nn.LSTM semantics of (h_0, c_0) -> (h_n, c_n): running a narrow-band layer over 3 chunks with the state carried
     gives bit-identical outputs to one run over the whole sequence, and the final state matches the oracle."""
     from fn_ssl_b200 import config, ops
     from fn_ssl_b200.packing import LSTMParams, run_lstm
     monkeypatch.setenv("FNSSL_TC_ROWS", rows)
-    monkeypatch.setenv("FNSSL_TC_KERNEL", "2")      # whole-sequence run on the same kernel generation the state path uses
+    if engine == "simt" and kernel != "4":
+        pytest.skip("kernel generations only exist in the tensor-core engine")
+    monkeypatch.setenv("FNSSL_TC_KERNEL", kernel)   # generations 4 (default) and 2 implement the carried state
     dt = config.grid_dtype(engine)
     nb, nt, nf = 2, 21, 75                           # 150 rows: ragged against both tile sizes
     torch.manual_seed(7)
