@@ -32,3 +32,9 @@ def golden_fnssl():
 def golden_ipdnet():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "ipdnet_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_ipdnet2():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "ipdnet2_golden.npz"))

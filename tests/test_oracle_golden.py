@@ -100,3 +100,37 @@ def test_decode_oracle_matches_reference(golden_fnssl):
         assert np.array_equal(doa.numpy(), g[f"dec_doa_{snm}"])
         _close(vad, g[f"dec_vad_{snm}"], 1e-5) if snm == "unkNum" else np.testing.assert_array_equal(vad.numpy(), g[f"dec_vad_{snm}"])
     _close(ss, g["dec_ss"], 1e-5)
+
+
+# ---- IPDnet2: tests/golden/make_golden_ipdnet2.py; the Mamba block itself is parity-unpinned ----
+
+def test_ipdnet2_frontend_matches_reference(golden_ipdnet2):
+    from oracle import ipdnet2_oracle as orc2
+    sig = _randn((2, 320 * 24 + 101, 3), 21)
+    s = orc2.stft_center(sig)
+    assert s.shape == (2, 257, 25, 3) == golden_ipdnet2["fe_stft_re"].shape    # nt = floor(n / 320 + 1)
+    _close(s.real, golden_ipdnet2["fe_stft_re"], 1e-6)
+    _close(s.imag, golden_ipdnet2["fe_stft_im"], 1e-6)
+    _close(orc2.preprocess_ipdnet2(sig), golden_ipdnet2["fe_feat"], 1e-5)
+
+
+def test_ipdnet2_network_matches_reference(golden_ipdnet2):
+    from oracle import ipdnet2_oracle as orc2
+    for tag, cfg, xshape, seed in (("small", dict(dim_input=6, dim_output=8, num_layers=3), (2, 6, 256, 27), 22),
+                                   ("default", dict(dim_input=10, dim_output=16, num_layers=8), (1, 10, 256, 40), 23)):
+        sd = orc2.seeded_ipdnet2_state_dict(seed, **cfg)
+        y = orc2.ipdnet2_forward(_randn(xshape, seed + 100), sd)
+        _close(y, golden_ipdnet2[f"net_{tag}_out"], 2e-5)
+
+
+def test_ipdnet2_mamba_scan_properties():
+    """The Mamba restatement has no reference to pin against (mamba_ssm absent): check the defining properties instead --
+    causality, and equality of whole-sequence and chunked evaluation is covered on the GPU side."""
+    from oracle import ipdnet2_oracle as orc2
+    sd = {k[len("layers.0.mhsa."):]: v for k, v in orc2.seeded_ipdnet2_state_dict(3, num_layers=1).items()
+          if k.startswith("layers.0.mhsa.")}
+    x = _randn((3, 20, 96), 5)
+    y = orc2.mamba(x, sd, "")
+    x2 = x.clone(); x2[:, 12:] += 1.0
+    y2 = orc2.mamba(x2, sd, "")
+    assert torch.equal(y[:, :12], y2[:, :12]) and not torch.allclose(y[:, 12:], y2[:, 12:])
