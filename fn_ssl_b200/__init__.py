@@ -4,11 +4,13 @@ Drop-in module surface (same names as the reference, Audio-WestlakeU/FN-SSL):
     fn_ssl_b200.Module            STFT, AddChToBatch, RemoveChFromBatch, forgetting_norm
     fn_ssl_b200.Model             FNblock, FN_SSL, FN_lightning
     fn_ssl_b200.FixedAarryIPDnet  FNblock, CausCnnBlock, IPDnet
+    fn_ssl_b200.IPDnet2           OnlineSpatialNet, SpatialNetLayer, FreqInverse, CausalConv1d, Mamba (parameter holder)
 plus the fused end-to-end pipelines (fn_ssl_b200.pipeline) and the multi-GPU helpers (fn_ssl_b200.distributed).
 All arithmetic runs in libfnssl_b200.so (hand-written CUDA, C ABI in include/fnssl_b200.h).
 """
 from . import config  # noqa: F401
 from .FixedAarryIPDnet import CausalConv1dBlock, CausCnnBlock, FixedArrayIPDnet, IPDnet  # noqa: F401
+from .IPDnet2 import IPDnet2_lightning, IPDnet2Pipeline, OnlineSpatialNet, SpatialNetLayer, data_preprocess_ipdnet2  # noqa: F401
 from .Model import FN_SSL, FN_lightning, FNblock, FullNarrowBlock  # noqa: F401
 from .Module import (DPIPD, STFT, AddChToBatch, RemoveChFromBatch, SourceDetectLocalize, forgetting_norm,  # noqa: F401
                      pred_ipd_to_doa)

@@ -33,6 +33,47 @@ class LstmArgs(C.Structure):
     ]
 
 
+_fp = C.c_void_p
+
+
+class SnFconvWeights(C.Structure):
+    """struct fnssl_sn_fconv_weights."""
+    _fields_ = [("ln_w", _fp), ("ln_b", _fp), ("conv_wp", _fp), ("conv_b", _fp), ("prelu", _fp)]
+
+
+class SnFreqArgs(C.Structure):
+    """struct fnssl_sn_freq_args."""
+    _fields_ = [
+        ("nb", C.c_int32), ("nt", C.c_int32), ("nf", C.c_int32),
+        ("hidden", C.c_int32), ("squeeze", C.c_int32), ("groups", C.c_int32), ("fkernel", C.c_int32),
+        ("is_first", C.c_int32),
+        ("x", _fp), ("cin", C.c_int32), ("x_ld", C.c_int32),
+        ("enc_wp", _fp), ("enc_b", _fp), ("enc_kernel", C.c_int32),
+        ("fconv1", SnFconvWeights),
+        ("lnf_w", _fp), ("lnf_b", _fp), ("sq_wt", _fp), ("sq_b", _fp), ("full_wt", _fp), ("full_b", _fp),
+        ("usq_w", _fp), ("usq_b", _fp),
+        ("fconv2", SnFconvWeights),
+        ("out", _fp),
+    ]
+
+
+class MambaWeights(C.Structure):
+    """struct fnssl_mamba_weights."""
+    _fields_ = [(n, _fp) for n in ("ln_w", "ln_b", "in_proj_wt", "conv_w", "conv_b", "x_proj_wt", "dt_proj_w",
+                                   "dt_proj_b", "A_log", "D", "out_proj_wt")]
+
+
+class SnTimeArgs(C.Structure):
+    """struct fnssl_sn_time_args."""
+    _fields_ = [
+        ("nb", C.c_int32), ("nt", C.c_int32), ("nf", C.c_int32), ("hidden", C.c_int32),
+        ("d_inner", C.c_int32), ("d_state", C.c_int32), ("dt_rank", C.c_int32), ("d_conv", C.c_int32),
+        ("pool", C.c_int32),
+        ("x", _fp), ("out", _fp),
+        ("m", MambaWeights * 2),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/fnssl_b200.h declares
 _vp, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 SIGNATURES = {
@@ -57,6 +98,10 @@ SIGNATURES = {
     "fnssl_ipd_head_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "fnssl_linear_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "fnssl_doa_decode_idl": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fnssl_reflect_pad": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "fnssl_sn_freq_forward": (_i, [C.POINTER(SnFreqArgs), _vp]),
+    "fnssl_sn_time_forward": (_i, [C.POINTER(SnTimeArgs), _vp]),
+    "fnssl_sn_head_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "fnssl_causcnn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "fnssl_causcnn_forward": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
 }
@@ -78,7 +123,7 @@ def load(build_if_missing: bool = True):
             fn = getattr(lib, name)   # AttributeError if the header and the library disagree
             fn.restype = res
             fn.argtypes = args
-        if lib.fnssl_abi_version() != 2:
+        if lib.fnssl_abi_version() != 3:
             raise RuntimeError("libfnssl_b200.so: ABI version mismatch, rebuild it")
         _lib = lib
         return lib

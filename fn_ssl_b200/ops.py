@@ -41,6 +41,18 @@ def _count(n: int) -> None:
     LAUNCHES += n
 
 
+def profiled(label: str, flops: float, nbytes: float, launch) -> None:
+    """Run `launch()` (one kernel launch); when profiling is on, bracket it with CUDA events on the current stream."""
+    if _PROFILE is None:
+        launch()
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launch()
+    e1.record()
+    _PROFILE.append((label, flops, nbytes, e0, e1))
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FNSSL_ABI_VERSION 2
+#define FNSSL_ABI_VERSION 3
 
 /* element types of grid tensors */
 #define FNSSL_F32 0
@@ -190,6 +190,78 @@ int fnssl_causcnn_forward(const void* src0, int c0, int ld0, const void* src1, i
 int fnssl_doa_decode_idl(const float* pred_ipd, const float* templ, const float* templ_t, int R, int K, int ncand,
                          int max_sources, int vad_mode, float* cur, float* map, float* ss, int* idx_out,
                          float* vad_out, void* stream);
+
+/* ---- IPDnet2: OnlineSpatialNet with Mamba time modules (scope row a11) --------------------------- */
+
+/* torch.stft(center=True)'s reflect padding (IPDnet2/Module.py:61-62): (nb, nsample, nch) -> (nb, nsample + 2 pad, nch).
+ * Followed by fnssl_stft_forward(hop = 320) this is IPDnet2's STFT: nt = floor(nsample / hop) + 1. */
+int fnssl_reflect_pad(const float* signal, int nb, int nsample, int nch, int pad, float* out, void* stream);
+
+/* LayerNorm + grouped Conv1d along frequency + PReLU (SpatialNetLayer.fconv1 / fconv2, IPDnet2.py:105-109,119-123). */
+typedef struct fnssl_sn_fconv_weights {
+  const float* ln_w;     /* (H)                                                                   */
+  const float* ln_b;     /* (H)                                                                   */
+  const float* conv_wp;  /* packed [group][k][in-channel of group][out-channel of group]         */
+  const float* conv_b;   /* (H)                                                                   */
+  const float* prelu;    /* (H)                                                                   */
+} fnssl_sn_fconv_weights;
+
+/* Frequency-axis half of one SpatialNetLayer (IPDnet2.py:146-153) [+ the CausalConv1d encoder (:335) when is_first]:
+ *   x = x + fconv1(x); [pool F/2]; x = x + unsqueeze(full(squeeze(LN(x)))); x = x + fconv2(x); [pool F/8]
+ * is_first: x is the feature grid (nb, nt, 256, x_ld) f32 with cin real channels (zero padded to x_ld, x_ld % 4 == 0);
+ *           out is (nb, nt, 16, H).   else: x and out are (nb, nt, nf = 16, H). */
+typedef struct fnssl_sn_freq_args {
+  int32_t nb, nt, nf;
+  int32_t hidden, squeeze, groups, fkernel;
+  int32_t is_first;
+  const float* x; int32_t cin; int32_t x_ld;
+  const float* enc_wp;   /* packed [k][c < x_ld][H] (zero rows for c >= cin)                      */
+  const float* enc_b;    /* (H)                                                                   */
+  int32_t enc_kernel;
+  fnssl_sn_fconv_weights fconv1;
+  const float* lnf_w; const float* lnf_b;    /* norm_full                                          */
+  const float* sq_wt;    /* squeeze weight TRANSPOSED (H, squeeze)                                */
+  const float* sq_b;
+  const float* full_wt;  /* full.weight TRANSPOSED (in f', out f)                                 */
+  const float* full_b;
+  const float* usq_w;    /* unsqueeze weight (H, squeeze)                                         */
+  const float* usq_b;
+  fnssl_sn_fconv_weights fconv2;
+  float* out;
+} fnssl_sn_freq_args;
+int fnssl_sn_freq_forward(const fnssl_sn_freq_args* args, void* stream);
+
+/* mamba_ssm.Mamba parameters (names as in IPDnet2/checkpoints/ipdnet2_small.ckpt) + the LayerNorm in front of it. */
+typedef struct fnssl_mamba_weights {
+  const float* ln_w; const float* ln_b;
+  const float* in_proj_wt;   /* in_proj.weight TRANSPOSED (d_model, 2 d_inner)                     */
+  const float* conv_w;       /* conv1d.weight (d_inner, d_conv)                                    */
+  const float* conv_b;
+  const float* x_proj_wt;    /* x_proj.weight TRANSPOSED (d_inner, dt_rank + 2 d_state)            */
+  const float* dt_proj_w;    /* (d_inner, dt_rank)                                                 */
+  const float* dt_proj_b;
+  const float* A_log;        /* (d_inner, d_state)                                                 */
+  const float* D;
+  const float* out_proj_wt;  /* out_proj.weight TRANSPOSED (d_inner, d_model)                      */
+} fnssl_mamba_weights;
+
+/* Time-axis half of one SpatialNetLayer (IPDnet2.py:155-163,166-181) [+ AvgPool over `pool` frames, :347]:
+ *   x = x + Mamba_0(LN_0(x)); x = x + Mamba_1(LN_1(x));   x: (nb, nt, nf, H) -> out: (nb, nt / pool, nf, H) */
+typedef struct fnssl_sn_time_args {
+  int32_t nb, nt, nf, hidden;
+  int32_t d_inner, d_state, dt_rank, d_conv;
+  int32_t pool;
+  const float* x;
+  float* out;
+  fnssl_mamba_weights m[2];
+} fnssl_sn_time_args;
+int fnssl_sn_time_forward(const fnssl_sn_time_args* args, void* stream);
+
+/* FreqInverse (IPDnet2.py:37-43) + decoder Linear (:361) + output reshape (:363-364, literal 2 generalised to n_src):
+ *   x (nb, nt, nfc, H) -> out (nb, nt, 2 * nfc * ratio, dim_out / (2 n_src), n_src)
+ *   trans_wt : trans2.weight TRANSPOSED (H, ratio * dim_out), channel = o * ratio + j */
+int fnssl_sn_head_forward(const float* x, int nb, int nt, int nfc, int hidden, const float* trans_wt, const float* trans_b,
+                          const float* dec_w, const float* dec_b, int dim_out, int ratio, int n_src, float* out, void* stream);
 
 #ifdef __cplusplus
 }

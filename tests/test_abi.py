@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in include/fnssl_b200.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(syms)
-    assert lib.fnssl_abi_version() == 2
+    assert lib.fnssl_abi_version() == 3
 
 
 def test_host_only_entry_points():
@@ -106,3 +106,26 @@ def test_addchtobatch_cpu_matches_oracle():
     x = torch.randn(2, 4, 3, 5, dtype=torch.complex64)
     for mode in ("M", "MM"):
         assert torch.equal(F.AddChToBatch(mode)(x), orc.add_ch_to_batch(x, mode))
+
+
+def test_ipdnet2_state_dict_surface_matches_reference_checkpoint():
+    """Key set and shapes equal the reference's shipped checkpoint (IPDnet2/checkpoints/ipdnet2_small.ckpt; its key /
+    shape table is oracle.ipdnet2_param_shapes, asserted against the checkpoint by tests/golden/make_golden_ipdnet2.py)."""
+    import os
+    import fn_ssl_b200 as F
+    from oracle import ipdnet2_oracle as orc2
+    net = F.IPDnet2_lightning()
+    shapes = orc2.ipdnet2_param_shapes(dim_input=10, dim_output=16, num_layers=8)
+    sd = net.state_dict()
+    assert set(sd) == {"arch." + k for k in shapes} and len(sd) == 326
+    for k, shp in shapes.items():
+        assert tuple(sd["arch." + k].shape) == tuple(shp), k
+    net.arch.load_state_dict(orc2.seeded_ipdnet2_state_dict(1), strict=True)
+    ck = "/root/reference/IPDnet2/checkpoints/ipdnet2_small.ckpt"      # only present in the build container
+    if os.path.exists(ck):
+        net.load_state_dict(torch.load(ck, map_location="cpu", weights_only=False)["state_dict"], strict=True)
+    with pytest.raises(Exception, match="configuration"):
+        F.OnlineSpatialNet(dim_input=10, dim_output=16, num_layers=2, dim_squeeze=8, num_freqs=256, dim_hidden=192,
+                           attention='mamba(16,4)')
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net.eval()(torch.zeros(1, 10, 256, 10))
