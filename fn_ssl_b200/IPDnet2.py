@@ -6,8 +6,8 @@ Same class names, constructor arguments and state_dict keys as the reference, so
     CausalConv1d      (IPDnet2.py:45-82)      parameter holder; fused into the first frequency-stage launch
     FreqInverse       (:23-43)                parameter holder; fused into the head launch
     Mamba             (mamba_ssm.Mamba, third party, :15-19,127,132)   parameter holder with the package's names
-    SpatialNetLayer   (:85-256)               2 launches: frequency stage (fnssl_sn_freq_forward), time stage
-                                              (fnssl_sn_time_forward)
+    SpatialNetLayer   (:85-256)               3 launches: frequency stage (fnssl_sn_freq_forward), time stage
+                                              (fnssl_sn_time_forward: one launch per Mamba block)
     OnlineSpatialNet  (:259-399)              forward(x: (B, 2M, 256, T)) -> (B, T//5, 512, M-1, 2)
 
 Only the configuration the reference runs is built (run_IPDnet2.py:103-119): dim_hidden 96, dim_squeeze 8, conv groups 8,
@@ -199,8 +199,9 @@ class SpatialNetLayer(nn.Module):
         ops.profiled("sn_freq_first" if self.is_first else "sn_freq", flops, nbytes,
                      lambda: _lib.check(lib.fnssl_sn_freq_forward(C.byref(fa), ops._stream())))
         z = torch.empty((nb, nt // pool, 16, H), dtype=torch.float32, device=x.device)
-        ta.nb, ta.nt, ta.nf, ta.pool, ta.x, ta.out = nb, nt, 16, pool, y.data_ptr(), z.data_ptr()
-        ops._count(1)
+        work = torch.empty_like(y)
+        ta.nb, ta.nt, ta.nf, ta.pool, ta.x, ta.work, ta.out = nb, nt, 16, pool, y.data_ptr(), work.data_ptr(), z.data_ptr()
+        ops._count(2)
         flops, nbytes = time_stage_work(nb * 16, nt, pool)
         ops.profiled("sn_time_T%d" % nt, flops, nbytes,
                      lambda: _lib.check(lib.fnssl_sn_time_forward(C.byref(ta), ops._stream())))

@@ -69,7 +69,7 @@ class SnTimeArgs(C.Structure):
         ("nb", C.c_int32), ("nt", C.c_int32), ("nf", C.c_int32), ("hidden", C.c_int32),
         ("d_inner", C.c_int32), ("d_state", C.c_int32), ("dt_rank", C.c_int32), ("d_conv", C.c_int32),
         ("pool", C.c_int32),
-        ("x", _fp), ("out", _fp),
+        ("x", _fp), ("work", _fp), ("out", _fp),
         ("m", MambaWeights * 2),
     ]
 

@@ -246,12 +246,14 @@ typedef struct fnssl_mamba_weights {
 } fnssl_mamba_weights;
 
 /* Time-axis half of one SpatialNetLayer (IPDnet2.py:155-163,166-181) [+ AvgPool over `pool` frames, :347]:
- *   x = x + Mamba_0(LN_0(x)); x = x + Mamba_1(LN_1(x));   x: (nb, nt, nf, H) -> out: (nb, nt / pool, nf, H) */
+ *   x = x + Mamba_0(LN_0(x)); x = x + Mamba_1(LN_1(x));   x: (nb, nt, nf, H) -> out: (nb, nt / pool, nf, H)
+ * Two launches (one per Mamba block); work: scratch of the size of x holding the intermediate. */
 typedef struct fnssl_sn_time_args {
   int32_t nb, nt, nf, hidden;
   int32_t d_inner, d_state, dt_rank, d_conv;
   int32_t pool;
   const float* x;
+  float* work;
   float* out;
   fnssl_mamba_weights m[2];
 } fnssl_sn_time_args;
