@@ -41,6 +41,56 @@ ipd_head_kernel(const T* __restrict__ x, int ld, int nb, int nt, int nf, int C, 
   }
 }
 
+// fp16 grids with C % 8 == 0: every lane reads 16 bytes (8 channels) per frame, so a 256-channel position is ONE
+// coalesced 512-byte warp access and the 12 frames of the pooling window are 12 independent loads in flight.
+__global__ void __launch_bounds__(256)
+ipd_head_h8_kernel(const __half* __restrict__ x, int ld, int nb, int nt, int nf, int C, const float* __restrict__ w,
+                   const float* __restrict__ bias, float* __restrict__ out) {
+  const int nt2 = nt / 12;
+  const int64_t total = (int64_t)nb * nt2 * nf;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= total) return;
+  const int f = (int)(warp % nf);
+  const int t2 = (int)((warp / nf) % nt2);
+  const int b = (int)(warp / ((int64_t)nf * nt2));
+  float a0 = 0.0f, a1 = 0.0f;
+  for (int c8 = lane; c8 * 8 < C; c8 += 32) {
+    uint4 v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      v[k] = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)b * nt + t2 * 12 + k) * nf + f) * ld + c8 * 8));
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[k]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 p = __half22float2(h[i]);
+        s[2 * i] += p.x; s[2 * i + 1] += p.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float m = s[i] * (1.0f / 12.0f);
+      a0 = fmaf(m, __ldg(w + c8 * 8 + i), a0);
+      a1 = fmaf(m, __ldg(w + C + c8 * 8 + i), a1);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  if (lane == 0) {
+    float* o = out + ((int64_t)b * nt2 + t2) * (2 * nf);
+    o[f] = tanhf(a0 + bias[0]);
+    o[nf + f] = tanhf(a1 + bias[1]);
+  }
+}
+
 // y[r][o] = b[o] + sum_k x[r][k] w[o][k]; one CTA per row, x row staged in shared memory
 __global__ void __launch_bounds__(256)
 linear_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, int in_f,
@@ -75,6 +125,8 @@ int fnssl_ipd_head_forward(const void* x, int dtype, int ld, int nb, int nt, int
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FNSSL_F32)
     ipd_head_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, ld, nb, nt, nf, C, w, b, out);
+  else if (dtype == FNSSL_F16 && C % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+    ipd_head_h8_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, ld, nb, nt, nf, C, w, b, out);
   else if (dtype == FNSSL_F16)
     ipd_head_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, ld, nb, nt, nf, C, w, b, out);
   else

@@ -291,6 +291,24 @@ def test_causcnn_tensor_core_path(monkeypatch, cin0, cin1):
 # end to end at BASELINE sizes (4 s @ 16 kHz): oracle on a small batch + size-independent properties
 # ---------------------------------------------------------------------------------------------
 
+@pytest.mark.parametrize("dtype,C,ld", [(torch.float16, 256, 256), (torch.float16, 264, 272), (torch.float16, 20, 32),
+                                         (torch.float32, 256, 256)])
+def test_ipd_head_kernels(dtype, C, ld):
+    """AvgPool(12) -> Linear(C, 2) -> tanh -> [ch0 | ch1] (Model.py:79-87): the 16-byte-per-lane fp16 kernel (C % 8 == 0),
+    the generic fp16 kernel and the fp32 kernel against the same arithmetic in torch on the dtype-rounded grid."""
+    from fn_ssl_b200 import ops
+    nb, nt, nf = 2, 38, 40                                                    # 38 frames -> 3 pooled frames, 2 dropped
+    g = torch.zeros((nb, nt, nf, ld), dtype=dtype, device=DEV)
+    g[..., :C] = _randn((nb, nt, nf, C), 3).to(DEV).to(dtype)
+    w, b = _randn((2, C), 4).to(DEV) * 0.2, _randn((2,), 5).to(DEV)
+    out = ops.ipd_head(g, C, w, b)
+    x = g[..., :C].float().cpu()[:, :36].reshape(nb, 3, 12, nf, C).mean(2)
+    y = torch.tanh(x @ w.cpu().t() + b.cpu())                                 # (nb, 3, nf, 2)
+    ref = torch.cat((y[..., 0], y[..., 1]), dim=-1)
+    assert out.shape == ref.shape == (nb, 3, 2 * nf)
+    assert _relerr(out, ref) <= 2e-5
+
+
 @pytest.mark.parametrize("online", [True, False])
 def test_fnssl_end_to_end_4s(online):
     import fn_ssl_b200 as F
