@@ -185,15 +185,20 @@ class SpatialNetLayer(nn.Module):
         self._packed = (key, fa, ta, keep)
         return fa, ta, keep
 
-    def _run(self, x: Tensor, nb: int, nt: int, encoder: Optional[CausalConv1d], pool: int) -> Tensor:
-        """x: feature grid (nb, nt, 256, ld) [first layer] or activation (nb, nt, 16, H); returns (nb, nt // pool, 16, H)."""
+    def _run(self, x: Tensor, nb: int, nt: int, encoder: Optional[CausalConv1d], pool: int, t_begin: int = 0,
+             state: Optional[Tuple[Tensor, Tensor]] = None) -> Tensor:
+        """x: feature grid (nb, nt, 256, ld) [first layer] or activation (nb, nt, 16, H); returns (nb, (nt - t_begin) // pool,
+        16, H).  t_begin (first layer): leading frames that are only history of the causal encoder.  state: the two Mamba
+        blocks' carried (nb*16, 19, 192) f32 buffers, read and updated in place (streaming)."""
         ops._need_cuda(x)
         lib = _lib.load()
         H = self.dim_hidden
         fa, ta, _ = self._pack(encoder, x.shape[-1] if self.is_first else 0)
         nf_in = x.shape[2]
+        fa.nb, fa.nt, fa.nf, fa.x, fa.t_begin = nb, nt, nf_in, x.data_ptr(), t_begin
+        nt = nt - t_begin
         y = torch.empty((nb, nt, 16, H), dtype=torch.float32, device=x.device)
-        fa.nb, fa.nt, fa.nf, fa.x, fa.out = nb, nt, nf_in, x.data_ptr(), y.data_ptr()
+        fa.out = y.data_ptr()
         ops._count(1)
         flops, nbytes = freq_stage_work(nb * nt, nf_in, x.shape[-1] if self.is_first else 0, self.is_first)
         ops.profiled("sn_freq_first" if self.is_first else "sn_freq", flops, nbytes,
@@ -201,6 +206,13 @@ class SpatialNetLayer(nn.Module):
         z = torch.empty((nb, nt // pool, 16, H), dtype=torch.float32, device=x.device)
         work = torch.empty_like(y)
         ta.nb, ta.nt, ta.nf, ta.pool, ta.x, ta.work, ta.out = nb, nt, 16, pool, y.data_ptr(), work.data_ptr(), z.data_ptr()
+        if state is not None:
+            for st in state:
+                if st.shape != (nb * 16, 19, 192) or st.dtype != torch.float32 or not st.is_contiguous() or st.device != x.device:
+                    raise RuntimeError("SpatialNetLayer: Mamba state must be a contiguous float32 (nb*16, 19, 192) tensor on the device")
+            ta.state[0], ta.state[1], ta.state_flags = state[0].data_ptr(), state[1].data_ptr(), 3
+        else:
+            ta.state[0], ta.state[1], ta.state_flags = None, None, 0
         ops._count(2)
         flops, nbytes = time_stage_work(nb * 16, nt, pool)
         ops.profiled("sn_time_T%d" % nt, flops, nbytes,
@@ -259,20 +271,23 @@ class OnlineSpatialNet(nn.Module):
             self._head = (key, ws)
         return self._head[1]
 
-    def forward_grid(self, g0: Tensor) -> Tensor:
-        """g0: feature grid (B, T, 256, ld) f32, ld = dim_input rounded up to 4 (zero padded)."""
+    def forward_grid(self, g0: Tensor, t_begin: int = 0, states=None) -> Tensor:
+        """g0: feature grid (B, T, 256, ld) f32, ld = dim_input rounded up to 4 (zero padded).
+        Streaming (fn_ssl_b200.IPDnet2.IPDnet2Stream): frames [0, t_begin) are encoder history, `states` holds one pair of
+        Mamba state buffers per layer."""
         _require_eval(self)
         ops._need_cuda(g0)
         B, T, F, ld = g0.shape
         if F != 256 or g0.dtype != torch.float32 or ld < self.dim_input or ld % 4:
             raise RuntimeError(f"OnlineSpatialNet: expected an f32 feature grid (B, T, 256, ld>={self.dim_input}), got {tuple(g0.shape)}")
         r = self.time_compression_ratio
-        if T < r:
+        if T - t_begin < r:
             raise RuntimeError(f"OnlineSpatialNet: needs at least {r} frames")
-        x = self.layers[0]._run(g0.contiguous(), B, T, self.encoder, r)
-        T5 = T // r
-        for layer in list(self.layers)[1:]:
-            x = layer._run(x, B, T5, None, 1)
+        st = states if states is not None else [None] * len(self.layers)
+        x = self.layers[0]._run(g0.contiguous(), B, T, self.encoder, r, t_begin=t_begin, state=st[0])
+        T5 = (T - t_begin) // r
+        for i, layer in enumerate(list(self.layers)[1:]):
+            x = layer._run(x, B, T5, None, 1, state=st[i + 1])
         tw, tb, dw, db = self._head_weights()
         K2 = self.dim_output // (2 * self.n_src)
         out = torch.empty((B, T5, 2 * F, K2, self.n_src), dtype=torch.float32, device=g0.device)
@@ -340,3 +355,81 @@ class IPDnet2Pipeline(nn.Module):
         spec, magsum = stft_center(signal, want_magsum=True)
         g0, _, _ = ops.features(spec, magsum, 'ALL', ops.NORM_FORGETTING, self.sample_length, self.eps, torch.float32)
         return self.arch.forward_grid(g0)
+
+
+class IPDnet2Stream:
+    """Chunked (streaming) inference for OnlineSpatialNet -- the model is causal by construction (causal encoder, Mamba
+    scans, per-frame frequency modules), so the whole-clip numbers are reproduced chunk by chunk with this state carried:
+
+      * the sample overlap of the center=True STFT (512/320; the left reflect padding is built once from samples 1..256)
+      * the forgetting-norm recursion mu_{t-1} and the absolute frame index        (utils_.py, sample_length 249)
+      * the last 4 feature frames (history of the kernel-5 causal encoder)         (IPDnet2.py:66-76)
+      * per layer and Mamba block: the selective-scan state and the depthwise conv's last 3 frames
+        (what mamba_ssm keeps in InferenceParams, IPDnet2.py:170-177)
+
+    Chunks are cut at multiples of 5 frames (the time pooling after layer 0); `push` accepts any number of samples and
+    returns the newly completed output frames.  A frame is emitted once its whole 512-sample window has arrived, so the
+    last frame(s) of a finite clip -- which the whole-clip STFT completes with right reflect padding -- are never emitted.
+
+        stream = IPDnet2Stream(arch, nb=4)
+        out = stream.push(block)          # None, or (nb, k, 512, M-1, 2) for the k newly completed output frames
+    """
+
+    def __init__(self, arch: OnlineSpatialNet, nb: int, eps: float = 1e-6, sample_length: int = 249,
+                 device: Optional[torch.device] = None):
+        if arch.training:
+            raise RuntimeError("IPDnet2Stream: call arch.eval() first")
+        self.arch, self.nb, self.nch = arch, nb, arch.dim_input // 2
+        self.eps, self.sample_length = eps, sample_length
+        self.device = torch.device(device) if device is not None else next(arch.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("IPDnet2Stream: the model must live on a CUDA device (there is no CPU path)")
+        self.reset()
+
+    def reset(self) -> None:
+        dev = self.device
+        self.frames_done = 0
+        self._started = False
+        self._pending = torch.empty((self.nb, 0, self.nch), dtype=torch.float32, device=dev)
+        self._mu = torch.zeros((self.nb,), dtype=torch.float32, device=dev)
+        self._hist = None
+        self._states = [(torch.zeros((self.nb * 16, 19, 192), dtype=torch.float32, device=dev),
+                         torch.zeros((self.nb * 16, 19, 192), dtype=torch.float32, device=dev)) for _ in self.arch.layers]
+
+    @property
+    def pending_samples(self) -> int:
+        return self._pending.shape[1]
+
+    @torch.no_grad()
+    def push(self, samples: Tensor) -> Optional[Tensor]:
+        if samples.dim() != 3 or samples.shape[0] != self.nb or samples.shape[2] != self.nch:
+            raise RuntimeError(f"IPDnet2Stream.push: expected ({self.nb}, n, {self.nch}), got {tuple(samples.shape)}")
+        if samples.device != self.device:
+            raise RuntimeError("IPDnet2Stream.push: samples must be on the stream's CUDA device")
+        buf = torch.cat((self._pending, samples.float()), dim=1) if self._pending.shape[1] else samples.float()
+        pad = IPDNET2_WIN // 2
+        if not self._started:
+            if buf.shape[1] <= pad:
+                self._pending = buf.contiguous()
+                return None
+            buf = torch.cat((buf[:, 1:pad + 1].flip(1), buf), dim=1)      # torch.stft(center=True)'s left reflect padding
+            self._started = True
+        n = buf.shape[1]
+        frames = (n - IPDNET2_WIN) // IPDNET2_HOP + 1 if n >= IPDNET2_WIN else 0
+        r = self.arch.time_compression_ratio
+        k = frames // r * r
+        if k == 0:
+            self._pending = buf.contiguous()
+            return None
+        used = buf[:, :IPDNET2_HOP * (k - 1) + IPDNET2_WIN].contiguous()
+        self._pending = buf[:, IPDNET2_HOP * k:].contiguous()
+        spec, magsum = ops.stft(used, IPDNET2_WIN, IPDNET2_HOP, IPDNET2_WIN, want_magsum=True)
+        mu = ops.norm_stream(magsum, 'ALL', self.sample_length, self.frames_done, self._mu)
+        g, _, _ = ops.features(spec, None, 'ALL', ops.NORM_GIVEN, self.sample_length, self.eps, torch.float32, mu=mu)
+        if self._hist is None:        # zero history == the causal encoder's zero padding at the start of a clip
+            self._hist = torch.zeros((self.nb, 4, g.shape[2], g.shape[3]), dtype=torch.float32, device=self.device)
+        gh = torch.cat((self._hist, g), dim=1)
+        self._hist = gh[:, -4:].contiguous()
+        out = self.arch.forward_grid(gh, t_begin=4, states=self._states)
+        self.frames_done += k
+        return out

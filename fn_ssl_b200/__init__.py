@@ -10,7 +10,7 @@ All arithmetic runs in libfnssl_b200.so (hand-written CUDA, C ABI in include/fns
 """
 from . import config  # noqa: F401
 from .FixedAarryIPDnet import CausalConv1dBlock, CausCnnBlock, FixedArrayIPDnet, IPDnet  # noqa: F401
-from .IPDnet2 import IPDnet2_lightning, IPDnet2Pipeline, OnlineSpatialNet, SpatialNetLayer, data_preprocess_ipdnet2  # noqa: F401
+from .IPDnet2 import IPDnet2_lightning, IPDnet2Pipeline, IPDnet2Stream, OnlineSpatialNet, SpatialNetLayer, data_preprocess_ipdnet2  # noqa: F401
 from .Model import FN_SSL, FN_lightning, FNblock, FullNarrowBlock  # noqa: F401
 from .Module import (DPIPD, STFT, AddChToBatch, RemoveChFromBatch, SourceDetectLocalize, forgetting_norm,  # noqa: F401
                      pred_ipd_to_doa)

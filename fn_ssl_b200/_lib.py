@@ -54,6 +54,7 @@ class SnFreqArgs(C.Structure):
         ("usq_w", _fp), ("usq_b", _fp),
         ("fconv2", SnFconvWeights),
         ("out", _fp),
+        ("t_begin", C.c_int32),
     ]
 
 
@@ -71,6 +72,7 @@ class SnTimeArgs(C.Structure):
         ("pool", C.c_int32),
         ("x", _fp), ("work", _fp), ("out", _fp),
         ("m", MambaWeights * 2),
+        ("state", _fp * 2), ("state_flags", C.c_int32),
     ]
 
 

@@ -253,7 +253,7 @@ sn_freq_kernel(const fnssl_sn_freq_args a) {
   float* W = smem + 2 * kRows * kH;
   const int tid = threadIdx.x;
   if constexpr (LD > 0) {
-    const int b = blockIdx.y, t = blockIdx.x;
+    const int b = blockIdx.y, t = blockIdx.x + a.t_begin;     // frames [0, t_begin) are history for the causal encoder only
     encoder<LD>(a, b, t, X, Y, tid);
     fconv(X, Y, a.fconv1, 256, 256, tid);
     // ---- AvgPool over pairs of bins (:148): 256 rows of X -> 128 rows in the Y region, then swap roles
@@ -266,7 +266,7 @@ sn_freq_kernel(const fnssl_sn_freq_args a) {
     full_band(X2, Y2, W, a, 128, 128, tid);
     fconv(X2, Y2, a.fconv2, 128, 128, tid);
     // ---- AvgPool over 8 bins (:153) and store (b, t, 16, 96)
-    float* out = a.out + ((size_t)b * a.nt + t) * 16 * kH;
+    float* out = a.out + ((size_t)b * (a.nt - a.t_begin) + (t - a.t_begin)) * 16 * kH;
     for (int i = tid; i < 16 * kH; i += kFT) {
       const int fc = i / kH, h = i - fc * kH;
       float s = 0.0f;
@@ -326,7 +326,8 @@ __device__ __forceinline__ void mv(float (&acc)[kTT], const float (&w)[KW], cons
 }
 
 __global__ void __launch_bounds__(kDI, 3)
-sn_time_kernel(const float* __restrict__ x, float* __restrict__ out, int nt, int nf, int pool, const fnssl_mamba_weights w) {
+sn_time_kernel(const float* __restrict__ x, float* __restrict__ out, int nt, int nf, int pool, const fnssl_mamba_weights w,
+               float* __restrict__ state, int state_flags) {
   __shared__ __align__(16) float xs[kTT * kH];            // residual stream of the chunk
   __shared__ __align__(16) float us[kTT * kH];            // LN(x)
   __shared__ __align__(16) float xc[kTT * kDI];           // conv + SiLU output; overwritten with the gated scan output
@@ -340,6 +341,12 @@ sn_time_kernel(const float* __restrict__ x, float* __restrict__ out, int nt, int
 #pragma unroll
   for (int n = 0; n < kNS; ++n) hst[n] = 0.0f;
   float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;                  // causal conv history (raw inner channel of the last 3 frames)
+  float* sp = state ? state + ((size_t)b * nf + f) * (kNS + kDK - 1) * kDI + d : nullptr;   // [seq][16 + 3][192]
+  if (sp && (state_flags & 1)) {                          // a chunk of a longer stream resumes the scan
+#pragma unroll
+    for (int n = 0; n < kNS; ++n) hst[n] = sp[n * kDI];
+    p0 = sp[kNS * kDI]; p1 = sp[(kNS + 1) * kDI]; p2 = sp[(kNS + 2) * kDI];
+  }
   const int nt_out = nt / pool;
   const float lw0 = __ldg(w.ln_w + lane), lw1 = __ldg(w.ln_w + lane + 32), lw2 = __ldg(w.ln_w + lane + 64);
   const float lb0 = __ldg(w.ln_b + lane), lb1 = __ldg(w.ln_b + lane + 32), lb2 = __ldg(w.ln_b + lane + 64);
@@ -501,6 +508,11 @@ sn_time_kernel(const float* __restrict__ x, float* __restrict__ out, int nt, int
     }
     __syncthreads();
   }
+  if (sp && (state_flags & 2)) {
+#pragma unroll
+    for (int n = 0; n < kNS; ++n) sp[n * kDI] = hst[n];
+    sp[kNS * kDI] = p0; sp[(kNS + 1) * kDI] = p1; sp[(kNS + 2) * kDI] = p2;
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -621,7 +633,8 @@ int fnssl_sn_freq_forward(const fnssl_sn_freq_args* a, void* stream) {
     FNSSL_REQUIRE(a->cin > 0 && a->x_ld >= a->cin && a->x_ld % 4 == 0 && a->x_ld <= 16,
                   "sn_freq(first): cin %d / ld %d (ld must be a multiple of 4, <= 16)", a->cin, a->x_ld);
     FNSSL_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & 15) == 0, "sn_freq(first): x must be 16-byte aligned");
-    dim3 grid(a->nt, a->nb);
+    FNSSL_REQUIRE(a->t_begin >= 0 && a->t_begin < a->nt, "sn_freq(first): t_begin %d outside [0, %d)", a->t_begin, a->nt);
+    dim3 grid(a->nt - a->t_begin, a->nb);
 #define FNSSL_SN_FIRST(LD)                                                                                              \
   do {                                                                                                                  \
     FNSSL_CUDA(cudaFuncSetAttribute(sn::sn_freq_kernel<LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
@@ -655,9 +668,12 @@ int fnssl_sn_time_forward(const fnssl_sn_time_args* a, void* stream) {
                   w.A_log && w.D && w.out_proj_wt, "sn_time: null weight pointer (mamba %d)", m);
   }
   dim3 grid(a->nf, a->nb);
-  sn::sn_time_kernel<<<grid, sn::kDI, 0, (cudaStream_t)stream>>>(a->x, a->work, a->nt, a->nf, 1, a->m[0]);
+  FNSSL_REQUIRE((a->state_flags & ~3) == 0 && (!a->state_flags || (a->state[0] && a->state[1])),
+                "sn_time: bad state_flags %d / null state", a->state_flags);
+  sn::sn_time_kernel<<<grid, sn::kDI, 0, (cudaStream_t)stream>>>(a->x, a->work, a->nt, a->nf, 1, a->m[0], a->state[0], a->state_flags);
   FNSSL_LAUNCH_CHECK("sn_time_kernel");
-  sn::sn_time_kernel<<<grid, sn::kDI, 0, (cudaStream_t)stream>>>(a->work, a->out, a->nt, a->nf, a->pool, a->m[1]);
+  sn::sn_time_kernel<<<grid, sn::kDI, 0, (cudaStream_t)stream>>>(a->work, a->out, a->nt, a->nf, a->pool, a->m[1], a->state[1],
+                                                              a->state_flags);
   FNSSL_LAUNCH_CHECK("sn_time_kernel");
   return 0;
 }

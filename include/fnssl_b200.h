@@ -228,6 +228,8 @@ typedef struct fnssl_sn_freq_args {
   const float* usq_b;
   fnssl_sn_fconv_weights fconv2;
   float* out;
+  int32_t t_begin;       /* is_first only: frames [0, t_begin) of x are history for the causal encoder (streaming); outputs
+                            are produced for frames [t_begin, nt): out is (nb, nt - t_begin, 16, H).  0 = whole clip.     */
 } fnssl_sn_freq_args;
 int fnssl_sn_freq_forward(const fnssl_sn_freq_args* args, void* stream);
 
@@ -256,6 +258,11 @@ typedef struct fnssl_sn_time_args {
   float* work;
   float* out;
   fnssl_mamba_weights m[2];
+  /* Optional carried state for chunked (streaming) inference, one buffer per Mamba block: (nb * nf, d_state + d_conv - 1,
+   * d_inner) f32 = the selective-scan state and the last d_conv - 1 raw inner-channel frames of the causal conv (what
+   * mamba_ssm keeps in InferenceParams, IPDnet2.py:170-177).  state_flags bit 0: resume from it; bit 1: write it back. */
+  float* state[2];
+  int32_t state_flags;
 } fnssl_sn_time_args;
 int fnssl_sn_time_forward(const fnssl_sn_time_args* args, void* stream);
 

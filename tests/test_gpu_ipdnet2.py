@@ -125,3 +125,31 @@ def test_causality_of_the_online_network():
     x2[..., 40:] += 1.0
     y, y2 = net(x), net(x2)
     assert torch.equal(y[:, :8], y2[:, :8]) and not torch.equal(y[:, 8:], y2[:, 8:])
+
+
+@pytest.mark.parametrize("pieces", [[3000, 5000, 157, 9000, 12000], [31000], [200, 100, 2000, 30000]])
+def test_stream_equals_whole_clip(pieces):
+    """IPDnet2Stream: feeding a clip in ragged pieces reproduces the whole-clip output bit for bit on every output frame
+    whose five 512-sample windows lie inside the received samples (carried: STFT overlap + left reflect pad, forgetting
+    norm, 4 encoder history frames, scan state and conv history of all Mamba blocks)."""
+    import fn_ssl_b200 as F
+    net, sd = _net(dict(dim_input=6, dim_output=8, num_layers=3), 17)
+    n = sum(pieces)
+    sig = _randn((2, n, 3), 18).to(DEV)
+    whole = F.IPDnet2Pipeline(net)(sig)
+    st = F.IPDnet2Stream(net, nb=2)
+    outs, pos = [], 0
+    for p in pieces:
+        o = st.push(sig[:, pos:pos + p])
+        pos += p
+        if o is not None:
+            outs.append(o)
+    got = torch.cat(outs, dim=1)
+    frames = (n + 256 - 512) // 320 + 1                     # frames whose window ends inside the clip
+    assert got.shape[1] == frames // 5 and got.shape[1] >= whole.shape[1] - 1
+    assert torch.equal(got, whole[:, :got.shape[1]])
+    assert _relerr(got, orc2.ipdnet2_forward(orc2.preprocess_ipdnet2(sig.cpu()), sd)[:, :got.shape[1]]) <= 5e-5
+    st.reset()
+    again = st.push(sig[:, :pieces[0]])
+    first = outs[0] if pieces[0] >= 2000 else None
+    assert (again is None and first is None) or torch.equal(again, first)
