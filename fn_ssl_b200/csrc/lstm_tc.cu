@@ -395,6 +395,44 @@ int make_grid_map(CUtensorMap* m, const void* base, int c, int ld, int nb, int n
   return make_map4(m, base, dims, str, box);
 }
 
+int make_small_grid_map(CUtensorMap* m, const void* base, int c, int ld, int nb, int nt, int nf, int axis, int mr) {
+  auto enc = get_encode();
+  FNSSL_REQUIRE(enc, "lstm(tcgen05): cuTensorMapEncodeTiled is unavailable in this driver");
+  FNSSL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld % 8) == 0 && c <= 16,
+                "lstm(tcgen05): small-source grid base / channel stride not 16-byte aligned or wider than 16 channels");
+  uint64_t dims[4], str[3];
+  uint32_t box[4];
+  if (axis == FNSSL_ALONG_FREQ) {
+    dims[0] = (uint64_t)c; dims[1] = (uint64_t)nf; dims[2] = (uint64_t)nb * nt; dims[3] = 1;
+    str[0] = (uint64_t)ld * 2; str[1] = (uint64_t)nf * ld * 2; str[2] = (uint64_t)nb * nt * nf * ld * 2;
+    box[0] = 16; box[1] = 1; box[2] = (uint32_t)mr; box[3] = 1;
+  } else {
+    dims[0] = (uint64_t)c; dims[1] = (uint64_t)nf; dims[2] = (uint64_t)nt; dims[3] = (uint64_t)nb;
+    str[0] = (uint64_t)ld * 2; str[1] = (uint64_t)nf * ld * 2; str[2] = (uint64_t)nt * nf * ld * 2;
+    box[0] = 16; box[1] = (uint32_t)mr; box[2] = 1; box[3] = 1;
+  }
+  const uint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, str, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FNSSL_REQUIRE(r == CUDA_SUCCESS, "lstm(tcgen05): small-source tensor map failed (%d)", (int)r);
+  return 0;
+}
+
+int make_small_weight_map(CUtensorMap* m, const void* weights, int nslabs, int nchunks_total) {
+  auto enc = get_encode();
+  FNSSL_REQUIRE(enc, "lstm(tcgen05): cuTensorMapEncodeTiled is unavailable in this driver");
+  const uint64_t dims[2] = {(uint64_t)nslabs * kSlabK, (uint64_t)nchunks_total * kChunkN};
+  const uint64_t str[1] = {(uint64_t)nslabs * kSlabK * 2};
+  const uint32_t box[2] = {16, kChunkN};
+  const uint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(weights), dims, str, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FNSSL_REQUIRE(r == CUDA_SUCCESS, "lstm(tcgen05): small weight tensor map failed (%d)", (int)r);
+  return 0;
+}
+
 int make_out_map(CUtensorMap* m, const void* base, int ld, int nb, int nt, int nf, int axis, int rows) {
   auto enc = get_encode();
   FNSSL_REQUIRE(enc, "lstm(tcgen05): cuTensorMapEncodeTiled is unavailable in this driver");

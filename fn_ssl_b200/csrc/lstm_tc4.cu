@@ -39,7 +39,9 @@ constexpr int kMaxXSlabs = 6;
 constexpr int kMaxXStages = 6;
 constexpr int kAccBufs = 3;
 constexpr int kSmemLimit = 232448;
-constexpr int kNumBars = 1 + 2 * kMaxXStages + 3 * kAccBufs + 4;
+constexpr int kNumBarsBase = 1 + 2 * kMaxXStages + 3 * kAccBufs + 4;
+constexpr int kNumBars = kNumBarsBase + 4;     // + X2_FULL / X2_EMPTY of the two-entry ring of the narrow second source
+constexpr int kWSmall = kChunkN * 32;          // [128 gate columns x 16] fp16 weight slab of a narrow source (32B swizzle)
 
 struct Params {
   int nxs;
@@ -94,15 +96,18 @@ __device__ __forceinline__ float lstm_cell_tanh(float gi, float gf, float gg, fl
   return so * tanh_approx(cn);
 }
 
-template <int H, int SUB, bool TRACE>
+// NARROW: the second source is <= 16 channels wide -- its x slabs travel through a two-entry ring of their own (32B swizzle,
+// 4 KB weight slab) and every CTA fetches its own x slabs (no multicast, local "slot empty" hand-shake); see make_plan.
+template <int H, int SUB, bool TRACE, bool NARROW>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_constant__ CUtensorMap map_src1,
-                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out0,
-                const __grid_constant__ CUtensorMap map_out1, const Params p) {
+                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w2,
+                const __grid_constant__ CUtensorMap map_out0, const __grid_constant__ CUtensorMap map_out1, const Params p) {
   constexpr int C = H / kChunkUnits;      // cluster size == number of 32-unit chunks
   constexpr int NHS = H / kSlabK;         // K slabs of h in the weight layout
   constexpr int kXSlab = SUB * 128;       // one [SUB x 64] fp16 x slab (128B swizzle)
   constexpr int kHTile = SUB * 64;        // one [SUB x 32] fp16 h tile (one chunk, 64B swizzle)
+  constexpr int kXSmall = SUB * 32;       // one [SUB x 16] fp16 x slab of a narrow second source (32B swizzle)
   constexpr int kTileRows = 2 * SUB;      // rows of a cluster tile (two sub-tiles)
   constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kChunkN >> 3) << 17) | ((uint32_t)(SUB >> 4) << 24);
   static_assert(H == 64 || H == 128 || H == 256, "H in {64,128,256}");
@@ -118,14 +123,17 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   const int tile = blockIdx.x / C;
   const uint16_t mask = (uint16_t)((1u << C) - 1u);
   const int nxs = p.nxs, XS = p.xstages, L = p.steps;
-  const int nslabs = nxs + NHS;
+  constexpr bool small1 = NARROW, nomc = NARROW;
+  const int nxb = small1 ? nxs - 1 : nxs;                           // x slabs that travel through the big ring
   const int nslots = 2 * L;
 
   const uint32_t dyn0 = (smem_addr(smem_dyn) + 1023u) & ~1023u;
-  const uint32_t w_base = dyn0;                                     // resident weights: nslabs tiles
-  const uint32_t hs_base = w_base + (uint32_t)nslabs * kWSlab;      // h operand: [sub][chunk] tiles (single buffer)
+  const uint32_t w_base = dyn0;                                     // resident weights: nxb x slabs, then NHS h slabs
+  const uint32_t w2_base = w_base + (uint32_t)(nxb + NHS) * kWSlab; // [128 x 16] slab of the narrow second source
+  const uint32_t hs_base = w2_base + (small1 ? (uint32_t)kWSmall : 0u);   // h operand: [sub][chunk] tiles (single buffer)
   const uint32_t xr_base = hs_base + 2u * C * kHTile;               // x ring: XS slabs
-  const uint32_t bias_base = xr_base + (uint32_t)XS * kXSlab;       // 128 floats
+  const uint32_t x2_base = xr_base + (uint32_t)XS * kXSlab;         // narrow-source ring: 2 slabs of kXSmall
+  const uint32_t bias_base = x2_base + (small1 ? 2u * kXSmall : 0u);   // 128 floats
   float* bias_s = reinterpret_cast<float*>(smem_dyn + (bias_base - smem_addr(smem_dyn)));
 
   const uint32_t bar0 = smem_addr(bars);
@@ -137,18 +145,22 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   auto H_FULL = [&](int sub) { return bar0 + 8u * (1 + 2 * kMaxXStages + 2 * kAccBufs + sub); };
   auto H_FREE = [&](int sub) { return bar0 + 8u * (1 + 2 * kMaxXStages + 2 * kAccBufs + 2 + sub); };
   auto XP_DONE = [&](int i) { return bar0 + 8u * (1 + 2 * kMaxXStages + 2 * kAccBufs + 4 + i); };
+  auto X2_FULL = [&](int i) { return bar0 + 8u * (kNumBarsBase + i); };
+  auto X2_EMPTY = [&](int i) { return bar0 + 8u * (kNumBarsBase + 2 + i); };
 
   if (tid == 0) {
     mbar_init(W_FULL, 1);
-    for (int i = 0; i < kMaxXStages; ++i) { mbar_init(X_FULL(i), 1); mbar_init(X_EMPTY(i), C); }
+    const int xe = nomc ? 1 : C;
+    for (int i = 0; i < kMaxXStages; ++i) { mbar_init(X_FULL(i), 1); mbar_init(X_EMPTY(i), xe); }
     for (int i = 0; i < kAccBufs; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), kEpiThreads); mbar_init(XP_DONE(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(X2_FULL(i), 1); mbar_init(X2_EMPTY(i), xe); }
     for (int sub = 0; sub < 2; ++sub) {
       mbar_init(H_FULL(sub), 5);    // MMA thread's expect_tx + 4 local quadrants (+ tx bytes of the C-1 remote tiles)
       mbar_init(H_FREE(sub), C);    // one multicast commit per CTA of the cluster
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0 && lane == 0) { prefetch_tmap(&map_src0); prefetch_tmap(&map_src1); prefetch_tmap(&map_w); }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&map_src0); prefetch_tmap(&map_src1); prefetch_tmap(&map_w); prefetch_tmap(&map_w2); }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -209,9 +221,12 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (elect_one()) {
-      mbar_expect_tx(W_FULL, (uint32_t)nslabs * kWSlab);
-      for (int j = 0; j < nslabs; ++j)
+      mbar_expect_tx(W_FULL, (uint32_t)(nxb + NHS) * kWSlab + (small1 ? (uint32_t)kWSmall : 0u));
+      for (int j = 0; j < nxb; ++j)
         tma_load_2d(w_base + j * kWSlab, &map_w, W_FULL, j * kSlabK, (dir * C + (int)rank) * kChunkN);
+      for (int j = 0; j < NHS; ++j)     // the h slabs follow ALL x slabs in the packed buffer
+        tma_load_2d(w_base + (nxb + j) * kWSlab, &map_w, W_FULL, (nxs + j) * kSlabK, (dir * C + (int)rank) * kChunkN);
+      if (small1) tma_load_2d(w2_base, &map_w2, W_FULL, nxb * kSlabK, (dir * C + (int)rank) * kChunkN);
       int stage = 0, fetcher = 0;
       uint32_t phase = 0;                 // parity of the X_EMPTY wait; the first pass over the ring does not wait
       bool wrapped = false;
@@ -240,10 +255,16 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         const int s = dir ? (L - 1 - t) : t;
         const int r0 = coord_r0 + sub * SUB;
         if (ahead && n + ahead < nslots) prefetch_slot(n + ahead);
-        for (int j = 0; j < nxs; ++j) {
+        for (int j = 0; j < nxb; ++j) {
           if (wrapped) mbar_wait(X_EMPTY(stage), phase, p.error_flag, 100 + stage);
           mbar_expect_tx(X_FULL(stage), kXSlab);
-          if ((uint32_t)fetcher == rank) {   // one CTA fetches the slab for the whole cluster
+          if (nomc) {
+            const CUtensorMap* m = ((p.xs_srcmask >> j) & 1) ? &map_src1 : &map_src0;
+            const uint32_t dst = xr_base + (uint32_t)stage * kXSlab;
+            const int k0 = (int)((p.xs_k0pack >> (8 * j)) & 0xff) * 16;
+            if (along_f) tma_load_4d(dst, m, X_FULL(stage), k0, s, r0, 0);
+            else tma_load_4d(dst, m, X_FULL(stage), k0, r0, s, coord_b);
+          } else if ((uint32_t)fetcher == rank) {   // one CTA fetches the slab for the whole cluster
             const CUtensorMap* m = ((p.xs_srcmask >> j) & 1) ? &map_src1 : &map_src0;
             const uint32_t dst = xr_base + (uint32_t)stage * kXSlab;
             const int k0 = (int)((p.xs_k0pack >> (8 * j)) & 0xff) * 16;
@@ -252,6 +273,21 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           }
           if (++fetcher == C) fetcher = 0;
           if (++stage == XS) { stage = 0; phase ^= wrapped ? 1u : 0u; wrapped = true; }
+        }
+        if (small1) {      // the narrow source's slab of this slot: entry n & 1 of its own ring, use number n >> 1
+          const int s2 = n & 1;
+          if (n >= 2) mbar_wait(X2_EMPTY(s2), (uint32_t)(((n >> 1) - 1) & 1), p.error_flag, 110 + s2);
+          mbar_expect_tx(X2_FULL(s2), kXSmall);
+          if (nomc) {
+            const uint32_t dst = x2_base + (uint32_t)s2 * kXSmall;
+            if (along_f) tma_load_4d(dst, &map_src1, X2_FULL(s2), 0, s, r0, 0);
+            else tma_load_4d(dst, &map_src1, X2_FULL(s2), 0, r0, s, coord_b);
+          } else if ((uint32_t)fetcher == rank) {
+            const uint32_t dst = x2_base + (uint32_t)s2 * kXSmall;
+            if (along_f) tma_load_4d_mc(dst, &map_src1, X2_FULL(s2), 0, s, r0, 0, mask);
+            else tma_load_4d_mc(dst, &map_src1, X2_FULL(s2), 0, r0, s, coord_b, mask);
+          }
+          if (++fetcher == C) fetcher = 0;
         }
       }
     }
@@ -278,7 +314,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         tc_fence_after();
         const uint32_t d_tmem = tmem_acc + (uint32_t)a * kChunkN;
         uint32_t nkp = p.xs_nkpack;
-        for (int j = 0; j < nxs; ++j, nkp >>= 4) {
+        for (int j = 0; j < nxb; ++j, nkp >>= 4) {
           const long long c1 = (TRACE && tp) ? clock64() : 0;
           mbar_wait(X_FULL(xstage), xphase, p.error_flag, 210 + xstage);
           if (TRACE && tp) w_acc += clock64() - c1;
@@ -289,8 +325,17 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             if ((uint32_t)k < nk) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (uint32_t)(j | k));
-          umma_commit_mc(X_EMPTY(xstage), mask);    // this CTA is done with the slab: tell every CTA's ring
+          if (nomc) umma_commit(X_EMPTY(xstage));
+          else umma_commit_mc(X_EMPTY(xstage), mask);    // this CTA is done with the slab: tell every CTA's ring
           if (++xstage == XS) { xstage = 0; xphase ^= 1u; }
+        }
+        if (small1) {      // one K = 16 step against the 4 KB weight slab, both operands in the 32B-swizzled layout
+          const int s2 = n & 1;
+          mbar_wait(X2_FULL(s2), (uint32_t)((n >> 1) & 1), p.error_flag, 216 + s2);
+          tc_fence_after();
+          umma_f16(d_tmem, make_sw32_desc(x2_base + (uint32_t)s2 * kXSmall), make_sw32_desc(w2_base), kIdesc, 1u);
+          if (nomc) umma_commit(X2_EMPTY(s2));
+          else umma_commit_mc(X2_EMPTY(s2), mask);
         }
         umma_commit(XP_DONE(a));
         if (TRACE && tp) { tp[9] = clock64(); tp[11] = e_acc; tp[12] = w_acc; }
@@ -303,7 +348,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
     if (elect_one()) {
       mbar_wait(W_FULL, 0, p.error_flag, 230);
       const uint64_t h_desc0 = make_sw64_desc(hs_base);
-      const uint64_t wh_desc0 = make_sw128_desc(w_base + (uint32_t)nxs * kWSlab);
+      const uint64_t wh_desc0 = make_sw128_desc(w_base + (uint32_t)nxb * kWSlab);
       int a = 0;
       uint32_t xp_par = 0;
       for (int n = 0; n < nslots; ++n) {
@@ -654,24 +699,35 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
 // host
 // ------------------------------------------------------------------------------------------------
 
-struct Plan { bool ok; int sub; int xstages; int nxs; size_t smem; };
+struct Plan { bool ok; int sub; int xstages; int nxs; size_t smem; bool small1; };
 
 static Plan make_plan(int H, int c0, int c1) {
-  Plan pl{false, 0, 0, 0, 0};
+  Plan pl{false, 0, 0, 0, 0, false};
   if (H != 64 && H != 128 && H != 256) return pl;
   if (c0 % 16 || c1 % 16 || c0 <= 0) return pl;
   const int nxs = (c0 + 63) / 64 + (c1 + 63) / 64;
   if (nxs > kMaxXSlabs) return pl;
-  const int C = H / kChunkUnits, NHS = H / 64, nslabs = nxs + NHS;
+  const int C = H / kChunkUnits, NHS = H / 64;
+  // A second source of <= 16 channels (the raw-feature skip of the first FN-SSL block and of every IPDnet layer) is one
+  // K = 16 step.  As a full [SUB x 64] slab it would cost a 16 KB weight slab and a whole ring stage per slot -- which leaves
+  // the 272-channel layers 2-3 stages for 5 slabs per slot.  It gets a 4 KB weight slab and a two-entry ring of [SUB x 16]
+  // slabs instead (32B swizzle), so the big ring carries 4 slabs per slot again.
+  // Measured (B200, profiles/r1_lstm_narrow_source_ring.txt): H = 256 layers 4.65 -> 3.2 ms (3 big stages instead of 2), and
+  // 3.0 ms when every CTA also fetches its own x slabs (no multicast: the cluster-wide "slot empty" hand-shake is what a
+  // short ring cannot hide); H = 128 layers are not faster, so the mode (template flag NARROW) is used for H = 256 only.
+  // FNSSL_TC_SMALL1 = 0 / 1 forces it off / on for every H (tests).
+  bool small1 = c1 > 0 && c1 <= 16 && H == 256;
+  if (const char* e = getenv("FNSSL_TC_SMALL1")) small1 = c1 > 0 && c1 <= 16 && atoi(e) != 0;
+  const int nslabs = (small1 ? nxs - 1 : nxs) + NHS;
   int sub_first = 128;
   if (const char* e = getenv("FNSSL_TC_ROWS")) { if (atoi(e) == 64) sub_first = 64; }   // tests / profiling
   for (int sub = sub_first; sub >= 64; sub -= 64) {
     const long xslab = sub * 128L, htile = sub * 64L;
-    const long fixed = (long)nslabs * kWSlab + 2L * C * htile + kChunkN * 4 + 1024;
+    const long fixed = (long)nslabs * kWSlab + (small1 ? kWSmall + 2L * sub * 32 : 0L) + 2L * C * htile + kChunkN * 4 + 1024;
     long xs = (kSmemLimit - 1024 - fixed) / xslab;
     if (xs > kMaxXStages) xs = kMaxXStages;
     if (xs >= 2) {
-      pl.ok = true; pl.sub = sub; pl.xstages = (int)xs; pl.nxs = nxs;
+      pl.ok = true; pl.sub = sub; pl.xstages = (int)xs; pl.nxs = nxs; pl.small1 = small1;
       pl.smem = (size_t)fixed + (size_t)xs * xslab;
       return pl;
     }
@@ -688,7 +744,7 @@ static long long* trace_buffer() {
   return g_trace_dev;
 }
 
-template <int H, int SUB, bool TRACE>
+template <int H, int SUB, bool TRACE, bool NARROW>
 static int launch_t(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
   constexpr int C = H / kChunkUnits, NHS = H / kSlabK;
   constexpr int kTileRows = 2 * SUB;
@@ -743,11 +799,14 @@ static int launch_t(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
   if (const char* e = getenv("FNSSL_TC_DEBUG")) p.debug = atoi(e);
   if (getenv("FNSSL_TC_TRACE")) p.trace = trace_buffer();
 
-  CUtensorMap m0, m1, mw;
+  CUtensorMap m0, m1, mw, mw2;
   if (make_grid_map(&m0, a->src0, a->c0, a->ld0, a->nb, a->nt, a->nf, a->axis, SUB)) return 1;
-  if (a->c1 > 0) { if (make_grid_map(&m1, a->src1, a->c1, a->ld1, a->nb, a->nt, a->nf, a->axis, SUB)) return 1; }
+  if (pl.small1) { if (make_small_grid_map(&m1, a->src1, a->c1, a->ld1, a->nb, a->nt, a->nf, a->axis, SUB)) return 1; }
+  else if (a->c1 > 0) { if (make_grid_map(&m1, a->src1, a->c1, a->ld1, a->nb, a->nt, a->nf, a->axis, SUB)) return 1; }
   else m1 = m0;
   if (make_weight_map(&mw, a->weights, nslabs, a->num_dirs * C)) return 1;
+  mw2 = mw;
+  if (pl.small1 && make_small_weight_map(&mw2, a->weights, nslabs, a->num_dirs * C)) return 1;
   // outputs through TMA: out0 as tile stores, out1 as an in-place reduce-add when it aliases the residual operand
   CUtensorMap mo0 = m0, mo1 = m0;
   const bool no_tma_out = getenv("FNSSL_TC_NO_TMA_OUT") != nullptr;
@@ -760,7 +819,7 @@ static int launch_t(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
     p.tma_out |= 2;
   }
 
-  auto kern = lstm_tc4_kernel<H, SUB, TRACE>;
+  auto kern = lstm_tc4_kernel<H, SUB, TRACE, NARROW>;
   FNSSL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)tiles * C, (unsigned)a->num_dirs, 1);
@@ -771,14 +830,15 @@ static int launch_t(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  FNSSL_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, mw, mo0, mo1, p));
+  FNSSL_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, mw, mw2, mo0, mo1, p));
   FNSSL_LAUNCH_CHECK("lstm_tc4_kernel");
   return 0;
 }
 
 template <int H, int SUB>
 static int launch(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
-  return getenv("FNSSL_TC_TRACE") ? launch_t<H, SUB, true>(a, pl, st) : launch_t<H, SUB, false>(a, pl, st);
+  if (pl.small1) return getenv("FNSSL_TC_TRACE") ? launch_t<H, SUB, true, true>(a, pl, st) : launch_t<H, SUB, false, true>(a, pl, st);
+  return getenv("FNSSL_TC_TRACE") ? launch_t<H, SUB, true, false>(a, pl, st) : launch_t<H, SUB, false, false>(a, pl, st);
 }
 
 }  // namespace tc4

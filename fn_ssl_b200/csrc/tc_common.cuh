@@ -159,6 +159,15 @@ __device__ __forceinline__ uint64_t make_sw64_desc(uint32_t saddr) {
   d |= (uint64_t)4 << 61;   // UMMA::LayoutType::SWIZZLE_64B
   return d;
 }
+// K-major, 32B-swizzled operand tile (rows of 32 B = one K=16 step of fp16; 8-row groups of 256 B)
+__device__ __forceinline__ uint64_t make_sw32_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;   // UMMA::LayoutType::SWIZZLE_32B
+  return d;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t saddr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -206,6 +215,9 @@ int make_grid_map(CUtensorMap* m, const void* base, int c, int ld, int nb, int n
 // output grid map: box = [rows x 32 channels] in the 64B-swizzled layout of an h tile (TMA stores out of the exchange tiles)
 int make_out_map(CUtensorMap* m, const void* base, int ld, int nb, int nt, int nf, int axis, int rows);
 int make_weight_map(CUtensorMap* m, const void* weights, int nslabs, int nchunks_total);
+// 16-channel (one K=16 step) variants in the 32B-swizzled layout: the narrow second source of a two-source layer
+int make_small_grid_map(CUtensorMap* m, const void* base, int c, int ld, int nb, int nt, int nf, int axis, int mr);
+int make_small_weight_map(CUtensorMap* m, const void* weights, int nslabs, int nchunks_total);
 int* tc_error_flag();
 
 // ---- thread-block cluster helpers ------------------------------------------------------------------

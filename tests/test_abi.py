@@ -48,6 +48,24 @@ def test_host_only_entry_points():
     assert b"axis" in lib.fnssl_last_error()
 
 
+def test_ipdnet2_entry_points_validate_before_any_cuda_call():
+    import ctypes
+    from fn_ssl_b200 import _lib
+    lib = _lib.load()
+    assert lib.fnssl_reflect_pad(None, 1, 100, 2, 256, None, None) != 0
+    fa = _lib.SnFreqArgs()
+    assert lib.fnssl_sn_freq_forward(ctypes.byref(fa), None) != 0 and b"null" in lib.fnssl_last_error()
+    fa.x, fa.out = 16, 16                                   # non-null dummies: the shape checks come first
+    fa.hidden, fa.squeeze, fa.groups, fa.fkernel = 192, 8, 8, 5
+    assert lib.fnssl_sn_freq_forward(ctypes.byref(fa), None) != 0 and b"dim_hidden 96" in lib.fnssl_last_error()
+    ta = _lib.SnTimeArgs()
+    ta.x, ta.out, ta.work = 16, 16, 16
+    ta.hidden, ta.d_inner, ta.d_state, ta.dt_rank, ta.d_conv = 96, 192, 16, 6, 3
+    assert lib.fnssl_sn_time_forward(ctypes.byref(ta), None) != 0 and b"Mamba" in lib.fnssl_last_error()
+    assert lib.fnssl_sn_head_forward(16, 1, 1, 16, 96, 16, 16, 16, 16, 30, 16, 2, 16, None) != 0    # 30 is not 2*n_src*pairs
+    assert b"dim_output" in lib.fnssl_last_error()
+
+
 def test_state_dict_surface_matches_reference(golden_fnssl):
     import fn_ssl_b200 as F
     from oracle import fnssl_oracle as orc

@@ -193,6 +193,22 @@ def test_lstm_layer_tcgen05(monkeypatch, kernel, rows, axis, H, bidir, c0, c1, a
         assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, H, bidir, addend, inplace=True) <= 1e-3
 
 
+@pytest.mark.parametrize("small1", ["1", "0"])
+@pytest.mark.parametrize("axis", [0, 1])
+@pytest.mark.parametrize("H,bidir,c0,c1,addend", [(128, True, 256, 4, True), (64, True, 128, 8, True), (256, False, 256, 8, True),
+                                                   (128, False, 64, 16, False)])
+def test_lstm_narrow_second_source_ring(monkeypatch, small1, axis, H, bidir, c0, c1, addend):
+    """Generation 4's handling of a <= 16-channel second source (own two-entry ring of 32B-swizzled [rows x 16] slabs, 4 KB
+    weight slab, every CTA fetching its own x slabs), forced on / off for every H (the dispatcher uses it for H = 256)."""
+    from fn_ssl_b200 import config
+    if not config.TC_AVAILABLE:
+        pytest.skip("tcgen05 engine not built")
+    monkeypatch.setenv("FNSSL_TC_KERNEL", "4")
+    monkeypatch.setenv("FNSSL_TC_SMALL1", small1)
+    nb, nt, nf = (2, 70, 256) if axis == 1 else (2, 70, 40)
+    assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, H, bidir, addend, inplace=addend) <= 1e-3
+
+
 @pytest.mark.parametrize("axis,nb,nt,nf", [(0, 3, 100, 7), (1, 1, 6, 300), (1, 2, 5, 515)])
 def test_lstm_layer_tcgen05_multi_tile(monkeypatch, axis, nb, nt, nf):
     """Generation 4 with more than one cluster tile and ragged last tiles on both sub-tiles (300 rows = 256 + 44,

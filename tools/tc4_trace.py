@@ -14,7 +14,11 @@ from fn_ssl_b200.packing import LSTMParams, run_lstm  # noqa: E402
 
 cfgs = [("full  in256 H128 x2 add", 0, 16, 249, 256, 256, 0, 128, True, True),
         ("full  in16  H128 x2    ", 0, 16, 249, 256, 16, 0, 128, True, False),
-        ("narrow in256 H256 x1 add", 1, 16, 249, 256, 256, 0, 256, False, True)]
+        ("narrow in256 H256 x1 add", 1, 16, 249, 256, 256, 0, 256, False, True),
+        ("narrow in256+16 H256 x1 add", 1, 16, 249, 256, 256, 16, 256, False, True),
+        ("narrow in256+16 H128 x2 add", 1, 16, 249, 256, 256, 16, 128, True, True)]
+if len(sys.argv) > 1:
+    cfgs = [c for c in cfgs if any(a in c[0] for a in sys.argv[1:])]
 names = {0: "h-mma: slot start", 1: "h-mma: h_full passed", 2: "h-mma: acc_full committed", 8: "x-mma: slot start",
          9: "x-mma: slot issued", 4: "epi: slot start", 5: "epi: acc_full passed", 6: "epi: math done", 7: "epi: published",
          10: "epi: wait H_FREE (cyc)", 11: "x-mma: wait ACC_EMPTY (cyc)", 12: "x-mma: wait X_FULL (cyc)"}
