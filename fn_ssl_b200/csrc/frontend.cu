@@ -30,13 +30,50 @@ constexpr int kWin = 512;
 constexpr int kBins = 257;
 constexpr int kStftThreads = 256;
 constexpr int kStftWarps = kStftThreads / 32;
+constexpr int kFftPad = 512 + 64;      // padded length of one real / imaginary work array (fft_pad)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 8-point DFT (forward, e^{-2 pi i mk/8}) in registers, natural order in and out: one decimation-in-frequency split
+// into two 4-point DFTs.
+__device__ __forceinline__ void dft8(float (&xr)[8], float (&xi)[8]) {
+  const float kS = 0.70710678118654752440f;
+  float ar[8], ai[8];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    ar[m] = xr[m] + xr[m + 4]; ai[m] = xi[m] + xi[m + 4];
+    ar[m + 4] = xr[m] - xr[m + 4]; ai[m + 4] = xi[m] - xi[m + 4];
+  }
+  {   // odd half: multiply by W8^1, W8^2 = -i, W8^3
+    const float r5 = (ar[5] + ai[5]) * kS, i5 = (ai[5] - ar[5]) * kS;
+    const float r6 = ai[6], i6 = -ar[6];
+    const float r7 = (ai[7] - ar[7]) * kS, i7 = -(ar[7] + ai[7]) * kS;
+    ar[5] = r5; ai[5] = i5; ar[6] = r6; ai[6] = i6; ar[7] = r7; ai[7] = i7;
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {   // 4-point DFT of (b0..b3) = a[4h..4h+3] -> X[2q + h], q = 0..3
+    const float c0r = ar[4 * h] + ar[4 * h + 2], c0i = ai[4 * h] + ai[4 * h + 2];
+    const float c1r = ar[4 * h] - ar[4 * h + 2], c1i = ai[4 * h] - ai[4 * h + 2];
+    const float c2r = ar[4 * h + 1] + ar[4 * h + 3], c2i = ai[4 * h + 1] + ai[4 * h + 3];
+    const float dr = ar[4 * h + 1] - ar[4 * h + 3], di = ai[4 * h + 1] - ai[4 * h + 3];
+    const float c3r = di, c3i = -dr;                                   // (b1 - b3) * (-i)
+    xr[h] = c0r + c2r;     xi[h] = c0i + c2i;
+    xr[2 + h] = c1r + c3r; xi[2 + h] = c1i + c3i;
+    xr[4 + h] = c0r - c2r; xi[4 + h] = c0i - c2i;
+    xr[6 + h] = c1r - c3r; xi[6 + h] = c1i - c3i;
+  }
+}
+
+__device__ __forceinline__ int fft_pad(int i) { return i + (i >> 3); }   // one pad word per 8: conflict-free radix-8 strides
 
 // One CTA = FR consecutive frames of one utterance, all channels.
 //  1. the sample span [(t0*hop)*nch, ...) is staged in shared memory with ONE 1-D TMA bulk copy
 //     (cp.async.bulk, completion on an mbarrier) when 16-byte aligned, else with plain loads;
-//  2. each warp runs 512-point radix-2 FFTs (one (frame, channel) job at a time) out of shared memory;
+//  2. each warp runs 512-point complex FFTs out of shared memory, one (frame, channel PAIR) job at a time: two real
+//     channels ride in the real and imaginary part of one transform and are separated afterwards
+//     (X0[k] = (Z[k] + conj Z[N-k]) / 2, X1[k] = (Z[k] - conj Z[N-k]) / 2i).  The transform is three radix-8 passes
+//     (512 = 8 x 8 x 8, decimation in frequency, digit-reversed result) with the 8-point DFTs in registers: two
+//     butterflies per lane per pass, two exchanges through a padded per-warp buffer instead of nine radix-2 passes;
 //  3. the (FR*nch) x 257 results are transposed through shared memory so that every bin row of the
 //     (nb, 257, nt, nch) output is written as one contiguous FR*nch*8-byte run.
 __global__ void __launch_bounds__(kStftThreads)
@@ -48,11 +85,17 @@ stft512_kernel(const float* __restrict__ signal, int nsample, int nch, int hop, 
   const int nfr = min(FR, nt - t0);
   const int span = ((nfr - 1) * hop + kWin) * nch;  // floats
 
-  float2* tw = reinterpret_cast<float2*>(smem_raw);                         // 256
-  float* hann = reinterpret_cast<float*>(tw + 256);                          // 512
-  float2* fftbuf = reinterpret_cast<float2*>(hann + kWin);                   // kStftWarps * 512
-  float2* stage = fftbuf + kStftWarps * kWin;                                // FR*nch*257
+  float2* tw = reinterpret_cast<float2*>(smem_raw);                         // 512: exp(-2 pi i q / 512)
+  float* hann = reinterpret_cast<float*>(tw + kWin);                         // 512
+  float* fftbuf = hann + kWin;                                               // kStftWarps * 2 * kFftPad
+  float2* stage = reinterpret_cast<float2*>(fftbuf + kStftWarps * 2 * kFftPad);   // FR*nch*257
   float* samples = reinterpret_cast<float*>(stage + (((size_t)FR * nch * kBins + 1) & ~(size_t)1));  // 16B aligned
+  // more than 2 channels: the interleaved span is re-laid channel-major (odd row pitch) so that the FFT's stride-64 sample
+  // reads are conflict-free instead of nch-way conflicted
+  const bool deint = nch > 2;
+  const int span_n = (FR - 1) * hop + kWin;
+  const int pitch = span_n | 1;
+  float* samples_t = samples + (((size_t)span_n * nch + 3) & ~(size_t)3);
   __shared__ __align__(8) unsigned long long mbar;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -75,12 +118,12 @@ stft512_kernel(const float* __restrict__ signal, int nsample, int nch, int hop, 
   } else {
     for (int i = tid; i < span; i += kStftThreads) samples[i] = src[i];
   }
-  // twiddles exp(-2*pi*i*k/512) and the periodic Hann window, computed with exact-argument sinpi/cospi
-  {
-    float s, c;
-    sincospif((float)tid * (1.0f / 256.0f), &s, &c);
-    tw[tid] = make_float2(c, -s);
-    for (int n = tid; n < kWin; n += kStftThreads) hann[n] = 0.5f - 0.5f * cospif((float)n * (1.0f / 256.0f));
+  // twiddles exp(-2*pi*i*q/512) and the periodic Hann window, computed with exact-argument sinpi/cospi
+  for (int n = tid; n < kWin; n += kStftThreads) {
+    float sn, cs;
+    sincospif((float)n * (1.0f / 256.0f), &sn, &cs);
+    tw[n] = make_float2(cs, -sn);
+    hann[n] = 0.5f - 0.5f * cs;
   }
   if (use_bulk) {
     // wait for the bulk copy (phase 0); bounded spin, then trap instead of hanging the GPU
@@ -96,49 +139,103 @@ stft512_kernel(const float* __restrict__ signal, int nsample, int nch, int hop, 
   }
   __syncthreads();
 
-  float2* buf = fftbuf + warp * kWin;
-  const int njobs = nfr * nch;
+  if (deint) {
+    for (int i = tid; i < span; i += kStftThreads) {
+      const int n = i / nch, c = i - n * nch;
+      samples_t[c * pitch + n] = samples[i];
+    }
+    __syncthreads();
+  }
+  float* wre = fftbuf + warp * 2 * kFftPad;
+  float* wim = wre + kFftPad;
+  const int npair = (nch + 1) >> 1;
+  const int njobs = nfr * npair;
   for (int job = warp; job < njobs; job += kStftWarps) {
-    const int tl = job / nch, ch = job - tl * nch;
-    const float* x = samples + (size_t)tl * hop * nch + ch;
-    // windowed load in bit-reversed order
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-      const int n = lane + 32 * i;
-      const int r = __brev((unsigned)n) >> 23;  // 9-bit reversal
-      buf[r] = make_float2(x[(size_t)n * nch] * hann[n], 0.0f);
+    const int tl = job / npair, pj = job - tl * npair;
+    const int c0 = 2 * pj;
+    const bool has1 = c0 + 1 < nch;
+    const float* x0 = deint ? samples_t + (size_t)c0 * pitch + tl * hop : samples + (size_t)tl * hop * nch + c0;
+    const int sn = deint ? 1 : nch, sc = deint ? pitch : 1;      // sample / channel strides of x0
+    // ---- pass 1 (span 512): butterfly j takes z[j + 64 m]; windowed samples straight from the staged span
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = lane + 32 * h;
+      float xr[8], xi[8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int n = j + 64 * m;
+        const float w = hann[n];
+        xr[m] = x0[n * sn] * w;
+        xi[m] = has1 ? x0[n * sn + sc] * w : 0.0f;
+      }
+      dft8(xr, xi);
+      wre[fft_pad(j)] = xr[0]; wim[fft_pad(j)] = xi[0];
+#pragma unroll
+      for (int r = 1; r < 8; ++r) {
+        const float2 t = tw[(j * r) & 511];
+        wre[fft_pad(j + 64 * r)] = xr[r] * t.x - xi[r] * t.y;
+        wim[fft_pad(j + 64 * r)] = xr[r] * t.y + xi[r] * t.x;
+      }
     }
     __syncwarp();
-    // 9 radix-2 DIT stages, 256 butterflies each (8 per lane)
-#pragma unroll 1
-    for (int s = 1; s <= 9; ++s) {
-      const int half = 1 << (s - 1);
-      const int tstep = 256 >> (s - 1);
+    // ---- pass 2 (span 64 inside each block of 64)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int j = lane + 32 * i;
-        const int pos = j & (half - 1);
-        const int i0 = ((j >> (s - 1)) << s) + pos;
-        const int i1 = i0 + half;
-        const float2 w = tw[pos * tstep];
-        const float2 a = buf[i0], c = buf[i1];
-        const float2 t = make_float2(w.x * c.x - w.y * c.y, w.x * c.y + w.y * c.x);
-        buf[i0] = make_float2(a.x + t.x, a.y + t.y);
-        buf[i1] = make_float2(a.x - t.x, a.y - t.y);
+    for (int h = 0; h < 2; ++h) {
+      const int t = lane + 32 * h, blk = t >> 3, j = t & 7;
+      float xr[8], xi[8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) { xr[m] = wre[fft_pad(64 * blk + j + 8 * m)]; xi[m] = wim[fft_pad(64 * blk + j + 8 * m)]; }
+      dft8(xr, xi);
+      wre[fft_pad(64 * blk + j)] = xr[0]; wim[fft_pad(64 * blk + j)] = xi[0];
+#pragma unroll
+      for (int r = 1; r < 8; ++r) {
+        const float2 tq = tw[(8 * j * r) & 511];
+        wre[fft_pad(64 * blk + j + 8 * r)] = xr[r] * tq.x - xi[r] * tq.y;
+        wim[fft_pad(64 * blk + j + 8 * r)] = xr[r] * tq.y + xi[r] * tq.x;
       }
-      __syncwarp();
     }
-    // bins 0..256 -> staging; magnitude sum for the normaliser
-    float2* st = stage + (size_t)job * kBins;
-    float msum = 0.0f;
-    for (int f = lane; f < kBins; f += 32) {
-      const float2 v = buf[f];
-      st[f] = v;
-      msum += sqrtf(v.x * v.x + v.y * v.y);
+    __syncwarp();
+    // ---- pass 3 (span 8): position 64 k0 + 8 k1 + k2 ends up holding Z[k0 + 8 k1 + 64 k2]
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = lane + 32 * h;
+      float xr[8], xi[8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) { xr[m] = wre[fft_pad(8 * c + m)]; xi[m] = wim[fft_pad(8 * c + m)]; }
+      dft8(xr, xi);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { wre[fft_pad(8 * c + r)] = xr[r]; wim[fft_pad(8 * c + r)] = xi[r]; }
+    }
+    __syncwarp();
+    // ---- separate the two real channels, bins 0..256 -> staging; magnitude sums for the normaliser
+    float2* st0 = stage + (size_t)(tl * nch + c0) * kBins;
+    float ms0 = 0.0f, ms1 = 0.0f;
+    for (int k = lane; k < kBins; k += 32) {
+      const int kn = (kWin - k) & (kWin - 1);
+      const int pk = fft_pad(64 * (k & 7) + 8 * ((k >> 3) & 7) + (k >> 6));
+      const int pn = fft_pad(64 * (kn & 7) + 8 * ((kn >> 3) & 7) + (kn >> 6));
+      const float a = wre[pk], bq = wim[pk];
+      if (has1) {
+        const float c = wre[pn], d = wim[pn];
+        const float2 v0 = make_float2(0.5f * (a + c), 0.5f * (bq - d));
+        const float2 v1 = make_float2(0.5f * (bq + d), 0.5f * (c - a));
+        st0[k] = v0; st0[kBins + k] = v1;
+        ms0 += sqrtf(v0.x * v0.x + v0.y * v0.y);
+        ms1 += sqrtf(v1.x * v1.x + v1.y * v1.y);
+      } else {
+        st0[k] = make_float2(a, bq);
+        ms0 += sqrtf(a * a + bq * bq);
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
-    if (lane == 0 && magsum) magsum[((size_t)b * nch + ch) * nt + t0 + tl] = msum;
+    for (int o = 16; o > 0; o >>= 1) {
+      ms0 += __shfl_xor_sync(0xffffffffu, ms0, o);
+      ms1 += __shfl_xor_sync(0xffffffffu, ms1, o);
+    }
+    if (lane == 0 && magsum) {
+      magsum[((size_t)b * nch + c0) * nt + t0 + tl] = ms0;
+      if (has1) magsum[((size_t)b * nch + c0 + 1) * nt + t0 + tl] = ms1;
+    }
     __syncwarp();
   }
   __syncthreads();
@@ -363,8 +460,9 @@ int fnssl_stft_forward(const float* signal, int nb, int nsample, int nch, int wi
   if (FR < 1) FR = 1;
   if (FR > nt) FR = nt;
   const size_t span = ((size_t)(FR - 1) * hop + kWin) * nch;
-  const size_t smem = 256 * sizeof(float2) + kWin * sizeof(float) + (size_t)kStftWarps * kWin * sizeof(float2) +
-                      (((size_t)FR * nch * kBins + 1) & ~(size_t)1) * sizeof(float2) + span * sizeof(float);
+  const size_t smem = kWin * sizeof(float2) + kWin * sizeof(float) + (size_t)kStftWarps * 2 * kFftPad * sizeof(float) +
+                      (((size_t)FR * nch * kBins + 1) & ~(size_t)1) * sizeof(float2) + ((span + 3) & ~(size_t)3) * sizeof(float) +
+                      (nch > 2 ? (size_t)nch * ((((size_t)(FR - 1) * hop + kWin)) | 1) * sizeof(float) : 0);
   FNSSL_REQUIRE(smem <= 200 * 1024, "stft: too many channels for one CTA (%d)", nch);
   const int use_bulk = ((reinterpret_cast<uintptr_t>(signal) & 15) == 0) && (((size_t)hop * nch * 4) % 16 == 0) &&
                        (((size_t)nsample * nch * 4) % 16 == 0) && (((size_t)kWin * nch * 4) % 16 == 0);
