@@ -267,7 +267,9 @@ __device__ __forceinline__ void row_channels(int r, int nch, int pairing, int& b
 __global__ void __launch_bounds__(32)
 norm_scan_kernel(const float* __restrict__ magsum, int R, int nt, int nch, int nbins, int pairing, int norm,
                  int sample_length, float* __restrict__ mu_out, long long t0, float* __restrict__ mu_state) {
-  extern __shared__ float fm[];   // [nt] frame means, overwritten by mu
+  extern __shared__ float fm[];   // [nt] frame means, overwritten by mu | [nt] a_t | [nt] 1 - a_t
+  float* ca = fm + nt;
+  float* com = ca + nt;
   const int r = blockIdx.x;
   const int lane = threadIdx.x;
   if (r >= R) return;
@@ -284,6 +286,15 @@ norm_scan_kernel(const float* __restrict__ magsum, int R, int nt, int nch, int n
       s = magsum[((size_t)b * nch + ci) * nt + t] + magsum[((size_t)b * nch + cj) * nt + t];
     }
     fm[t] = s / cnt;
+    // recursion coefficients (fp32 tensor arithmetic in the reference, utils_.py:31), one frame per lane
+    const double alpha = (double)(sample_length - 1) / (double)(sample_length + 1);
+    const long long tt = t0 + t;
+    if (tt < sample_length) {
+      const float a = (float)fmin((double)(tt - 1) / (double)(tt + 1), alpha);
+      ca[t] = a; com[t] = 1.0f - a;
+    } else {
+      ca[t] = (float)alpha; com[t] = (float)(1.0 - alpha);
+    }
   }
   __syncwarp();
   if (lane == 0) {
@@ -293,19 +304,9 @@ norm_scan_kernel(const float* __restrict__ magsum, int R, int nt, int nch, int n
       const float m = s / (float)nt;
       for (int t = 0; t < nt; ++t) fm[t] = m;
     } else {
-      const double alpha = (double)(sample_length - 1) / (double)(sample_length + 1);
       float mu = (t0 > 0 && mu_state) ? mu_state[r] : 0.0f;   // a chunk of a longer stream resumes the recursion
       for (int t = 0; t < nt; ++t) {
-        float a, om;
-        const long long tt = t0 + t;
-        if (tt < sample_length) {
-          a = (float)fmin((double)(tt - 1) / (double)(tt + 1), alpha);  // fp32 tensor in the reference (:31)
-          om = 1.0f - a;
-        } else {
-          a = (float)alpha;
-          om = (float)(1.0 - alpha);
-        }
-        mu = a * mu + om * fm[t];
+        mu = ca[t] * mu + com[t] * fm[t];
         fm[t] = mu;
       }
       if (mu_state) mu_state[r] = mu;
@@ -322,11 +323,28 @@ norm_scan_kernel(const float* __restrict__ magsum, int R, int nt, int nch, int n
 constexpr int kAsmTF = 16;  // bins per tile
 constexpr int kAsmTT = 32;  // frames per tile
 
-template <typename T>
+// store `n` consecutive channels (n = 8 halves or 4 floats = 16 bytes) of one grid position
+__device__ __forceinline__ void st_chunk(__half* dst, const float (&v)[8]) {
+  const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+  const __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+  uint4 pk;
+  pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+  pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(dst) = pk;
+}
+__device__ __forceinline__ void st_chunk(float* dst, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// VEC: ld is a multiple of the 16-byte chunk (8 halves / 4 floats) and the grid is 16-byte aligned: one thread owns one
+// (frame, bin) position and writes its ld channels as 16-byte stores, consecutive threads = consecutive bins, so a warp
+// writes one contiguous run of 32 * ld elements.
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
 assemble_kernel(const float2* __restrict__ spec, const float* __restrict__ mu, int nb, int nt, int nch, int pairing,
                 int norm, float eps, T* __restrict__ feat, int ld, float* __restrict__ feat_cfirst) {
-  extern __shared__ float2 tile[];  // [kAsmTF][kAsmTT][nch]
+  extern __shared__ float2 tile[];  // [kAsmTT][kAsmTF][nch]
+  constexpr int kChunk = sizeof(T) == 2 ? 8 : 4;
   const int b = blockIdx.z;
   const int f0 = 1 + blockIdx.y * kAsmTF;  // spectrum bin of the first feature bin in the tile
   const int t0 = blockIdx.x * kAsmTT;
@@ -336,7 +354,8 @@ assemble_kernel(const float2* __restrict__ spec, const float* __restrict__ mu, i
   const int runlen = tn * nch;
   for (int idx = tid; idx < kAsmTF * runlen; idx += blockDim.x) {
     const int fl = idx / runlen, j = idx - fl * runlen;
-    tile[(size_t)fl * kAsmTT * nch + j] = spec[((size_t)b * kBins + f0 + fl) * nt * nch + (size_t)t0 * nch + j];
+    const int tl = j / nch, ch = j - tl * nch;
+    tile[((size_t)tl * kAsmTF + fl) * nch + ch] = spec[((size_t)b * kBins + f0 + fl) * nt * nch + (size_t)t0 * nch + j];
   }
   __syncthreads();
   const bool all = (pairing == FNSSL_PAIRS_ALL);
@@ -347,20 +366,46 @@ assemble_kernel(const float2* __restrict__ spec, const float* __restrict__ mu, i
     const int r = b * P + p;
     int bb, ci, cj;
     row_channels(r, nch, pairing, bb, ci, cj);
-    // grid write: (t, f, c), c fastest
-    for (int idx = tid; idx < tn * kAsmTF * ld; idx += blockDim.x) {
-      const int c = idx % ld;
-      const int fl = (idx / ld) % kAsmTF;
-      const int tl = idx / (ld * kAsmTF);
-      float v = 0.0f;
-      if (c < C) {
-        const int k = (c < half) ? c : c - half;
-        const int ch = all ? k : (k == 0 ? ci : cj);
-        const float2 x = tile[((size_t)fl * kAsmTT + tl) * nch + ch];
-        v = (c < half) ? x.x : x.y;
-        if (norm != FNSSL_NORM_NONE) v = v / (mu[(size_t)r * nt + t0 + tl] + eps);
+    if (VEC) {
+      for (int idx = tid; idx < tn * kAsmTF; idx += blockDim.x) {
+        const int fl = idx % kAsmTF, tl = idx / kAsmTF;
+        const float2* src = tile + ((size_t)tl * kAsmTF + fl) * nch;
+        const float den = norm != FNSSL_NORM_NONE ? mu[(size_t)r * nt + t0 + tl] + eps : 1.0f;
+        T* dst = feat + (((size_t)r * nt + t0 + tl) * 256 + (f0 - 1 + fl)) * ld;
+        for (int c0 = 0; c0 < ld; c0 += kChunk) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < kChunk; ++i) {
+            const int c = c0 + i;
+            float x = 0.0f;
+            if (c < C) {
+              const int k = (c < half) ? c : c - half;
+              const int ch = all ? k : (k == 0 ? ci : cj);
+              const float2 z = src[ch];
+              x = (c < half) ? z.x : z.y;
+              if (norm != FNSSL_NORM_NONE) x = x / den;
+            }
+            v[i] = x;
+          }
+          st_chunk(dst + c0, v);
+        }
       }
-      st_act<T>(feat + (((size_t)r * nt + t0 + tl) * 256 + (f0 - 1 + fl)) * ld + c, v);
+    } else {
+      // grid write: (t, f, c), c fastest
+      for (int idx = tid; idx < tn * kAsmTF * ld; idx += blockDim.x) {
+        const int c = idx % ld;
+        const int fl = (idx / ld) % kAsmTF;
+        const int tl = idx / (ld * kAsmTF);
+        float v = 0.0f;
+        if (c < C) {
+          const int k = (c < half) ? c : c - half;
+          const int ch = all ? k : (k == 0 ? ci : cj);
+          const float2 x = tile[((size_t)tl * kAsmTF + fl) * nch + ch];
+          v = (c < half) ? x.x : x.y;
+          if (norm != FNSSL_NORM_NONE) v = v / (mu[(size_t)r * nt + t0 + tl] + eps);
+        }
+        st_act<T>(feat + (((size_t)r * nt + t0 + tl) * 256 + (f0 - 1 + fl)) * ld + c, v);
+      }
     }
     if (feat_cfirst) {
       for (int idx = tid; idx < C * kAsmTF * tn; idx += blockDim.x) {
@@ -369,7 +414,7 @@ assemble_kernel(const float2* __restrict__ spec, const float* __restrict__ mu, i
         const int c = idx / (tn * kAsmTF);
         const int k = (c < half) ? c : c - half;
         const int ch = all ? k : (k == 0 ? ci : cj);
-        const float2 x = tile[((size_t)fl * kAsmTT + tl) * nch + ch];
+        const float2 x = tile[((size_t)tl * kAsmTF + fl) * nch + ch];
         float v = (c < half) ? x.x : x.y;
         if (norm != FNSSL_NORM_NONE) v = v / (mu[(size_t)r * nt + t0 + tl] + eps);
         feat_cfirst[(((size_t)r * C + c) * 256 + (f0 - 1 + fl)) * nt + t0 + tl] = v;
@@ -488,9 +533,9 @@ int fnssl_norm_forward(const float* magsum, int nb, int nch, int nt, int nbins, 
   FNSSL_REQUIRE(norm == FNSSL_NORM_FORGETTING || norm == FNSSL_NORM_GLOBAL, "norm: bad norm %d", norm);
   FNSSL_REQUIRE(pairing == FNSSL_PAIRS_ALL || nch >= 2, "norm: pair modes need >= 2 channels");
   const int R = fnssl_feature_rows(nb, nch, pairing);
-  FNSSL_REQUIRE((size_t)nt * 4 <= 200 * 1024, "norm: too many frames (%d)", nt);
-  FNSSL_CUDA(cudaFuncSetAttribute(norm_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nt * 4));
-  norm_scan_kernel<<<R, 32, (size_t)nt * 4, (cudaStream_t)stream>>>(magsum, R, nt, nch, nbins, pairing, norm, sample_length, mu,
+  FNSSL_REQUIRE((size_t)nt * 12 <= 200 * 1024, "norm: too many frames (%d)", nt);
+  FNSSL_CUDA(cudaFuncSetAttribute(norm_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nt * 12));
+  norm_scan_kernel<<<R, 32, (size_t)nt * 12, (cudaStream_t)stream>>>(magsum, R, nt, nch, nbins, pairing, norm, sample_length, mu,
                                                                     0, nullptr);
   FNSSL_LAUNCH_CHECK("norm_scan_kernel");
   return 0;
@@ -502,9 +547,9 @@ int fnssl_norm_stream_forward(const float* magsum, int nb, int nch, int nt, int 
   FNSSL_REQUIRE(pairing >= 0 && pairing <= 2, "norm(stream): bad pairing %d", pairing);
   FNSSL_REQUIRE(pairing == FNSSL_PAIRS_ALL || nch >= 2, "norm(stream): pair modes need >= 2 channels");
   const int R = fnssl_feature_rows(nb, nch, pairing);
-  FNSSL_REQUIRE((size_t)nt * 4 <= 200 * 1024, "norm(stream): too many frames (%d)", nt);
-  FNSSL_CUDA(cudaFuncSetAttribute(norm_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nt * 4));
-  norm_scan_kernel<<<R, 32, (size_t)nt * 4, (cudaStream_t)stream>>>(magsum, R, nt, nch, nbins, pairing, FNSSL_NORM_FORGETTING,
+  FNSSL_REQUIRE((size_t)nt * 12 <= 200 * 1024, "norm(stream): too many frames (%d)", nt);
+  FNSSL_CUDA(cudaFuncSetAttribute(norm_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nt * 12));
+  norm_scan_kernel<<<R, 32, (size_t)nt * 12, (cudaStream_t)stream>>>(magsum, R, nt, nch, nbins, pairing, FNSSL_NORM_FORGETTING,
                                                                     sample_length, mu, t0, mu_state);
   FNSSL_LAUNCH_CHECK("norm_scan_kernel");
   return 0;
@@ -527,15 +572,19 @@ int fnssl_features_forward(const float* spec, const float* magsum, int nb, int n
   }
   dim3 grid((nt + kAsmTT - 1) / kAsmTT, 256 / kAsmTF, nb);
   const size_t smem = (size_t)kAsmTF * kAsmTT * nch * sizeof(float2);
+#define FNSSL_ASM(T, VEC)                                                                                              \
+  do {                                                                                                                   \
+    FNSSL_CUDA(cudaFuncSetAttribute(assemble_kernel<T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    assemble_kernel<T, VEC><<<grid, 256, smem, st>>>(reinterpret_cast<const float2*>(spec), mu, nb, nt, nch, pairing, norm, \
+                                                     eps, (T*)feat, ld, feat_cfirst);                                    \
+  } while (0)
+  const bool al16 = (reinterpret_cast<uintptr_t>(feat) & 15) == 0;
   if (dtype == FNSSL_F32) {
-    FNSSL_CUDA(cudaFuncSetAttribute(assemble_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    assemble_kernel<float><<<grid, 256, smem, st>>>(reinterpret_cast<const float2*>(spec), mu, nb, nt, nch, pairing, norm,
-                                                    eps, (float*)feat, ld, feat_cfirst);
+    if (al16 && ld % 4 == 0) FNSSL_ASM(float, true); else FNSSL_ASM(float, false);
   } else {
-    FNSSL_CUDA(cudaFuncSetAttribute(assemble_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    assemble_kernel<__half><<<grid, 256, smem, st>>>(reinterpret_cast<const float2*>(spec), mu, nb, nt, nch, pairing, norm,
-                                                     eps, (__half*)feat, ld, feat_cfirst);
+    if (al16 && ld % 8 == 0) FNSSL_ASM(__half, true); else FNSSL_ASM(__half, false);
   }
+#undef FNSSL_ASM
   FNSSL_LAUNCH_CHECK("assemble_kernel");
   return 0;
 }
