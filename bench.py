@@ -180,8 +180,9 @@ def main():
         return D.all_gather_outputs(out, counts)           # per-utterance outputs gathered on every rank
 
     def step_e2e():
-        x = sig_host.to(dev, non_blocking=True)
-        out = D.all_gather_outputs(pipe(x), counts)
+        # the public end-to-end call: pinned host input -> (H2D on a side stream, double-buffered, so step i+1's copy
+        # overlaps step i's kernels) -> forward -> all-gather -> D2H of the result; every step copies its own input
+        out = D.all_gather_outputs(pipe.run_host(sig_host), counts)
         out_host.copy_(out, non_blocking=True)
         return out
 

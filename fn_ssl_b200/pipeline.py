@@ -38,6 +38,42 @@ def data_preprocess_ipdnet(mic_sig_batch: Tensor, eps: float = 1e-6, sample_leng
     return [cf]
 
 
+class _HostStaging:
+    """Double-buffered host -> device staging on a side stream: the copy of call i+1 overlaps the kernels of call i
+    (every call still copies its own input; a buffer is reused only after the forward that read it has finished)."""
+
+    def __init__(self):
+        self.copy = None
+        self.bufs = None
+        self.idx = 0
+
+    def stage(self, host: Tensor, dev: torch.device) -> Tensor:
+        if host.is_cuda:
+            return host
+        if not host.is_pinned():
+            raise RuntimeError("run_host: the input must be a pinned host tensor (tensor.pin_memory())")
+        if self.copy is None:
+            self.copy = torch.cuda.Stream(device=dev)
+        if self.bufs is None or self.bufs[0].shape != host.shape or self.bufs[0].device != dev:
+            self.bufs = [torch.empty(host.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+            self.ready = [torch.cuda.Event() for _ in range(2)]
+            self.free = [torch.cuda.Event() for _ in range(2)]
+            self.idx = 0
+        i = self.idx
+        self.idx ^= 1
+        main = torch.cuda.current_stream(dev)
+        self.copy.wait_event(self.free[i])               # the forward that last read bufs[i] is done (no-op the first time)
+        with torch.cuda.stream(self.copy):
+            self.bufs[i].copy_(host, non_blocking=True)
+            self.ready[i].record(self.copy)
+        main.wait_event(self.ready[i])
+        self._last = i
+        return self.bufs[i]
+
+    def release(self, dev: torch.device) -> None:
+        self.free[self._last].record(torch.cuda.current_stream(dev))
+
+
 class FNSSLPipeline(nn.Module):
     """signal (nb, nsample, nch) f32 [device] -> FN_SSL output (nb*P, nt//12, 512 | 180)."""
 
@@ -53,6 +89,23 @@ class FNSSLPipeline(nn.Module):
         g0, _, _ = ops.features(spec, magsum, self.ch_mode, ops.NORM_FORGETTING, self.sample_length, self.eps,
                                 config.grid_dtype(eng))
         return self.arch.forward_grid(g0, eng)
+
+    @torch.no_grad()
+    def run_host(self, signal_host: Tensor, out_host: Optional[Tensor] = None) -> Tensor:
+        """End-to-end call for a serving loop: `signal_host` is a PINNED host tensor (nb, nsample, nch).  The host -> device
+        copy runs on a side stream into one of two device buffers, so the copy of the next call overlaps this call's
+        kernels; the result is optionally copied back into the pinned `out_host` (asynchronously, on the current stream).
+        Returns the device output.  Synchronise the current stream before reading `out_host`."""
+        dev = next(self.arch.parameters()).device
+        if not hasattr(self, "_staging"):
+            self._staging = _HostStaging()
+        x = self._staging.stage(signal_host, dev)
+        out = self.forward(x)
+        if not signal_host.is_cuda:
+            self._staging.release(dev)
+        if out_host is not None:
+            out_host.copy_(out, non_blocking=True)
+        return out
 
 
 class IPDnetPipeline(nn.Module):

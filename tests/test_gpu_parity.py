@@ -578,3 +578,21 @@ def test_ipdnet_stream_equals_whole_clip(kw, nch):
     sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
     ref = orc.ipdnet_forward(orc.preprocess_ipdnet(sig.cpu()), sd)
     assert _relerr(got, ref) <= 1e-3
+
+
+def test_run_host_staging_matches_device_call():
+    """FNSSLPipeline.run_host: pinned host input through the double-buffered side-stream copy == the device-tensor call,
+    for a sequence of different inputs (buffer reuse must wait for the forward that read the buffer)."""
+    import fn_ssl_b200 as F
+    torch.manual_seed(0)
+    net = F.FN_SSL(is_online=True).eval().to(DEV)
+    pipe = F.FNSSLPipeline(net)
+    sigs = [_randn((2, 512 + 256 * 23, 2), 70 + i).pin_memory() for i in range(5)]
+    outs_host = [torch.empty((2, 2, 512), dtype=torch.float32).pin_memory() for _ in range(5)]
+    outs = [pipe.run_host(s, o).clone() for s, o in zip(sigs, outs_host)]
+    torch.cuda.synchronize()
+    for s, o, oh in zip(sigs, outs, outs_host):
+        ref = pipe(s.to(DEV))
+        assert torch.equal(o, ref) and torch.equal(oh.to(DEV), ref)
+    with pytest.raises(RuntimeError, match="pinned"):
+        pipe.run_host(torch.zeros(2, 8192, 2))
