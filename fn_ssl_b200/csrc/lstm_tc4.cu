@@ -701,7 +701,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
 
 struct Plan { bool ok; int sub; int xstages; int nxs; size_t smem; bool small1; };
 
-static Plan make_plan(int H, int c0, int c1) {
+static Plan make_plan(int H, int c0, int c1, int axis = -1) {
   Plan pl{false, 0, 0, 0, 0, false};
   if (H != 64 && H != 128 && H != 256) return pl;
   if (c0 % 16 || c1 % 16 || c0 <= 0) return pl;
@@ -714,9 +714,10 @@ static Plan make_plan(int H, int c0, int c1) {
   // slabs instead (32B swizzle), so the big ring carries 4 slabs per slot again.
   // Measured (B200, profiles/r1_lstm_narrow_source_ring.txt): H = 256 layers 4.65 -> 3.2 ms (3 big stages instead of 2), and
   // 3.0 ms when every CTA also fetches its own x slabs (no multicast: the cluster-wide "slot empty" hand-shake is what a
-  // short ring cannot hide); H = 128 layers are not faster, so the mode (template flag NARROW) is used for H = 256 only.
+  // short ring cannot hide); H = 128: along-frequency layers 2.38 -> 2.08 ms (IPDnet cfg3), along-time layers not faster
+  // (1.23 -> 1.27 ms), so the mode (template flag NARROW) is used for H = 256 and for H = 128 full-band layers.
   // FNSSL_TC_SMALL1 = 0 / 1 forces it off / on for every H (tests).
-  bool small1 = c1 > 0 && c1 <= 16 && H == 256;
+  bool small1 = c1 > 0 && c1 <= 16 && (H == 256 || (H == 128 && axis == FNSSL_ALONG_FREQ));
   if (const char* e = getenv("FNSSL_TC_SMALL1")) small1 = c1 > 0 && c1 <= 16 && atoi(e) != 0;
   const int nslabs = (small1 ? nxs - 1 : nxs) + NHS;
   int sub_first = 128;
@@ -852,7 +853,7 @@ extern "C" int fnssl_lstm_tc4_trace(long long* out256) {
 bool lstm_tc4_supports(int hidden, int c0, int c1) { return tc4::make_plan(hidden, c0, c1).ok; }
 
 int lstm_forward_tc4(const fnssl_lstm_args* a, cudaStream_t st) {
-  const tc4::Plan pl = tc4::make_plan(a->hidden, a->c0, a->c1);
+  const tc4::Plan pl = tc4::make_plan(a->hidden, a->c0, a->c1, a->axis);
   FNSSL_REQUIRE(pl.ok, "lstm(tcgen05 two-chain kernel): unsupported layer (H=%d c0=%d c1=%d)", a->hidden, a->c0, a->c1);
   if (a->hidden == 64) return pl.sub == 128 ? tc4::launch<64, 128>(a, pl, st) : tc4::launch<64, 64>(a, pl, st);
   if (a->hidden == 128) return pl.sub == 128 ? tc4::launch<128, 128>(a, pl, st) : tc4::launch<128, 64>(a, pl, st);

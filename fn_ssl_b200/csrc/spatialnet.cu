@@ -35,6 +35,11 @@ constexpr int kFT = kH * kQ;    // 384 threads: thread = (channel, row quarter)
 constexpr int kEncK = 5;
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // ----------------------------------------------------------------------------------------------------------------
 // frequency stage.  The tile [rows x 96] lives in shared memory twice: X (the residual stream) and Y (the normalised
@@ -376,32 +381,43 @@ sn_time_kernel(const float* __restrict__ x, float* __restrict__ out, int nt, int
       us[t * kH + lane + 64] = d2 * rstd * lw2 + lb2;
     }
     __syncthreads();
-    // ---- in_proj (96 -> 2 x 192, no bias) + causal depthwise conv (k = 4) + SiLU on the x half
+    // ---- in_proj (96 -> 2 x 192, no bias): the x and the gate output of channel d share every LDS.128 of LN(x)
+    //      (16 + 16 weights in registers per pass, 4 shared-memory reads per 32 FMAs) + causal depthwise conv (k = 4) + SiLU
     {
-      float acc[kTT], wr[kKW];
+      float ax[kTT], az[kTT];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {               // 0: x branch, 1: gate branch z
+      for (int t = 0; t < kTT; ++t) { ax[t] = 0.0f; az[t] = 0.0f; }
+#pragma unroll 1
+      for (int ps = 0; ps < kH / 16; ++ps) {
+        float wx[16], wz[16];
 #pragma unroll
-        for (int t = 0; t < kTT; ++t) acc[t] = 0.0f;
-#pragma unroll
-        for (int ps = 0; ps < kH / kKW; ++ps) {
-#pragma unroll
-          for (int i = 0; i < kKW; ++i) wr[i] = __ldg(w.in_proj_wt + (ps * kKW + i) * 2 * kDI + half * kDI + d);
-          mv<kH, kKW>(acc, wr, us + ps * kKW);
+        for (int i = 0; i < 16; ++i) {
+          wx[i] = __ldg(w.in_proj_wt + (ps * 16 + i) * 2 * kDI + d);
+          wz[i] = __ldg(w.in_proj_wt + (ps * 16 + i) * 2 * kDI + kDI + d);
         }
-        if (half == 0) {
-          const float c0 = __ldg(w.conv_w + d * kDK + 0), c1 = __ldg(w.conv_w + d * kDK + 1),
-                      c2 = __ldg(w.conv_w + d * kDK + 2), c3 = __ldg(w.conv_w + d * kDK + 3), cb = __ldg(w.conv_b + d);
 #pragma unroll
-          for (int t = 0; t < kTT; ++t) {
-            const float v = acc[t];
-            xc[t * kDI + d] = silu_f(fmaf(c0, p0, fmaf(c1, p1, fmaf(c2, p2, fmaf(c3, v, cb)))));
-            if (t < nval) { p0 = p1; p1 = p2; p2 = v; }
+        for (int t = 0; t < kTT; ++t) {
+          const float4* p4 = reinterpret_cast<const float4*>(us + t * kH + ps * 16);
+          float x0 = 0.0f, x1 = 0.0f, z0 = 0.0f, z1 = 0.0f;
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 v = p4[i4];
+            x0 = fmaf(wx[i4 * 4 + 0], v.x, x0); x1 = fmaf(wx[i4 * 4 + 1], v.y, x1);
+            x0 = fmaf(wx[i4 * 4 + 2], v.z, x0); x1 = fmaf(wx[i4 * 4 + 3], v.w, x1);
+            z0 = fmaf(wz[i4 * 4 + 0], v.x, z0); z1 = fmaf(wz[i4 * 4 + 1], v.y, z1);
+            z0 = fmaf(wz[i4 * 4 + 2], v.z, z0); z1 = fmaf(wz[i4 * 4 + 3], v.w, z1);
           }
-        } else {
-#pragma unroll
-          for (int t = 0; t < kTT; ++t) zs[t * kDI + d] = acc[t];
+          ax[t] += x0 + x1; az[t] += z0 + z1;
         }
+      }
+      const float c0 = __ldg(w.conv_w + d * kDK + 0), c1 = __ldg(w.conv_w + d * kDK + 1),
+                  c2 = __ldg(w.conv_w + d * kDK + 2), c3 = __ldg(w.conv_w + d * kDK + 3), cb = __ldg(w.conv_b + d);
+#pragma unroll
+      for (int t = 0; t < kTT; ++t) {
+        const float v = ax[t];
+        xc[t * kDI + d] = silu_f(fmaf(c0, p0, fmaf(c1, p1, fmaf(c2, p2, fmaf(c3, v, cb)))));
+        zs[t * kDI + d] = az[t];
+        if (t < nval) { p0 = p1; p1 = p2; p2 = v; }
       }
     }
     __syncthreads();
@@ -436,7 +452,7 @@ sn_time_kernel(const float* __restrict__ x, float* __restrict__ out, int nt, int
 #pragma unroll
       for (int r = 0; r < kDR; ++r) wd[r] = __ldg(w.dt_proj_w + d * kDR + r);
 #pragma unroll
-      for (int n = 0; n < kNS; ++n) A[n] = -__expf(__ldg(w.A_log + d * kNS + n));   // A = -exp(A_log)
+      for (int n = 0; n < kNS; ++n) A[n] = -1.4426950408889634f * __expf(__ldg(w.A_log + d * kNS + n));   // A log2(e), A = -exp(A_log)
       const float bd = __ldg(w.dt_proj_b + d), Dd = __ldg(w.D + d);
 #pragma unroll 1
       for (int t = 0; t < nval; ++t) {
@@ -456,7 +472,7 @@ sn_time_kernel(const float* __restrict__ x, float* __restrict__ out, int nt, int
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int n = n4 * 4 + q;
-            hst[n] = fmaf(__expf(delta * A[n]), hst[n], dx * bb[q]);
+            hst[n] = fmaf(ex2_fast(delta * A[n]), hst[n], dx * bb[q]);      // exp(delta A) = 2^(delta A log2 e)
             if (q & 1) y1 = fmaf(cc[q], hst[n], y1); else y0 = fmaf(cc[q], hst[n], y0);
           }
         }
