@@ -55,22 +55,30 @@ __device__ __forceinline__ void ln_rows(const float* __restrict__ X, float* __re
   const int warp = tid >> 5, lane = tid & 31;
   const float w0 = __ldg(lw + lane), w1 = __ldg(lw + lane + 32), w2 = __ldg(lw + lane + 64);
   const float b0 = __ldg(lb + lane), b1 = __ldg(lb + lane + 32), b2 = __ldg(lb + lane + 64);
-  for (int r = warp; r < nrows; r += kFT / 32) {
-    const float* x = X + r * kH;
-    const float v0 = x[lane], v1 = x[lane + 32], v2 = x[lane + 64];
-    float s = v0 + v1 + v2;
+  constexpr int kNW = kFT / 32;
+  for (int r = warp; r < nrows; r += 2 * kNW) {       // two independent rows per iteration: the shuffle chains overlap
+    const int r2 = r + kNW;
+    const bool has2 = r2 < nrows;
+    const float* xa = X + r * kH;
+    const float* xb = X + (has2 ? r2 : r) * kH;
+    const float a0 = xa[lane], a1 = xa[lane + 32], a2 = xa[lane + 64];
+    const float c0 = xb[lane], c1 = xb[lane + 32], c2 = xb[lane + 64];
+    float sa = a0 + a1 + a2, sb = c0 + c1 + c2;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * (1.0f / kH);
-    const float d0 = v0 - mean, d1 = v1 - mean, d2 = v2 - mean;
-    float q = d0 * d0 + d1 * d1 + d2 * d2;
+    for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+    const float ma = sa * (1.0f / kH), mb = sb * (1.0f / kH);
+    const float da0 = a0 - ma, da1 = a1 - ma, da2 = a2 - ma;
+    const float db0 = c0 - mb, db1 = c1 - mb, db2 = c2 - mb;
+    float qa = da0 * da0 + da1 * da1 + da2 * da2, qb = db0 * db0 + db1 * db1 + db2 * db2;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q * (1.0f / kH) + 1e-5f);
-    float* y = Y + r * kH;
-    y[lane] = d0 * rstd * w0 + b0;
-    y[lane + 32] = d1 * rstd * w1 + b1;
-    y[lane + 64] = d2 * rstd * w2 + b2;
+    for (int o = 16; o > 0; o >>= 1) { qa += __shfl_xor_sync(0xffffffffu, qa, o); qb += __shfl_xor_sync(0xffffffffu, qb, o); }
+    const float ra = rsqrtf(qa * (1.0f / kH) + 1e-5f), rb = rsqrtf(qb * (1.0f / kH) + 1e-5f);
+    float* ya = Y + r * kH;
+    ya[lane] = da0 * ra * w0 + b0; ya[lane + 32] = da1 * ra * w1 + b1; ya[lane + 64] = da2 * ra * w2 + b2;
+    if (has2) {
+      float* yb = Y + r2 * kH;
+      yb[lane] = db0 * rb * w0 + b0; yb[lane + 32] = db1 * rb * w1 + b1; yb[lane + 64] = db2 * rb * w2 + b2;
+    }
   }
 }
 
@@ -229,7 +237,7 @@ __device__ __forceinline__ void encoder(const fnssl_sn_freq_args& a, int b, int 
     for (int c = 0; c < LD; ++c) wr[k][c] = __ldg(a.enc_wp + (k * LD + c) * kH + h);
   const float bias = __ldg(a.enc_b + h);
   __syncthreads();
-#pragma unroll 2
+#pragma unroll 4
   for (int f = q * 64; f < (q + 1) * 64; ++f) {
     float a0 = bias, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll
