@@ -145,6 +145,12 @@ def main():
         print(json.dumps(line))
         return
 
+    # rank 0 prints ONE JSON line on stdout: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION, printed to stdout at
+    # communicator creation) out of it; an explicit INFO / TRACE setting is left alone (its output then goes to stderr)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    else:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     import fn_ssl_b200 as F

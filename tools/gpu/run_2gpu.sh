@@ -1,6 +1,4 @@
 set -x
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_v6_2gpu.json 2> gpurun_out/bench_v6_2gpu.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 > gpurun_out/bench_v6_2gpu_ref.json 2> gpurun_out/bench_v6_2gpu_ref.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_v6_ref.json 2> gpurun_out/bench_v6_ref.err
-cut -c1-900 gpurun_out/bench_v6_2gpu.json; cat gpurun_out/bench_v6_2gpu_ref.json; cat gpurun_out/bench_v6_ref.json; tail -3 gpurun_out/bench_v6_2gpu.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_v8_2gpu.json 2> gpurun_out/bench_v8_2gpu.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 > gpurun_out/bench_v8_2gpu_ref.json 2> gpurun_out/bench_v8_2gpu_ref.err
