@@ -147,9 +147,10 @@ def main():
 
     # rank 0 prints ONE JSON line on stdout: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION, printed to stdout at
     # communicator creation) out of it; an explicit INFO / TRACE setting is left alone (its output then goes to stderr)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
-    else:
+    # (NCCL prints the banner at the VERSION *and* the WARN level; only an unset NCCL_DEBUG is silent)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        del os.environ["NCCL_DEBUG"]
+    elif os.environ.get("NCCL_DEBUG"):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
