@@ -147,3 +147,58 @@ def test_ipdnet2_state_dict_surface_matches_reference_checkpoint():
                            attention='mamba(16,4)')
     with pytest.raises(RuntimeError, match="CUDA"):
         net.eval()(torch.zeros(1, 10, 256, 10))
+
+
+def test_ctypes_structures_match_the_c_header(tmp_path):
+    """Compile a C program against include/fnssl_b200.h (gcc, host only) and compare sizeof / offsetof of every argument
+    struct with the ctypes mirror in fn_ssl_b200/_lib.py -- a silent layout mismatch would corrupt kernel arguments."""
+    import ctypes
+    import shutil
+    import subprocess
+    from fn_ssl_b200 import _lib
+    gcc = shutil.which("gcc") or shutil.which("cc")
+    if not gcc:
+        pytest.skip("no C compiler")
+    structs = {"fnssl_lstm_args": _lib.LstmArgs, "fnssl_sn_fconv_weights": _lib.SnFconvWeights,
+               "fnssl_sn_freq_args": _lib.SnFreqArgs, "fnssl_mamba_weights": _lib.MambaWeights,
+               "fnssl_sn_time_args": _lib.SnTimeArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fnssl_b200.h"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert int(out[cname]) == ctypes.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
+
+
+def test_library_links_from_plain_c(tmp_path):
+    """The boundary is a C ABI: a C99 program links against libfnssl_b200.so with nothing but the header (no C++ name
+    mangling, no torch / Python dependency) and calls the host-only entry points."""
+    import shutil
+    import subprocess
+    from fn_ssl_b200 import _lib
+    _lib.load()
+    gcc = shutil.which("gcc") or shutil.which("cc")
+    if not gcc:
+        pytest.skip("no C compiler")
+    src = tmp_path / "host.c"
+    src.write_text('#include <stdio.h>\n#include "fnssl_b200.h"\nint main(void) {\n'
+                   '  printf("%d %d %d\\n", fnssl_abi_version(), fnssl_stft_num_frames(64000, 512, 256), fnssl_feature_rows(3, 4, FNSSL_PAIRS_MM));\n'
+                   '  if (fnssl_stft_forward(NULL, 1, 64000, 2, 400, 160, 400, NULL, NULL, NULL) == 0) return 1;\n'
+                   '  printf("%s\\n", fnssl_last_error());\n  return 0;\n}\n')
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                    "-l:libfnssl_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    first, second = res.stdout.splitlines()[:2]
+    assert first.split() == ["3", "249", "18"] and "512" in second
