@@ -27,6 +27,18 @@ def _worker(rank, world, port, q):
     counts = [D.shard_range(n_utt, r, world)[1] - D.shard_range(n_utt, r, world)[0] for r in range(world)]
     full = torch.arange(n_utt * 20 * 4, dtype=torch.float32).reshape(n_utt, 20, 4)
     out = D.all_gather_outputs(full[lo:hi].clone(), counts)
+    # IPDnet2: a second model family through the same helpers (326 tensors, 5-D per-utterance outputs)
+    from fn_ssl_b200 import OnlineSpatialNet
+    torch.manual_seed(200 + rank)
+    net2 = OnlineSpatialNet(dim_input=10, dim_output=16, num_layers=8, dim_squeeze=8, num_freqs=256, dim_hidden=96,
+                            attention='mamba(16,4)')
+    D.broadcast_weights(net2, src=0)
+    ref2 = torch.cat([p.detach().reshape(-1) for p in net2.parameters()])
+    g2 = [torch.empty_like(ref2) for _ in range(world)]
+    dist.all_gather(g2, ref2)
+    full5 = torch.arange(n_utt * 3 * 8 * 4 * 2, dtype=torch.float32).reshape(n_utt, 3, 8, 4, 2)
+    out5 = D.all_gather_outputs(full5[lo:hi].clone(), counts)
+    same = same and all(torch.equal(g, g2[0]) for g in g2) and torch.equal(out5, full5)
     q.put((rank, same, nbytes, torch.equal(out, full), (lo, hi)))
     dist.destroy_process_group()
 
