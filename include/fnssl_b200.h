@@ -1,10 +1,10 @@
 /*
- * fnssl_b200 -- C ABI of the B200-native (sm_100a) FN-SSL / IPDnet forward hot path.
+ * fnssl_b200 -- C ABI of the B200-native (sm_100a) FN-SSL / IPDnet / IPDnet2 forward hot path.
  *
  * The reference (Audio-WestlakeU/FN-SSL) has no FFI: its "plugin surface" for this path is the
  * Python nn.Module contract.  This header is the drop-in boundary one level
  * below it: plain device pointers and sizes, no torch types.  Each entry point names the reference
- * call site it replaces.  fn_ssl_b200/{Module,Model,FixedAarryIPDnet}.py bind these through ctypes
+ * call site it replaces.  fn_ssl_b200/{Module,Model,FixedAarryIPDnet,IPDnet2}.py bind these through ctypes
  * and re-create the reference's module classes on top.
  *
  * Conventions
@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FNSSL_ABI_VERSION 3
+#define FNSSL_ABI_VERSION 3 /* 2: carried LSTM state; 3: IPDnet2 entry points (fnssl_reflect_pad, fnssl_sn_*) */
 
 /* element types of grid tensors */
 #define FNSSL_F32 0
