@@ -185,6 +185,7 @@ class SpatialNetLayer(nn.Module):
         self._packed = (key, fa, ta, keep)
         return fa, ta, keep
 
+    @ops.on_tensor_device
     def _run(self, x: Tensor, nb: int, nt: int, encoder: Optional[CausalConv1d], pool: int, t_begin: int = 0,
              state: Optional[Tuple[Tensor, Tensor]] = None) -> Tensor:
         """x: feature grid (nb, nt, 256, ld) [first layer] or activation (nb, nt, 16, H); returns (nb, (nt - t_begin) // pool,
@@ -271,6 +272,7 @@ class OnlineSpatialNet(nn.Module):
             self._head = (key, ws)
         return self._head[1]
 
+    @ops.on_tensor_device
     def forward_grid(self, g0: Tensor, t_begin: int = 0, states=None) -> Tensor:
         """g0: feature grid (B, T, 256, ld) f32, ld = dim_input rounded up to 4 (zero padded).
         Streaming (fn_ssl_b200.IPDnet2.IPDnet2Stream): frames [0, t_begin) are encoder history, `states` holds one pair of
@@ -323,6 +325,7 @@ class IPDnet2_lightning(nn.Module):
 IPDNET2_WIN, IPDNET2_HOP = 512, 320          # run_IPDnet2.py:91-93 (win_shift_ratio 0.625)
 
 
+@ops.on_tensor_device
 def stft_center(signal: Tensor, want_magsum: bool = False):
     """IPDnet2's STFT (IPDnet2/Module.py:46-64): torch.stft(center=True) = reflect pad 256 + framing, hop 320."""
     ops._need_cuda(signal)

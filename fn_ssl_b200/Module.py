@@ -68,6 +68,7 @@ class RemoveChFromBatch(nn.Module):
         return data.reshape((nb, nmic) + tuple(data.shape[1:])).float().contiguous()
 
 
+@ops.on_tensor_device
 def forgetting_norm(input: Tensor, sample_length: int = 298) -> Tensor:
     """input [B, C, F, T] magnitudes -> [B, 1, 1, T] recursive frame-mean normaliser (utils_.py:9-55).
     The per-frame sums over F are a torch reduction (plumbing); the T-sequential recursion runs in
@@ -150,6 +151,7 @@ class SourceDetectLocalize(nn.Module):
         self.meth_mode = meth_mode
         self._tcache = None
 
+    @ops.on_tensor_device
     def forward(self, pred_ipd: Tensor, dpipd_template, doa_candidate):
         if self.meth_mode != 'IDL':
             raise Exception("fn_ssl_b200.SourceDetectLocalize: only meth_mode='IDL' is implemented")

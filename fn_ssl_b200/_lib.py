@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libfnssl_b200.so")
 _lock = threading.Lock()
 _lib = None
 
+ABI_VERSION = 4
 F32, F16 = 0, 1
 ALONG_FREQ, ALONG_TIME = 0, 1
 ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
@@ -95,7 +96,6 @@ SIGNATURES = {
     "fnssl_lstm_forward": (_i, [C.POINTER(LstmArgs), _vp]),
     "fnssl_lstm_tc_supported": (_i, [_i, _i, _i]),
     "fnssl_lstm_tc_error_site": (_i, []),
-    "fnssl_lstm_tc_trace": (_i, [C.POINTER(C.c_longlong)]),
     "fnssl_lstm_tc4_trace": (_i, [C.POINTER(C.c_longlong)]),
     "fnssl_ipd_head_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "fnssl_linear_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
@@ -115,17 +115,23 @@ def load(build_if_missing: bool = True):
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            if not build_if_missing:
-                raise RuntimeError(f"{LIB_PATH} is missing: run `python -m fn_ssl_b200.build`")
-            from . import build as _build
+        # The library is git-ignored but lives in the working tree: after an edit of csrc/*.cu a plain import must not run a
+        # stale binary.  build() is stamp-checked (sha256 of every source + header + flags), so when nvcc is present it is
+        # called on every first load and only recompiles what changed; without nvcc the existing library must match HEAD.
+        from . import build as _build
+        if build_if_missing and _build.have_nvcc():
             _build.build()
+        elif not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -m fn_ssl_b200.build`")
+        elif _build.stale_sources():
+            raise RuntimeError(f"{LIB_PATH} is older than its sources ({', '.join(_build.stale_sources())}) and nvcc is not "
+                               "available to rebuild it: run `python -m fn_ssl_b200.build` where nvcc exists")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)   # AttributeError if the header and the library disagree
             fn.restype = res
             fn.argtypes = args
-        if lib.fnssl_abi_version() != 3:
+        if lib.fnssl_abi_version() != ABI_VERSION:
             raise RuntimeError("libfnssl_b200.so: ABI version mismatch, rebuild it")
         _lib = lib
         return lib

@@ -32,6 +32,24 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libfnssl_b200.so")
 
 
+def have_nvcc() -> bool:
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
+def stale_sources():
+    """Sources whose object stamp does not match their current digest (empty list = the library matches the tree)."""
+    out = []
+    for src in _sources():
+        stamp = os.path.join(BUILD, src[:-3] + ".o.sha")
+        if not os.path.exists(stamp) or open(stamp).read() != _digest(os.path.join(CSRC, src)):
+            out.append(src)
+    return out
+
+
 def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 

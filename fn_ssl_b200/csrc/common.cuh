@@ -41,7 +41,9 @@ template <> __device__ __forceinline__ float ld_act<float>(const float* p) { ret
 template <> __device__ __forceinline__ float ld_act<__half>(const __half* p) { return __half2float(*p); }
 template <typename T> __device__ __forceinline__ void st_act(T* p, float v);
 template <> __device__ __forceinline__ void st_act<float>(float* p, float v) { *p = v; }
-template <> __device__ __forceinline__ void st_act<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+// fp16 stores saturate at +-65504 instead of overflowing to inf (an inf activation becomes NaN in a recurrent state); NaN stays NaN
+__device__ __forceinline__ float sat_f16(float x) { return x != x ? x : fminf(fmaxf(x, -65504.0f), 65504.0f); }
+template <> __device__ __forceinline__ void st_act<__half>(__half* p, float v) { *p = __float2half_rn(sat_f16(v)); }
 
 __host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

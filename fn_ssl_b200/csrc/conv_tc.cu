@@ -223,7 +223,7 @@ static int launch_conv(const void* src0, int c0, int ld0, const void* src1, int 
   p.nslab = ns;
   p.nt_in = nt_in; p.nt_out = nt_in / POOL; p.nf = nf; p.ftiles = (nf + 127) / 128;
   p.out = out;
-  p.error_flag = tc_error_flag();
+  p.error_flag = tc_wait_timeout_enabled() ? tc_error_flag() : nullptr;
   CUtensorMap m0, m1, mw;
   if (make_grid_map(&m0, src0, c0, ld0, nb, nt_in, nf, FNSSL_ALONG_TIME, 128)) return 1;
   if (c1 > 0) { if (make_grid_map(&m1, src1, c1, ld1, nb, nt_in, nf, FNSSL_ALONG_TIME, 128)) return 1; }

@@ -59,11 +59,20 @@ doa_idl_step_kernel(const float* __restrict__ map, const float* __restrict__ tem
   __shared__ int s_idx[256];
   __shared__ float s_num[256], s_den[256];
   const int r = blockIdx.x, tid = threadIdx.x;
+  // torch.argmax semantics (Module.py:558): first maximum, and a NaN counts as the maximum (first NaN wins) -- so a row of
+  // NaN / -inf still yields a valid candidate index instead of an out-of-range one
+  auto better = [](float v, int i, float bv, int bi) {
+    if (bi == 0x7fffffff) return true;                 // nothing held yet
+    if (i == 0x7fffffff) return false;
+    const bool vn = v != v, bn = bv != bv;
+    if (vn || bn) return vn && (!bn || i < bi);
+    return v > bv || (v == bv && i < bi);
+  };
   float best = -INFINITY;
   int bi = 0x7fffffff;
   for (int c = tid; c < ncand; c += 256) {
     const float v = map[(size_t)r * ncand + c];
-    if (v > best) { best = v; bi = c; }     // strided scan keeps the smallest index per thread for equal values
+    if (better(v, c, best, bi)) { best = v; bi = c; }
   }
   s_val[tid] = best; s_idx[tid] = bi;
   __syncthreads();
@@ -71,11 +80,11 @@ doa_idl_step_kernel(const float* __restrict__ map, const float* __restrict__ tem
     if (tid < o) {
       const float v = s_val[tid + o];
       const int i = s_idx[tid + o];
-      if (v > s_val[tid] || (v == s_val[tid] && i < s_idx[tid])) { s_val[tid] = v; s_idx[tid] = i; }
+      if (better(v, i, s_val[tid], s_idx[tid])) { s_val[tid] = v; s_idx[tid] = i; }
     }
     __syncthreads();
   }
-  const int cs = s_idx[0];
+  const int cs = min(max(s_idx[0], 0), ncand - 1);
   const float* t = templ + (size_t)cs * K;
   float* x = cur + (size_t)r * K;
   float num = 0.0f, den = 0.0f;

@@ -324,9 +324,11 @@ constexpr int kAsmTF = 16;  // bins per tile
 constexpr int kAsmTT = 32;  // frames per tile
 
 // store `n` consecutive channels (n = 8 halves or 4 floats = 16 bytes) of one grid position
+// fp16 grids saturate at +-65504: a normalised feature re/(mu+eps) can exceed the fp16 range (worst case C*257/(1-alpha), e.g.
+// a tonal onset after digital silence), and an inf would turn into NaN in the along-time LSTM's carried state (sat_f16, common.cuh)
 __device__ __forceinline__ void st_chunk(__half* dst, const float (&v)[8]) {
-  const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-  const __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+  const __half2 h0 = __floats2half2_rn(sat_f16(v[0]), sat_f16(v[1])), h1 = __floats2half2_rn(sat_f16(v[2]), sat_f16(v[3]));
+  const __half2 h2 = __floats2half2_rn(sat_f16(v[4]), sat_f16(v[5])), h3 = __floats2half2_rn(sat_f16(v[6]), sat_f16(v[7]));
   uint4 pk;
   pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
   pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);

@@ -1,6 +1,6 @@
 // Two-chain cluster-resident tcgen05 LSTM kernel (fourth generation of FNSSL_ENGINE_TCGEN05), H in {64, 128, 256}.
 //
-// Same decomposition as lstm_tc2.cu -- the 4H gate columns are split over a cluster of C = H/32 CTAs, each keeping its
+// Decomposition -- the 4H gate columns are split over a cluster of C = H/32 CTAs, each keeping its
 // weight slice resident in shared memory, x_t slabs TMA-multicast to the cluster, h_t exchanged by DSMEM bulk copies --
 // but a cluster now owns TWO full row tiles (sub-tiles A and B, SUB = 128 rows each; 64 for H = 256) whose recurrences
 // are independent and run half a step apart.  Generation 2's step is a serial chain (h-part MMA -> gate math -> DSMEM
@@ -21,6 +21,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
+
+#include <mutex>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -736,13 +738,22 @@ static Plan make_plan(int H, int c0, int c1, int axis = -1) {
   return pl;
 }
 
-long long* g_trace_dev = nullptr;   // device memory: stores into host-mapped memory stall the traced threads for ~2 k cycles per slot
+// FNSSL_TC_TRACE buffers: device memory (stores into host-mapped memory stall the traced threads for ~2 k cycles per slot),
+// one per device, created under a lock
+constexpr int kMaxDevices = 64;
+static long long* g_trace_dev[kMaxDevices] = {};
+static int g_trace_last = -1;
+static std::mutex g_trace_mu;
 static long long* trace_buffer() {
-  if (!g_trace_dev) {
-    if (cudaMalloc(&g_trace_dev, 256 * sizeof(long long)) != cudaSuccess) { g_trace_dev = nullptr; return nullptr; }
-    cudaMemset(g_trace_dev, 0, 256 * sizeof(long long));
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  if (!g_trace_dev[dev]) {
+    if (cudaMalloc(&g_trace_dev[dev], 256 * sizeof(long long)) != cudaSuccess) { g_trace_dev[dev] = nullptr; return nullptr; }
+    cudaMemset(g_trace_dev[dev], 0, 256 * sizeof(long long));
   }
-  return g_trace_dev;
+  g_trace_last = dev;
+  return g_trace_dev[dev];
 }
 
 template <int H, int SUB, bool TRACE, bool NARROW>
@@ -796,7 +807,7 @@ static int launch_t(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
                                (reinterpret_cast<uintptr_t>(a->addend) & 3) == 0 && a->addend_ld % 2 == 0),
                   "lstm(tcgen05): out1/addend must be 4-byte aligned");
   }
-  p.error_flag = tc_error_flag();
+  p.error_flag = tc_wait_timeout_enabled() ? tc_error_flag() : nullptr;
   if (const char* e = getenv("FNSSL_TC_DEBUG")) p.debug = atoi(e);
   if (getenv("FNSSL_TC_TRACE")) p.trace = trace_buffer();
 
@@ -846,8 +857,9 @@ static int launch(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
 
 // diagnostic: copy the last trace (16 slots x 16 clock64 stamps) recorded with FNSSL_TC_TRACE=1
 extern "C" int fnssl_lstm_tc4_trace(long long* out256) {
-  if (!tc4::g_trace_dev) return 0;
-  return cudaMemcpy(out256, tc4::g_trace_dev, 256 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 1 : 0;
+  std::lock_guard<std::mutex> lk(tc4::g_trace_mu);
+  if (tc4::g_trace_last < 0 || !tc4::g_trace_dev[tc4::g_trace_last]) return 0;
+  return cudaMemcpy(out256, tc4::g_trace_dev[tc4::g_trace_last], 256 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 1 : 0;
 }
 
 bool lstm_tc4_supports(int hidden, int c0, int c1) { return tc4::make_plan(hidden, c0, c1).ok; }

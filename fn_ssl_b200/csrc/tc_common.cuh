@@ -1,4 +1,4 @@
-// PTX wrappers shared by the tcgen05 LSTM kernels (lstm_tc.cu, lstm_tc2.cu): mbarrier, TMA, tcgen05, cluster.
+// PTX wrappers shared by the tcgen05 kernels (lstm_tc4.cu, conv_tc.cu): mbarrier, TMA, tcgen05, cluster.
 #pragma once
 #include <cuda.h>
 
@@ -30,17 +30,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// bounded wait: ~1 s of SM clock, then record the site and trap (fails the launch, never hangs the box)
+// Bounded wait (debug aid, opt-in through FNSSL_TC_WAIT_TIMEOUT -> flag != nullptr): ~2 s of SM clock, then record the site and
+// trap -- a protocol bug fails the launch instead of hanging the box.  Production launches pass flag == nullptr and spin without
+// a bound: a trap poisons the whole CUDA context, and preemption / MPS time-slicing / a debugger can legitimately stretch a wait.
+constexpr long long kMbarTimeoutCycles = 4000000000LL;
 static __device__ __noinline__ void mbar_timeout(int* flag, int site) {
-  if (flag) { *reinterpret_cast<volatile int*>(flag) = site; }   // host-mapped: survives the trap
+  *reinterpret_cast<volatile int*>(flag) = site;   // host-mapped: survives the trap
   __threadfence_system();
   __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* flag, int site) {
   if (mbar_try_wait(bar, parity)) return;
+  if (!flag) {
+    while (!mbar_try_wait(bar, parity)) {}
+    return;
+  }
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 2000000000LL) mbar_timeout(flag, site);
+    if (clock64() - t0 > kMbarTimeoutCycles) mbar_timeout(flag, site);
   }
 }
 
@@ -210,7 +217,7 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// ---- host-side helpers implemented in lstm_tc.cu ----------------------------------------------------
+// ---- host-side helpers implemented in tc_host.cu ----------------------------------------------------
 int make_grid_map(CUtensorMap* m, const void* base, int c, int ld, int nb, int nt, int nf, int axis, int mr);
 // output grid map: box = [rows x 32 channels] in the 64B-swizzled layout of an h tile (TMA stores out of the exchange tiles)
 int make_out_map(CUtensorMap* m, const void* base, int ld, int nb, int nt, int nf, int axis, int rows);
@@ -219,6 +226,7 @@ int make_weight_map(CUtensorMap* m, const void* weights, int nslabs, int nchunks
 int make_small_grid_map(CUtensorMap* m, const void* base, int c, int ld, int nb, int nt, int nf, int axis, int mr);
 int make_small_weight_map(CUtensorMap* m, const void* weights, int nslabs, int nchunks_total);
 int* tc_error_flag();
+bool tc_wait_timeout_enabled();   // FNSSL_TC_WAIT_TIMEOUT != 0 (read once): kernels get the error flag, i.e. bounded waits
 
 // ---- thread-block cluster helpers ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -265,9 +273,13 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* flag, int site) {
   if (mbar_try_wait_cluster(bar, parity)) return;
+  if (!flag) {
+    while (!mbar_try_wait_cluster(bar, parity)) {}
+    return;
+  }
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 2000000000LL) mbar_timeout(flag, site);
+    if (clock64() - t0 > kMbarTimeoutCycles) mbar_timeout(flag, site);
   }
 }
 __device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,

@@ -68,10 +68,11 @@ def all_gather_outputs(local_out: Tensor, counts: List[int]) -> Tensor:
     assert len(counts) == world and local_out.shape[0] == counts[dist.get_rank()]
     mx = max(counts)
     tail = tuple(local_out.shape[1:])
-    padded = local_out.new_zeros((mx,) + tail)
-    padded[: local_out.shape[0]] = local_out
     out = local_out.new_empty((world * mx,) + tail)
-    dist.all_gather_into_tensor(out, padded.contiguous())
-    if all(c == mx for c in counts):
+    if all(c == mx for c in counts):                     # the usual case: equal shards, no staging copy at all
+        dist.all_gather_into_tensor(out, local_out.contiguous())
         return out
+    padded = local_out.new_empty((mx,) + tail)           # uneven shards: pad to the largest (the padding rows are dropped below)
+    padded[: local_out.shape[0]] = local_out
+    dist.all_gather_into_tensor(out, padded)
     return torch.cat([out[r * mx: r * mx + counts[r]] for r in range(world)], dim=0)

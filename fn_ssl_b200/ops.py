@@ -6,6 +6,7 @@ libfnssl_b200.so.  Inputs that are not CUDA tensors raise -- there is no CPU fal
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Optional, Tuple
 
 import torch
@@ -54,14 +55,46 @@ def profiled(label: str, flops: float, nbytes: float, launch) -> None:
 
 
 def _stream() -> int:
+    """Current stream of the CURRENT device -- every entry point runs under `on_tensor_device`, which makes the device of its
+    tensors current first, so this is the current stream of the tensors' device."""
     return torch.cuda.current_stream().cuda_stream
 
 
+def on_tensor_device(fn):
+    """Run `fn` with the device of its first CUDA tensor argument as the current device.  The C ABI takes raw pointers and a
+    stream: cudaFuncSetAttribute, tensor-map encodes, the launch itself and `_stream()` all act on the *current* device, so a
+    model living on cuda:1 while cuda:0 is current would otherwise launch into the wrong context."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None:
+            for a in kwargs.values():
+                if isinstance(a, torch.Tensor) and a.is_cuda:
+                    dev = a.device
+                    break
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def _need_cuda(*tensors: Tensor) -> None:
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("fn_ssl_b200 runs on CUDA (sm_100a) only; got a %s tensor -- no CPU fallback exists"
                                % t.device.type)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"fn_ssl_b200: tensors of one call live on different devices ({dev} and {t.device})")
 
 
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
@@ -90,6 +123,7 @@ def stft_num_frames(nsample: int, win_len: int = 512, hop: int = 256) -> int:
     return _lib.load().fnssl_stft_num_frames(nsample, win_len, hop)
 
 
+@on_tensor_device
 def stft(signal: Tensor, win_len: int = 512, hop: int = 256, nfft: int = 512,
          want_magsum: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
     """(nb, nsample, nch) f32 -> ((nb, nfft/2+1, nt, nch) complex64, magsum (nb, nch, nt) | None)."""
@@ -113,6 +147,7 @@ def stft(signal: Tensor, win_len: int = 512, hop: int = 256, nfft: int = 512,
 NORM_GIVEN = 3   # FNSSL_NORM_GIVEN: mu is an input of features() (streaming)
 
 
+@on_tensor_device
 def norm_stream(magsum: Tensor, pairing: str, sample_length: int, t0: int, mu_state: Tensor) -> Tensor:
     """forgetting_norm for frames [t0, t0+nt) of a stream; mu_state (R,) f32 is read (t0 > 0) and updated in place."""
     _need_cuda(magsum, mu_state)
@@ -129,6 +164,7 @@ def norm_stream(magsum: Tensor, pairing: str, sample_length: int, t0: int, mu_st
     return mu
 
 
+@on_tensor_device
 def features(spec: Tensor, magsum: Optional[Tensor], pairing: str, norm: int, sample_length: int, eps: float,
              dtype: torch.dtype, want_cfirst: bool = False, mu: Optional[Tensor] = None
              ) -> Tuple[Tensor, Optional[Tensor], Optional[Tensor]]:
@@ -157,6 +193,7 @@ def features(spec: Tensor, magsum: Optional[Tensor], pairing: str, norm: int, sa
     return feat, mu, cf
 
 
+@on_tensor_device
 def cfirst_to_grid(x: Tensor, dtype: torch.dtype, ld: Optional[int] = None, nt_alloc: Optional[int] = None) -> Tensor:
     """(nb, C, nf, nt) f32 -> grid (nb, nt_alloc or nt, nf, ld) of dtype; padding channels / frames are zero."""
     _need_cuda(x)
@@ -179,6 +216,7 @@ def cfirst_to_grid(x: Tensor, dtype: torch.dtype, ld: Optional[int] = None, nt_a
     return g
 
 
+@on_tensor_device
 def grid_to_cfirst(g: Tensor, Cc: int, ch_off: int = 0) -> Tensor:
     _need_cuda(g)
     lib = _lib.load()
@@ -189,6 +227,7 @@ def grid_to_cfirst(g: Tensor, Cc: int, ch_off: int = 0) -> Tensor:
     return out
 
 
+@on_tensor_device
 def grid_copy(src: Tensor, Cc: int, dst_dtype: torch.dtype, dst_ld: Optional[int] = None, src_off: int = 0) -> Tensor:
     """Copy / convert / re-pad the first Cc channels (from src_off) of a grid into a new grid."""
     _need_cuda(src)
@@ -204,6 +243,7 @@ def grid_copy(src: Tensor, Cc: int, dst_dtype: torch.dtype, dst_ld: Optional[int
     return dst
 
 
+@on_tensor_device
 def grid_add(a: Tensor, b: Tensor) -> Tensor:
     _need_cuda(a, b)
     if a.shape != b.shape or a.dtype != b.dtype:
@@ -219,6 +259,7 @@ def grid_add(a: Tensor, b: Tensor) -> Tensor:
 # LSTM
 # ---------------------------------------------------------------------------------------------
 
+@on_tensor_device
 def lstm(engine: int, axis: int, src0: Tensor, c0: int, src1: Optional[Tensor], c1: int, weights: Tensor, hidden: int,
          num_dirs: int, addend: Optional[Tensor] = None, want_h: bool = True,
          out0: Optional[Tensor] = None, out0_off: int = 0,
@@ -289,6 +330,7 @@ def lstm(engine: int, axis: int, src0: Tensor, c0: int, src1: Optional[Tensor], 
 # heads
 # ---------------------------------------------------------------------------------------------
 
+@on_tensor_device
 def ipd_head(x: Tensor, Cc: int, weight: Tensor, bias: Tensor) -> Tensor:
     _need_cuda(x, weight, bias)
     nb, nt, nf, ld = x.shape
@@ -301,6 +343,7 @@ def ipd_head(x: Tensor, Cc: int, weight: Tensor, bias: Tensor) -> Tensor:
     return out
 
 
+@on_tensor_device
 def linear(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
     _need_cuda(x, weight, bias)
     shp = x.shape
@@ -314,6 +357,7 @@ def linear(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
     return y.reshape(*shp[:-1], w.shape[0])
 
 
+@on_tensor_device
 def causcnn(src0: Tensor, c0: int, src1: Optional[Tensor], c1: int, w1: Tensor, w2: Tensor, w3: Tensor) -> Tensor:
     """CausCnnBlock over grid inputs -> (nb, cout, nf, nt//12) f32."""
     _need_cuda(src0, src1, w1, w2, w3)

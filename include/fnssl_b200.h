@@ -26,7 +26,8 @@
 extern "C" {
 #endif
 
-#define FNSSL_ABI_VERSION 3 /* 2: carried LSTM state; 3: IPDnet2 entry points (fnssl_reflect_pad, fnssl_sn_*) */
+#define FNSSL_ABI_VERSION 4 /* 2: carried LSTM state; 3: IPDnet2 entry points (fnssl_reflect_pad, fnssl_sn_*); 4: one tcgen05 LSTM kernel
+                             (fnssl_lstm_tc_trace of the retired generations removed), training-side targets / loss */
 
 /* element types of grid tensors */
 #define FNSSL_F32 0
@@ -150,9 +151,8 @@ int fnssl_lstm_forward(const fnssl_lstm_args* args, void* stream);
 int fnssl_lstm_tc_supported(int hidden, int c0, int c1);
 /* diagnostic: site code written by a timed-out pipeline wait inside the tcgen05 kernel (0 = none) */
 int fnssl_lstm_tc_error_site(void);
-/* diagnostic: last in-kernel timeline (8 steps x 16 SM-clock stamps + 32 per-warp stamps) recorded when FNSSL_TC_TRACE is set; 0 if none */
-int fnssl_lstm_tc_trace(long long* out160);
-/* same for the two-chain kernel (lstm_tc4.cu): 16 slots x 16 stamps */
+/* diagnostic: last in-kernel timeline of the cluster kernel (lstm_tc4.cu; 16 slots x 16 SM-clock stamps) recorded when
+ * FNSSL_TC_TRACE is set; 0 if none */
 int fnssl_lstm_tc4_trace(long long* out256);
 
 /* ---- heads ---------------------------------------------------------------------------------- */

@@ -8,6 +8,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# GPU tests run the tcgen05 kernels with BOUNDED pipeline waits (a protocol bug traps with a site code instead of hanging the
+# box); production launches spin without a bound (tc_common.cuh).  Must be set before the library reads it (first launch).
+os.environ.setdefault("FNSSL_TC_WAIT_TIMEOUT", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in include/fnssl_b200.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(syms)
-    assert lib.fnssl_abi_version() == 3
+    assert lib.fnssl_abi_version() == 4
 
 
 def test_host_only_entry_points():
@@ -201,4 +201,4 @@ def test_library_links_from_plain_c(tmp_path):
     res = subprocess.run([str(exe)], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     first, second = res.stdout.splitlines()[:2]
-    assert first.split() == ["3", "249", "18"] and "512" in second
+    assert first.split() == ["4", "249", "18"] and "512" in second

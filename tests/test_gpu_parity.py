@@ -167,29 +167,24 @@ def test_lstm_layer_simt(axis, H, bidir, c0, c1, addend):
     assert _lstm_case("simt", axis, 2, 7, 19, c0, c1, H, bidir, addend) <= 2e-5
 
 
-@pytest.mark.parametrize("kernel", ["4", "3", "2", "1"])
 @pytest.mark.parametrize("rows", ["64", "128"])
 @pytest.mark.parametrize("axis", [0, 1])
 @pytest.mark.parametrize("H,bidir,c0,c1,addend", [
     (128, True, 4, 0, False), (128, True, 256, 0, True), (128, True, 256, 4, True), (128, False, 256, 0, False),
     (128, True, 256, 8, False), (64, True, 8, 0, False), (128, False, 128, 8, False), (64, True, 128, 8, True),
     (256, False, 256, 4, True), (256, False, 256, 0, False), (256, False, 256, 8, False)])
-def test_lstm_layer_tcgen05(monkeypatch, kernel, rows, axis, H, bidir, c0, c1, addend):
-    """All tensor-core kernel generations (4 = cluster-resident, two row tiles per cluster half a step apart,
-    3 = cluster-resident + interleaved sub-tiles, 2 = cluster-resident,
-    1 = weight streaming; a generation that does not support a shape hands it to the next lower one), both row-tile shapes (128 / 64
-    sequences per tile), ragged tiles (70 frames / 40 bins are not multiples of the tile), two-source inputs and
-    the fused residual output."""
+def test_lstm_layer_tcgen05(monkeypatch, rows, axis, H, bidir, c0, c1, addend):
+    """The tensor-core cluster kernel (lstm_tc4.cu): both row-tile shapes (128 / 64 sequences per sub-tile), ragged tiles
+    (70 frames / 40 bins are not multiples of the tile), two-source inputs and the fused residual output."""
     from fn_ssl_b200 import config
     if not config.TC_AVAILABLE:
         pytest.skip("tcgen05 engine not built")
     if H == 256 and rows == "128":
         pytest.skip("H = 256 only exists with 64-row tiles")
     monkeypatch.setenv("FNSSL_TC_ROWS", rows)
-    monkeypatch.setenv("FNSSL_TC_KERNEL", kernel)
     nb, nt, nf = (2, 70, 256) if axis == 1 else (2, 70, 40)
     assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, H, bidir, addend) <= 1e-3
-    if addend:   # residual sum accumulated in place (generation 4: TMA reduce-add; older generations: same threads)
+    if addend:   # residual sum accumulated in place (TMA reduce-add onto the residual operand)
         assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, H, bidir, addend, inplace=True) <= 1e-3
 
 
@@ -203,7 +198,6 @@ def test_lstm_narrow_second_source_ring(monkeypatch, small1, axis, H, bidir, c0,
     from fn_ssl_b200 import config
     if not config.TC_AVAILABLE:
         pytest.skip("tcgen05 engine not built")
-    monkeypatch.setenv("FNSSL_TC_KERNEL", "4")
     monkeypatch.setenv("FNSSL_TC_SMALL1", small1)
     nb, nt, nf = (2, 70, 256) if axis == 1 else (2, 70, 40)
     assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, H, bidir, addend, inplace=addend) <= 1e-3
@@ -216,7 +210,6 @@ def test_lstm_layer_tcgen05_multi_tile(monkeypatch, axis, nb, nt, nf):
     from fn_ssl_b200 import config
     if not config.TC_AVAILABLE:
         pytest.skip("tcgen05 engine not built")
-    monkeypatch.setenv("FNSSL_TC_KERNEL", "4")
     for rows in ("128", "64"):
         monkeypatch.setenv("FNSSL_TC_ROWS", rows)
         assert _lstm_case("tcgen05", axis, nb, nt, nf, 64, 4, 128, True, True, inplace=True) <= 1e-3
@@ -444,19 +437,17 @@ def test_decode_many_pairs_and_sources():
 # "next" row: stateful (streaming) API -- carried LSTM state, forgetting-norm state, STFT overlap
 # ------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("kernel", ["4", "2"])
 @pytest.mark.parametrize("rows", ["64", "128"])
 @pytest.mark.parametrize("engine,H,c0,c1", [("simt", 64, 20, 0), ("simt", 256, 256, 4), ("tcgen05", 64, 64, 0),
                                             ("tcgen05", 128, 256, 16), ("tcgen05", 256, 256, 0), ("tcgen05", 256, 128, 16)])
-def test_lstm_carried_state_equals_whole_sequence(monkeypatch, kernel, rows, engine, H, c0, c1):
+def test_lstm_carried_state_equals_whole_sequence(monkeypatch, rows, engine, H, c0, c1):
     """nn.LSTM semantics of (h_0, c_0) -> (h_n, c_n): running a narrow-band layer over 3 chunks with the state carried
     gives bit-identical outputs to one run over the whole sequence, and the final state matches the oracle."""
     from fn_ssl_b200 import config, ops
     from fn_ssl_b200.packing import LSTMParams, run_lstm
     monkeypatch.setenv("FNSSL_TC_ROWS", rows)
-    if engine == "simt" and kernel != "4":
-        pytest.skip("kernel generations only exist in the tensor-core engine")
-    monkeypatch.setenv("FNSSL_TC_KERNEL", kernel)   # generations 4 (default) and 2 implement the carried state
+    if engine == "simt" and rows == "64":
+        pytest.skip("row-tile shapes only exist in the tensor-core engine")
     dt = config.grid_dtype(engine)
     nb, nt, nf = 2, 21, 75                           # 150 rows: ragged against both tile sizes
     torch.manual_seed(7)
