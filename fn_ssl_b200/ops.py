@@ -23,6 +23,7 @@ PAIRING = {"M": PAIRS_M, "MM": PAIRS_MM, "ALL": PAIRS_ALL}
 
 # launch accounting / per-layer timing (used by bench.py; off by default)
 LAUNCHES = 0                 # kernels of libfnssl_b200.so enqueued so far
+TC_LSTM_LAUNCHES = 0         # ... of which LSTM layers on the tcgen05 engine (tests assert the product engine really ran)
 _PROFILE = None              # list of (label, flops, bytes, start_event, end_event) when enabled
 
 
@@ -309,6 +310,9 @@ def lstm(engine: int, axis: int, src0: Tensor, c0: int, src1: Optional[Tensor], 
                 raise RuntimeError(f"lstm: state tensors must be contiguous float32 ({rows}, {hidden}) on {dev}")
         a.h_state, a.c_state, a.state_flags = state[0].data_ptr(), state[1].data_ptr(), 3
     _count(1)
+    if engine == ENGINE_TCGEN05:
+        global TC_LSTM_LAUNCHES
+        TC_LSTM_LAUNCHES += 1
     if _PROFILE is not None:
         rows, steps = (nb * nt, nf) if axis == ALONG_FREQ else (nb * nf, nt)
         flops = 2.0 * rows * steps * num_dirs * 4 * hidden * (c0 + c1 + hidden)

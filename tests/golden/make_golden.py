@@ -88,6 +88,25 @@ def gen_fnssl():
     out["blk_next_y"], out["blk_next_fb"], out["blk_next_nb"] = y2.numpy(), fb2.numpy(), nbs2.numpy()
     for k, v in blk2.state_dict().items():
         out["blk_next_sd." + k] = v.numpy()
+    # ---- the same two blocks at the paper's hidden size 256 (the shapes the tensor-core engine is built for): weights are
+    # NOT stored (3 MB) -- `torch.manual_seed(s); FNblock(...)` reproduces them (asserted here against the oracle's seeded
+    # generator, which follows nn.LSTM's registration order)
+    xb = _randn((1, 6, 8, 4), 17)
+    torch.manual_seed(15)
+    blk = ref_model.FNblock(input_size=4, hidden_size=256, is_online=True, is_first=True).eval()
+    torch.manual_seed(15)
+    sd = {}
+    orc._lstm_init(sd, "fullLstm.", 4, 128, True)
+    orc._lstm_init(sd, "narrLstm.", 260, 256, False)
+    assert all(torch.equal(sd[k], v) for k, v in blk.state_dict().items()) and len(sd) == len(blk.state_dict())
+    with torch.no_grad():
+        y, fb, nbs = blk(xb)
+    out["blk256_first_y"], out["blk256_first_fb"], out["blk256_first_nb"] = y.numpy(), fb.numpy(), nbs.numpy()
+    torch.manual_seed(16)
+    blk2 = ref_model.FNblock(input_size=256, hidden_size=256, is_online=False, is_first=False).eval()
+    with torch.no_grad():
+        y2, fb2, nbs2 = blk2(y, fb_skip=fb, nb_skip=nbs)
+    out["blk256_next_y"], out["blk256_next_fb"], out["blk256_next_nb"] = y2.numpy(), fb2.numpy(), nbs2.numpy()
     # ---- "next" row: DPIPD templates + SourceDetectLocalize (IDL) + PredDOA.predgt2DOA
     mic3 = np.array(((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0), (0.0, 0.05, 0.01)))
     for mode in ("M", "MM"):

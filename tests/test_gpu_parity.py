@@ -248,6 +248,37 @@ def test_fnblock_module_api_matches_reference_golden(golden_fnssl):
     assert _relerr(y2, g["blk_next_y"]) <= 2e-5 and _relerr(fb2, g["blk_next_fb"]) <= 2e-5 and _relerr(nbs2, g["blk_next_nb"]) <= 2e-5
 
 
+def test_fnblock_module_api_hidden256_both_engines(golden_fnssl):
+    """The public FNblock.forward (grid_copy / grid_add / .float() glue, Model.py:31-50) at the paper's hidden size on BOTH
+    engines -- i.e. including the tcgen05 product engine -- against the unmodified reference's outputs.  Weights:
+    `torch.manual_seed(s); FNblock(...)` reproduces the reference module's default init (asserted in make_golden.py)."""
+    import fn_ssl_b200 as F
+    g = golden_fnssl
+    xb = _randn((1, 6, 8, 4), 17).to(DEV)
+    for eng in _engines():
+        torch.manual_seed(15)
+        blk = F.FNblock(input_size=4, hidden_size=256, is_online=True, is_first=True).eval().to(DEV)
+        torch.manual_seed(16)
+        blk2 = F.FNblock(input_size=256, hidden_size=256, is_online=False, is_first=False).eval().to(DEV)
+        blk.engine = blk2.engine = eng
+        before = _tc_launches()
+        y, fb, nbs = blk(xb)
+        tol = TOL[eng]
+        assert y.shape == (1, 6, 8, 256) and fb.shape == (6, 8, 256) and nbs.shape == (8, 6, 256)
+        assert _relerr(y, g["blk256_first_y"]) <= tol and _relerr(fb, g["blk256_first_fb"]) <= tol and _relerr(nbs, g["blk256_first_nb"]) <= tol
+        # second block fed with the REFERENCE's first-block outputs, so its error is not compounded
+        y2, fb2, nbs2 = blk2(torch.from_numpy(g["blk256_first_y"]).to(DEV), fb_skip=torch.from_numpy(g["blk256_first_fb"]).to(DEV),
+                             nb_skip=torch.from_numpy(g["blk256_first_nb"]).to(DEV))
+        assert _relerr(y2, g["blk256_next_y"]) <= tol and _relerr(fb2, g["blk256_next_fb"]) <= tol and _relerr(nbs2, g["blk256_next_nb"]) <= tol
+        if eng == "tcgen05":
+            assert _tc_launches() - before == 4      # all four LSTM layers ran on the tensor-core kernel
+
+
+def _tc_launches():
+    from fn_ssl_b200 import ops
+    return ops.TC_LSTM_LAUNCHES
+
+
 @pytest.mark.parametrize("tag,kw", [("d2", dict(input_size=4, hidden_size=128, max_track=2, is_online=True)),
                                     ("m4", dict(input_size=8, hidden_size=256, max_track=2, is_online=True)),
                                     ("off", dict(input_size=4, hidden_size=128, max_track=2, is_online=False))])
@@ -353,6 +384,90 @@ def test_fnssl_batch16_properties():
         assert torch.equal(solo[0], out[b]), b
 
 
+@pytest.mark.parametrize("tag,kw,B", [("cfg2 offline", dict(is_online=False), 16), ("cfg4 doa", dict(is_online=False, is_doa=True), 32),
+                                      ("cfg4 doa online", dict(is_online=True, is_doa=True), 32)])
+def test_fnssl_benched_configs_at_size(tag, kw, B):
+    """The configurations bench.py measures, at their per-GPU batch sizes (cfg2: 16 x 4 s offline; cfg4: the 32-utterance
+    shard of the global 256 batch at 8 GPUs, DOA head): one utterance of the batch against the oracle, and every probed
+    utterance bit-identical to its solo run (utterances are independent)."""
+    import fn_ssl_b200 as F
+    sig = orc.white_noise(B, 64000, 2)
+    sd = orc.seeded_fnssl_state_dict(0, **kw)
+    net = F.FN_SSL(**kw).eval()
+    net.load_state_dict(sd)
+    pipe = F.FNSSLPipeline(net.to(DEV))
+    out = pipe(sig.to(DEV))
+    width = 180 if kw.get("is_doa") else 512
+    assert out.shape == (B, 20, width) and torch.isfinite(out).all()
+    k = B - 3
+    ref = orc.fnssl_forward(orc.preprocess_fnssl(sig[k:k + 1]), sd, fast=True)
+    assert _relerr(out[k:k + 1], ref) <= TOL[net._engine()]
+    for b in (0, k, B - 1):
+        assert torch.equal(pipe(sig[b:b + 1].to(DEV))[0], out[b]), b
+
+
+def test_ipdnet_cfg3_at_size():
+    """BASELINE configs[2]: IPDnet 4-mic, hidden 256, online, batch 32 x 4 s -- one utterance against the oracle, solo runs
+    bit-identical."""
+    import fn_ssl_b200 as F
+    B = 32
+    sig = orc.white_noise(B, 64000, 4)
+    kw = dict(input_size=8, hidden_size=256, max_track=2, is_online=True)
+    sd = orc.seeded_ipdnet_state_dict(0, **kw)
+    net = F.IPDnet(**kw).eval()
+    net.load_state_dict(sd)
+    pipe = F.IPDnetPipeline(net.to(DEV))
+    out = pipe(sig.to(DEV))
+    assert out.shape == (B, 20, 512, 3, 2) and torch.isfinite(out).all()
+    k = 21
+    ref = orc.ipdnet_forward(orc.preprocess_ipdnet(sig[k:k + 1]), sd, fast=True)
+    assert _relerr(out[k:k + 1], ref) <= TOL[net._engine()]
+    for b in (0, k, B - 1):
+        assert torch.equal(pipe(sig[b:b + 1].to(DEV))[0], out[b]), b
+
+
+def test_silence_then_tone_stays_finite_on_fp16_grids():
+    """A tonal onset after digital silence drives re/(mu+eps) beyond the fp16 range (mu is still ~0 when the tone starts):
+    the fp16 feature grid saturates at +-65504 instead of overflowing to inf, so the along-time LSTM state stays finite and the
+    output stays close to the fp32 engine's."""
+    import fn_ssl_b200 as F
+    n = 64000
+    t = torch.arange(n, dtype=torch.float32) / 16000.0
+    sig = torch.zeros(1, n, 2)
+    sig[0, 20000:, 0] = 1000.0 * torch.sin(2 * np.pi * 1000.0 * t[20000:])
+    sig[0, 20000:, 1] = 1000.0 * torch.sin(2 * np.pi * 1000.0 * t[20000:] + 0.3)
+    sd = orc.seeded_fnssl_state_dict(0)
+    outs = {}
+    for eng in _engines():
+        net = F.FN_SSL().eval()
+        net.load_state_dict(sd)
+        net.to(DEV).engine = eng
+        outs[eng] = F.FNSSLPipeline(net)(sig.to(DEV))
+        assert torch.isfinite(outs[eng]).all(), eng
+    from fn_ssl_b200 import ops
+    spec, magsum = ops.stft(sig.to(DEV), want_magsum=True)
+    g16, _, _ = ops.features(spec, magsum, "MM", ops.NORM_FORGETTING, 298, 1e-6, torch.float16)
+    assert torch.isfinite(g16).all() and float(g16.float().abs().max()) <= 65504.0
+
+
+def test_tensors_on_a_non_current_device():
+    """Models / tensors living on cuda:1 while cuda:0 is the current device: every wrapper makes the tensors' device
+    current for the launch (ops.on_tensor_device), so results equal the cuda:0 run bit for bit."""
+    import fn_ssl_b200 as F
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sig = orc.white_noise(2, 512 + 256 * 25, 2, seed=9)
+    sd = orc.seeded_fnssl_state_dict(0)
+    outs = []
+    torch.cuda.set_device(0)
+    for dev in ("cuda:0", "cuda:1"):
+        net = F.FN_SSL().eval()
+        net.load_state_dict(sd)
+        outs.append(F.FNSSLPipeline(net.to(dev))(sig.to(dev)).cpu())
+        assert torch.cuda.current_device() == 0
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_ipdnet_end_to_end_4mic():
     import fn_ssl_b200 as F
     sig = orc.white_noise(1, 64000, 4)
@@ -431,6 +546,31 @@ def test_decode_many_pairs_and_sources():
     doa, vad, ss = sdl(pred.to(DEV), T, d.doa_candidate)
     assert np.array_equal(doa.cpu().numpy(), ref[0].numpy())
     assert _relerr(vad, ref[1]) <= 1e-4 and _relerr(ss, ref[2]) <= 1e-4
+
+
+def test_source_detect_localize_degenerate_rows_follow_torch_argmax():
+    """Rows whose spatial spectrum is all NaN / all -inf (e.g. a NaN network output): torch.argmax -- what the reference calls
+    at Module.py:558 -- returns the first NaN (NaN counts as the maximum) or index 0; the kernel must do the same and never
+    index the templates out of range."""
+    import fn_ssl_b200 as F
+    d = F.DPIPD(ndoa_candidate=[37, 73], mic_location=np.array(((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0))), nf=257, fre_max=8000,
+                ch_mode="MM", speed=340)
+    t2, cand = orc.doa_templates_for_decode(d.dpipd_template)      # horizontal plane, azimuth 0..pi: (1, 37, 512, 1)
+    T = torch.from_numpy(t2)
+    pred = 0.8 * T[0, 11][None, None].repeat(1, 4, 1, 1) + 0.01 * _randn((1, 4, 512, 1), 3)
+    pred[0, 1] = float("nan")                       # whole row NaN -> spectrum row all NaN
+    pred[0, 2, 5, 0] = float("inf")                 # inf * (+/-) template values -> NaN / +-inf mix
+    sdl = F.SourceDetectLocalize(max_num_sources=1, source_num_mode="kNum", meth_mode="IDL")
+    doa, vad, ss = sdl(pred.to(DEV), T, cand)
+    torch.cuda.synchronize()                        # a bad index would have faulted by now
+    smap = (pred.reshape(4, 512) @ T.reshape(37, 512).t()) / 256.0
+    want = smap.argmax(dim=1)
+    assert int(want[0]) == 11 and int(want[1]) == 0
+    azi = torch.as_tensor(np.asarray(cand[1]), dtype=torch.float32)
+    got = doa.cpu()[0, :, 1, 0]
+    assert torch.equal(got[[0, 3]], azi[want[[0, 3]]])          # ordinary rows
+    assert float(got[1]) == float(azi[want[1]])                 # all-NaN row: first NaN = candidate 0, as torch.argmax
+    assert 0.0 <= float(got[2]) <= float(azi[-1])               # mixed row: a valid candidate
 
 
 # ------------------------------------------------------------------------------------------------

@@ -7,7 +7,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["FNSSL_TC_TRACE"] = "1"
-os.environ["FNSSL_TC_KERNEL"] = "4"
+os.environ.setdefault("FNSSL_TC_WAIT_TIMEOUT", "1")
 import torch  # noqa: E402
 from fn_ssl_b200 import _lib  # noqa: E402
 from fn_ssl_b200.packing import LSTMParams, run_lstm  # noqa: E402
