@@ -104,6 +104,9 @@ SIGNATURES = {
     "fnssl_sn_freq_forward": (_i, [C.POINTER(SnFreqArgs), _vp]),
     "fnssl_sn_time_forward": (_i, [C.POINTER(SnTimeArgs), _vp]),
     "fnssl_sn_head_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "fnssl_dpipd_targets": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "fnssl_ipd_mse_loss": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "fnssl_ipd_pit_mse_loss": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "fnssl_causcnn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "fnssl_causcnn_forward": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
 }
@@ -119,14 +122,17 @@ def load(build_if_missing: bool = True):
         # stale binary.  build() is stamp-checked (sha256 of every source + header + flags), so when nvcc is present it is
         # called on every first load and only recompiles what changed; without nvcc the existing library must match HEAD.
         from . import build as _build
-        if build_if_missing and _build.have_nvcc():
+        path = os.environ.get("FNSSL_B200_LIB")            # development / profiling only: an experimental variant library
+        if path:                                            # (tools/build_variant.py); never set in production
+            pass
+        elif build_if_missing and _build.have_nvcc():
             _build.build()
         elif not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -m fn_ssl_b200.build`")
         elif _build.stale_sources():
             raise RuntimeError(f"{LIB_PATH} is older than its sources ({', '.join(_build.stale_sources())}) and nvcc is not "
                                "available to rebuild it: run `python -m fn_ssl_b200.build` where nvcc exists")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path or LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)   # AttributeError if the header and the library disagree
             fn.restype = res

@@ -30,8 +30,43 @@
 namespace fnssl {
 namespace tc4 {
 
-constexpr int kThreads = 608;          // producer warp + h-part MMA warp + 16 epilogue warps + x-part MMA warp
+// Build-time variants (A/B measured on the B200, profiles/r2_lstm_variants.txt):
+//   TC4_PROD2 : a second single-lane TMA producer (warp 19) -- the x ring was producer-ISSUE bound (~300 instructions per slot)
+//   TC4_PUB   : 1 or 2 publisher warps take the h exchange (DSMEM pushes) and the TMA output stores off the epilogue warps,
+//               which then never meet on a named barrier nor wait for a bulk store to drain (0 = the epilogue publishes itself)
+//   (more than 20 warps per CTA cap the kernel at 80 registers per thread: 6 warps on one SM sub-partition)
+#ifndef TC4_PROD2
+#define TC4_PROD2 1
+#endif
+#ifndef TC4_PUB
+#define TC4_PUB 1
+#endif
+//   TC4_CREG  : the cell state lives in the epilogue threads' registers (8 or 4 values per sub-tile) instead of TMEM: one
+//               tcgen05.ld less per slot and no tcgen05.st / wait::st on the epilogue's serial path
+//   TC4_HFREE_EARLY : the "h_{t-1} has been read everywhere" barrier is polled (non-blocking test_wait) BEFORE the gate math so
+//               that its ~100-cycle latency hides under the MUFU work; the blocking wait only runs if that poll failed
+//   (both measured neutral-to-slightly-negative on the B200 -- the epilogue is MUFU-pipe bound, not latency bound -- and CREG
+//   costs registers, so they are off by default)
+//   TC4_XORDER : the x-part of slot n+2 is issued only after the h-part of slot n HAS BEEN ISSUED, so the tensor pipe runs
+//               h(n) x(n+2) h(n+1) x(n+3) ...  Without it the x-part is issued as soon as its accumulator buffer drains, i.e.
+//               shortly BEFORE h(n) becomes ready, and the latency-critical h-part queues behind up to 1 k cycles of x-part MMAs
+#ifndef TC4_CREG
+#define TC4_CREG 0
+#endif
+#ifndef TC4_HFREE_EARLY
+#define TC4_HFREE_EARLY 0
+#endif
+#ifndef TC4_XORDER
+#define TC4_XORDER 1
+#endif
 constexpr int kXWarp = 18;
+constexpr int kProd2Warp = TC4_PROD2 ? 19 : -1;          // second TMA producer lane (odd ring stages + the L2 prefetch)
+constexpr int kPubWarp0 = 19 + (TC4_PROD2 ? 1 : 0);      // publisher warps (kNumPub of them)
+constexpr int kNumPub = TC4_PUB;
+constexpr int kQPerPub = kNumPub ? 4 / kNumPub : 4;     // TMEM lane quadrants served by one publisher warp
+static_assert(kNumPub == 0 || kNumPub == 1 || kNumPub == 2, "TC4_PUB in {0, 1, 2}");
+// producer warp + h-part MMA warp + 16 epilogue warps + x-part MMA warp [+ 2nd producer warp] [+ 2 publisher warps]
+constexpr int kThreads = 32 * (19 + (TC4_PROD2 ? 1 : 0) + kNumPub);
 constexpr int kEpiThreads = 512;
 constexpr int kSlabK = 64;
 constexpr int kWSlab = 128 * 128;      // [128 gate columns x 64] fp16
@@ -42,7 +77,7 @@ constexpr int kMaxXStages = 6;
 constexpr int kAccBufs = 3;
 constexpr int kSmemLimit = 232448;
 constexpr int kNumBarsBase = 1 + 2 * kMaxXStages + 3 * kAccBufs + 4;
-constexpr int kNumBars = kNumBarsBase + 4;     // + X2_FULL / X2_EMPTY of the two-entry ring of the narrow second source
+constexpr int kNumBars = kNumBarsBase + 4 + 8 + kAccBufs;   // + X2_FULL / X2_EMPTY of the narrow second source's ring, + H_READY[sub][quadrant], + HP_ISSUED[acc buffer]
 constexpr int kWSmall = kChunkN * 32;          // [128 gate columns x 16] fp16 weight slab of a narrow source (32B swizzle)
 
 struct Params {
@@ -149,16 +184,21 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   auto XP_DONE = [&](int i) { return bar0 + 8u * (1 + 2 * kMaxXStages + 2 * kAccBufs + 4 + i); };
   auto X2_FULL = [&](int i) { return bar0 + 8u * (kNumBarsBase + i); };
   auto X2_EMPTY = [&](int i) { return bar0 + 8u * (kNumBarsBase + 2 + i); };
+  auto H_READY = [&](int sub, int q) { return bar0 + 8u * (kNumBarsBase + 4 + sub * 4 + q); };   // quadrant q of h_t(sub) is in shared memory
+  auto HP_ISSUED = [&](int i) { return bar0 + 8u * (kNumBarsBase + 12 + i); };                    // the h-part of the slot using buffer i has been issued
 
   if (tid == 0) {
     mbar_init(W_FULL, 1);
     const int xe = nomc ? 1 : C;
     for (int i = 0; i < kMaxXStages; ++i) { mbar_init(X_FULL(i), 1); mbar_init(X_EMPTY(i), xe); }
-    for (int i = 0; i < kAccBufs; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), kEpiThreads); mbar_init(XP_DONE(i), 1); }
+    for (int i = 0; i < kAccBufs; ++i) {
+      mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), kEpiThreads / 32); mbar_init(XP_DONE(i), 1); mbar_init(HP_ISSUED(i), 1);
+    }
     for (int i = 0; i < 2; ++i) { mbar_init(X2_FULL(i), 1); mbar_init(X2_EMPTY(i), xe); }
     for (int sub = 0; sub < 2; ++sub) {
       mbar_init(H_FULL(sub), 5);    // MMA thread's expect_tx + 4 local quadrants (+ tx bytes of the C-1 remote tiles)
-      mbar_init(H_FREE(sub), C);    // one multicast commit per CTA of the cluster
+      mbar_init(H_FREE(sub), C + kNumPub);    // one multicast commit per CTA of the cluster (+ the publishers: stores drained)
+      for (int q = 0; q < 4; ++q) mbar_init(H_READY(sub, q), 4);   // the four epilogue warps of a quadrant
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -220,15 +260,24 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   // tensor pipe's 1.5 k), so they are kept lean: the elected lane runs the whole loop (ptxas emits tcgen05 / TMA
   // instructions straight-line behind an elect.sync predicate), descriptors are base + offset adds, and the x-part and
   // the h-part are issued by two different warps.
-  if (warp == 0) {
-    // ============================== TMA producer ==============================
+  if (warp == 0 || warp == kProd2Warp) {
+    // ============================== TMA producers ==============================
+    // Two single-lane producers walk the same slab sequence (stage / phase / fetcher counters advance for every slab) but
+    // producer `pid` only ACTS on the ring stages with (stage & 1) == pid, so the per-slab issue work is split in two.  The
+    // split is by STAGE, not by slab: all uses of one stage must be refilled by the same lane in program order, otherwise a
+    // lane running ahead of the other could pass a parity wait one phase early (mbarrier parity only disambiguates
+    // consecutive phases).
+    // Producer 0 also loads the weights and feeds the narrow-source ring; producer 1 also issues the L2 prefetches.
+    const int pid = TC4_PROD2 ? (warp == 0 ? 0 : 1) : 2;     // 2 = the only producer: acts on every stage
     if (elect_one()) {
+      if (pid != 1) {
       mbar_expect_tx(W_FULL, (uint32_t)(nxb + NHS) * kWSlab + (small1 ? (uint32_t)kWSmall : 0u));
       for (int j = 0; j < nxb; ++j)
         tma_load_2d(w_base + j * kWSlab, &map_w, W_FULL, j * kSlabK, (dir * C + (int)rank) * kChunkN);
       for (int j = 0; j < NHS; ++j)     // the h slabs follow ALL x slabs in the packed buffer
         tma_load_2d(w_base + (nxb + j) * kWSlab, &map_w, W_FULL, (nxs + j) * kSlabK, (dir * C + (int)rank) * kChunkN);
       if (small1) tma_load_2d(w2_base, &map_w2, W_FULL, nxb * kSlabK, (dir * C + (int)rank) * kChunkN);
+      }
       int stage = 0, fetcher = 0;
       uint32_t phase = 0;                 // parity of the X_EMPTY wait; the first pass over the ring does not wait
       bool wrapped = false;
@@ -240,24 +289,22 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         const int tt = nn >> 1;
         const int ss = dir ? (L - 1 - tt) : tt;
         const int rr0 = coord_r0 + (nn & 1) * SUB;
-        int f = (nn * nxs) % C;
-        for (int j = 0; j < nxs; ++j) {
-          if ((uint32_t)f == rank) {
-            const CUtensorMap* m = ((p.xs_srcmask >> j) & 1) ? &map_src1 : &map_src0;
-            const int k0 = (int)((p.xs_k0pack >> (8 * j)) & 0xff) * 16;
-            if (along_f) tma_prefetch_l2_4d(m, k0, ss, rr0, 0);
-            else tma_prefetch_l2_4d(m, k0, rr0, ss, coord_b);
-          }
-          if (++f == C) f = 0;
+        // slab j of slot nn is fetched by CTA (nn * nxs + j) % C: visit only this CTA's slabs
+        for (int j = (int)((rank + (uint32_t)C - (uint32_t)((nn * nxs) % C)) % (uint32_t)C); j < nxs; j += C) {
+          const CUtensorMap* m = ((p.xs_srcmask >> j) & 1) ? &map_src1 : &map_src0;
+          const int k0 = (int)((p.xs_k0pack >> (8 * j)) & 0xff) * 16;
+          if (along_f) tma_prefetch_l2_4d(m, k0, ss, rr0, 0);
+          else tma_prefetch_l2_4d(m, k0, rr0, ss, coord_b);
         }
       };
-      for (int nn = 1; nn < ahead && nn < nslots; ++nn) prefetch_slot(nn);
+      if (pid != 0) for (int nn = 1; nn < ahead && nn < nslots; ++nn) prefetch_slot(nn);
       for (int n = 0; n < nslots; ++n) {
         const int t = n >> 1, sub = n & 1;
         const int s = dir ? (L - 1 - t) : t;
         const int r0 = coord_r0 + sub * SUB;
-        if (ahead && n + ahead < nslots) prefetch_slot(n + ahead);
+        if (pid != 0 && ahead && n + ahead < nslots) prefetch_slot(n + ahead);
         for (int j = 0; j < nxb; ++j) {
+          if (pid == 2 || (stage & 1) == pid) {
           if (wrapped) mbar_wait(X_EMPTY(stage), phase, p.error_flag, 100 + stage);
           mbar_expect_tx(X_FULL(stage), kXSlab);
           if (nomc) {
@@ -273,10 +320,12 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
             if (along_f) tma_load_4d_mc(dst, m, X_FULL(stage), k0, s, r0, 0, mask);
             else tma_load_4d_mc(dst, m, X_FULL(stage), k0, r0, s, coord_b, mask);
           }
+          }
           if (++fetcher == C) fetcher = 0;
           if (++stage == XS) { stage = 0; phase ^= wrapped ? 1u : 0u; wrapped = true; }
         }
-        if (small1) {      // the narrow source's slab of this slot: entry n & 1 of its own ring, use number n >> 1
+        if (small1 && pid == 1) { if (++fetcher == C) fetcher = 0; }
+        if (small1 && pid != 1) {      // the narrow source's slab of this slot: entry n & 1 of its own ring, use number n >> 1
           const int s2 = n & 1;
           if (n >= 2) mbar_wait(X2_EMPTY(s2), (uint32_t)(((n >> 1) - 1) & 1), p.error_flag, 110 + s2);
           mbar_expect_tx(X2_FULL(s2), kXSmall);
@@ -304,6 +353,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       const uint64_t b_desc0 = make_sw128_desc(w_base);
       int xstage = 0, a = 0;
       uint32_t xphase = 0, empty_par = 0;
+      [[maybe_unused]] uint32_t hp_par = 0;
       for (int n = 0; n < nslots; ++n) {
         long long* tp = (TRACE && tr_cta && n >= 16 && n < 32) ? p.trace + (n - 16) * 16 : nullptr;
         long long w_acc = 0, e_acc = 0;
@@ -311,6 +361,11 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         if (n >= kAccBufs) {
           mbar_wait(ACC_EMPTY(a), (empty_par >> a) & 1u, p.error_flag, 201 + a);
           empty_par ^= 1u << a;
+        }
+        if (TC4_XORDER && n >= 2) {     // queue behind the h-part of slot n-2 (buffer (n-2) % 3 == (a+1) % 3), never ahead of it
+          const int b = (a == kAccBufs - 1) ? 0 : a + 1;
+          mbar_wait(HP_ISSUED(b), (hp_par >> b) & 1u, p.error_flag, 205 + b);
+          hp_par ^= 1u << b;
         }
         if (TRACE && tp) e_acc = clock64() - e_acc;
         tc_fence_after();
@@ -382,8 +437,72 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           tc_fence_after();
         }
         umma_commit(ACC_FULL(a));            // fires when the h-part (and G_x, complete since XP_DONE) is done
+        if (TC4_XORDER) mbar_arrive(HP_ISSUED(a));   // the x-part issuer may now queue G_x of slot n+2 behind these MMAs
         if (TRACE && tp) tp[2] = clock64();
         a = (a == kAccBufs - 1) ? 0 : a + 1;
+      }
+    }
+    __syncwarp();
+  } else if (TC4_PUB && warp >= kPubWarp0) {
+    // ============================== publisher warps ==============================
+    // One elected lane per warp serves kQPerPub TMEM lane quadrants: as soon as a quadrant's four epilogue warps have written
+    // their part of h_t into the CTA's own exchange tile (H_READY), it pushes that 1-2 KB region to every peer (DSMEM bulk
+    // copies completing tx bytes on the peers' H_FULL), arrives locally, and issues the TMA tile store / reduce-add of the
+    // same region to HBM.  The epilogue warps therefore never wait for each other or for a bulk operation.
+    // Write-after-read on the tile: the stores of slot n (committed as one bulk group) must have READ the tile before the
+    // epilogue overwrites it at slot n + 2; the publisher checks that after issuing slot n + 1 (wait_group.read 1) and then
+    // arrives on H_FREE(sub(n)) -- the barrier the epilogue already waits on for "every CTA's h-part has read h_{t-1}".
+    const int pw = warp - kPubWarp0;
+    if (elect_one()) {
+      constexpr uint32_t kQuadBytes = (SUB == 128) ? 2048u : 1024u;
+      constexpr int kQuadRows = SUB / 4;
+      const bool along_f = p.axis == FNSSL_ALONG_FREQ;
+      const int out_c = p.out0_off + dir * H + (int)rank * kChunkUnits;
+      const int out1_c = dir * H + (int)rank * kChunkUnits;
+      uint32_t peer_hs[C > 1 ? C - 1 : 1], peer_bar0[C > 1 ? C - 1 : 1], peer_bar1[C > 1 ? C - 1 : 1];
+#pragma unroll
+      for (int dd = 1; dd < C; ++dd) {
+        const uint32_t d = (rank + (uint32_t)dd) % C;
+        peer_hs[dd - 1] = mapa_shared(hs_base, d);
+        peer_bar0[dd - 1] = mapa_shared(H_FULL(0), d);
+        peer_bar1[dd - 1] = mapa_shared(H_FULL(1), d);
+      }
+      if (hoff) { mbar_arrive(H_FREE(0)); mbar_arrive(H_FREE(1)); }   // the first phase has no earlier stores to wait for
+      const bool tma_any = p.tma_out != 0;
+      for (int n = 0; n < nslots; ++n) {
+        const int t = n >> 1, sub = n & 1;
+        const int s = dir ? (L - 1 - t) : t;
+        const bool push = t + 1 < L;
+        if (push || tma_any) {
+#pragma unroll
+          for (int qq = 0; qq < kQPerPub; ++qq) {
+            const int q = kQPerPub * pw + qq;
+            mbar_wait(H_READY(sub, q), (uint32_t)(t & 1), p.error_flag, 400 + sub * 4 + q);
+            const uint32_t off = (uint32_t)(sub * C + (int)rank) * kHTile + (uint32_t)q * kQuadBytes;
+            if (push) {
+#pragma unroll
+              for (int dd = 1; dd < C; ++dd)
+                bulk_copy_s2c(peer_hs[dd - 1] + off, hs_base + off, kQuadBytes, sub ? peer_bar1[dd - 1] : peer_bar0[dd - 1]);
+              mbar_arrive(H_FULL(sub));     // the local copy of this quadrant is in place
+            }
+            if (tma_any) {
+              const int r0 = coord_r0 + sub * SUB + q * kQuadRows;
+              if (p.tma_out & 1) {
+                if (along_f) tma_store_4d(&map_out0, hs_base + off, out_c, s, r0, 0);
+                else tma_store_4d(&map_out0, hs_base + off, out_c, r0, s, coord_b);
+              }
+              if (p.tma_out & 2) {
+                if (along_f) tma_reduce_add_4d(&map_out1, hs_base + off, out1_c, s, r0, 0);
+                else tma_reduce_add_4d(&map_out1, hs_base + off, out1_c, r0, s, coord_b);
+              }
+            }
+          }
+          if (tma_any) bulk_commit_group();
+        }
+        if (n >= 1) {     // slot n-1's stores (the other sub-tile's exchange tile) have read their source
+          if (tma_any) bulk_wait_read_1();
+          mbar_arrive(H_FREE(sub ^ 1));
+        }
       }
     }
     __syncwarp();
@@ -398,7 +517,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
     const bool fast = !(p.debug & 32);
     const bool tr = tr_cta && warp == 2 && lane == 0;
     constexpr uint32_t kQuadBytes = (SUB == 128) ? 2048u : 1024u;   // a quadrant's rows x 64 B of the CTA's own h tile
-    const uint32_t hquad = (uint32_t)rank * kHTile + (uint32_t)q * kQuadBytes;
+    [[maybe_unused]] const uint32_t hquad = (uint32_t)rank * kHTile + (uint32_t)q * kQuadBytes;
 
     // publish the quadrant's region of the CTA's own h tile: 4 warps meet, one thread pushes it to every peer
     // The same shared-memory tile feeds the HBM outputs: one TMA tile store per quadrant writes h_t (out0), one TMA
@@ -412,6 +531,11 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
     const bool along_f = p.axis == FNSSL_ALONG_FREQ;
     auto publish_quadrant = [&](uint32_t buf, int sub, int s, bool push) {
       fence_async_smem();
+#if TC4_PUB
+      // hand the quadrant to the publisher warp: one arrive per warp, no rendezvous of the epilogue warps
+      __syncwarp();
+      if (lane == 0) mbar_arrive(H_READY(sub, q));
+#else
       named_bar_sync(1 + q, 128);
       {
         if (pusher) {
@@ -438,6 +562,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           }
         }
       }
+#endif
     };
     const bool thr_out0 = p.out0 && !(p.tma_out & 1);     // per-thread stores (fallback paths)
     const bool thr_out1 = p.out1 && !(p.tma_out & 2);
@@ -467,6 +592,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       // this thread's 16-byte h piece inside the CTA's own [128 x 32] tile (64B swizzle: chunk ^= (row >> 1) & 3)
       const uint32_t hpiece = (uint32_t)rank * kHTile + (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u +
                               (uint32_t)((sg ^ ((r >> 1) & 3)) << 4);
+      [[maybe_unused]] float creg[2][8];      // TC4_CREG: this thread's cell state per sub-tile (the sub loop is unrolled)
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {
         float z[8];
@@ -476,9 +602,14 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
 #pragma unroll
           for (int i = 0; i < 8; ++i) z[i] = __ldg(p.c_state + (row0 + sub * SUB + r) * H + ua + i);
         }
+#if TC4_CREG
+#pragma unroll
+        for (int i = 0; i < 8; ++i) creg[sub][i] = z[i];
+#else
         tmem_st8(tmem_c + (uint32_t)(sub * 32) + lane_off + u0, z);
+#endif
       }
-      tmem_wait_st();
+      if (!TC4_CREG) tmem_wait_st();
 #pragma unroll 1
       for (int t = 0; t < L; ++t) {
         const int s = dir ? (L - 1 - t) : t;
@@ -491,24 +622,35 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
             const long long posn = base[sub] + (long long)(dir ? (L - 2 - t) : (t + 1)) * sstride;
             addv_next[sub] = __ldg(reinterpret_cast<const uint4*>(p.addend + posn * p.addend_ld + dir * H + ua));
           }
-          if (tma_any && pusher) bulk_wait_read_all();   // the tile stores of the previous slot have read their source
+          if (!TC4_PUB && tma_any && pusher) bulk_wait_read_all();   // the tile stores of the previous slot have read their source
           if (TRACE && tp) tp[4] = clock64();
           mbar_wait(ACC_FULL(a), (full_par >> a) & 1u, p.error_flag, 300 + a);
           full_par ^= 1u << a;
           if (TRACE && tp) tp[5] = clock64();
           tc_fence_after();
           const uint32_t acc = tmem_acc + (uint32_t)a * kChunkN + lane_off + u0;
-          const uint32_t cad = tmem_c + (uint32_t)(sub * 32) + lane_off + u0;
-          float gti[8], gtf[8], gtg[8], gto[8], cs[8];
+          [[maybe_unused]] const uint32_t cad = tmem_c + (uint32_t)(sub * 32) + lane_off + u0;
+          float gti[8], gtf[8], gtg[8], gto[8];
+#if TC4_CREG
+          float (&cs)[8] = creg[sub];
+#else
+          float cs[8];
+#endif
           tmem_ld8(acc + 0 * kChunkUnits, gti);
           tmem_ld8(acc + 1 * kChunkUnits, gtf);
           tmem_ld8(acc + 2 * kChunkUnits, gtg);
           tmem_ld8(acc + 3 * kChunkUnits, gto);
-          tmem_ld8(cad, cs);
+          if (!TC4_CREG) tmem_ld8(cad, cs);
+          // poll "h_{t-1} has been read by every CTA" now: the answer is only needed after the gate math
+          const bool will_publish = t + 1 < L || tma_any;
+          bool hfree_ok = !(will_publish && t + hoff > 0);
+          if (TC4_HFREE_EARLY && !hfree_ok) hfree_ok = mbar_test_wait_cluster(H_FREE(sub), (uint32_t)((t - 1 + hoff) & 1));
           tmem_wait_ld();
-          tmem_ld_dep(gti); tmem_ld_dep(gtf); tmem_ld_dep(gtg); tmem_ld_dep(gto); tmem_ld_dep(cs);
+          tmem_ld_dep(gti); tmem_ld_dep(gtf); tmem_ld_dep(gtg); tmem_ld_dep(gto);
+          if (!TC4_CREG) tmem_ld_dep(cs);
           tc_fence_before();
-          mbar_arrive(ACC_EMPTY(a));      // accumulator drained: the MMA thread may produce G_x of slot n+3 into it
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ACC_EMPTY(a));      // accumulator drained (this warp): the MMA thread may produce G_x of slot n+3 into it
           a = (a == kAccBufs - 1) ? 0 : a + 1;
           float hv[8];
           if (p.debug & 1) {
@@ -531,17 +673,17 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           pk.x = *reinterpret_cast<uint32_t*>(&h01); pk.y = *reinterpret_cast<uint32_t*>(&h23);
           pk.z = *reinterpret_cast<uint32_t*>(&h45); pk.w = *reinterpret_cast<uint32_t*>(&h67);
           if (TRACE && tp) tp[6] = clock64();
-          if (t + 1 < L || tma_any) {
+          if (will_publish) {
             // every CTA's h-part of step t has finished reading h_{t-1} (and with it all pushes of h_{t-1} have landed)
             const long long c2 = (TRACE && tp) ? clock64() : 0;
-            if (t + hoff > 0) mbar_wait_cluster(H_FREE(sub), (uint32_t)((t - 1 + hoff) & 1), p.error_flag, 320 + sub);
+            if (!hfree_ok) mbar_wait_cluster(H_FREE(sub), (uint32_t)((t - 1 + hoff) & 1), p.error_flag, 320 + sub);
             if (TRACE && tp) tp[10] = clock64() - c2;
             const uint32_t buf = hs_base + (uint32_t)(sub * C) * kHTile;
             st_shared_v4(buf + hpiece, pk);
             publish_quadrant(buf, sub, s, t + 1 < L);
           }
           if (TRACE && tp) tp[7] = clock64();
-          tmem_st8(cad, cs);
+          if (!TC4_CREG) tmem_st8(cad, cs);
           if ((p.state_flags & 2) && t + 1 == L && valid[sub]) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -563,7 +705,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
               *reinterpret_cast<uint4*>(p.out1 + pos * p.out1_ld + dir * H + ua) = ok;
             }
           }
-          tmem_wait_st();
+          if (!TC4_CREG) tmem_wait_st();
         }
       }
     } else {
@@ -596,6 +738,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           }
         }
       }
+      [[maybe_unused]] float creg[2][4];
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {
         float z[4] = {0.f, 0.f, 0.f, 0.f};
@@ -605,9 +748,14 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
             if (valid[sub][e >> 1])
               z[e] = __ldg(p.c_state + (row0 + sub * SUB + q * 16 + (lane >> 2) + 8 * (e >> 1)) * H + ua + (e & 1));
         }
+#if TC4_CREG
+#pragma unroll
+        for (int e = 0; e < 4; ++e) creg[sub][e] = z[e];
+#else
         tmem_st4_16x256(tmem_c + (uint32_t)(sub * 32) + lane_off + u0, z);
+#endif
       }
-      tmem_wait_st();
+      if (!TC4_CREG) tmem_wait_st();
 #pragma unroll 1
       for (int t = 0; t < L; ++t) {
         const int s = dir ? (L - 1 - t) : t;
@@ -623,24 +771,34 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
                 addn[sub][i] = __ldg(reinterpret_cast<const unsigned int*>(p.addend + posn * p.addend_ld + dir * H + ua));
               }
           }
-          if (tma_any && pusher) bulk_wait_read_all();
+          if (!TC4_PUB && tma_any && pusher) bulk_wait_read_all();
           if (TRACE && tp) tp[4] = clock64();
           mbar_wait(ACC_FULL(a), (full_par >> a) & 1u, p.error_flag, 300 + a);
           full_par ^= 1u << a;
           if (TRACE && tp) tp[5] = clock64();
           tc_fence_after();
           const uint32_t acc = tmem_acc + (uint32_t)a * kChunkN + lane_off + u0;
-          const uint32_t cad = tmem_c + (uint32_t)(sub * 32) + lane_off + u0;
-          float gi[4], gf[4], gg[4], go[4], cs[4];
+          [[maybe_unused]] const uint32_t cad = tmem_c + (uint32_t)(sub * 32) + lane_off + u0;
+          float gi[4], gf[4], gg[4], go[4];
+#if TC4_CREG
+          float (&cs)[4] = creg[sub];
+#else
+          float cs[4];
+#endif
           tmem_ld4_16x256(acc + 0 * kChunkUnits, gi);
           tmem_ld4_16x256(acc + 1 * kChunkUnits, gf);
           tmem_ld4_16x256(acc + 2 * kChunkUnits, gg);
           tmem_ld4_16x256(acc + 3 * kChunkUnits, go);
-          tmem_ld4_16x256(cad, cs);
+          if (!TC4_CREG) tmem_ld4_16x256(cad, cs);
+          const bool will_publish = t + 1 < L || tma_any;
+          bool hfree_ok = !(will_publish && t + hoff > 0);
+          if (TC4_HFREE_EARLY && !hfree_ok) hfree_ok = mbar_test_wait_cluster(H_FREE(sub), (uint32_t)((t - 1 + hoff) & 1));
           tmem_wait_ld();
-          tmem_ld_dep4(gi); tmem_ld_dep4(gf); tmem_ld_dep4(gg); tmem_ld_dep4(go); tmem_ld_dep4(cs);
+          tmem_ld_dep4(gi); tmem_ld_dep4(gf); tmem_ld_dep4(gg); tmem_ld_dep4(go);
+          if (!TC4_CREG) tmem_ld_dep4(cs);
           tc_fence_before();
-          mbar_arrive(ACC_EMPTY(a));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ACC_EMPTY(a));
           a = (a == kAccBufs - 1) ? 0 : a + 1;
           float hv[4];
 #pragma unroll
@@ -652,15 +810,15 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           }
           __half2 hp[2] = {__floats2half2_rn(hv[0], hv[1]), __floats2half2_rn(hv[2], hv[3])};
           if (TRACE && tp) tp[6] = clock64();
-          if (t + 1 < L || tma_any) {
-            if (t + hoff > 0) mbar_wait_cluster(H_FREE(sub), (uint32_t)((t - 1 + hoff) & 1), p.error_flag, 320 + sub);
+          if (will_publish) {
+            if (!hfree_ok) mbar_wait_cluster(H_FREE(sub), (uint32_t)((t - 1 + hoff) & 1), p.error_flag, 320 + sub);
             const uint32_t buf = hs_base + (uint32_t)(sub * C) * kHTile;
             st_shared_b32(buf + hpiece[0], *reinterpret_cast<uint32_t*>(&hp[0]));
             st_shared_b32(buf + hpiece[1], *reinterpret_cast<uint32_t*>(&hp[1]));
             publish_quadrant(buf, sub, s, t + 1 < L);
           }
           if (TRACE && tp) tp[7] = clock64();
-          tmem_st4_16x256(cad, cs);
+          if (!TC4_CREG) tmem_st4_16x256(cad, cs);
           if ((p.state_flags & 2) && t + 1 == L) {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
@@ -681,7 +839,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
                   __floats2half2_rn(hv[2 * i] + __low2float(av), hv[2 * i + 1] + __high2float(av));
             }
           }
-          tmem_wait_st();
+          if (!TC4_CREG) tmem_wait_st();
         }
       }
     }

@@ -191,6 +191,32 @@ int fnssl_doa_decode_idl(const float* pred_ipd, const float* templ, const float*
                          int max_sources, int vad_mode, float* cur, float* map, float* ss, int* idx_out,
                          float* vad_out, void* stream);
 
+/* ---- training-side forward pieces --------------------------------------------- */
+
+/* DP-IPD regression targets: DPIPD.forward(source_doa) + the ground-truth branch of data_preprocess
+ * (FN-SSL/Lightning/Module.py:464-497, main.py:227-265; IPDnet/runIPDnetOn.py:256-290).
+ *   source_doa : (nb, nt, 2, ns) f32 [elevation, azimuth] radians;  vad : (nb, nt, ns) f32 or NULL (no gating)
+ *   mic_pos : (nmic, 3) f32;  pairs : (P, 2) int32 microphone pairs (m1, m2) in DPIPD.data_adjust order
+ *   phase(b,t,s,p,k) = 2 pi f_k r(b,t,s).(mic[m1] - mic[m2]) / speed,  f_k = fre_max * (bin_lo + k) / (nf - 1), computed in double
+ *   per_source = 0 : out (nb, nt, 2*nbins, P)     = sum_s gate_s [cos | sin]      gate_s = vad > vad_threshold (1 if vad NULL)
+ *   per_source = 1 : out (nb, nt, 2*nbins, P, ns) = gate_s [cos | sin]; where gate_s = 0 and nonsrc != NULL the (2*nbins, P)
+ *                    non-source target is written instead (IPDnet's silent-source target) */
+int fnssl_dpipd_targets(const float* source_doa, const float* vad, const float* mic_pos, const int* pairs, int nb, int nt,
+                        int ns, int nmic, int P, int nf, float fre_max, float speed, int bin_lo, int nbins,
+                        float vad_threshold, int per_source, const float* nonsrc, float* out, void* stream);
+
+/* cal_loss of FN-SSL (main.py:191-198): pred (nb*P, nt, nf2) [row b*P + p], gt (nb, nt, nf2, P) -> mean squared error.
+ *   workspace : nb*nt floats;  loss : 1 float (device).  Deterministic (fixed-order two-stage sum). */
+int fnssl_ipd_mse_loss(const float* pred, const float* gt, int nb, int P, int nt, int nf2, float* workspace, float* loss,
+                       void* stream);
+
+/* Frame-level PIT loss of IPDnet (runIPDnetOn.py:188-206): pred, gt (rows, K, ns), rows = nb*nt frames, ns <= 4 sources.
+ * Per frame the permutation of the predicted sources with the smallest squared error (exhaustive, itertools order, first
+ * minimum) is applied; loss = mean over rows*K*ns.  best_perm (rows, ns) int32 or NULL: prediction index per target source.
+ *   workspace : rows floats */
+int fnssl_ipd_pit_mse_loss(const float* pred, const float* gt, int rows, int K, int ns, float* workspace, float* loss,
+                           int* best_perm, void* stream);
+
 /* ---- IPDnet2: OnlineSpatialNet with Mamba time modules (scope row a11) --------------------------- */
 
 /* torch.stft(center=True)'s reflect padding (IPDnet2/Module.py:61-62): (nb, nsample, nch) -> (nb, nsample + 2 pad, nch).

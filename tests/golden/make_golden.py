@@ -194,9 +194,98 @@ def gen_ipdnet():
     print("wrote ipdnet_golden.npz:", {k: v.shape for k, v in out.items() if 'sd.' not in k})
 
 
+def gen_train():
+    """Training-side forward pieces: DP-IPD targets and losses.  The Lightning modules cannot be
+    imported (pytorch_lightning / torchmetrics absent), so the reference's own DPIPD / RemoveChFromBatch classes are run and
+    the few tensor lines of data_preprocess / cal_loss around them are restated here verbatim."""
+    _shim()
+    sys.path.insert(0, os.path.join(REF, "FN-SSL", "Lightning"))
+    import Module as ref_module        # FN-SSL/Lightning/Module.py
+    from copy import deepcopy
+    from oracle import training_oracle as tro
+
+    out = {}
+    rng = np.random.default_rng(7)
+    fre_range_used = range(1, 257)
+    for tag, mic, ch_mode in (("2mic", np.array(((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0))), "MM"),
+                              ("3mic", np.array(((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0), (0.0, 0.05, 0.01))), "MM"),
+                              ("3micM", np.array(((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0), (0.0, 0.05, 0.01))), "M")):
+        gd = ref_module.DPIPD(ndoa_candidate=[37, 73], mic_location=mic, nf=257, fre_max=8000, ch_mode=ch_mode, speed=340)
+        nb, nt, ns = 2, 5, 2
+        doa = np.stack((rng.uniform(0, np.pi, (nb, nt, ns)), rng.uniform(-np.pi, np.pi, (nb, nt, ns))), axis=2).astype(np.float32)
+        vad = rng.uniform(0, 1, (nb, nt, ns)).astype(np.float32)
+        vad[rng.uniform(size=vad.shape) < 0.3] = 0.0
+        # ---- FN-SSL/Lightning/main.py:227-259 (gt branch of data_preprocess), tar_useVAD = True
+        _, ipd_batch, _ = gd(source_doa=doa)
+        ipd_batch = np.concatenate((ipd_batch.real[:, :, fre_range_used, :, :], ipd_batch.imag[:, :, fre_range_used, :, :]),
+                                   axis=2).astype(np.float32)
+        ipd_batch = torch.from_numpy(ipd_batch)
+        vad_batch = torch.from_numpy(vad)
+        nb_, nt_, nf_, nmic_, num_source = ipd_batch.shape
+        th = 0
+        vad_batch_copy = deepcopy(vad_batch)
+        vad_batch_copy[vad_batch_copy <= th] = th
+        vad_batch_copy[vad_batch_copy > 0] = 1
+        vad_batch_expand = vad_batch_copy[:, :, np.newaxis, np.newaxis, :].expand(nb_, nt_, nf_, nmic_, num_source)
+        per_source = ipd_batch.clone()
+        ipd_sum = torch.sum(ipd_batch * vad_batch_expand, dim=-1)
+        out[f"{tag}_doa"], out[f"{tag}_vad"], out[f"{tag}_mic"] = doa, vad, mic
+        out[f"{tag}_ipd_gt"] = ipd_sum.numpy()
+        out[f"{tag}_ipd_per_source"] = per_source.numpy()
+        assert float((tro.fnssl_targets(doa, vad, mic, ch_mode) - ipd_sum).abs().max()) <= 1e-6
+        # ---- cal_loss, main.py:191-198 with the reference's RemoveChFromBatch
+        P = nmic_
+        pred = _randn((nb * P, nt, 2 * 256), 50 + P).tanh()
+        reb = ref_module.RemoveChFromBatch(ch_mode=ch_mode)(pred, nb).permute(0, 2, 3, 1)
+        loss = torch.nn.functional.mse_loss(reb.contiguous(), ipd_sum.contiguous())
+        out[f"{tag}_pred"], out[f"{tag}_loss"] = pred.numpy(), np.float32(loss.item())
+        assert abs(float(tro.fnssl_loss(pred, ipd_sum)) - float(loss)) <= 1e-7
+    # ---- IPDnet: per-source targets with the non-source (Bessel) target, IPDnet/runIPDnetOn.py:209-222,256-283.  IPDnet's own
+    # DPIPD (IPDnet/Module.py) differs from FN-SSL's only in the candidate grid and in skipping the unused mic pairs of mode 'M'
+    # (same arithmetic for the pairs it keeps), so the FN-SSL class imported above produces its values.
+    from scipy.special import jn
+    mic4 = np.array(((0.0, 0.0, 0.0), (0.03, 0.0, 0.0), (0.0, 0.04, 0.0), (-0.035, -0.02, 0.01)))
+    gd = ref_module.DPIPD(ndoa_candidate=[1, 37], mic_location=mic4, nf=257, fre_max=8000, ch_mode="M", speed=340)
+    nb, nt, ns = 2, 4, 2
+    doa = np.stack((np.full((nb, nt, ns), np.pi / 2), rng.uniform(0, np.pi, (nb, nt, ns))), axis=2).astype(np.float32)
+    dp_vad = rng.uniform(0, 0.5, (nb, nt, ns)).astype(np.float32)
+    dp_vad[rng.uniform(size=dp_vad.shape) < 0.4] = 0.0005          # below the 0.001 threshold -> silent
+    fre_use = list(fre_range_used)
+    # euclidean_distances_to_bessel (:209-222)
+    distances = np.sqrt(np.sum((mic4[1:] - mic4[0, :]) ** 2, axis=1))
+    frequencies = (2 * np.pi * np.linspace(0, 8000, 257) / 340)[fre_use]
+    non_source_tar = np.array([np.concatenate((jn(0, frequencies * d), np.zeros(256))) for d in distances]).T
+    non_source_tar_t = torch.from_numpy(non_source_tar)
+    _, ipd_batch, _ = gd(source_doa=doa)
+    ipd_batch = np.concatenate((ipd_batch.real[:, :, fre_use, :, :], ipd_batch.imag[:, :, fre_use, :, :]), axis=2).astype(np.float32)
+    ipd_batch = torch.from_numpy(ipd_batch)
+    nb_, nt_, nf_, nmic_, nsrc = ipd_batch.shape
+    vad_batch_copy = deepcopy(torch.from_numpy(dp_vad))
+    th = 0.001
+    vad_batch_copy[vad_batch_copy <= th] = 0
+    vad_batch_copy[vad_batch_copy > th] = 1
+    ipd_batch = ipd_batch * vad_batch_copy[:, :, np.newaxis, np.newaxis, :].expand(nb_, nt_, nf_, nmic_, nsrc)
+    for i in range(nb_):
+        for j in range(nt_):
+            for k in range(nsrc):
+                if (ipd_batch[i, j, :, :, k] == 0).all():
+                    ipd_batch[i, j, :, :, k] = non_source_tar_t.to(ipd_batch)
+    out["ipdnet_doa"], out["ipdnet_vad"], out["ipdnet_mic"] = doa, dp_vad, mic4
+    out["ipdnet_non_source"] = non_source_tar
+    out["ipdnet_ipd_gt"] = ipd_batch.numpy()
+    assert float((tro.ipdnet_targets(doa, dp_vad, mic4, non_source_tar) - ipd_batch).abs().max()) <= 1e-6
+    # frame-level PIT loss (:196-206); torchmetrics' permutation search restated by the oracle (exhaustive, first minimum)
+    pred = (ipd_batch[:, :, :, :, [1, 0]] + 0.3 * _randn(tuple(ipd_batch.shape), 61))
+    pred[0, 1] = ipd_batch[0, 1] + 0.3 * _randn(tuple(ipd_batch.shape[2:]), 62)        # one frame in identity order
+    loss, perm = tro.ipdnet_pit_loss(pred, ipd_batch.view(nb_ * nt_, nf_, nmic_, nsrc))
+    out["ipdnet_pred"], out["ipdnet_pit_loss"], out["ipdnet_pit_perm"] = pred.numpy(), np.float32(loss.item()), perm.numpy()
+    np.savez_compressed(os.path.join(HERE, "train_golden.npz"), **out)
+    print("wrote train_golden.npz:", {k: np.asarray(v).shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
-        {"fnssl": gen_fnssl, "ipdnet": gen_ipdnet}[sys.argv[1]]()
+        {"fnssl": gen_fnssl, "ipdnet": gen_ipdnet, "train": gen_train}[sys.argv[1]]()
     else:
-        for which in ("fnssl", "ipdnet"):
+        for which in ("fnssl", "ipdnet", "train"):
             subprocess.check_call([sys.executable, os.path.abspath(__file__), which])

@@ -9,13 +9,13 @@ python __graft_entry__.py smoke > $O/r2_smoke_1.log 2>&1; tail -3 $O/r2_smoke_1.
 python bench.py > $O/r2_bench_1.json 2> $O/r2_bench_1.err; tail -c 1500 $O/r2_bench_1.err
 python bench.py --impl reference --steps 2 --warmup 1 > $O/r2_bench_1_ref.json 2> $O/r2_bench_1_ref.err
 python bench.py --workload cfg4 --variant online --no-extra --no-cpu-baseline --steps 5 > $O/r2_bench_1_cfg4_online.json 2> $O/r2_bench_1_cfg4_online.err
-for c in lstm128 lstm128f lstm256 lstm256n conv; do
+for c in lstm128 lstm256n conv; do
   for tool in racecheck synccheck; do
-    timeout 600 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_cases.py $c > $O/r2_sanitizer_${tool}_${c}.log 2>&1
+    timeout 200 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_cases.py $c > $O/r2_sanitizer_${tool}_${c}.log 2>&1
     echo "$tool $c rc=$?"; tail -4 $O/r2_sanitizer_${tool}_${c}.log
   done
 done
-timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_cases.py lstm128 lstm256n conv > $O/r2_sanitizer_memcheck.log 2>&1; tail -4 $O/r2_sanitizer_memcheck.log
+timeout 300 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_cases.py lstm128 lstm256n conv > $O/r2_sanitizer_memcheck.log 2>&1; tail -4 $O/r2_sanitizer_memcheck.log
 python tools/tc4_trace.py > $O/r2_tc4_trace_1.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/r2_launches_cfg4_b32.csv python bench.py --workload cfg4 --batch 32 --steps 2 --warmup 3 --no-cpu-baseline --no-extra > $O/r2_ncu_a.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:lstm_tc4 -s 6 -c 6 -o $O/r2_prof_tc4_online python bench.py --workload cfg2 --variant online --steps 1 --warmup 1 --no-cpu-baseline --no-extra > $O/r2_ncu_b.log 2>&1
