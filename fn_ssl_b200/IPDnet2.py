@@ -326,8 +326,8 @@ IPDNET2_WIN, IPDNET2_HOP = 512, 320          # run_IPDnet2.py:91-93 (win_shift_r
 
 
 @ops.on_tensor_device
-def stft_center(signal: Tensor, want_magsum: bool = False):
-    """IPDnet2's STFT (IPDnet2/Module.py:46-64): torch.stft(center=True) = reflect pad 256 + framing, hop 320."""
+def reflect_padded(signal: Tensor) -> Tensor:
+    """torch.stft(center=True)'s reflect padding by 256 samples on both sides (IPDnet2/Module.py:46-64)."""
     ops._need_cuda(signal)
     lib = _lib.load()
     x = signal.contiguous().float()
@@ -336,7 +336,13 @@ def stft_center(signal: Tensor, want_magsum: bool = False):
     xp = torch.empty((nb, n + 2 * pad, nch), dtype=torch.float32, device=x.device)
     ops._count(1)
     _lib.check(lib.fnssl_reflect_pad(x.data_ptr(), nb, n, nch, pad, xp.data_ptr(), ops._stream()))
-    return ops.stft(xp, IPDNET2_WIN, IPDNET2_HOP, IPDNET2_WIN, want_magsum=want_magsum)
+    return xp
+
+
+@ops.on_tensor_device
+def stft_center(signal: Tensor, want_magsum: bool = False):
+    """IPDnet2's STFT (IPDnet2/Module.py:46-64): torch.stft(center=True) = reflect pad 256 + framing, hop 320."""
+    return ops.stft(reflect_padded(signal), IPDNET2_WIN, IPDNET2_HOP, IPDNET2_WIN, want_magsum=want_magsum)
 
 
 def data_preprocess_ipdnet2(mic_sig_batch: Tensor, eps: float = 1e-6, sample_length: int = 249) -> List[Tensor]:
@@ -355,8 +361,11 @@ class IPDnet2Pipeline(nn.Module):
 
     @torch.no_grad()
     def forward(self, signal: Tensor) -> Tensor:
-        spec, magsum = stft_center(signal, want_magsum=True)
-        g0, _, _ = ops.features(spec, magsum, 'ALL', ops.NORM_FORGETTING, self.sample_length, self.eps, torch.float32)
+        # fused front end (ops.stft_features): reflect pad, then FFT -> sum|X| -> normaliser -> FFT again -> feature grid;
+        # the (B, 257, T, M) complex spectrum is never written to HBM
+        with torch.cuda.device(signal.device):
+            g0, _ = ops.stft_features(reflect_padded(signal), 'ALL', ops.NORM_FORGETTING, self.sample_length, self.eps,
+                                      torch.float32, IPDNET2_WIN, IPDNET2_HOP, IPDNET2_WIN)
         return self.arch.forward_grid(g0)
 
 

@@ -89,6 +89,7 @@ SIGNATURES = {
     "fnssl_feature_rows": (_i, [_i, _i, _i]),
     "fnssl_feature_channels": (_i, [_i, _i]),
     "fnssl_features_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _i, _i, _vp, _vp]),
+    "fnssl_stft_features_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp]),
     "fnssl_cfirst_to_grid": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "fnssl_grid_to_cfirst": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "fnssl_grid_copy": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i64, _i, _vp]),

@@ -10,6 +10,8 @@
 // All three kernels are HBM-bound (about 4 FLOP/B); algorithmic bytes per TF-frame: 3080*M.
 #include <stdarg.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace fnssl {
@@ -76,9 +78,24 @@ __device__ __forceinline__ int fft_pad(int i) { return i + (i >> 3); }   // one 
 //     butterflies per lane per pass, two exchanges through a padded per-warp buffer instead of nine radix-2 passes;
 //  3. the (FR*nch) x 257 results are transposed through shared memory so that every bin row of the
 //     (nb, 257, nt, nch) output is written as one contiguous FR*nch*8-byte run.
+//  4. FUSED FEATURE MODE (fnssl_stft_features_forward, T != void): instead of the spectrum the CTA writes the normalised
+//     network features of its frames straight into the channels-last grid (R, nt, 256, ld) -- re/(mu+eps), im/(mu+eps) of the
+//     row's channels, bins 1..256 (main.py:206-225) -- so the complex spectrum never exists in HBM.  mu comes from a first
+//     pass of this same kernel that only produces the per-frame magnitude sums (spec == feat == nullptr).
+struct StftFeat {
+  void* feat;          // grid (R, nt, 256, ld) of T; nullptr = not in feature mode
+  const float* mu;     // (R, nt) normaliser (nullptr with norm == NONE)
+  int ld, pairing, norm;
+  float eps;
+};
+
+template <typename T> __device__ __forceinline__ void st_chunk(T* dst, const float (&v)[8]);
+__device__ __forceinline__ void row_channels(int r, int nch, int pairing, int& b, int& ci, int& cj);
+
+template <typename T>
 __global__ void __launch_bounds__(kStftThreads)
 stft512_kernel(const float* __restrict__ signal, int nsample, int nch, int hop, int nt, int FR, int use_bulk,
-               float2* __restrict__ spec, float* __restrict__ magsum) {
+               float2* __restrict__ spec, float* __restrict__ magsum, const StftFeat ff) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * FR;
@@ -239,11 +256,51 @@ stft512_kernel(const float* __restrict__ signal, int nsample, int nch, int hop, 
     __syncwarp();
   }
   __syncthreads();
-  // transposed, coalesced write: spec[b][f][t0 + tl][ch], (tl, ch) fastest
-  const int run = nfr * nch;
-  for (int idx = tid; idx < kBins * run; idx += kStftThreads) {
-    const int f = idx / run, j = idx - f * run;
-    spec[((size_t)b * kBins + f) * nt * nch + (size_t)t0 * nch + j] = stage[(size_t)j * kBins + f];
+  if (spec) {
+    // transposed, coalesced write: spec[b][f][t0 + tl][ch], (tl, ch) fastest
+    const int run = nfr * nch;
+    for (int idx = tid; idx < kBins * run; idx += kStftThreads) {
+      const int f = idx / run, j = idx - f * run;
+      spec[((size_t)b * kBins + f) * nt * nch + (size_t)t0 * nch + j] = stage[(size_t)j * kBins + f];
+    }
+  }
+  if constexpr (!std::is_same<T, void>::value) {
+    if (ff.feat) {
+      // one thread = one (row, frame, bin) position: its ld channels as 16-byte chunks; consecutive threads = consecutive bins,
+      // so a warp writes one contiguous run of 32 * ld elements and a frame of one row is one contiguous 256 * ld run
+      constexpr int kChunk = sizeof(T) == 2 ? 8 : 4;
+      const bool all = (ff.pairing == FNSSL_PAIRS_ALL);
+      const int P = all ? 1 : (ff.pairing == FNSSL_PAIRS_M ? nch - 1 : nch * (nch - 1) / 2);
+      const int C = all ? 2 * nch : 4;
+      const int half = C / 2;
+      T* feat = reinterpret_cast<T*>(ff.feat);
+      for (int idx = tid; idx < P * nfr * 256; idx += kStftThreads) {
+        const int fl = idx & 255, tl = (idx >> 8) % nfr, pp = (idx >> 8) / nfr;
+        const int r = b * P + pp;
+        int bb, ci, cj;
+        row_channels(r, nch, ff.pairing, bb, ci, cj);
+        const float den = ff.norm != FNSSL_NORM_NONE ? ff.mu[(size_t)r * nt + t0 + tl] + ff.eps : 1.0f;
+        const float2* src = stage + (size_t)tl * nch * kBins + 1 + fl;          // + ch * kBins: bin 1 + fl of channel ch
+        T* dst = feat + (((size_t)r * nt + t0 + tl) * 256 + fl) * ff.ld;
+        for (int c0 = 0; c0 < ff.ld; c0 += kChunk) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < kChunk; ++i) {
+            const int c = c0 + i;
+            float x = 0.0f;
+            if (c < C) {
+              const int k = (c < half) ? c : c - half;
+              const int ch = all ? k : (k == 0 ? ci : cj);
+              const float2 z = src[(size_t)ch * kBins];
+              x = (c < half) ? z.x : z.y;
+              if (ff.norm != FNSSL_NORM_NONE) x = x / den;
+            }
+            v[i] = x;
+          }
+          st_chunk(dst + c0, v);
+        }
+      }
+    }
   }
 }
 
@@ -326,7 +383,7 @@ constexpr int kAsmTT = 32;  // frames per tile
 // store `n` consecutive channels (n = 8 halves or 4 floats = 16 bytes) of one grid position
 // fp16 grids saturate at +-65504: a normalised feature re/(mu+eps) can exceed the fp16 range (worst case C*257/(1-alpha), e.g.
 // a tonal onset after digital silence), and an inf would turn into NaN in the along-time LSTM's carried state (sat_f16, common.cuh)
-__device__ __forceinline__ void st_chunk(__half* dst, const float (&v)[8]) {
+template <> __device__ __forceinline__ void st_chunk<__half>(__half* dst, const float (&v)[8]) {
   const __half2 h0 = __floats2half2_rn(sat_f16(v[0]), sat_f16(v[1])), h1 = __floats2half2_rn(sat_f16(v[2]), sat_f16(v[3]));
   const __half2 h2 = __floats2half2_rn(sat_f16(v[4]), sat_f16(v[5])), h3 = __floats2half2_rn(sat_f16(v[6]), sat_f16(v[7]));
   uint4 pk;
@@ -334,7 +391,7 @@ __device__ __forceinline__ void st_chunk(__half* dst, const float (&v)[8]) {
   pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
   *reinterpret_cast<uint4*>(dst) = pk;
 }
-__device__ __forceinline__ void st_chunk(float* dst, const float (&v)[8]) {
+template <> __device__ __forceinline__ void st_chunk<float>(float* dst, const float (&v)[8]) {
   *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
@@ -475,6 +532,17 @@ __global__ void grid_copy_kernel(const TS* __restrict__ src, int src_ld, int src
   }
 }
 
+// same dtype, same channel stride, no offsets: a plain 16-byte-vector copy at HBM rate (4 vectors in flight per thread)
+__global__ void __launch_bounds__(256) grid_copy_vec_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t nvec) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    const uint4 a = __ldcs(src + i), b = __ldcs(src + i + stride), c = __ldcs(src + i + 2 * stride), d = __ldcs(src + i + 3 * stride);
+    dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+  }
+  for (; i < nvec; i += stride) dst[i] = __ldcs(src + i);
+}
+
 template <typename T>
 __global__ void grid_add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ dst, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -495,14 +563,12 @@ int fnssl_stft_num_frames(int nsample, int win_len, int hop) {
   return (nsample - win_len) / hop + 1;
 }
 
-int fnssl_stft_forward(const float* signal, int nb, int nsample, int nch, int win_len, int hop, int nfft, float* spec,
-                       float* magsum, void* stream) {
-  FNSSL_REQUIRE(win_len == 512 && nfft == 512, "stft: only win_len = nfft = 512 is implemented (got %d/%d)", win_len, nfft);
-  FNSSL_REQUIRE(hop > 0 && hop <= 512, "stft: hop must be in (0, 512] (got %d)", hop);
-  FNSSL_REQUIRE(nb > 0 && nch > 0 && nch <= 64, "stft: bad nb/nch (%d/%d)", nb, nch);
-  const int nt = fnssl_stft_num_frames(nsample, win_len, hop);
-  FNSSL_REQUIRE(nt > 0, "stft: signal shorter than one window (nsample=%d)", nsample);
-  FNSSL_REQUIRE(signal && spec, "stft: null pointer");
+}  // extern "C"
+
+// shared launcher of the three modes of stft512_kernel: spectrum (+ magnitude sums), magnitude sums only, fused features
+template <typename T>
+static int launch_stft(const float* signal, int nb, int nsample, int nch, int hop, int nt, float* spec, float* magsum,
+                       const fnssl::StftFeat& ff, cudaStream_t st) {
   int FR = 16 / nch;
   if (FR < 1) FR = 1;
   if (FR > nt) FR = nt;
@@ -513,12 +579,58 @@ int fnssl_stft_forward(const float* signal, int nb, int nsample, int nch, int wi
   FNSSL_REQUIRE(smem <= 200 * 1024, "stft: too many channels for one CTA (%d)", nch);
   const int use_bulk = ((reinterpret_cast<uintptr_t>(signal) & 15) == 0) && (((size_t)hop * nch * 4) % 16 == 0) &&
                        (((size_t)nsample * nch * 4) % 16 == 0) && (((size_t)kWin * nch * 4) % 16 == 0);
-  FNSSL_CUDA(cudaFuncSetAttribute(stft512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FNSSL_CUDA(cudaFuncSetAttribute(stft512_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((nt + FR - 1) / FR, nb);
-  stft512_kernel<<<grid, kStftThreads, smem, (cudaStream_t)stream>>>(signal, nsample, nch, hop, nt, FR, use_bulk,
-                                                                    reinterpret_cast<float2*>(spec), magsum);
+  stft512_kernel<T><<<grid, kStftThreads, smem, st>>>(signal, nsample, nch, hop, nt, FR, use_bulk, reinterpret_cast<float2*>(spec),
+                                                    magsum, ff);
   FNSSL_LAUNCH_CHECK("stft512_kernel");
   return 0;
+}
+
+extern "C" {
+
+int fnssl_stft_forward(const float* signal, int nb, int nsample, int nch, int win_len, int hop, int nfft, float* spec,
+                       float* magsum, void* stream) {
+  FNSSL_REQUIRE(win_len == 512 && nfft == 512, "stft: only win_len = nfft = 512 is implemented (got %d/%d)", win_len, nfft);
+  FNSSL_REQUIRE(hop > 0 && hop <= 512, "stft: hop must be in (0, 512] (got %d)", hop);
+  FNSSL_REQUIRE(nb > 0 && nch > 0 && nch <= 64, "stft: bad nb/nch (%d/%d)", nb, nch);
+  const int nt = fnssl_stft_num_frames(nsample, win_len, hop);
+  FNSSL_REQUIRE(nt > 0, "stft: signal shorter than one window (nsample=%d)", nsample);
+  FNSSL_REQUIRE(signal && spec, "stft: null pointer");
+  return launch_stft<void>(signal, nb, nsample, nch, hop, nt, spec, magsum, fnssl::StftFeat{nullptr, nullptr, 0, 0, 0, 0.0f},
+                           (cudaStream_t)stream);
+}
+
+int fnssl_norm_forward(const float* magsum, int nb, int nch, int nt, int nbins, int pairing, int norm, int sample_length,
+                       float* mu, void* stream);
+
+int fnssl_stft_features_forward(const float* signal, int nb, int nsample, int nch, int win_len, int hop, int nfft, int pairing,
+                                int norm, int sample_length, float eps, float* magsum, float* mu, void* feat, int dtype, int ld,
+                                void* stream) {
+  FNSSL_REQUIRE(win_len == 512 && nfft == 512, "stft_features: only win_len = nfft = 512 is implemented (got %d/%d)", win_len, nfft);
+  FNSSL_REQUIRE(hop > 0 && hop <= 512, "stft_features: hop must be in (0, 512] (got %d)", hop);
+  FNSSL_REQUIRE(nb > 0 && nch > 0 && nch <= 64, "stft_features: bad nb/nch (%d/%d)", nb, nch);
+  FNSSL_REQUIRE(pairing >= 0 && pairing <= 2, "stft_features: bad pairing %d", pairing);
+  FNSSL_REQUIRE(pairing == FNSSL_PAIRS_ALL || nch >= 2, "stft_features: pair modes need >= 2 channels");
+  FNSSL_REQUIRE(norm >= 0 && norm <= 3, "stft_features: bad norm %d", norm);
+  FNSSL_REQUIRE(dtype == FNSSL_F32 || dtype == FNSSL_F16, "stft_features: bad dtype %d", dtype);
+  const int nt = fnssl_stft_num_frames(nsample, win_len, hop);
+  FNSSL_REQUIRE(nt > 0, "stft_features: signal shorter than one window (nsample=%d)", nsample);
+  const int C = fnssl_feature_channels(nch, pairing);
+  FNSSL_REQUIRE(ld >= C && ld % (dtype == FNSSL_F16 ? 8 : 4) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0,
+                "stft_features: the grid must be 16-byte aligned with ld (%d) >= %d channels and a multiple of 16 bytes", ld, C);
+  FNSSL_REQUIRE(signal && feat && (norm == FNSSL_NORM_NONE || mu) && (norm == FNSSL_NORM_NONE || norm == FNSSL_NORM_GIVEN || magsum),
+                "stft_features: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (norm == FNSSL_NORM_FORGETTING || norm == FNSSL_NORM_GLOBAL) {
+    // pass 1: FFT -> per-(utterance, channel, frame) sums of |X| only; then the T-sequential recursion (utils_.py:27-44)
+    if (launch_stft<void>(signal, nb, nsample, nch, hop, nt, nullptr, magsum, fnssl::StftFeat{nullptr, nullptr, 0, 0, 0, 0.0f}, st)) return 1;
+    if (fnssl_norm_forward(magsum, nb, nch, nt, kBins, pairing, norm, sample_length, mu, stream)) return 1;
+  }
+  // pass 2: FFT again (the signal is L2-resident), features written directly
+  const fnssl::StftFeat ff{feat, norm == FNSSL_NORM_NONE ? nullptr : mu, ld, pairing, norm, eps};
+  if (dtype == FNSSL_F16) return launch_stft<__half>(signal, nb, nsample, nch, hop, nt, nullptr, nullptr, ff, st);
+  return launch_stft<float>(signal, nb, nsample, nch, hop, nt, nullptr, nullptr, ff, st);
 }
 
 int fnssl_feature_rows(int nb, int nch, int pairing) {
@@ -642,6 +754,18 @@ int fnssl_grid_copy(const void* src, int src_dtype, int src_ld, int src_off, voi
   const int64_t total = npos * C;
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const size_t esz = src_dtype == FNSSL_F16 ? 2 : 4;
+    const size_t bytes = (size_t)npos * C * esz;
+    if (src_dtype == dst_dtype && src_ld == C && dst_ld == C && src_off == 0 && dst_off == 0 && bytes % 16 == 0 &&
+        ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+      const int64_t nvec = (int64_t)(bytes / 16);
+      const int vblocks = (int)((nvec + 1023) / 1024 < 148 * 8 ? (nvec + 1023) / 1024 : 148 * 8);
+      grid_copy_vec_kernel<<<vblocks > 0 ? vblocks : 1, 256, 0, st>>>((const uint4*)src, (uint4*)dst, nvec);
+      FNSSL_LAUNCH_CHECK("grid_copy_vec_kernel");
+      return 0;
+    }
+  }
 #define FNSSL_GC(TS, TD) \
   grid_copy_kernel<TS, TD><<<blocks, 256, 0, st>>>((const TS*)src, src_ld, src_off, (TD*)dst, dst_ld, dst_off, npos, C)
   if (src_dtype == FNSSL_F32 && dst_dtype == FNSSL_F32) FNSSL_GC(float, float);

@@ -36,7 +36,7 @@ namespace tc4 {
 //               which then never meet on a named barrier nor wait for a bulk store to drain (0 = the epilogue publishes itself)
 //   (more than 20 warps per CTA cap the kernel at 80 registers per thread: 6 warps on one SM sub-partition)
 #ifndef TC4_PROD2
-#define TC4_PROD2 1
+#define TC4_PROD2 0
 #endif
 #ifndef TC4_PUB
 #define TC4_PUB 1
@@ -56,8 +56,19 @@ namespace tc4 {
 #ifndef TC4_HFREE_EARLY
 #define TC4_HFREE_EARLY 0
 #endif
+//   TC4_HTILE : one "h_{t-1} tile has arrived" barrier per SOURCE CTA instead of one per sub-tile: the h-part MMAs of a chunk
+//               are issued as soon as that chunk's tile is in place (own tile first, then the peers in push order), so the ~0.5 k
+//               cycles of h-part issue overlap the tail of the DSMEM exchange instead of following it
 #ifndef TC4_XORDER
-#define TC4_XORDER 1
+#define TC4_XORDER 0
+#endif
+#ifndef TC4_HTILE
+#define TC4_HTILE 1
+#endif
+// timing experiments only (wrong results): FNSSL_TC_DEBUG bit 2 = one x-part MMA per slab instead of four, bit 4 = no TMA output
+// stores, bit 16 = one h-part MMA per chunk instead of two
+#ifndef TC4_EXPERIMENT
+#define TC4_EXPERIMENT 0
 #endif
 constexpr int kXWarp = 18;
 constexpr int kProd2Warp = TC4_PROD2 ? 19 : -1;          // second TMA producer lane (odd ring stages + the L2 prefetch)
@@ -77,7 +88,9 @@ constexpr int kMaxXStages = 6;
 constexpr int kAccBufs = 3;
 constexpr int kSmemLimit = 232448;
 constexpr int kNumBarsBase = 1 + 2 * kMaxXStages + 3 * kAccBufs + 4;
-constexpr int kNumBars = kNumBarsBase + 4 + 8 + kAccBufs;   // + X2_FULL / X2_EMPTY of the narrow second source's ring, + H_READY[sub][quadrant], + HP_ISSUED[acc buffer]
+constexpr int kMaxC = 8;                        // largest cluster (H = 256)
+constexpr int kNumBars = kNumBarsBase + 4 + 8 + kAccBufs + 2 * kMaxC;   // + X2_FULL / X2_EMPTY of the narrow second source's ring, + H_READY[sub][quadrant], + HP_ISSUED[acc buffer],
+                                                                    // + H_TILE[sub][source CTA] (TC4_HTILE)
 constexpr int kWSmall = kChunkN * 32;          // [128 gate columns x 16] fp16 weight slab of a narrow source (32B swizzle)
 
 struct Params {
@@ -185,7 +198,11 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   auto X2_FULL = [&](int i) { return bar0 + 8u * (kNumBarsBase + i); };
   auto X2_EMPTY = [&](int i) { return bar0 + 8u * (kNumBarsBase + 2 + i); };
   auto H_READY = [&](int sub, int q) { return bar0 + 8u * (kNumBarsBase + 4 + sub * 4 + q); };   // quadrant q of h_t(sub) is in shared memory
-  auto HP_ISSUED = [&](int i) { return bar0 + 8u * (kNumBarsBase + 12 + i); };                    // the h-part of the slot using buffer i has been issued
+  auto HP_ISSUED = [&](int i) { return bar0 + 8u * (kNumBarsBase + 12 + i); };
+  // TC4_HTILE: chunk `src` of h_{t-1}(sub) is in this CTA's shared memory (own chunk: 4 quadrant arrives; a peer's: tx bytes)
+  auto H_TILE = [&](int sub, int src) { return bar0 + 8u * (kNumBarsBase + 12 + kAccBufs + sub * kMaxC + src); };
+  // the barrier the quadrant pushes of CTA `src` complete on / the local quadrant arrives go to
+  auto H_IN = [&](int sub, int src) { return TC4_HTILE ? H_TILE(sub, src) : H_FULL(sub); };                    // the h-part of the slot using buffer i has been issued
 
   if (tid == 0) {
     mbar_init(W_FULL, 1);
@@ -197,6 +214,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
     for (int i = 0; i < 2; ++i) { mbar_init(X2_FULL(i), 1); mbar_init(X2_EMPTY(i), xe); }
     for (int sub = 0; sub < 2; ++sub) {
       mbar_init(H_FULL(sub), 5);    // MMA thread's expect_tx + 4 local quadrants (+ tx bytes of the C-1 remote tiles)
+      for (int src = 0; src < C; ++src) mbar_init(H_TILE(sub, src), (uint32_t)src == rank ? 4 : 1);
       mbar_init(H_FREE(sub), C + kNumPub);    // one multicast commit per CTA of the cluster (+ the publishers: stores drained)
       for (int q = 0; q < 4; ++q) mbar_init(H_READY(sub, q), 4);   // the four epilogue warps of a quadrant
     }
@@ -381,7 +399,8 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           const uint32_t nk = nkp & 15u;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if ((uint32_t)k < nk) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (uint32_t)(j | k));
+            if ((uint32_t)k < nk && !(TC4_EXPERIMENT && (p.debug & 2) && k > 0))
+              umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (uint32_t)(j | k));
           if (nomc) umma_commit(X_EMPTY(xstage));
           else umma_commit_mc(X_EMPTY(xstage), mask);    // this CTA is done with the slab: tell every CTA's ring
           if (++xstage == XS) { xstage = 0; xphase ^= 1u; }
@@ -408,6 +427,16 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       const uint64_t wh_desc0 = make_sw128_desc(w_base + (uint32_t)nxb * kWSlab);
       int a = 0;
       uint32_t xp_par = 0;
+      // per-chunk operand descriptor offsets and arrival barriers in the order the chunks are consumed (constant per CTA)
+      uint32_t a_off[C], b_off[C], tbar0[C], tbar1[C];
+#pragma unroll
+      for (int i = 0; i < C; ++i) {
+        const int kc = TC4_HTILE ? (int)((rank + (uint32_t)(C - i)) % C) : i;   // own chunk first, then rank-1, rank-2, ... (push order)
+        a_off[i] = (uint32_t)(kc * (kHTile >> 4));
+        b_off[i] = (uint32_t)((kc >> 1) * (kWSlab >> 4) + 4 * (kc & 1));         // W columns inside 128B-swizzled slab kc/2
+        tbar0[i] = H_TILE(0, kc);
+        tbar1[i] = H_TILE(1, kc);
+      }
       for (int n = 0; n < nslots; ++n) {
         const int t = n >> 1, sub = n & 1;
         long long* tp = (TRACE && tr_cta && n >= 16 && n < 32) ? p.trace + (n - 16) * 16 : nullptr;
@@ -415,21 +444,30 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         mbar_wait(XP_DONE(a), (xp_par >> a) & 1u, p.error_flag, 240 + a);     // G_x of this slot is complete
         xp_par ^= 1u << a;
         if (t > 0 || hoff) {
-          if (t > 0) {
+          if (t > 0 && !TC4_HTILE) {
             // h_{t-1} of this sub-tile: C-1 remote tiles arrive as DSMEM bulk copies (tx bytes), the local one by arrives
             mbar_expect_tx(H_FULL(sub), (uint32_t)((C - 1) * kHTile));
             mbar_wait_cluster(H_FULL(sub), (uint32_t)((t - 1) & 1), p.error_flag, 220 + sub);
           }   // t == 0 with a carried state: h_{-1} was placed in the tiles before the roles split
+          if (t > 0 && TC4_HTILE) {     // arm every remote tile's barrier first, then take the tiles as they arrive
+#pragma unroll
+            for (int i = 1; i < C; ++i) mbar_expect_tx(sub ? tbar1[i] : tbar0[i], (uint32_t)kHTile);
+          }
           if (TRACE && tp) tp[1] = clock64();
           tc_fence_after();
           const uint32_t d_tmem = tmem_acc + (uint32_t)a * kChunkN;
           const uint64_t a_sub = h_desc0 + (uint64_t)(sub * C * (kHTile >> 4));
 #pragma unroll
-          for (int kc = 0; kc < C; ++kc) {   // K = 32 units of chunk kc: two K=16 steps; W columns inside 128B-swizzled slab kc/2
-            const uint64_t a_desc = a_sub + (uint64_t)(kc * (kHTile >> 4));
-            const uint64_t b_desc = wh_desc0 + (uint64_t)((kc >> 1) * (kWSlab >> 4) + 4 * (kc & 1));
+          for (int i = 0; i < C; ++i) {   // K = 32 units of one chunk: two K=16 steps
+            if (TC4_HTILE && t > 0) {
+              mbar_wait_cluster(sub ? tbar1[i] : tbar0[i], (uint32_t)((t - 1) & 1), p.error_flag, 220 + sub);
+              tc_fence_after();
+            }
+            const uint64_t a_desc = a_sub + (uint64_t)a_off[i];
+            const uint64_t b_desc = wh_desc0 + (uint64_t)b_off[i];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+            for (int k = 0; k < 2; ++k)
+              if (!(TC4_EXPERIMENT && (p.debug & 16) && k > 0)) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, 1u);
           }
           // h_{t-1} has been read once these MMAs retire: every CTA may then overwrite its copy with h_t
           umma_commit_mc(H_FREE(sub), mask);
@@ -464,28 +502,36 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       for (int dd = 1; dd < C; ++dd) {
         const uint32_t d = (rank + (uint32_t)dd) % C;
         peer_hs[dd - 1] = mapa_shared(hs_base, d);
-        peer_bar0[dd - 1] = mapa_shared(H_FULL(0), d);
-        peer_bar1[dd - 1] = mapa_shared(H_FULL(1), d);
+        peer_bar0[dd - 1] = mapa_shared(H_IN(0, (int)rank), d);
+        peer_bar1[dd - 1] = mapa_shared(H_IN(1, (int)rank), d);
       }
       if (hoff) { mbar_arrive(H_FREE(0)); mbar_arrive(H_FREE(1)); }   // the first phase has no earlier stores to wait for
-      const bool tma_any = p.tma_out != 0;
+      const bool tma_any = p.tma_out != 0 && !(TC4_EXPERIMENT && (p.debug & 4));
       for (int n = 0; n < nslots; ++n) {
         const int t = n >> 1, sub = n & 1;
         const int s = dir ? (L - 1 - t) : t;
         const bool push = t + 1 < L;
         if (push || tma_any) {
+          // the exchange first (it sits on the recurrence's critical path), the HBM stores of all quadrants afterwards: issuing a
+          // TMA store / reduce-add costs this single lane ~50 cycles each, which used to delay the next quadrant's pushes
+          // (measured: 0.82 -> 0.73 ms per 256-channel layer without the stores, profiles/r2_lstm_variants.txt)
 #pragma unroll
           for (int qq = 0; qq < kQPerPub; ++qq) {
             const int q = kQPerPub * pw + qq;
             mbar_wait(H_READY(sub, q), (uint32_t)(t & 1), p.error_flag, 400 + sub * 4 + q);
-            const uint32_t off = (uint32_t)(sub * C + (int)rank) * kHTile + (uint32_t)q * kQuadBytes;
             if (push) {
+              const uint32_t off = (uint32_t)(sub * C + (int)rank) * kHTile + (uint32_t)q * kQuadBytes;
 #pragma unroll
               for (int dd = 1; dd < C; ++dd)
                 bulk_copy_s2c(peer_hs[dd - 1] + off, hs_base + off, kQuadBytes, sub ? peer_bar1[dd - 1] : peer_bar0[dd - 1]);
-              mbar_arrive(H_FULL(sub));     // the local copy of this quadrant is in place
+              mbar_arrive(H_IN(sub, (int)rank));     // the local copy of this quadrant is in place
             }
-            if (tma_any) {
+          }
+          if (tma_any) {
+#pragma unroll
+            for (int qq = 0; qq < kQPerPub; ++qq) {
+              const int q = kQPerPub * pw + qq;
+              const uint32_t off = (uint32_t)(sub * C + (int)rank) * kHTile + (uint32_t)q * kQuadBytes;
               const int r0 = coord_r0 + sub * SUB + q * kQuadRows;
               if (p.tma_out & 1) {
                 if (along_f) tma_store_4d(&map_out0, hs_base + off, out_c, s, r0, 0);
@@ -496,8 +542,8 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
                 else tma_reduce_add_4d(&map_out1, hs_base + off, out1_c, r0, s, coord_b);
               }
             }
+            bulk_commit_group();
           }
-          if (tma_any) bulk_commit_group();
         }
         if (n >= 1) {     // slot n-1's stores (the other sub-tile's exchange tile) have read their source
           if (tma_any) bulk_wait_read_1();
@@ -540,7 +586,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       {
         if (pusher) {
           if (push) {
-            const uint32_t hb = H_FULL(sub);
+            const uint32_t hb = H_IN(sub, (int)rank);
 #pragma unroll
             for (int dd = 1; dd < C; ++dd) {
               const uint32_t d = (rank + (uint32_t)dd) % C;
@@ -861,7 +907,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
 
 struct Plan { bool ok; int sub; int xstages; int nxs; size_t smem; bool small1; };
 
-static Plan make_plan(int H, int c0, int c1, int axis = -1) {
+static Plan make_plan(int H, int c0, int c1, int axis = -1, bool small_grid = false) {
   Plan pl{false, 0, 0, 0, 0, false};
   if (H != 64 && H != 128 && H != 256) return pl;
   if (c0 % 16 || c1 % 16 || c0 <= 0) return pl;
@@ -880,8 +926,12 @@ static Plan make_plan(int H, int c0, int c1, int axis = -1) {
   bool small1 = c1 > 0 && c1 <= 16 && (H == 256 || (H == 128 && axis == FNSSL_ALONG_FREQ));
   if (const char* e = getenv("FNSSL_TC_SMALL1")) small1 = c1 > 0 && c1 <= 16 && atoi(e) != 0;
   const int nslabs = (small1 ? nxs - 1 : nxs) + NHS;
-  int sub_first = 128;
-  if (const char* e = getenv("FNSSL_TC_ROWS")) { if (atoi(e) == 64) sub_first = 64; }   // tests / profiling
+  // Small grids (few utterances): with 64-row sub-tiles the layer has twice the clusters, each slot half the gate math and half
+  // the exchange -- the recurrence is latency bound there, so the half-rate M = 64 MMAs do not matter.  Measured (B200, one
+  // utterance, profiles/r2_lstm_variants.txt): full in16 0.71 -> 0.59 ms, narrow in272 0.92 -> 0.66 ms; 2 utterances in256
+  // 0.79 -> 0.66 ms.  Used whenever the 64-row plan still fits the GPU in one wave (lstm_forward_tc4).
+  int sub_first = small_grid ? 64 : 128;
+  if (const char* e = getenv("FNSSL_TC_ROWS")) { sub_first = atoi(e) == 64 ? 64 : 128; }   // tests / profiling
   for (int sub = sub_first; sub >= 64; sub -= 64) {
     const long xslab = sub * 128L, htile = sub * 64L;
     const long fixed = (long)nslabs * kWSlab + (small1 ? kWSmall + 2L * sub * 32 : 0L) + 2L * C * htile + kChunkN * 4 + 1024;
@@ -1023,7 +1073,10 @@ extern "C" int fnssl_lstm_tc4_trace(long long* out256) {
 bool lstm_tc4_supports(int hidden, int c0, int c1) { return tc4::make_plan(hidden, c0, c1).ok; }
 
 int lstm_forward_tc4(const fnssl_lstm_args* a, cudaStream_t st) {
-  const tc4::Plan pl = tc4::make_plan(a->hidden, a->c0, a->c1, a->axis);
+  // cluster tiles of the 64-row plan (2 x 64 rows each); one wave = 132 co-resident CTAs for clusters of 4 (33 clusters)
+  const long long tiles64 = a->axis == FNSSL_ALONG_FREQ ? ((long long)a->nb * a->nt + 127) / 128 : (long long)a->nb * ((a->nf + 127) / 128);
+  const bool small_grid = tiles64 * a->num_dirs * (a->hidden / 32) <= 132;
+  const tc4::Plan pl = tc4::make_plan(a->hidden, a->c0, a->c1, a->axis, small_grid);
   FNSSL_REQUIRE(pl.ok, "lstm(tcgen05 two-chain kernel): unsupported layer (H=%d c0=%d c1=%d)", a->hidden, a->c0, a->c1);
   if (a->hidden == 64) return pl.sub == 128 ? tc4::launch<64, 128>(a, pl, st) : tc4::launch<64, 64>(a, pl, st);
   if (a->hidden == 128) return pl.sub == 128 ? tc4::launch<128, 128>(a, pl, st) : tc4::launch<128, 64>(a, pl, st);

@@ -19,6 +19,7 @@ Tensor = torch.Tensor
 
 _DTYPES = {torch.float32: F32, torch.float16: F16}
 PAIRING = {"M": PAIRS_M, "MM": PAIRS_MM, "ALL": PAIRS_ALL}
+NORM_GIVEN = 3   # FNSSL_NORM_GIVEN: mu is an input of features() / stft_features() (streaming)
 
 
 # launch accounting / per-layer timing (used by bench.py; off by default)
@@ -145,7 +146,6 @@ def stft(signal: Tensor, win_len: int = 512, hop: int = 256, nfft: int = 512,
     return torch.view_as_complex(spec), magsum
 
 
-NORM_GIVEN = 3   # FNSSL_NORM_GIVEN: mu is an input of features() (streaming)
 
 
 @on_tensor_device
@@ -192,6 +192,39 @@ def features(spec: Tensor, magsum: Optional[Tensor], pairing: str, norm: int, sa
     _lib.check(lib.fnssl_features_forward(sp.data_ptr(), _ptr(magsum), nb, nt, nch, pm, norm, sample_length, float(eps),
                                           mu.data_ptr(), feat.data_ptr(), code_of(dtype), ld, _ptr(cf), _stream()))
     return feat, mu, cf
+
+
+@on_tensor_device
+def stft_features(signal: Tensor, pairing: str, norm: int, sample_length: int, eps: float, dtype: torch.dtype,
+                  win_len: int = 512, hop: int = 256, nfft: int = 512, mu: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
+    """Fused front end: (nb, nsample, nch) f32 -> (grid (R, nt, 256, ld) of dtype, mu (R, nt) | None); the complex spectrum is
+    never written to HBM (two FFT passes over the L2-resident signal; see fnssl_stft_features_forward)."""
+    _need_cuda(signal, mu)
+    lib = _lib.load()
+    if signal.dim() != 3:
+        raise RuntimeError("stft_features: expected (nbatch, nsample, nch)")
+    x = signal.contiguous().float()
+    nb, nsample, nch = x.shape
+    nt = lib.fnssl_stft_num_frames(nsample, win_len, hop)
+    if nt <= 0:
+        raise RuntimeError(f"stft_features: signal of {nsample} samples is shorter than one {win_len}-sample window")
+    pm = PAIRING[pairing]
+    R = lib.fnssl_feature_rows(nb, nch, pm)
+    ld = pad_channels(lib.fnssl_feature_channels(nch, pm), dtype)
+    feat = torch.empty((R, nt, 256, ld), dtype=dtype, device=x.device)
+    magsum = None
+    if norm in (NORM_FORGETTING, NORM_GLOBAL):
+        magsum = torch.empty((nb, nch, nt), dtype=torch.float32, device=x.device)
+        mu = torch.empty((R, nt), dtype=torch.float32, device=x.device)
+    elif norm == NORM_GIVEN:
+        if mu is None or mu.shape != (R, nt) or mu.dtype != torch.float32 or not mu.is_contiguous():
+            raise RuntimeError("stft_features: NORM_GIVEN needs a contiguous float32 mu of shape (R, nt)")
+    else:
+        mu = None
+    _count(3 if magsum is not None else 1)
+    _lib.check(lib.fnssl_stft_features_forward(x.data_ptr(), nb, nsample, nch, win_len, hop, nfft, pm, norm, sample_length,
+                                               float(eps), _ptr(magsum), _ptr(mu), feat.data_ptr(), code_of(dtype), ld, _stream()))
+    return feat, mu
 
 
 @on_tensor_device

@@ -85,9 +85,10 @@ class FNSSLPipeline(nn.Module):
     @torch.no_grad()
     def forward(self, signal: Tensor) -> Tensor:
         eng = self.arch._engine()
-        spec, magsum = ops.stft(signal, WIN_LEN, HOP, NFFT, want_magsum=True)
-        g0, _, _ = ops.features(spec, magsum, self.ch_mode, ops.NORM_FORGETTING, self.sample_length, self.eps,
-                                config.grid_dtype(eng))
+        # fused front end: the complex spectrum is never written to HBM (ops.stft_features: FFT -> sum|X| -> normaliser ->
+        # FFT again -> normalised feature grid)
+        g0, _ = ops.stft_features(signal, self.ch_mode, ops.NORM_FORGETTING, self.sample_length, self.eps,
+                                  config.grid_dtype(eng), WIN_LEN, HOP, NFFT)
         return self.arch.forward_grid(g0, eng)
 
     @torch.no_grad()
@@ -120,10 +121,9 @@ class IPDnetPipeline(nn.Module):
     @torch.no_grad()
     def forward(self, signal: Tensor, offline_inference: bool = False) -> Tensor:
         eng = self.arch._engine()
-        spec, magsum = ops.stft(signal, WIN_LEN, HOP, NFFT, want_magsum=True)
         offline = not self.arch.is_online
         norm = ops.NORM_GLOBAL if offline else ops.NORM_FORGETTING
-        g0, _, _ = ops.features(spec, magsum, 'ALL', norm, self.sample_length, self.eps, config.grid_dtype(eng))
+        g0, _ = ops.stft_features(signal, 'ALL', norm, self.sample_length, self.eps, config.grid_dtype(eng), WIN_LEN, HOP, NFFT)
         nt = g0.shape[1]
         chunked = offline and offline_inference
         if chunked and nt % self.arch.n:

@@ -27,7 +27,8 @@ extern "C" {
 #endif
 
 #define FNSSL_ABI_VERSION 4 /* 2: carried LSTM state; 3: IPDnet2 entry points (fnssl_reflect_pad, fnssl_sn_*); 4: one tcgen05 LSTM kernel
-                             (fnssl_lstm_tc_trace of the retired generations removed), training-side targets / loss */
+                             (fnssl_lstm_tc_trace of the retired generations removed), training-side targets / losses,
+                             fused fnssl_stft_features_forward */
 
 /* element types of grid tensors */
 #define FNSSL_F32 0
@@ -95,6 +96,17 @@ int fnssl_feature_channels(int nch, int pairing);
 int fnssl_features_forward(const float* spec, const float* magsum, int nb, int nt, int nch, int pairing,
                            int norm, int sample_length, float eps, float* mu, void* feat, int dtype, int ld,
                            float* feat_cfirst, void* stream);
+
+/* FUSED front end for the pipelines: signal -> normalised feature grid, without ever writing the complex spectrum to HBM
+ * (STFT.forward + data_preprocess in one entry point: FN-SSL/Lightning/Module.py:48-68 + main.py:206-225; IPDnet/
+ * runIPDnetOn.py:240-254).  Two passes over the (L2-resident) signal: pass 1 = FFT -> per-frame sums of |X| only -> the
+ * normaliser recursion; pass 2 = FFT again -> re/(mu+eps), im/(mu+eps), bins 1..256, written straight into the grid.
+ *   magsum : workspace (nb, nch, nt) f32 (unused for FNSSL_NORM_NONE / _GIVEN);  mu : (R, nt) f32, output (input for _GIVEN)
+ *   feat   : 16-byte aligned grid (R, nt, 256, ld) of `dtype`, ld a multiple of 16 bytes; channels C..ld-1 are written as zero
+ * Same numbers as fnssl_stft_forward + fnssl_features_forward (the same FFT code runs twice). */
+int fnssl_stft_features_forward(const float* signal, int nb, int nsample, int nch, int win_len, int hop, int nfft, int pairing,
+                                int norm, int sample_length, float eps, float* magsum, float* mu, void* feat, int dtype, int ld,
+                                void* stream);
 
 /* (nb, C, nf, nt) f32  <->  grid (nb, nt, nf, ld) of dtype at channel offset `ch_off`
  * (FN_SSL.forward's x.permute(0,3,2,1), Model.py:73; IPDnet :93,:111). */

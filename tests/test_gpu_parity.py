@@ -119,6 +119,27 @@ def test_feature_grid_layout(dtype):
     assert torch.equal(g2, g)
 
 
+@pytest.mark.parametrize("nch,pairing", [(2, "MM"), (3, "MM"), (3, "M"), (4, "ALL"), (8, "ALL"), (5, "ALL")])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_fused_stft_features_equals_two_step_front_end(nch, pairing, dtype):
+    """ops.stft_features (the pipelines' front end: two FFT passes, the complex spectrum never written) is bit-identical to
+    ops.stft + ops.features for every pairing / normaliser, including a ragged last frame tile and hop 320 (IPDnet2)."""
+    from fn_ssl_b200 import ops
+    sig = _randn((2, 512 + 256 * 37 + 19, nch), 31).to(DEV)
+    for norm, hop in ((ops.NORM_FORGETTING, 256), (ops.NORM_GLOBAL, 256), (ops.NORM_NONE, 256), (ops.NORM_FORGETTING, 320)):
+        spec, magsum = ops.stft(sig, 512, hop, 512, want_magsum=True)
+        g_ref, mu_ref, _ = ops.features(spec, magsum, pairing, norm, 31, 1e-6, dtype)      # sample_length 31 < nt: both branches
+        g, mu = ops.stft_features(sig, pairing, norm, 31, 1e-6, dtype, 512, hop, 512)
+        assert g.shape == g_ref.shape and torch.equal(g, g_ref), (norm, hop)
+        if norm != ops.NORM_NONE:
+            assert torch.equal(mu, mu_ref)
+    # the reference oracle on top (FN-SSL pairing only: the oracle's preprocess is the 'MM' path)
+    if pairing == "MM":
+        g, _ = ops.stft_features(sig, "MM", ops.NORM_FORGETTING, 298, 1e-6, torch.float32)
+        ref = orc.preprocess_fnssl(sig.cpu())
+        assert _relerr(g[..., :4].permute(0, 3, 2, 1), ref) <= 1e-5
+
+
 # ---------------------------------------------------------------------------------------------
 # LSTM layer, both axes, both engines
 # ---------------------------------------------------------------------------------------------

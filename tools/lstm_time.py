@@ -20,6 +20,9 @@ CFGS = [("full_in16_H128x2", 0, 16, 249, 256, 16, 0, 128, True, False),
         ("narrow_in256_H256x1_add", 1, 16, 249, 256, 256, 0, 256, False, True),
         ("full_in256+16_H128x2", 0, 32, 249, 256, 256, 16, 128, True, False),
         ("full_in256_H128x2_add_B2", 0, 2, 249, 256, 256, 0, 128, True, True),
+        ("full_in16_H128x2_B1", 0, 1, 249, 256, 16, 0, 128, True, False),
+        ("narrow_in256+16_H128x2_B1", 1, 1, 249, 256, 256, 16, 128, True, False),
+        ("narrow_in256+16_H256x1_B1", 1, 1, 249, 256, 256, 16, 256, False, False),
         ("full_in256_H128x2_add_B64", 0, 64, 249, 256, 256, 0, 128, True, True)]
 
 
