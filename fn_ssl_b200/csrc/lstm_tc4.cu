@@ -1064,7 +1064,10 @@ static int launch(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
 }  // namespace tc4
 
 // diagnostic: copy the last trace (16 slots x 16 clock64 stamps) recorded with FNSSL_TC_TRACE=1
+long long* lstm_tc5_trace_buffer();      // lstm_tc5.cu (we are inside namespace fnssl)
 extern "C" int fnssl_lstm_tc4_trace(long long* out256) {
+  if (long long* t5 = lstm_tc5_trace_buffer())      // the pair kernel ran with FNSSL_TC_TRACE: its timeline takes precedence
+    return cudaMemcpy(out256, t5, 256 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 1 : 0;
   std::lock_guard<std::mutex> lk(tc4::g_trace_mu);
   if (tc4::g_trace_last < 0 || !tc4::g_trace_dev[tc4::g_trace_last]) return 0;
   return cudaMemcpy(out256, tc4::g_trace_dev[tc4::g_trace_last], 256 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 1 : 0;

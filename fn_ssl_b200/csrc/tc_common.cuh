@@ -273,7 +273,16 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
       : "memory");
   return ok != 0;
 }
-// non-blocking poll (test_wait does not suspend the thread): true if the phase with `parity` has completed
+// non-blocking polls (test_wait does not suspend the thread): true if the phase with `parity` has completed
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ bool mbar_test_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

@@ -209,6 +209,21 @@ def test_lstm_layer_tcgen05(monkeypatch, rows, axis, H, bidir, c0, c1, addend):
         assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, H, bidir, addend, inplace=True) <= 1e-3
 
 
+@pytest.mark.parametrize("axis", [0, 1])
+@pytest.mark.parametrize("bidir,c0,c1,addend", [(True, 4, 0, False), (True, 256, 0, True), (True, 256, 4, True), (False, 256, 0, False),
+                                                 (True, 256, 8, False), (False, 128, 8, False), (True, 64, 0, True)])
+def test_lstm_layer_tcgen05_pair_kernel(monkeypatch, axis, bidir, c0, c1, addend):
+    """The CTA-pair kernel (lstm_tc5.cu, tcgen05 cta_group::2; H = 128) forced on small layers: ragged chains (70 frames /
+    40 bins against 256-row chains), an absent second chain, two-source inputs, the in-place residual output."""
+    from fn_ssl_b200 import config
+    if not config.TC_AVAILABLE:
+        pytest.skip("tcgen05 engine not built")
+    monkeypatch.setenv("FNSSL_TC_PAIR", "1")
+    monkeypatch.setenv("FNSSL_TC_PAIR_MIN", "1")
+    for nb, nt, nf in (((3, 5, 256), (2, 70, 300)) if axis == 1 else ((2, 70, 40), (5, 130, 7))):
+        assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, 128, bidir, addend, inplace=addend) <= 1e-3
+
+
 @pytest.mark.parametrize("small1", ["1", "0"])
 @pytest.mark.parametrize("axis", [0, 1])
 @pytest.mark.parametrize("H,bidir,c0,c1,addend", [(128, True, 256, 4, True), (64, True, 128, 8, True), (256, False, 256, 8, True),
@@ -407,7 +422,7 @@ def test_fnssl_batch16_properties():
 
 @pytest.mark.parametrize("tag,kw,B", [("cfg2 offline", dict(is_online=False), 16), ("cfg4 doa", dict(is_online=False, is_doa=True), 32),
                                       ("cfg4 doa online", dict(is_online=True, is_doa=True), 32)])
-def test_fnssl_benched_configs_at_size(tag, kw, B):
+def test_fnssl_benched_configs_at_size(tag, kw, B, monkeypatch):
     """The configurations bench.py measures, at their per-GPU batch sizes (cfg2: 16 x 4 s offline; cfg4: the 32-utterance
     shard of the global 256 batch at 8 GPUs, DOA head): one utterance of the batch against the oracle, and every probed
     utterance bit-identical to its solo run (utterances are independent)."""
@@ -423,8 +438,14 @@ def test_fnssl_benched_configs_at_size(tag, kw, B):
     k = B - 3
     ref = orc.fnssl_forward(orc.preprocess_fnssl(sig[k:k + 1]), sd, fast=True)
     assert _relerr(out[k:k + 1], ref) <= TOL[net._engine()]
+    # At these sizes the H = 128 layers run the CTA-pair kernel (lstm_tc5.cu); a solo utterance is a small grid and runs
+    # lstm_tc4.cu, whose h-part accumulates the chunks in a different order -- so the bit-for-bit solo comparison is made with
+    # the pair kernel switched off, and the two kernels are compared with each other at the engine's tolerance.
+    monkeypatch.setenv("FNSSL_TC_PAIR", "0")
+    out4 = pipe(sig.to(DEV))
+    assert _relerr(out, out4) <= TOL[net._engine()]
     for b in (0, k, B - 1):
-        assert torch.equal(pipe(sig[b:b + 1].to(DEV))[0], out[b]), b
+        assert torch.equal(pipe(sig[b:b + 1].to(DEV))[0], out4[b]), b
 
 
 def test_ipdnet_cfg3_at_size():

@@ -2,7 +2,7 @@
 
     python tools/build_variant.py TAG -DTC4_PROD2=0 -DTC4_PUB=1 ...   ->  fn_ssl_b200/variants/libfnssl_b200_TAG.so
 
-Only lstm_tc4.cu is recompiled with the extra defines; every other object is the regular build's.  Select a variant at run
+Only the sources named in VARIANT_SRC (default lstm_tc4.cu) are recompiled with the extra defines; every other object is the regular build's.  Select a variant at run
 time with FNSSL_B200_LIB=<path> (fn_ssl_b200/_lib.py; development / profiling only -- the product loads libfnssl_b200.so).
 """
 import os
@@ -19,13 +19,17 @@ def main():
     B.build()
     vdir = os.path.join(B.HERE, "variants")
     os.makedirs(vdir, exist_ok=True)
-    obj = os.path.join(B.BUILD, f"variant_lstm_tc4_{tag}.o")
-    cmd = [B._nvcc()] + B.NVCC_FLAGS + defines + ["-c", os.path.join(B.CSRC, "lstm_tc4.cu"), "-o", obj]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise SystemExit(res.stdout + res.stderr)
-    regs = [l for l in res.stderr.splitlines() if "registers" in l or "spill" in l]
-    objs = [os.path.join(B.BUILD, s[:-3] + ".o") for s in B._sources() if s != "lstm_tc4.cu"] + [obj]
+    srcs = os.environ.get("VARIANT_SRC", "lstm_tc4.cu").split(",")      # the sources the defines apply to
+    regs, vobjs = [], []
+    for src in srcs:
+        obj = os.path.join(B.BUILD, f"variant_{src[:-3]}_{tag}.o")
+        cmd = [B._nvcc()] + B.NVCC_FLAGS + defines + ["-c", os.path.join(B.CSRC, src), "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise SystemExit(res.stdout + res.stderr)
+        regs += [l for l in res.stderr.splitlines() if "registers" in l or "spill" in l]
+        vobjs.append(obj)
+    objs = [os.path.join(B.BUILD, s[:-3] + ".o") for s in B._sources() if s not in srcs] + vobjs
     lib = os.path.join(vdir, f"libfnssl_b200_{tag}.so")
     subprocess.run([B._nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs, check=True)
     worst = max((int(l.split("Used ")[1].split()[0]) for l in regs if "Used " in l), default=0)
