@@ -128,6 +128,8 @@ bool lstm_tc4_supports(int hidden, int c0, int c1);
 int lstm_forward_tc4(const fnssl_lstm_args* a, cudaStream_t st);
 bool lstm_tc5_wants(const fnssl_lstm_args* a);      // CTA-pair (cta_group::2) kernel: H = 128 layers with enough rows
 int lstm_forward_tc5(const fnssl_lstm_args* a, cudaStream_t st);
+bool lstm_tc6_wants(const fnssl_lstm_args* a);      // CTA-pair kernel for H = 256 single-source layers (full-rate M = 128 MMAs)
+int lstm_forward_tc6(const fnssl_lstm_args* a, cudaStream_t st);
 
 int lstm_forward_tc(const fnssl_lstm_args* a, cudaStream_t st) {
   FNSSL_REQUIRE(a->dtype == FNSSL_F16, "lstm(tcgen05): grids must be fp16");
@@ -136,6 +138,7 @@ int lstm_forward_tc(const fnssl_lstm_args* a, cudaStream_t st) {
   FNSSL_REQUIRE(lstm_tc4_supports(a->hidden, a->c0, a->c1),
                 "lstm(tcgen05): layer shape H=%d c0=%d c1=%d is not built (H in {64,128,256}, <= 6 input slabs of 64 channels); "
                 "use FNSSL_ENGINE_SIMT for it", a->hidden, a->c0, a->c1);
+  if (lstm_tc6_wants(a)) return lstm_forward_tc6(a, st);
   if (lstm_tc5_wants(a)) return lstm_forward_tc5(a, st);
   return lstm_forward_tc4(a, st);
 }

@@ -8,7 +8,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 CASES = [
-    # name, axis, nb, nt, nf, c0, c1, bidir, addend (in place)
+    # name, axis, nb, nt, nf, c0, c1, bidir, addend (in place)   [H = 128 unless the name starts with h256]
+    ("h256_time_c64_uni_L1", 1, 2, 1, 256, 64, 0, False, False),
+    ("h256_time_c64_uni_L3", 1, 2, 3, 256, 64, 0, False, False),
+    ("h256_time_c256_uni_add", 1, 3, 7, 256, 256, 0, False, True),
+    ("h256_freq_c256_uni_ragged", 0, 3, 100, 5, 256, 0, False, False),
+    ("h256_time_c16_bi_nf300", 1, 2, 4, 300, 16, 0, True, False),
     ("time_c64_uni_L1", 1, 2, 1, 256, 64, 0, False, False),
     ("time_c64_uni_L2", 1, 2, 2, 256, 64, 0, False, False),
     ("time_c64_uni_L5", 1, 2, 5, 256, 64, 0, False, False),
@@ -26,7 +31,7 @@ def run_case(idx):
     from fn_ssl_b200.packing import LSTMParams, run_lstm
     from oracle import fnssl_oracle as orc
     name, axis, nb, nt, nf, c0, c1, bidir, use_add = CASES[idx]
-    H, dev = 128, "cuda"
+    H, dev = (256 if name.startswith("h256") else 128), "cuda"
     torch.manual_seed(idx)
     p = LSTMParams(c0 + c1, H, bidirectional=bidir).to(dev)
     g = torch.Generator().manual_seed(100 + idx)
@@ -74,8 +79,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         run_case(int(sys.argv[1]))
     else:
+        only = os.environ.get("PAIR_DEBUG_ONLY", "")
         for i in range(len(CASES)):
-            env = dict(os.environ, FNSSL_TC_PAIR="1", FNSSL_TC_PAIR_MIN="1", FNSSL_TC_WAIT_TIMEOUT="1")
+            if only and only not in CASES[i][0]:
+                continue
+            env = dict(os.environ, FNSSL_TC_PAIR="1", FNSSL_TC_PAIR_MIN="1", FNSSL_TC_PAIR256_MIN="1", FNSSL_TC_WAIT_TIMEOUT="1")
             r = subprocess.run([sys.executable, os.path.abspath(__file__), str(i)], capture_output=True, text=True, timeout=300, env=env)
             print(r.stdout.strip())
             if r.returncode != 0:
