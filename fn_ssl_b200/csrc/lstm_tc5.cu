@@ -1,5 +1,6 @@
-// CTA-pair (tcgen05 cta_group::2) cluster LSTM kernel for H = 128 -- an EXPERIMENTAL fifth generation of FNSSL_ENGINE_TCGEN05
-// (off by default, FNSSL_TC_PAIR=1; see lstm_tc5_wants below for what was measured).  The product kernel is lstm_tc4.cu.
+// CTA-pair (tcgen05 cta_group::2) cluster LSTM kernel for H = 128: the kernel of FNSSL_ENGINE_TCGEN05 for LARGE layers (at
+// least one wave of clusters, see lstm_tc5_wants below; FNSSL_TC_PAIR=0 disables it).  Smaller layers run lstm_tc4.cu, whose
+// 128-row tiles fill the GPU at small batch.
 //
 // Why.  lstm_tc4.cu splits the 4H gate columns over a cluster of 4 CTAs that all hold the SAME rows, so every step each CTA
 // pushes its [128 x 32] h tile to 3 peers and receives 3 tiles: 48 KB per slot through DSMEM, which measures at ~17-20 B/clk per
@@ -17,7 +18,7 @@
 //
 //   warp 0        TMA producer (both CTAs load their own rows; the "full" barrier lives on the pair's leader, rank 2p)
 //   warp 1        leader: h-part MMA issuer;  other CTA: relay ("my weights / my h tiles are in place" -> leader's barriers)
-//   warps 2..17   epilogue: two groups of 8 warps, group g = unit half g of every (step, chain), running concurrently
+//   warps 2..17   epilogue: all 16 warps take the half-slots one after the other (thread = row x 8 hidden units)
 //   warp 18       leader: x-part MMA issuer
 //   warp 19       publisher: DSMEM push of the CTA's h tile to its ONE peer, TMA output stores
 //
@@ -26,7 +27,8 @@
 // it overwrites its tile.  The h-parts of uh = 0 and uh = 1 are issued back to back, so that wait is over long before the gate
 // math of uh = 0 finishes.
 //
-// TMEM (per CTA, allocated with cta_group::2): columns [0,128) cell state (chain, uh) x 32, [128,512) three accumulators.
+// TMEM (per CTA, allocated with cta_group::2): four accumulators of 128 columns, one pair (both unit halves) per chain; the cell
+// state lives in the epilogue threads' registers.
 // Replaces nn.LSTM at FN-SSL/Lightning/Model.py:38,46 and IPDnet/FixedAarryIPDnet.py:32,36 (+ glue :35-37,41-45,49).
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -54,7 +56,10 @@ constexpr int kWHalf = 64 * 128;           // [64 gate columns x 64] fp16: this 
 constexpr int kXSlab = kRows * 128;        // [128 rows x 64] fp16
 constexpr int kHTile = kRows * 64;         // [128 rows x 32 units] fp16 (64B swizzle)
 constexpr int kChunkN = 128;
-constexpr int kMaxXSlabs = 6, kMaxXStages = 6, kAccBufs = 3;
+#ifndef TC5_ACCBUFS
+#define TC5_ACCBUFS 4      // 4: one accumulator PAIR per chain (the x-part of one chain overlaps the other chain's h-part / epilogue)
+#endif
+constexpr int kMaxXSlabs = 6, kMaxXStages = 6, kAccBufs = TC5_ACCBUFS;
 constexpr int kSmemLimit = 232448;
 // barriers
 constexpr int B_WFULL = 0, B_WMATE = 1, B_XFULL = 2, B_XEMPTY = B_XFULL + kMaxXStages, B_ACCFULL = B_XEMPTY + kMaxXStages,
@@ -181,7 +186,7 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
   [[maybe_unused]] const uint32_t tmem_c = tmem;             // (cell state lives in registers; columns [0,128) are free)
-  const uint32_t tmem_acc = tmem + 128;     // gate accumulators: kAccBufs buffers x 128 columns
+  const uint32_t tmem_acc = tmem + (uint32_t)(512 - kAccBufs * 128);     // gate accumulators: kAccBufs buffers x 128 columns
 
   // per-chain coordinates of this CTA's 128 rows
   const bool along_f = p.axis == FNSSL_ALONG_FREQ;
@@ -435,7 +440,7 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       for (int b = 0; b < 2; ++b)
 #pragma unroll
         for (int i = 0; i < 8; ++i) creg[c][b][i] = 0.0f;
-    int a = g, use = 0;                        // half-slot n = 4t + 2c + g uses buffer n % 3; `use` = n / 3 (phase parity of that buffer)
+    int a = g, use = 0;                        // half-slot n = 4t + 2c + g uses buffer n % kAccBufs; `use` = n / kAccBufs (phase parity of that buffer)
 #pragma unroll 1
     for (int t = 0; t < L; ++t) {
 #pragma unroll
@@ -489,7 +494,7 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_HREADY + cu * 4 + q));
         }
-        a += 2; if (a >= kAccBufs) { a -= kAccBufs; ++use; }
+        a += 2; if (a >= kAccBufs) { a -= kAccBufs; ++use; }      // (4 buffers: a = 2c + g, use = t)
       }
     }
   }
@@ -637,8 +642,7 @@ static int make_half_weight_map(CUtensorMap* m, const void* weights, int nslabs,
 // + TMEM loads + MUFU-bound gate math ~1.4 k + hand-off = 2.2-2.8 k cycles), which both kernels share.  Kept as the starting point
 // for the H = 256 version (M = 128 per pair turns that layer's half-rate M = 64 MMAs into full-rate ones) and tested.
 bool lstm_tc5_wants(const fnssl_lstm_args* a) {
-  const char* on = getenv("FNSSL_TC_PAIR");
-  if (!on || atoi(on) == 0) return false;
+  if (const char* on = getenv("FNSSL_TC_PAIR")) { if (atoi(on) == 0) return false; }      // FNSSL_TC_PAIR=0: lstm_tc4.cu only
   if (a->hidden != 128 || a->state_flags) return false;
   if (!tc5::make_plan(a->c0, a->c1).ok) return false;
   if (a->out0 && a->out0_off % 8) return false;

@@ -44,7 +44,7 @@ constexpr int kHTile = kRows * 64;         // [64 rows x 32 units] fp16 (64B swi
 constexpr int kChunkN = 128;
 constexpr int kNH = H / 32;                // 8 chunk tiles of h per chain
 constexpr int kNHS = H / kSlabK;           // 4 K slabs of W_h
-constexpr int kMaxXSlabs = 4, kMaxXStages = 6, kAccBufs = 3;
+constexpr int kMaxXSlabs = 4, kMaxXStages = 6, kAccBufs = 4;      // accumulators: one PAIR (both unit halves) per chain
 constexpr int kAccCols = 64;               // TMEM columns of one accumulator (N / 2)
 constexpr int kSmemLimit = 232448;
 constexpr int B_WFULL = 0, B_WMATE = 1, B_XFULL = 2, B_XEMPTY = B_XFULL + kMaxXStages, B_ACCFULL = B_XEMPTY + kMaxXStages,
@@ -166,7 +166,7 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
   // (columns [0,64) are unused: the cell state lives in the epilogue threads' registers)
-  const uint32_t tmem_acc = tmem + 64;      // gate accumulators: kAccBufs buffers x 64 columns
+  const uint32_t tmem_acc = tmem;           // gate accumulators: kAccBufs buffers x 64 columns (all 256 allocated columns)
 
   const bool along_f = p.axis == FNSSL_ALONG_FREQ;
   int cb_[2], cr0_[2];
@@ -527,9 +527,15 @@ bool lstm_tc6_wants(const fnssl_lstm_args* a) {
   if (a->out1 && !(a->out1 == a->addend && a->out1_ld == a->addend_ld)) return false;
   const long long chains = a->axis == FNSSL_ALONG_FREQ ? ((long long)a->nb * a->nt + 127) / 128 : (long long)a->nb * ((a->nf + 127) / 128);
   const long long clusters = (chains + 1) / 2 * a->num_dirs;
-  int min_clusters = 8;
-  if (const char* e = getenv("FNSSL_TC_PAIR256_MIN")) min_clusters = atoi(e);
-  return clusters >= min_clusters;
+  if (const char* e = getenv("FNSSL_TC_PAIR256_MIN")) return clusters >= atoi(e);
+  // Both H = 256 kernels run clusters of 8 CTAs with one CTA per SM: kResident of them fit the GPU at a time (measured:
+  // cudaOccupancyMaxActiveClusters = 15 on a 148-SM B200), so a launch takes ceil(clusters / kResident) waves.  A wave of this
+  // kernel covers twice the rows of one of lstm_tc4.cu (256 vs 128 per cluster) in 1.62x its time (1.147 vs 0.71 ms at
+  // c0 = 256, 249 steps: profiles/r2_lstm_variants.txt) -- it wins when the wave counts quantise in its favour or are large.
+  constexpr long long kResident = 15;
+  const long long waves6 = (clusters + kResident - 1) / kResident;
+  const long long waves4 = (chains * a->num_dirs + kResident - 1) / kResident;
+  return waves6 * 13 < waves4 * 8;
 }
 
 int lstm_forward_tc6(const fnssl_lstm_args* a, cudaStream_t st) {

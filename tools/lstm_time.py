@@ -23,7 +23,13 @@ CFGS = [("full_in16_H128x2", 0, 16, 249, 256, 16, 0, 128, True, False),
         ("full_in16_H128x2_B1", 0, 1, 249, 256, 16, 0, 128, True, False),
         ("narrow_in256+16_H128x2_B1", 1, 1, 249, 256, 256, 16, 128, True, False),
         ("narrow_in256+16_H256x1_B1", 1, 1, 249, 256, 256, 16, 256, False, False),
-        ("full_in256_H128x2_add_B64", 0, 64, 249, 256, 256, 0, 128, True, True)]
+        ("full_in256_H128x2_add_B64", 0, 64, 249, 256, 256, 0, 128, True, True),
+        ("full_in16_H128x2_b256", 0, 256, 249, 256, 16, 0, 128, True, False),
+        ("narrow_in256+16_H128x2_add_b256", 1, 256, 249, 256, 256, 16, 128, True, True),
+        ("full_in256_H128x2_add_b256", 0, 256, 249, 256, 256, 0, 128, True, True),
+        ("narrow_in256_H128x2_add_b256", 1, 256, 249, 256, 256, 0, 128, True, True),
+        ("narrow_in256_H256x1_add_b15", 1, 15, 249, 256, 256, 0, 256, False, True),
+        ("narrow_in256_H256x1_add_b60", 1, 60, 249, 256, 256, 0, 256, False, True)]
 
 
 def main():

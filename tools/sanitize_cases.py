@@ -2,7 +2,7 @@
 
     compute-sanitizer --tool racecheck python tools/sanitize_cases.py lstm128
 Cases: lstm128 (H=128, cluster of 4, 128-row sub-tiles, residual reduce-add), lstm256 (H=256, cluster of 8, 64-row sub-tiles),
-lstm256n (H=256 with the narrow second-source ring), conv (CausCnnBlock tcgen05 implicit GEMM).  Each prints its error against
+lstm256n (H=256 with the narrow second-source ring), pair128 / pair128f / pair256 (the CTA-pair kernels), conv (CausCnnBlock tcgen05 implicit GEMM).  Each prints its error against
 the CPU oracle so a sanitizer-clean run is also a correct run.  Pipeline waits are unbounded here (the tool slows kernels ~100x).
 """
 import os
@@ -21,12 +21,19 @@ LSTM = {  # axis, nb, nt, nf, c0, c1, H, bidir, addend(in place)
     "lstm128f": (0, 1, 140, 6, 64, 16, 128, True, False),
     "lstm256": (1, 1, 5, 128, 256, 0, 256, False, True),
     "lstm256n": (1, 1, 5, 128, 256, 16, 256, False, False),
+    # the CTA-pair kernels (cta_group::2), forced on small layers: lstm_tc5.cu (H = 128) and lstm_tc6.cu (H = 256)
+    "pair128": (1, 1, 5, 300, 256, 0, 128, True, True),
+    "pair128f": (0, 1, 300, 6, 64, 16, 128, True, False),
+    "pair256": (1, 1, 5, 300, 256, 0, 256, False, True),
 }
 
 
 def lstm_case(name):
     axis, nb, nt, nf, c0, c1, H, bidir, add = LSTM[name]
     dev = "cuda"
+    os.environ["FNSSL_TC_PAIR"] = "1" if name.startswith("pair") else "0"
+    os.environ["FNSSL_TC_PAIR_MIN"] = "1"
+    os.environ["FNSSL_TC_PAIR256_MIN"] = "1" if name.startswith("pair") else "1000000"
     torch.manual_seed(1)
     p = LSTMParams(c0 + c1, H, bidirectional=bidir).to(dev)
     g = torch.Generator().manual_seed(2)

@@ -13,7 +13,8 @@ import torch  # noqa: E402
 from fn_ssl_b200 import _lib  # noqa: E402
 from fn_ssl_b200.packing import LSTMParams, run_lstm  # noqa: E402
 
-cfgs = [("full in16", 0, 16, 249, 256, 16, 0, True, False), ("full in256 add", 0, 16, 249, 256, 256, 0, True, True)]
+NB = int(os.environ.get("TRACE_NB", "64"))
+cfgs = [("full in16", 0, NB, 249, 256, 16, 0, True, False), ("full in256 add", 0, NB, 249, 256, 256, 0, True, True)]
 names = {0: "h-iss: top", 1: "h-iss: XP_DONE passed", 2: "h-iss: H_FULL passed", 3: "h-iss: H_MATE passed", 4: "h-iss: ACC_FULL committed",
          5: "epi: top", 6: "epi: ACC_FULL passed", 7: "epi: math done", 8: "epi: handed to publisher",
          9: "x-iss: pass top", 10: "x-iss: buffers free", 11: "x-iss: pass issued", 12: "pub: top", 13: "pub: pushes issued", 14: "pub: stores issued"}
