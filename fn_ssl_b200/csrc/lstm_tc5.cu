@@ -247,7 +247,7 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       mbar_wait(BAR(B_WMATE), 0, p.error_flag, 201);
       const uint64_t a_desc0 = make_sw128_desc(xr_base);
       const uint64_t b_desc0 = make_sw128_desc(w_base);
-      int xstage = 0, a0 = 0;
+      int xstage = 0, a0 = 0, gslab = 0;
       uint32_t xphase = 0, empty_par = 0;
       for (int n2 = 0; n2 < 2 * L; ++n2) {
         const int a1 = (a0 == kAccBufs - 1) ? 0 : a0 + 1;
@@ -264,7 +264,11 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         TP(2 * n2, 10);
         const uint32_t d0 = tmem_acc + (uint32_t)a0 * kChunkN, d1 = tmem_acc + (uint32_t)a1 * kChunkN;
         uint32_t nkp = p.xs_nkpack;
-        for (int j = 0; j < nxs; ++j, nkp >>= 4) {
+        for (int j = 0; j < nxs; ++j, nkp >>= 4, ++gslab) {
+          if ((p.debug & 128) && gslab >= 2) {     // experiment: at most two slabs of x-part MMAs queued ahead of a ready h-part
+            const int g2 = gslab - 2;
+            mbar_wait(BAR(B_XEMPTY + g2 % XS), (uint32_t)((g2 / XS) & 1), p.error_flag, 216);
+          }
           mbar_wait(BAR(B_XFULL + xstage), xphase, p.error_flag, 210 + xstage);    // both CTAs' copies of the slab have landed
           tc_fence_after();
           const uint64_t a_desc = a_desc0 + (uint64_t)(xstage * (kXSlab >> 4));
@@ -416,23 +420,25 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   } else {
 #if TC5_SPLIT
     // ============================== epilogue warps ==============================
-    // Two GROUPS of 8 warps (2 per TMEM lane quadrant): group g takes the unit half uh = g of every (step, chain).  The two
-    // unit halves of a (step, chain) become ready half a kilo-cycle apart and are independent, so the groups run concurrently
-    // and out of phase: one group's non-MUFU work (barrier wake-up, TMEM loads, tile store, publish hand-off) overlaps the other
-    // group's gate math on the same SM sub-partition.  With all 16 warps on one half-slot at a time (lstm_tc4.cu) the four warps
-    // of a sub-partition are in the same phase and the MUFU pipe idles ~half of every slot.
+    // Two GROUPS of 8 warps (2 per TMEM lane quadrant = 2 per SM sub-partition); a thread covers 16 units of a half-slot in two
+    // batches of 8.
+    //   TC5_SPLIT = 1: group g takes the unit half uh = g of every (step, chain).  The two unit halves become ready 0.5 k cycles
+    //                  apart, so the groups run IN phase: no overlap is won and every chain's step gets longer (measured -7..-13 %).
+    //   TC5_SPLIT = 2: group g takes CHAIN g (both unit halves, one after the other).  The two chains run half a step apart by
+    //                  construction, so one group's barrier wake-ups, TMEM loads, tile stores and its wait for the chain's next
+    //                  h-part overlap the other group's gate math on the same MUFU pipe.
     const int q = warp & 3;                    // TMEM lane quadrant of this warp
     const int widx = (warp - 2) >> 2;          // 0..3
-    const int g = widx & 1;                    // group == unit half
+    const int g = widx & 1;                    // group
     const int ubase = (widx >> 1) * 16;        // this warp's 16 of the half-slot's 32 units (two batches of 8)
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int r = q * 32 + lane;               // row of this thread inside the CTA's 128 rows
     const uint32_t hrow = (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u;     // row offset inside a [128 x 32] tile (64B swizzle)
     const uint32_t hsw = (uint32_t)((r >> 1) & 3);                                  // 16-byte chunk ^= (row >> 1) & 3
     const bool tma_any = p.tma_out != 0;
-    const float* bias_g = bias_s + g * kChunkN;
+    static_assert(kAccBufs == 4, "the split epilogues assume one accumulator pair per chain (buffer = 2 chain + unit half)");
 
-    // the cell state of this thread's (chain, batch) x 8 units lives in registers (no tcgen05.ld / st / wait::st for it)
+    // the cell state of this thread's two half-slots x two batches x 8 units lives in registers
     float creg[2][2][8];
 #pragma unroll
     for (int c = 0; c < 2; ++c)
@@ -440,32 +446,37 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       for (int b = 0; b < 2; ++b)
 #pragma unroll
         for (int i = 0; i < 8; ++i) creg[c][b][i] = 0.0f;
-    int a = g, use = 0;                        // half-slot n = 4t + 2c + g uses buffer n % kAccBufs; `use` = n / kAccBufs (phase parity of that buffer)
 #pragma unroll 1
     for (int t = 0; t < L; ++t) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int cu = 2 * c + g;
-        mbar_wait(BAR(B_ACCFULL + a), (uint32_t)(use & 1), p.error_flag, 300 + a);
+      for (int k = 0; k < 2; ++k) {            // the group's two half-slots of this step
+        const int c = (TC5_SPLIT == 2) ? g : k, uh = (TC5_SPLIT == 2) ? k : g;
+        const int cu = 2 * c + uh, a = cu;
+        const bool trw = warp == 2 + 4 * g && lane == 0 && g == 0;
+        if (trw) TP(4 * t + cu, 5);
+        mbar_wait(BAR(B_ACCFULL + a), (uint32_t)(t & 1), p.error_flag, 300 + a);
+        if (trw) TP(4 * t + cu, 6);
         tc_fence_after();
         const bool will_publish = t + 1 < L || tma_any;
-        const uint32_t tile = hs_base + (uint32_t)(c * 4 + 2 * pair + g) * kHTile + hrow;
+        const uint32_t tile = hs_base + (uint32_t)(c * 4 + 2 * pair + uh) * kHTile + hrow;
+        const float* bias_g = bias_s + uh * kChunkN;
         bool hfree_ok = true;
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
           const int u0 = ubase + 8 * b;
           const uint32_t acc = tmem_acc + (uint32_t)a * kChunkN + lane_off + u0;
-          float (&cs)[8] = creg[c][b];
+          float (&cs)[8] = creg[k][b];
           float gti[8], gtf[8], gtg[8], gto[8];
           tmem_ld8(acc + 0 * 32, gti);
           tmem_ld8(acc + 1 * 32, gtf);
           tmem_ld8(acc + 2 * 32, gtg);
           tmem_ld8(acc + 3 * 32, gto);
           // poll "h_{t-1} of this chain has been read everywhere" now; the answer is only needed after the gate math
-          if (b == 0) hfree_ok = !(will_publish && t > 0) || mbar_test_wait_cluster(BAR(B_HFREE + c), (uint32_t)((t - 1) & 1));
+          if (b == 0) hfree_ok = !(will_publish && t > 0) || mbar_test_wait(BAR(B_HFREE + c), (uint32_t)((t - 1) & 1));
           tmem_wait_ld();
           tmem_ld_dep(gti); tmem_ld_dep(gtf); tmem_ld_dep(gtg); tmem_ld_dep(gto);
           if (b == 1) {       // accumulator drained (this warp): the leader's x-part issuer may refill it
+            if (trw) TP(4 * t + cu, 15);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -485,16 +496,17 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           if (will_publish) {
             // both pairs' h-parts of step t have finished reading h_{t-1} of this chain, the peer's pushes of h_{t-1} have
             // landed and the stores that read these tiles have drained
-            if (b == 0 && !hfree_ok) mbar_wait_cluster(BAR(B_HFREE + c), (uint32_t)((t - 1) & 1), p.error_flag, 320 + c);
+            if (b == 0 && !hfree_ok) mbar_wait(BAR(B_HFREE + c), (uint32_t)((t - 1) & 1), p.error_flag, 320 + c);
             st_shared_v4(tile + ((((uint32_t)(u0 >> 3)) ^ hsw) << 4), pk);
           }
         }
+        if (trw) TP(4 * t + cu, 7);
         if (will_publish) {
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_HREADY + cu * 4 + q));
         }
-        a += 2; if (a >= kAccBufs) { a -= kAccBufs; ++use; }      // (4 buffers: a = 2c + g, use = t)
+        if (trw) TP(4 * t + cu, 8);
       }
     }
   }
@@ -542,6 +554,7 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
                                               : mbar_test_wait(BAR(B_HFREE + c), (uint32_t)((t - 1) & 1)));
         tmem_wait_ld();
         tmem_ld_dep(gti); tmem_ld_dep(gtf); tmem_ld_dep(gtg); tmem_ld_dep(gto);
+        if (trw) TP(4 * t + cu, 15);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {      // accumulator drained (this warp): the leader's x-part issuer may refill it

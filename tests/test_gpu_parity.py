@@ -456,13 +456,14 @@ def test_fnssl_benched_configs_at_size(tag, kw, B, monkeypatch):
     # lstm_tc4.cu, whose h-part accumulates the chunks in a different order -- so the bit-for-bit solo comparison is made with
     # the pair kernel switched off, and the two kernels are compared with each other at the engine's tolerance.
     monkeypatch.setenv("FNSSL_TC_PAIR", "0")
+    monkeypatch.setenv("FNSSL_TC_PAIR256", "0")      # (the online model's H = 256 layers: lstm_tc6.cu at batch size, lstm_tc4.cu solo)
     out4 = pipe(sig.to(DEV))
     assert _relerr(out, out4) <= TOL[net._engine()]
     for b in (0, k, B - 1):
         assert torch.equal(pipe(sig[b:b + 1].to(DEV))[0], out4[b]), b
 
 
-def test_ipdnet_cfg3_at_size():
+def test_ipdnet_cfg3_at_size(monkeypatch):
     """BASELINE configs[2]: IPDnet 4-mic, hidden 256, online, batch 32 x 4 s -- one utterance against the oracle, solo runs
     bit-identical."""
     import fn_ssl_b200 as F
@@ -478,8 +479,13 @@ def test_ipdnet_cfg3_at_size():
     k = 21
     ref = orc.ipdnet_forward(orc.preprocess_ipdnet(sig[k:k + 1]), sd, fast=True)
     assert _relerr(out[k:k + 1], ref) <= TOL[net._engine()]
+    # (as above: the full-band BLSTM(2x128) layers run the CTA-pair kernel at this size and lstm_tc4.cu solo)
+    monkeypatch.setenv("FNSSL_TC_PAIR", "0")
+    monkeypatch.setenv("FNSSL_TC_PAIR256", "0")
+    out4 = pipe(sig.to(DEV))
+    assert _relerr(out, out4) <= TOL[net._engine()]
     for b in (0, k, B - 1):
-        assert torch.equal(pipe(sig[b:b + 1].to(DEV))[0], out[b]), b
+        assert torch.equal(pipe(sig[b:b + 1].to(DEV))[0], out4[b]), b
 
 
 def test_silence_then_tone_stays_finite_on_fp16_grids():

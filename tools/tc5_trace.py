@@ -17,7 +17,7 @@ NB = int(os.environ.get("TRACE_NB", "64"))
 cfgs = [("full in16", 0, NB, 249, 256, 16, 0, True, False), ("full in256 add", 0, NB, 249, 256, 256, 0, True, True)]
 names = {0: "h-iss: top", 1: "h-iss: XP_DONE passed", 2: "h-iss: H_FULL passed", 3: "h-iss: H_MATE passed", 4: "h-iss: ACC_FULL committed",
          5: "epi: top", 6: "epi: ACC_FULL passed", 7: "epi: math done", 8: "epi: handed to publisher",
-         9: "x-iss: pass top", 10: "x-iss: buffers free", 11: "x-iss: pass issued", 12: "pub: top", 13: "pub: pushes issued", 14: "pub: stores issued"}
+         9: "x-iss: pass top", 10: "x-iss: buffers free", 11: "x-iss: pass issued", 12: "pub: top", 13: "pub: pushes issued", 14: "pub: stores issued", 15: "epi: TMEM loads done"}
 for name, axis, nb, nt, nf, c0, c1, bidir, add in cfgs:
     torch.manual_seed(0)
     p = LSTMParams(c0 + c1, 128, bidirectional=bidir).cuda()
@@ -33,5 +33,5 @@ for name, axis, nb, nt, nf, c0, c1, bidir, add in cfgs:
     tr = [[buf[s * 16 + k] for k in range(16)] for s in range(16)]
     t0 = tr[0][5]
     print(f"== {name}: epilogue half-slot period = {[tr[s + 1][5] - tr[s][5] for s in range(15)]}")
-    for k in (9, 10, 11, 0, 1, 2, 3, 4, 5, 6, 7, 8, 12, 13, 14):
+    for k in (9, 10, 11, 0, 1, 2, 3, 4, 5, 6, 15, 7, 8, 12, 13, 14):
         print(f"   {names[k]:28s}" + "".join(f" n{s + 32}:{(tr[s][k] - t0) if tr[s][k] else 0:6d}" for s in range(0, 9)))
