@@ -359,8 +359,11 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             mbar_expect_tx(BAR(B_HFULL + c), 2u * kHTile);
+            TP(4 * t + 2 * c, 1);
             mbar_wait_cluster(BAR(B_HFULL + c), (uint32_t)((t - 1) & 1), p.error_flag, 252 + c);
+            TP(4 * t + 2 * c, 2);
             mbar_arrive_remote(lead_hmate0 + 8u * (uint32_t)c);
+            TP(4 * t + 2 * c, 3);
           }
         }
       }

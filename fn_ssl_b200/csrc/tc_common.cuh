@@ -261,13 +261,28 @@ __device__ __forceinline__ void st_async_v2(uint32_t caddr, uint32_t x, uint32_t
                "r"(y), "r"(cbar)
                : "memory");
 }
+// Scope of the barrier operations that order ASYNC-proxy traffic between CTAs (DSMEM bulk copies -> complete_tx -> tcgen05.mma
+// reads; tcgen05.commit arrives; relayed "drained" / "landed" signals).  No generic-proxy data travels through these barriers,
+// so the CTA-scope forms are sufficient (the async operations themselves complete at the barrier) -- as in every TMA-multicast
+// pipeline.  The cluster-scope forms compile to MEMBAR.ALL.GPU before a remote arrive and CCTL.IVALL after every successful
+// wait (cuobjdump -sass), which put ~1 k cycles on the relay path of the CTA-pair kernels.  FNSSL_TC_SCOPE_CLUSTER=1 restores them.
+#ifndef FNSSL_TC_SCOPE_CLUSTER
+#define FNSSL_TC_SCOPE_CLUSTER 0
+#endif
+#if FNSSL_TC_SCOPE_CLUSTER
+#define FNSSL_ACQ_CLUSTER ".acquire.cluster"
+#define FNSSL_REL_CLUSTER ".release.cluster"
+#else
+#define FNSSL_ACQ_CLUSTER ""
+#define FNSSL_REL_CLUSTER ""
+#endif
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t caddr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+  asm volatile("mbarrier.arrive" FNSSL_REL_CLUSTER ".shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
-      "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity" FNSSL_ACQ_CLUSTER ".shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
@@ -286,7 +301,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ bool mbar_test_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
-      "{\n .reg .pred p;\n mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      "{\n .reg .pred p;\n mbarrier.test_wait.parity" FNSSL_ACQ_CLUSTER ".shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
