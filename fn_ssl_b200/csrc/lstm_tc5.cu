@@ -247,7 +247,7 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       mbar_wait(BAR(B_WMATE), 0, p.error_flag, 201);
       const uint64_t a_desc0 = make_sw128_desc(xr_base);
       const uint64_t b_desc0 = make_sw128_desc(w_base);
-      int xstage = 0, a0 = 0, gslab = 0;
+      int xstage = 0, a0 = 0;
       uint32_t xphase = 0, empty_par = 0;
       for (int n2 = 0; n2 < 2 * L; ++n2) {
         const int a1 = (a0 == kAccBufs - 1) ? 0 : a0 + 1;
@@ -264,11 +264,7 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         TP(2 * n2, 10);
         const uint32_t d0 = tmem_acc + (uint32_t)a0 * kChunkN, d1 = tmem_acc + (uint32_t)a1 * kChunkN;
         uint32_t nkp = p.xs_nkpack;
-        for (int j = 0; j < nxs; ++j, nkp >>= 4, ++gslab) {
-          if ((p.debug & 128) && gslab >= 2) {     // experiment: at most two slabs of x-part MMAs queued ahead of a ready h-part
-            const int g2 = gslab - 2;
-            mbar_wait(BAR(B_XEMPTY + g2 % XS), (uint32_t)((g2 / XS) & 1), p.error_flag, 216);
-          }
+        for (int j = 0; j < nxs; ++j, nkp >>= 4) {
           mbar_wait(BAR(B_XFULL + xstage), xphase, p.error_flag, 210 + xstage);    // both CTAs' copies of the slab have landed
           tc_fence_after();
           const uint64_t a_desc = a_desc0 + (uint64_t)(xstage * (kXSlab >> 4));
