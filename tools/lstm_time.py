@@ -56,6 +56,20 @@ def main():
             if i >= 2:
                 ts.append(e0.elapsed_time(e1))
         ms = sorted(ts)[len(ts) // 2]
+        if os.environ.get("LSTM_TIME_BURST"):      # K launches back to back between one pair of events: host launch latency amortised
+            K = 10
+            gas = [ga0.clone() for _ in range(K)] if add else [None] * K
+            torch.cuda.synchronize()
+            import time
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0 = time.perf_counter()
+            e0.record()
+            for k in range(K):
+                run_lstm(p, "tcgen05", axis, g0, c0, g1, c1, addend=gas[k], inplace_addend=add)
+            e1.record()
+            h1 = time.perf_counter()
+            torch.cuda.synchronize()
+            print(f"    burst of {K}: {e0.elapsed_time(e1) / K:.3f} ms per launch on the device, host issue {1e3 * (h1 - h0) / K:.3f} ms per launch", flush=True)
         ck = int(h.view(torch.int16).to(torch.int64).sum()) ^ (int(hs.view(torch.int16).to(torch.int64).sum()) if add else 0)
         print(f"[{tag}] {name}: {ms:.3f} ms  {flop / ms / 1e9:.0f} TFLOP/s  checksum {ck & 0xffffffff:08x}  finite={bool(torch.isfinite(h).all())}", flush=True)
 
