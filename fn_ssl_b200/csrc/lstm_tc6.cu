@@ -19,7 +19,9 @@
 // row x 4 units), one [64 x 32] h tile.  Roles as lstm_tc5.cu: warp 0 TMA producer (both CTAs), warp 1 leader: h-part issuer /
 // other CTA: relay of "weights loaded" and "h tiles complete", warps 2..17 epilogue, warp 18 leader: x-part issuer / other CTA:
 // relay of "accumulator drained", warp 19 publisher.
-// Not supported here (-> lstm_tc4.cu): a second input source, carried (h, c) state, outputs that cannot go through TMA.
+// A second source of <= 16 channels (the raw-feature skip of IPDnet / of FN-SSL's first narrow-band layer) is one K = 16 step with
+// a 2 KB weight half per unit half and a two-entry ring of [64 x 16] slabs of its own (32B swizzle), as lstm_tc4.cu's NARROW mode.
+// Not supported here (-> lstm_tc4.cu): a wider second source, carried (h, c) state, outputs that cannot go through TMA.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -41,6 +43,8 @@ constexpr int kChainRows = 128;            // rows per chain (pair: 2 x 64)
 constexpr int kWHalf = 64 * 128;           // [64 B rows x 64 K] fp16: this CTA's half of a chunk's [128 x 64] weight slab
 constexpr int kXSlab = kRows * 128;        // [64 rows x 64] fp16
 constexpr int kHTile = kRows * 64;         // [64 rows x 32 units] fp16 (64B swizzle)
+constexpr int kXSmall = kRows * 32;        // [64 rows x 16 channels] fp16 (32B swizzle): a slab of the narrow second source
+constexpr int kWSmall = 64 * 32;           // [64 B rows x 16 K] fp16 (32B swizzle): this CTA's half of a chunk's narrow weight slab
 constexpr int kChunkN = 128;
 constexpr int kNH = H / 32;                // 8 chunk tiles of h per chain
 constexpr int kNHS = H / kSlabK;           // 4 K slabs of W_h
@@ -49,11 +53,13 @@ constexpr int kAccCols = 64;               // TMEM columns of one accumulator (N
 constexpr int kSmemLimit = 232448;
 constexpr int B_WFULL = 0, B_WMATE = 1, B_XFULL = 2, B_XEMPTY = B_XFULL + kMaxXStages, B_ACCFULL = B_XEMPTY + kMaxXStages,
               B_ACCEMPTY = B_ACCFULL + kAccBufs, B_XPDONE = B_ACCEMPTY + kAccBufs, B_HFULL = B_XPDONE + kAccBufs,
-              B_HMATE = B_HFULL + 2, B_HFREE = B_HMATE + 2, B_HREADY = B_HFREE + 2, B_ACCDRAIN = B_HREADY + 8, kNumBars = B_ACCDRAIN + kAccBufs;
+              B_HMATE = B_HFULL + 2, B_HFREE = B_HMATE + 2, B_HREADY = B_HFREE + 2, B_ACCDRAIN = B_HREADY + 8, B_X2FULL = B_ACCDRAIN + kAccBufs,
+              B_X2EMPTY = B_X2FULL + 2, kNumBars = B_X2EMPTY + 2;
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kChunkN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f16 x f16 -> f32, M = 128, N = 128
 
 struct Params {
-  int nxs;
+  int nxs;                         // 64-channel slabs of the first source
+  int small;                       // 1: a second source of <= 16 channels (one K = 16 step, own two-entry ring, 32B swizzle)
   uint32_t xs_nkpack;              // nibble j: K=16 steps of slab j (1..4)
   int xstages;
   int steps, axis, nf, nt;
@@ -108,8 +114,9 @@ __device__ __forceinline__ void st_shared_v2(uint32_t saddr, uint32_t x, uint32_
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_constant__ CUtensorMap map_w,
-                const __grid_constant__ CUtensorMap map_out0, const __grid_constant__ CUtensorMap map_out1, const Params p) {
+lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_constant__ CUtensorMap map_src1, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_out0, const __grid_constant__ CUtensorMap map_out1,
+                const Params p) {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) unsigned long long bars[kNumBars];
   __shared__ uint32_t tmem_base_slot;
@@ -126,11 +133,14 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   const int nhalf = 4 * L;
 
   const uint32_t dyn0 = (smem_addr(smem_dyn) + 1023u) & ~1023u;
-  const int nslabs = nxs + kNHS;
+  const int nslabs = nxs + kNHS;                                          // RESIDENT 64-wide slabs (the packed buffer has p.small more)
+  const bool small1 = p.small != 0;
   const uint32_t w_base = dyn0;                                           // [uh][slab: nxs x, then 4 h] halves of 8 KB
-  const uint32_t hs_base = w_base + (uint32_t)(2 * nslabs) * kWHalf;      // h operand: [chain][chunk 0..7] tiles of 4 KB
+  const uint32_t w2_base = w_base + (uint32_t)(2 * nslabs) * kWHalf;      // [uh] halves of the narrow weight slab (2 KB each)
+  const uint32_t hs_base = w2_base + (small1 ? 2u * kWSmall : 0u);        // h operand: [chain][chunk 0..7] tiles of 4 KB
   const uint32_t xr_base = hs_base + (uint32_t)(2 * kNH) * kHTile;        // x ring
-  const uint32_t bias_base = xr_base + (uint32_t)XS * kXSlab;             // 256 floats: [uh][gate][unit]
+  const uint32_t x2_base = xr_base + (uint32_t)XS * kXSlab;               // two-entry ring of the narrow source
+  const uint32_t bias_base = x2_base + (small1 ? 2u * kXSmall : 0u);      // 256 floats: [uh][gate][unit]
   float* bias_s = reinterpret_cast<float*>(smem_dyn + (bias_base - smem_addr(smem_dyn)));
 
   const uint32_t bar0 = smem_addr(bars);
@@ -152,9 +162,10 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
       mbar_init(BAR(B_HFREE + c), 5);     // the four pair leaders' commits + the publisher ("stores drained")
     }
     for (int i = 0; i < 8; ++i) mbar_init(BAR(B_HREADY + i), 8);     // [(chain, uh)][row half]: that row half's 8 epilogue warps
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_X2FULL + i), 1); mbar_init(BAR(B_X2EMPTY + i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0 && lane == 0) { prefetch_tmap(&map_src0); prefetch_tmap(&map_w); }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&map_src0); prefetch_tmap(&map_w); if (small1) { prefetch_tmap(&map_src1); prefetch_tmap(&map_w2); } }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_addr(&tmem_base_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -190,14 +201,22 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
     // ============================== TMA producer (both CTAs) ==============================
     if (elect_one()) {
       // resident weights: for each unit half, gate g, the 16 rows of units 16 jh .. 16 jh + 15 of chunk 2 pair + uh, every K slab
-      mbar_expect_tx(BAR(B_WFULL), (uint32_t)(2 * nslabs) * kWHalf);
-      for (int uh = 0; uh < 2; ++uh)
+      // (packed column blocks: nxs slabs of the first source, the narrow slab if any, 4 h slabs)
+      mbar_expect_tx(BAR(B_WFULL), (uint32_t)(2 * nslabs) * kWHalf + (small1 ? 2u * kWSmall : 0u));
+      for (int uh = 0; uh < 2; ++uh) {
         for (int j = 0; j < nslabs; ++j)
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            tma_load_2d(w_base + (uint32_t)(uh * nslabs + j) * kWHalf + (uint32_t)g * 2048u, &map_w, BAR(B_WFULL), j * kSlabK,
+            tma_load_2d(w_base + (uint32_t)(uh * nslabs + j) * kWHalf + (uint32_t)g * 2048u, &map_w, BAR(B_WFULL),
+                        (j < nxs ? j : j + p.small) * kSlabK, (dir * kNH + 2 * pair + uh) * kChunkN + g * 32 + 16 * jh);
+        if (small1)
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            tma_load_2d(w2_base + (uint32_t)uh * kWSmall + (uint32_t)g * 512u, &map_w2, BAR(B_WFULL), nxs * kSlabK,
                         (dir * kNH + 2 * pair + uh) * kChunkN + g * 32 + 16 * jh);
+      }
       const uint32_t lead_xfull0 = mapa_shared(BAR(B_XFULL), leader_rank);
+      const uint32_t lead_x2full0 = mapa_shared(BAR(B_X2FULL), leader_rank);
       int stage = 0;
       uint32_t phase = 0;
       bool wrapped = false;
@@ -212,6 +231,15 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           if (along_f) tma2_load_4d(dst, &map_src0, fb, j * kSlabK, s, CR0(c), 0);
           else tma2_load_4d(dst, &map_src0, fb, j * kSlabK, CR0(c), s, CB(c));
           if (++stage == XS) { stage = 0; phase ^= wrapped ? 1u : 0u; wrapped = true; }
+        }
+        if (small1) {      // the narrow source's slab of this pass: entry n2 & 1 of its own ring, use number n2 >> 1
+          const int s2 = n2 & 1;
+          if (n2 >= 2) mbar_wait(BAR(B_X2EMPTY + s2), (uint32_t)(((n2 >> 1) - 1) & 1), p.error_flag, 110 + s2);
+          if (leader) mbar_expect_tx(BAR(B_X2FULL + s2), 2u * kXSmall);
+          const uint32_t dst = x2_base + (uint32_t)s2 * kXSmall;
+          const uint32_t fb = lead_x2full0 + 8u * (uint32_t)s2;
+          if (along_f) tma2_load_4d(dst, &map_src1, fb, 0, s, CR0(c), 0);
+          else tma2_load_4d(dst, &map_src1, fb, 0, CR0(c), s, CB(c));
         }
       }
     }
@@ -253,6 +281,15 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
             if ((uint32_t)k < nk) umma2_f16(d1, a_desc + 2u * k, b1 + 2u * k, kIdesc, (uint32_t)(j | k));
           umma2_commit_mc(BAR(B_XEMPTY + xstage), pair_mask);
           if (++xstage == XS) { xstage = 0; xphase ^= 1u; }
+        }
+        if (small1) {      // one K = 16 step per unit half against the 2 KB weight halves, both operands in the 32B-swizzled layout
+          const int s2 = n2 & 1;
+          mbar_wait(BAR(B_X2FULL + s2), (uint32_t)((n2 >> 1) & 1), p.error_flag, 216 + s2);
+          tc_fence_after();
+          const uint64_t a2 = make_sw32_desc(x2_base + (uint32_t)s2 * kXSmall);
+          umma2_f16(d0, a2, make_sw32_desc(w2_base), kIdesc, 1u);
+          umma2_f16(d1, a2, make_sw32_desc(w2_base + kWSmall), kIdesc, 1u);
+          umma2_commit_mc(BAR(B_X2EMPTY + s2), pair_mask);
         }
         umma2_commit_mc(BAR(B_XPDONE + a0), (uint16_t)(1u << leader_rank));
         umma2_commit_mc(BAR(B_XPDONE + a1), (uint16_t)(1u << leader_rank));
@@ -479,23 +516,24 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   }
 }
 
-struct Plan { bool ok; int xstages; int nxs; size_t smem; };
+struct Plan { bool ok; int xstages; int nxs; int small; size_t smem; };
 
-static Plan make_plan(int c0) {
-  Plan pl{false, 0, 0, 0};
-  if (c0 % 16 || c0 <= 0) return pl;
+static Plan make_plan(int c0, int c1) {
+  Plan pl{false, 0, 0, 0, 0};
+  if (c0 % 16 || c0 <= 0 || c1 < 0 || c1 > 16 || c1 % 16) return pl;      // second source: none, or one K = 16 step
   const int nxs = (c0 + 63) / 64;
   if (nxs > kMaxXSlabs) return pl;
-  const long fixed = 2L * (nxs + kNHS) * kWHalf + 2L * kNH * kHTile + 2 * kChunkN * 4 + 1024;
+  const int small = c1 > 0 ? 1 : 0;
+  const long fixed = 2L * (nxs + kNHS) * kWHalf + 2L * kNH * kHTile + 2 * kChunkN * 4 + 1024 + small * 2L * (kWSmall + kXSmall);
   long xs = (kSmemLimit - 1024 - fixed) / kXSlab;
   if (xs > kMaxXStages) xs = kMaxXStages;
   if (xs < 2) return pl;
-  pl.ok = true; pl.xstages = (int)xs; pl.nxs = nxs; pl.smem = (size_t)fixed + (size_t)xs * kXSlab;
+  pl.ok = true; pl.xstages = (int)xs; pl.nxs = nxs; pl.small = small; pl.smem = (size_t)fixed + (size_t)xs * kXSlab;
   return pl;
 }
 
 // 2-D fp16 map over the packed weights, box = [16 rows x 64 K]: one gate's 16 units of one CTA's half of a slab
-static int make_gate_weight_map(CUtensorMap* m, const void* weights, int nslabs, int nchunks_total) {
+static int make_gate_weight_map(CUtensorMap* m, const void* weights, int nslabs, int nchunks_total, bool small = false) {
   static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
   if (!enc) {
     void* ptr = nullptr;
@@ -506,10 +544,10 @@ static int make_gate_weight_map(CUtensorMap* m, const void* weights, int nslabs,
   FNSSL_REQUIRE(enc, "lstm(tcgen05): cuTensorMapEncodeTiled is unavailable in this driver");
   const uint64_t dims[2] = {(uint64_t)nslabs * kSlabK, (uint64_t)nchunks_total * kChunkN};
   const uint64_t str[1] = {(uint64_t)nslabs * kSlabK * 2};
-  const uint32_t box[2] = {kSlabK, 16};
+  const uint32_t box[2] = {small ? 16u : (uint32_t)kSlabK, 16};      // narrow slab: [16 rows x 16 K], 32B swizzle
   const uint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(weights), dims, str, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, small ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FNSSL_REQUIRE(r == CUDA_SUCCESS, "lstm(tcgen05): gate-slab weight tensor map failed (%d)", (int)r);
   return 0;
@@ -521,8 +559,8 @@ static int make_gate_weight_map(CUtensorMap* m, const void* weights, int nslabs,
 // FNSSL_TC_PAIR256_MIN [8] 256-row cluster tiles (FNSSL_TC_PAIR256=0 switches it off).
 bool lstm_tc6_wants(const fnssl_lstm_args* a) {
   if (const char* e = getenv("FNSSL_TC_PAIR256")) { if (atoi(e) == 0) return false; }
-  if (a->hidden != 256 || a->state_flags || a->c1 != 0) return false;
-  if (!tc6::make_plan(a->c0).ok) return false;
+  if (a->hidden != 256 || a->state_flags) return false;
+  if (!tc6::make_plan(a->c0, a->c1).ok) return false;
   if (a->out0 && a->out0_off % 8) return false;
   if (a->out1 && !(a->out1 == a->addend && a->out1_ld == a->addend_ld)) return false;
   const long long chains = a->axis == FNSSL_ALONG_FREQ ? ((long long)a->nb * a->nt + 127) / 128 : (long long)a->nb * ((a->nf + 127) / 128);
@@ -530,18 +568,18 @@ bool lstm_tc6_wants(const fnssl_lstm_args* a) {
   if (const char* e = getenv("FNSSL_TC_PAIR256_MIN")) return clusters >= atoi(e);
   // Both H = 256 kernels run clusters of 8 CTAs with one CTA per SM: kResident of them fit the GPU at a time (measured:
   // cudaOccupancyMaxActiveClusters = 15 on a 148-SM B200), so a launch takes ceil(clusters / kResident) waves.  A wave of this
-  // kernel covers twice the rows of one of lstm_tc4.cu (256 vs 128 per cluster) in 1.62x its time (1.147 vs 0.71 ms at
-  // c0 = 256, 249 steps: profiles/r2_lstm_variants.txt) -- it wins when the wave counts quantise in its favour or are large.
+  // kernel covers twice the rows of one of lstm_tc4.cu (256 vs 128 per cluster) in ~1.35x its time (0.93-1.0 vs 0.71 ms at
+  // c0 = 256, 249 steps: profiles/r2_lstm_variants.txt) -- it wins unless the wave counts quantise against it.
   constexpr long long kResident = 15;
   const long long waves6 = (clusters + kResident - 1) / kResident;
   const long long waves4 = (chains * a->num_dirs + kResident - 1) / kResident;
-  return waves6 * 13 < waves4 * 8;
+  return waves6 * 27 < waves4 * 20;
 }
 
 int lstm_forward_tc6(const fnssl_lstm_args* a, cudaStream_t st) {
   using namespace tc6;
-  const Plan pl = make_plan(a->c0);
-  FNSSL_REQUIRE(pl.ok && a->hidden == 256 && a->c1 == 0, "lstm(tcgen05 pair kernel, H = 256): unsupported layer (H=%d c0=%d c1=%d)", a->hidden, a->c0, a->c1);
+  const Plan pl = make_plan(a->c0, a->c1);
+  FNSSL_REQUIRE(pl.ok && a->hidden == 256, "lstm(tcgen05 pair kernel, H = 256): unsupported layer (H=%d c0=%d c1=%d)", a->hidden, a->c0, a->c1);
   Params p{};
   int nxs = 0;
   for (int k0 = 0; k0 < a->c0; k0 += kSlabK) {
@@ -549,8 +587,9 @@ int lstm_forward_tc6(const fnssl_lstm_args* a, cudaStream_t st) {
     ++nxs;
   }
   p.nxs = nxs;
+  p.small = pl.small;
   p.xstages = pl.xstages;
-  const int nslabs = nxs + kNHS;
+  const int nslabs = nxs + pl.small + kNHS;      // 64-wide column blocks of the packed buffer
   const int64_t wbytes = (int64_t)a->num_dirs * kNH * kChunkN * nslabs * kSlabK * 2;
   const int64_t need = wbytes + (int64_t)a->num_dirs * 4 * H * 4;
   FNSSL_REQUIRE(a->weights_bytes == need, "lstm(tcgen05): packed weight buffer is %lld bytes, expected %lld",
@@ -573,6 +612,11 @@ int lstm_forward_tc6(const fnssl_lstm_args* a, cudaStream_t st) {
   CUtensorMap m0, mw;
   if (make_grid_map(&m0, a->src0, a->c0, a->ld0, a->nb, a->nt, a->nf, a->axis, kRows)) return 1;
   if (make_gate_weight_map(&mw, a->weights, nslabs, a->num_dirs * kNH)) return 1;
+  CUtensorMap m1 = m0, mw2 = mw;
+  if (pl.small) {
+    if (make_small_grid_map(&m1, a->src1, a->c1, a->ld1, a->nb, a->nt, a->nf, a->axis, kRows)) return 1;
+    if (make_gate_weight_map(&mw2, a->weights, nslabs, a->num_dirs * kNH, true)) return 1;
+  }
   CUtensorMap mo0 = m0, mo1 = m0;
   if (a->out0) {
     if (make_out_map(&mo0, a->out0, a->out0_ld, a->nb, a->nt, a->nf, a->axis, 32)) return 1;
@@ -592,7 +636,7 @@ int lstm_forward_tc6(const fnssl_lstm_args* a, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  FNSSL_CUDA(cudaLaunchKernelEx(&cfg, lstm_tc6_kernel, m0, mw, mo0, mo1, p));
+  FNSSL_CUDA(cudaLaunchKernelEx(&cfg, lstm_tc6_kernel, m0, m1, mw, mw2, mo0, mo1, p));
   FNSSL_LAUNCH_CHECK("lstm_tc6_kernel");
   return 0;
 }

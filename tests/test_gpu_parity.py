@@ -225,17 +225,18 @@ def test_lstm_layer_tcgen05_pair_kernel(monkeypatch, axis, bidir, c0, c1, addend
 
 
 @pytest.mark.parametrize("axis", [0, 1])
-@pytest.mark.parametrize("bidir,c0,addend", [(False, 256, True), (False, 256, False), (False, 64, False), (True, 16, False), (False, 128, True)])
-def test_lstm_layer_tcgen05_pair_kernel_h256(monkeypatch, axis, bidir, c0, addend):
+@pytest.mark.parametrize("bidir,c0,c1,addend", [(False, 256, 0, True), (False, 256, 0, False), (False, 64, 0, False), (True, 16, 0, False),
+                                                 (False, 128, 0, True), (False, 256, 4, True), (False, 256, 8, False), (True, 64, 16, True)])
+def test_lstm_layer_tcgen05_pair_kernel_h256(monkeypatch, axis, bidir, c0, c1, addend):
     """The H = 256 CTA-pair kernel (lstm_tc6.cu: cta_group::2 with M = 128, 8-CTA clusters, 2x2 TMEM accumulator layout) forced on
-    small layers: ragged 128-row chains, an absent second chain, the in-place residual output.  (A layer with a second source or a
-    carried state runs lstm_tc4.cu -- covered by the other LSTM tests.)"""
+    small layers: ragged 128-row chains, an absent second chain, the in-place residual output, a narrow (<= 16 channel) second
+    source through its own ring.  (A layer with a carried state runs lstm_tc4.cu -- covered by the other LSTM tests.)"""
     from fn_ssl_b200 import config
     if not config.TC_AVAILABLE:
         pytest.skip("tcgen05 engine not built")
     monkeypatch.setenv("FNSSL_TC_PAIR256_MIN", "1")
     for nb, nt, nf in (((3, 5, 256), (2, 33, 300)) if axis == 1 else ((2, 70, 40), (5, 130, 7))):
-        assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, 0, 256, bidir, addend, inplace=addend) <= 1e-3
+        assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, 256, bidir, addend, inplace=addend) <= 1e-3
 
 
 @pytest.mark.parametrize("small1", ["1", "0"])

@@ -28,6 +28,8 @@ CFGS = [("full_in16_H128x2", 0, 16, 249, 256, 16, 0, 128, True, False),
         ("narrow_in256+16_H128x2_add_b256", 1, 256, 249, 256, 256, 16, 128, True, True),
         ("full_in256_H128x2_add_b256", 0, 256, 249, 256, 256, 0, 128, True, True),
         ("narrow_in256_H128x2_add_b256", 1, 256, 249, 256, 256, 0, 128, True, True),
+        ("narrow_in256+16_H256x1_add_b15", 1, 15, 249, 256, 256, 16, 256, False, True),
+        ("narrow_in256+16_H256x1_add_b60", 1, 60, 249, 256, 256, 16, 256, False, True),
         ("narrow_in256_H256x1_add_b15", 1, 15, 249, 256, 256, 0, 256, False, True),
         ("narrow_in256_H256x1_add_b60", 1, 60, 249, 256, 256, 0, 256, False, True)]
 

@@ -14,6 +14,9 @@ CASES = [
     ("h256_time_c256_uni_add", 1, 3, 7, 256, 256, 0, False, True),
     ("h256_freq_c256_uni_ragged", 0, 3, 100, 5, 256, 0, False, False),
     ("h256_time_c16_bi_nf300", 1, 2, 4, 300, 16, 0, True, False),
+    ("h256_time_c64+16_uni_L1", 1, 2, 1, 256, 64, 16, False, False),
+    ("h256_time_c256+16_uni_add", 1, 3, 7, 256, 256, 16, False, True),
+    ("h256_freq_c256+16_uni_ragged", 0, 3, 100, 5, 256, 16, False, False),
     ("time_c64_uni_L1", 1, 2, 1, 256, 64, 0, False, False),
     ("time_c64_uni_L2", 1, 2, 2, 256, 64, 0, False, False),
     ("time_c64_uni_L5", 1, 2, 5, 256, 64, 0, False, False),
