@@ -420,9 +420,11 @@ def test_fnssl_end_to_end_4s(online):
         assert _relerr(out2, ref) <= TOL[eng], eng
 
 
-def test_fnssl_batch16_properties():
-    """cfg2 size (B=16, 4 s): utterances are independent -- any utterance of the batch equals its solo run
-    (bit-exact: same kernels, same per-row arithmetic), outputs are tanh-bounded and finite."""
+def test_fnssl_batch16_properties(monkeypatch):
+    """cfg2 size (B=16, 4 s), the code-default (online) model: utterances are independent -- any utterance of the batch equals
+    its solo run (bit-exact when the same kernel serves both: at B = 16 the H = 256 layers run the CTA-pair kernel lstm_tc6.cu,
+    a solo utterance lstm_tc4.cu, whose h-part accumulates in a different order -- so the bit-for-bit comparison is made with
+    the pair kernels off and the two dispatches are compared at the engine's tolerance); outputs are tanh-bounded and finite."""
     import fn_ssl_b200 as F
     sig = orc.white_noise(16, 64000, 2).to(DEV)
     net = F.FN_SSL().eval()
@@ -430,9 +432,13 @@ def test_fnssl_batch16_properties():
     pipe = F.FNSSLPipeline(net.to(DEV))
     out = pipe(sig)
     assert out.shape == (16, 20, 512) and torch.isfinite(out).all() and float(out.abs().max()) <= 1.0
+    monkeypatch.setenv("FNSSL_TC_PAIR", "0")
+    monkeypatch.setenv("FNSSL_TC_PAIR256", "0")
+    out4 = pipe(sig)
+    assert _relerr(out, out4) <= TOL[net._engine()]
     for b in (0, 7, 15):
         solo = pipe(sig[b:b + 1])
-        assert torch.equal(solo[0], out[b]), b
+        assert torch.equal(solo[0], out4[b]), b
 
 
 @pytest.mark.parametrize("tag,kw,B", [("cfg2 offline", dict(is_online=False), 16), ("cfg4 doa", dict(is_online=False, is_doa=True), 32),

@@ -25,6 +25,7 @@ LSTM = {  # axis, nb, nt, nf, c0, c1, H, bidir, addend(in place)
     "pair128": (1, 1, 5, 300, 256, 0, 128, True, True),
     "pair128f": (0, 1, 300, 6, 64, 16, 128, True, False),
     "pair256": (1, 1, 5, 300, 256, 0, 256, False, True),
+    "pair256n": (1, 1, 5, 300, 256, 16, 256, False, True),
 }
 
 
