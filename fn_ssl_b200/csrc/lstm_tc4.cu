@@ -1016,7 +1016,7 @@ static int launch_t(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
                   "lstm(tcgen05): out1/addend must be 4-byte aligned");
   }
   p.error_flag = tc_wait_timeout_enabled() ? tc_error_flag() : nullptr;
-  if (const char* e = getenv("FNSSL_TC_DEBUG")) p.debug = atoi(e);
+  p.debug = tc_debug_bits(32 | 64);
   if (getenv("FNSSL_TC_TRACE")) p.trace = trace_buffer();
 
   CUtensorMap m0, m1, mw, mw2;

@@ -704,7 +704,7 @@ int lstm_forward_tc5(const fnssl_lstm_args* a, cudaStream_t st) {
   p.bias = reinterpret_cast<const float*>(reinterpret_cast<const char*>(a->weights) + wbytes);
   p.out0_off = a->out0_off;
   p.error_flag = tc_wait_timeout_enabled() ? tc_error_flag() : nullptr;
-  if (const char* e = getenv("FNSSL_TC_DEBUG")) p.debug = atoi(e);
+  p.debug = tc_debug_bits(16 | 32);
   if (getenv("FNSSL_TC_TRACE")) {
     if (!g_trace5) { if (cudaMalloc(&g_trace5, 256 * sizeof(long long)) != cudaSuccess) g_trace5 = nullptr; }
     if (g_trace5) cudaMemsetAsync(g_trace5, 0, 256 * sizeof(long long), st);

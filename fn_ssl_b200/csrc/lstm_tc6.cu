@@ -32,8 +32,6 @@
 namespace fnssl {
 namespace tc6 {
 
-constexpr int H = 256;
-constexpr int kCluster = 8;
 constexpr int kThreads = 640;
 constexpr int kXWarp = 18, kPubWarp = 19;
 constexpr int kEpiWarps = 16;
@@ -46,8 +44,6 @@ constexpr int kHTile = kRows * 64;         // [64 rows x 32 units] fp16 (64B swi
 constexpr int kXSmall = kRows * 32;        // [64 rows x 16 channels] fp16 (32B swizzle): a slab of the narrow second source
 constexpr int kWSmall = 64 * 32;           // [64 B rows x 16 K] fp16 (32B swizzle): this CTA's half of a chunk's narrow weight slab
 constexpr int kChunkN = 128;
-constexpr int kNH = H / 32;                // 8 chunk tiles of h per chain
-constexpr int kNHS = H / kSlabK;           // 4 K slabs of W_h
 constexpr int kMaxXSlabs = 4, kMaxXStages = 6, kAccBufs = 4;      // accumulators: one PAIR (both unit halves) per chain
 constexpr int kAccCols = 64;               // TMEM columns of one accumulator (N / 2)
 constexpr int kSmemLimit = 232448;
@@ -113,10 +109,15 @@ __device__ __forceinline__ void st_shared_v2(uint32_t saddr, uint32_t x, uint32_
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(x), "r"(y) : "memory");
 }
 
+template <int H>      // 256: cluster of 8 = 4 pairs; 128: cluster of 4 = 2 pairs (mid-size layers, see lstm_tc6_wants)
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_constant__ CUtensorMap map_src1, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_out0, const __grid_constant__ CUtensorMap map_out1,
                 const Params p) {
+  constexpr int kCluster = H / 32;           // CTAs per cluster
+  constexpr int kPairs = kCluster / 2;
+  constexpr int kNH = H / 32;                // chunk tiles of h per chain
+  constexpr int kNHS = H / kSlabK;           // K slabs of W_h
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) unsigned long long bars[kNumBars];
   __shared__ uint32_t tmem_base_slot;
@@ -159,7 +160,7 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
     for (int c = 0; c < 2; ++c) {
       mbar_init(BAR(B_HFULL + c), 5);     // expect_tx arrive + 2 unit halves x 2 row halves of the CTA's own tiles (+ 24 KB of tx from 3 peers)
       mbar_init(BAR(B_HMATE + c), 1);
-      mbar_init(BAR(B_HFREE + c), 5);     // the four pair leaders' commits + the publisher ("stores drained")
+      mbar_init(BAR(B_HFREE + c), kPairs + 1);     // the pair leaders' commits + the publisher ("stores drained")
     }
     for (int i = 0; i < 8; ++i) mbar_init(BAR(B_HREADY + i), 8);     // [(chain, uh)][row half]: that row half's 8 epilogue warps
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_X2FULL + i), 1); mbar_init(BAR(B_X2EMPTY + i), 1); }
@@ -324,7 +325,7 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           xp_par ^= 1u << a;
           if (t > 0) {
             if (uh == 0) {
-              mbar_expect_tx(BAR(B_HFULL + c), 6u * kHTile);      // the three peers' two tiles each
+              mbar_expect_tx(BAR(B_HFULL + c), (uint32_t)(2 * (kPairs - 1)) * kHTile);      // the peers' two tiles each
               mbar_wait_cluster(BAR(B_HFULL + c), (uint32_t)((t - 1) & 1), p.error_flag, 220 + c);
               mbar_wait_cluster(BAR(B_HMATE + c), (uint32_t)((t - 1) & 1), p.error_flag, 222 + c);
             }
@@ -339,7 +340,7 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
 #pragma unroll
               for (int k = 0; k < 2; ++k) umma2_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, 1u);
             }
-            if (uh == 1) umma2_commit_mc(BAR(B_HFREE + c), (uint16_t)0xFF);
+            if (uh == 1) umma2_commit_mc(BAR(B_HFREE + c), (uint16_t)((1u << kCluster) - 1u));
           } else {
             tc_fence_after();
           }
@@ -356,7 +357,7 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         for (int t = 1; t < L; ++t) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            mbar_expect_tx(BAR(B_HFULL + c), 6u * kHTile);
+            mbar_expect_tx(BAR(B_HFULL + c), (uint32_t)(2 * (kPairs - 1)) * kHTile);
             mbar_wait_cluster(BAR(B_HFULL + c), (uint32_t)((t - 1) & 1), p.error_flag, 252 + c);
             mbar_arrive_remote(lead_hmate0 + 8u * (uint32_t)c);
           }
@@ -367,10 +368,10 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
   } else if (warp == kPubWarp) {
     // ============================== publisher ==============================
     if (elect_one()) {
-      uint32_t peer_hs[3], peer_hfull0[3];
+      uint32_t peer_hs[kPairs - 1], peer_hfull0[kPairs - 1];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const uint32_t pr = (uint32_t)(2 * ((pair + 1 + d) & 3) + jh);      // the CTAs that hold the same rows in the other pairs
+      for (int d = 0; d < kPairs - 1; ++d) {
+        const uint32_t pr = (uint32_t)(2 * ((pair + 1 + d) % kPairs) + jh);      // the CTAs that hold the same rows in the other pairs
         peer_hs[d] = mapa_shared(hs_base, pr);
         peer_hfull0[d] = mapa_shared(BAR(B_HFULL), pr);
       }
@@ -388,7 +389,7 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
             if (push) {
               const uint32_t off = tile_off + (uint32_t)rh * 2048u;
 #pragma unroll
-              for (int d = 0; d < 3; ++d) bulk_copy_s2c(peer_hs[d] + off, hs_base + off, 2048u, peer_hfull0[d] + 8u * (uint32_t)c);
+              for (int d = 0; d < kPairs - 1; ++d) bulk_copy_s2c(peer_hs[d] + off, hs_base + off, 2048u, peer_hfull0[d] + 8u * (uint32_t)c);
               mbar_arrive(BAR(B_HFULL + c));
             }
           }
@@ -518,7 +519,8 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
 
 struct Plan { bool ok; int xstages; int nxs; int small; size_t smem; };
 
-static Plan make_plan(int c0, int c1) {
+static Plan make_plan(int H, int c0, int c1) {
+  const int kNH = H / 32, kNHS = H / kSlabK;
   Plan pl{false, 0, 0, 0, 0};
   if (c0 % 16 || c0 <= 0 || c1 < 0 || c1 > 16 || c1 % 16) return pl;      // second source: none, or one K = 16 step
   const int nxs = (c0 + 63) / 64;
@@ -553,33 +555,9 @@ static int make_gate_weight_map(CUtensorMap* m, const void* weights, int nslabs,
   return 0;
 }
 
-}  // namespace tc6
-
-// Used for H = 256 single-source layers without carried state whose outputs all go through TMA, when the layer has at least
-// FNSSL_TC_PAIR256_MIN [8] 256-row cluster tiles (FNSSL_TC_PAIR256=0 switches it off).
-bool lstm_tc6_wants(const fnssl_lstm_args* a) {
-  if (const char* e = getenv("FNSSL_TC_PAIR256")) { if (atoi(e) == 0) return false; }
-  if (a->hidden != 256 || a->state_flags) return false;
-  if (!tc6::make_plan(a->c0, a->c1).ok) return false;
-  if (a->out0 && a->out0_off % 8) return false;
-  if (a->out1 && !(a->out1 == a->addend && a->out1_ld == a->addend_ld)) return false;
-  const long long chains = a->axis == FNSSL_ALONG_FREQ ? ((long long)a->nb * a->nt + 127) / 128 : (long long)a->nb * ((a->nf + 127) / 128);
-  const long long clusters = (chains + 1) / 2 * a->num_dirs;
-  if (const char* e = getenv("FNSSL_TC_PAIR256_MIN")) return clusters >= atoi(e);
-  // Both H = 256 kernels run clusters of 8 CTAs with one CTA per SM: kResident of them fit the GPU at a time (measured:
-  // cudaOccupancyMaxActiveClusters = 15 on a 148-SM B200), so a launch takes ceil(clusters / kResident) waves.  A wave of this
-  // kernel covers twice the rows of one of lstm_tc4.cu (256 vs 128 per cluster) in ~1.35x its time (0.93-1.0 vs 0.71 ms at
-  // c0 = 256, 249 steps: profiles/r2_lstm_variants.txt) -- it wins unless the wave counts quantise against it.
-  constexpr long long kResident = 15;
-  const long long waves6 = (clusters + kResident - 1) / kResident;
-  const long long waves4 = (chains * a->num_dirs + kResident - 1) / kResident;
-  return waves6 * 27 < waves4 * 20;
-}
-
-int lstm_forward_tc6(const fnssl_lstm_args* a, cudaStream_t st) {
-  using namespace tc6;
-  const Plan pl = make_plan(a->c0, a->c1);
-  FNSSL_REQUIRE(pl.ok && a->hidden == 256, "lstm(tcgen05 pair kernel, H = 256): unsupported layer (H=%d c0=%d c1=%d)", a->hidden, a->c0, a->c1);
+template <int H>
+static int launch(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
+  constexpr int kCluster = H / 32, kNH = H / 32, kNHS = H / kSlabK;
   Params p{};
   int nxs = 0;
   for (int k0 = 0; k0 < a->c0; k0 += kSlabK) {
@@ -607,7 +585,7 @@ int lstm_forward_tc6(const fnssl_lstm_args* a, cudaStream_t st) {
   p.bias = reinterpret_cast<const float*>(reinterpret_cast<const char*>(a->weights) + wbytes);
   p.out0_off = a->out0_off;
   p.error_flag = tc_wait_timeout_enabled() ? tc_error_flag() : nullptr;
-  if (const char* e = getenv("FNSSL_TC_DEBUG")) p.debug = atoi(e);
+  p.debug = tc_debug_bits(0);
 
   CUtensorMap m0, mw;
   if (make_grid_map(&m0, a->src0, a->c0, a->ld0, a->nb, a->nt, a->nf, a->axis, kRows)) return 1;
@@ -626,7 +604,7 @@ int lstm_forward_tc6(const fnssl_lstm_args* a, cudaStream_t st) {
     if (make_out_map(&mo1, a->out1, a->out1_ld, a->nb, a->nt, a->nf, a->axis, 32)) return 1;
     p.tma_out |= 2;
   }
-  FNSSL_CUDA(cudaFuncSetAttribute(lstm_tc6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  FNSSL_CUDA(cudaFuncSetAttribute(lstm_tc6_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)clusters * kCluster, (unsigned)a->num_dirs, 1);
   cfg.blockDim = dim3(kThreads, 1, 1);
@@ -636,9 +614,55 @@ int lstm_forward_tc6(const fnssl_lstm_args* a, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  FNSSL_CUDA(cudaLaunchKernelEx(&cfg, lstm_tc6_kernel, m0, m1, mw, mw2, mo0, mo1, p));
+  FNSSL_CUDA(cudaLaunchKernelEx(&cfg, lstm_tc6_kernel<H>, m0, m1, mw, mw2, mo0, mo1, p));
   FNSSL_LAUNCH_CHECK("lstm_tc6_kernel");
   return 0;
+}
+
+}  // namespace tc6
+
+// lstm_tc6.cu serves
+//  * H = 256 layers without carried state whose outputs all go through TMA (FNSSL_TC_PAIR256=0 switches it off), by wave count:
+//    both H = 256 kernels run clusters of 8 CTAs with one CTA per SM, kResident of them fit the GPU at a time (measured:
+//    cudaOccupancyMaxActiveClusters = 15 on a 148-SM B200), so a launch takes ceil(clusters / kResident) waves; a wave of this
+//    kernel covers twice the rows of one of lstm_tc4.cu (256 vs 128 per cluster) in ~1.35x its time (0.93-1.0 vs 0.71 ms at
+//    c0 = 256, 249 steps: profiles/r2_lstm_variants.txt) -- it wins unless the wave counts quantise against it;
+//  * H = 128 TWO-SOURCE layers of the same kind that are too small for lstm_tc5.cu (< 30 clusters of 512 rows; the dispatcher asks
+//    that kernel first) and too large for lstm_tc4.cu's 64-row small-grid plan: clusters of 4 = 2 pairs x 2 chains of 128 rows --
+//    the same CTA count as lstm_tc4.cu, a third of its DSMEM traffic, six x-ring stages instead of three (FNSSL_TC_PAIR=0
+//    switches it off).
+bool lstm_tc6_wants(const fnssl_lstm_args* a) {
+  if (a->hidden != 256 && a->hidden != 128) return false;
+  if (const char* e = getenv(a->hidden == 256 ? "FNSSL_TC_PAIR256" : "FNSSL_TC_PAIR")) { if (atoi(e) == 0) return false; }
+  if (a->state_flags) return false;
+  if (!tc6::make_plan(a->hidden, a->c0, a->c1).ok) return false;
+  if (a->out0 && a->out0_off % 8) return false;
+  if (a->out1 && !(a->out1 == a->addend && a->out1_ld == a->addend_ld)) return false;
+  const long long chains = a->axis == FNSSL_ALONG_FREQ ? ((long long)a->nb * a->nt + 127) / 128 : (long long)a->nb * ((a->nf + 127) / 128);
+  const long long clusters = (chains + 1) / 2 * a->num_dirs;
+  if (a->hidden == 128) {
+    if (const char* e = getenv("FNSSL_TC_PAIR128_MIN")) return clusters >= atoi(e);
+    // lstm_tc4.cu's small-grid plan (64-row tiles while they fit one wave: twice the CTAs) keeps the smallest layers
+    const long long tiles64 = a->axis == FNSSL_ALONG_FREQ ? ((long long)a->nb * a->nt + 63) / 64 : (long long)a->nb * ((a->nf + 63) / 64);
+    if (tiles64 * a->num_dirs * 4 <= 132) return false;
+    // Measured at cfg2 size (16 utterances, ms): in16 0.73 vs 0.68 for lstm_tc4.cu, in256 0.82-0.84 vs 0.81-0.83 -- a draw, the step is
+    // the same serial epilogue chain in both -- but 0.86 vs 1.07 for the two-source layer (in 256 + 16), where lstm_tc4.cu's x ring
+    // is one stage short: only that shape is taken.
+    return a->c1 > 0 && clusters >= 8;
+  }
+  if (const char* e = getenv("FNSSL_TC_PAIR256_MIN")) return clusters >= atoi(e);
+  constexpr long long kResident = 15;
+  const long long waves6 = (clusters + kResident - 1) / kResident;
+  const long long waves4 = (chains * a->num_dirs + kResident - 1) / kResident;
+  return waves6 * 27 < waves4 * 20;
+}
+
+int lstm_forward_tc6(const fnssl_lstm_args* a, cudaStream_t st) {
+  using namespace tc6;
+  const Plan pl = make_plan(a->hidden, a->c0, a->c1);
+  FNSSL_REQUIRE(pl.ok && (a->hidden == 256 || a->hidden == 128), "lstm(tcgen05 pair kernel, M = 128): unsupported layer (H=%d c0=%d c1=%d)",
+                a->hidden, a->c0, a->c1);
+  return a->hidden == 256 ? launch<256>(a, pl, st) : launch<128>(a, pl, st);
 }
 
 }  // namespace fnssl

@@ -228,6 +228,7 @@ int make_weight_map(CUtensorMap* m, const void* weights, int nslabs, int nchunks
 int make_small_grid_map(CUtensorMap* m, const void* base, int c, int ld, int nb, int nt, int nf, int axis, int mr);
 int make_small_weight_map(CUtensorMap* m, const void* weights, int nslabs, int nchunks_total);
 int* tc_error_flag();
+int tc_debug_bits(int safe_mask);  // FNSSL_TC_DEBUG; bits outside safe_mask need FNSSL_TC_UNSAFE_EXPERIMENTS=1 (they give wrong results)
 bool tc_wait_timeout_enabled();   // FNSSL_TC_WAIT_TIMEOUT != 0 (read once): kernels get the error flag, i.e. bounded waits
 
 // ---- thread-block cluster helpers ------------------------------------------------------------------

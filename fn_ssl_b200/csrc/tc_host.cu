@@ -124,11 +124,21 @@ bool tc_wait_timeout_enabled() {
   return v == 1;
 }
 
+// FNSSL_TC_DEBUG selects timing experiments inside the kernels.  Bits outside `safe_mask` make a kernel skip work (WRONG results)
+// or drop a hand-shake; they are honoured only together with FNSSL_TC_UNSAFE_EXPERIMENTS=1 (tools/ sets both).
+int tc_debug_bits(int safe_mask) {
+  const char* e = getenv("FNSSL_TC_DEBUG");
+  if (!e) return 0;
+  const int v = atoi(e);
+  const char* u = getenv("FNSSL_TC_UNSAFE_EXPERIMENTS");
+  return (u && atoi(u) != 0) ? v : (v & safe_mask);
+}
+
 bool lstm_tc4_supports(int hidden, int c0, int c1);
 int lstm_forward_tc4(const fnssl_lstm_args* a, cudaStream_t st);
 bool lstm_tc5_wants(const fnssl_lstm_args* a);      // CTA-pair (cta_group::2) kernel: H = 128 layers with enough rows
 int lstm_forward_tc5(const fnssl_lstm_args* a, cudaStream_t st);
-bool lstm_tc6_wants(const fnssl_lstm_args* a);      // CTA-pair kernel for H = 256 single-source layers (full-rate M = 128 MMAs)
+bool lstm_tc6_wants(const fnssl_lstm_args* a);      // CTA-pair kernel with M = 128 MMAs (64 rows per CTA): H = 256, mid-size H = 128 layers
 int lstm_forward_tc6(const fnssl_lstm_args* a, cudaStream_t st);
 
 int lstm_forward_tc(const fnssl_lstm_args* a, cudaStream_t st) {
@@ -138,8 +148,8 @@ int lstm_forward_tc(const fnssl_lstm_args* a, cudaStream_t st) {
   FNSSL_REQUIRE(lstm_tc4_supports(a->hidden, a->c0, a->c1),
                 "lstm(tcgen05): layer shape H=%d c0=%d c1=%d is not built (H in {64,128,256}, <= 6 input slabs of 64 channels); "
                 "use FNSSL_ENGINE_SIMT for it", a->hidden, a->c0, a->c1);
-  if (lstm_tc6_wants(a)) return lstm_forward_tc6(a, st);
-  if (lstm_tc5_wants(a)) return lstm_forward_tc5(a, st);
+  if (lstm_tc5_wants(a)) return lstm_forward_tc5(a, st);      // H = 128, at least one wave of 512-row cluster tiles
+  if (lstm_tc6_wants(a)) return lstm_forward_tc6(a, st);      // H = 256 by wave count; mid-size H = 128 layers
   return lstm_forward_tc4(a, st);
 }
 

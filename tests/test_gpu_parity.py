@@ -144,6 +144,12 @@ def test_fused_stft_features_equals_two_step_front_end(nch, pairing, dtype):
 # LSTM layer, both axes, both engines
 # ---------------------------------------------------------------------------------------------
 
+def _tc4_only(monkeypatch):
+    """Route every tensor-core layer to lstm_tc4.cu (the CTA-pair kernels lstm_tc5.cu / lstm_tc6.cu off)."""
+    monkeypatch.setenv("FNSSL_TC_PAIR", "0")
+    monkeypatch.setenv("FNSSL_TC_PAIR256", "0")
+
+
 def _lstm_case(engine, axis, nb, nt, nf, c0, c1, H, bidir, use_addend, seed=0, inplace=False):
     from fn_ssl_b200 import config, ops
     from fn_ssl_b200.packing import LSTMParams, run_lstm
@@ -202,7 +208,8 @@ def test_lstm_layer_tcgen05(monkeypatch, rows, axis, H, bidir, c0, c1, addend):
         pytest.skip("tcgen05 engine not built")
     if H == 256 and rows == "128":
         pytest.skip("H = 256 only exists with 64-row tiles")
-    monkeypatch.setenv("FNSSL_TC_ROWS", rows)
+    monkeypatch.setenv("FNSSL_TC_ROWS", rows)      # (a knob of lstm_tc4.cu: keep the pair kernels out of this test)
+    _tc4_only(monkeypatch)
     nb, nt, nf = (2, 70, 256) if axis == 1 else (2, 70, 40)
     assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, H, bidir, addend) <= 1e-3
     if addend:   # residual sum accumulated in place (TMA reduce-add onto the residual operand)
@@ -239,6 +246,21 @@ def test_lstm_layer_tcgen05_pair_kernel_h256(monkeypatch, axis, bidir, c0, c1, a
         assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, 256, bidir, addend, inplace=addend) <= 1e-3
 
 
+@pytest.mark.parametrize("axis", [0, 1])
+@pytest.mark.parametrize("bidir,c0,c1,addend", [(True, 16, 0, False), (True, 256, 0, True), (True, 256, 4, True), (False, 64, 0, False),
+                                                 (True, 256, 8, False), (False, 128, 16, True)])
+def test_lstm_layer_tcgen05_pair_kernel_m128_h128(monkeypatch, axis, bidir, c0, c1, addend):
+    """lstm_tc6.cu instantiated for H = 128 (clusters of 4 = 2 pairs, 128-row chains, M = 128 cta_group::2 MMAs) -- the kernel of
+    mid-size H = 128 layers (cfg2's 16 utterances) -- forced on small layers: ragged chains, an absent second chain, both
+    directions, the narrow second source, the in-place residual output."""
+    from fn_ssl_b200 import config
+    if not config.TC_AVAILABLE:
+        pytest.skip("tcgen05 engine not built")
+    monkeypatch.setenv("FNSSL_TC_PAIR128_MIN", "1")
+    for nb, nt, nf in (((3, 5, 256), (2, 33, 300)) if axis == 1 else ((2, 70, 40), (5, 130, 7))):
+        assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, 128, bidir, addend, inplace=addend) <= 1e-3
+
+
 @pytest.mark.parametrize("small1", ["1", "0"])
 @pytest.mark.parametrize("axis", [0, 1])
 @pytest.mark.parametrize("H,bidir,c0,c1,addend", [(128, True, 256, 4, True), (64, True, 128, 8, True), (256, False, 256, 8, True),
@@ -250,6 +272,7 @@ def test_lstm_narrow_second_source_ring(monkeypatch, small1, axis, H, bidir, c0,
     if not config.TC_AVAILABLE:
         pytest.skip("tcgen05 engine not built")
     monkeypatch.setenv("FNSSL_TC_SMALL1", small1)
+    _tc4_only(monkeypatch)
     nb, nt, nf = (2, 70, 256) if axis == 1 else (2, 70, 40)
     assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, H, bidir, addend, inplace=addend) <= 1e-3
 
@@ -262,7 +285,8 @@ def test_lstm_layer_tcgen05_multi_tile(monkeypatch, axis, nb, nt, nf):
     if not config.TC_AVAILABLE:
         pytest.skip("tcgen05 engine not built")
     for rows in ("128", "64"):
-        monkeypatch.setenv("FNSSL_TC_ROWS", rows)
+        monkeypatch.setenv("FNSSL_TC_ROWS", rows)      # (a knob of lstm_tc4.cu: keep the pair kernels out of this test)
+        _tc4_only(monkeypatch)
         assert _lstm_case("tcgen05", axis, nb, nt, nf, 64, 4, 128, True, True, inplace=True) <= 1e-3
         assert _lstm_case("tcgen05", axis, nb, nt, nf, 16, 0, 64, False, False) <= 1e-3
 
@@ -654,7 +678,8 @@ def test_lstm_carried_state_equals_whole_sequence(monkeypatch, rows, engine, H, 
     gives bit-identical outputs to one run over the whole sequence, and the final state matches the oracle."""
     from fn_ssl_b200 import config, ops
     from fn_ssl_b200.packing import LSTMParams, run_lstm
-    monkeypatch.setenv("FNSSL_TC_ROWS", rows)
+    monkeypatch.setenv("FNSSL_TC_ROWS", rows)      # (a knob of lstm_tc4.cu: keep the pair kernels out of this test)
+    _tc4_only(monkeypatch)
     if engine == "simt" and rows == "64":
         pytest.skip("row-tile shapes only exist in the tensor-core engine")
     dt = config.grid_dtype(engine)

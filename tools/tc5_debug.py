@@ -17,6 +17,10 @@ CASES = [
     ("h256_time_c64+16_uni_L1", 1, 2, 1, 256, 64, 16, False, False),
     ("h256_time_c256+16_uni_add", 1, 3, 7, 256, 256, 16, False, True),
     ("h256_freq_c256+16_uni_ragged", 0, 3, 100, 5, 256, 16, False, False),
+    ("m128_time_c64_uni_L1", 1, 2, 1, 256, 64, 0, False, False),
+    ("m128_time_c64_uni_L3", 1, 2, 3, 256, 64, 0, False, False),
+    ("m128_time_c256+16_bi_add", 1, 3, 7, 256, 256, 16, True, True),
+    ("m128_freq_c16_bi_ragged", 0, 3, 100, 5, 16, 0, True, False),
     ("time_c64_uni_L1", 1, 2, 1, 256, 64, 0, False, False),
     ("time_c64_uni_L2", 1, 2, 2, 256, 64, 0, False, False),
     ("time_c64_uni_L5", 1, 2, 5, 256, 64, 0, False, False),
@@ -87,6 +91,8 @@ if __name__ == "__main__":
             if only and only not in CASES[i][0]:
                 continue
             env = dict(os.environ, FNSSL_TC_PAIR="1", FNSSL_TC_PAIR_MIN="1", FNSSL_TC_PAIR256_MIN="1", FNSSL_TC_WAIT_TIMEOUT="1")
+            if CASES[i][0].startswith("m128"):      # lstm_tc6.cu's H = 128 instantiation instead of lstm_tc5.cu
+                env.update(FNSSL_TC_PAIR_MIN="1000000", FNSSL_TC_PAIR128_MIN="1")
             r = subprocess.run([sys.executable, os.path.abspath(__file__), str(i)], capture_output=True, text=True, timeout=300, env=env)
             print(r.stdout.strip())
             if r.returncode != 0:
