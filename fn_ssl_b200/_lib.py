@@ -96,6 +96,7 @@ SIGNATURES = {
     "fnssl_grid_add": (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
     "fnssl_lstm_forward": (_i, [C.POINTER(LstmArgs), _vp]),
     "fnssl_lstm_tc_supported": (_i, [_i, _i, _i]),
+    "fnssl_lstm_tc_kernel_for": (_i, [C.POINTER(LstmArgs)]),
     "fnssl_lstm_tc_error_site": (_i, []),
     "fnssl_lstm_tc4_trace": (_i, [C.POINTER(C.c_longlong)]),
     "fnssl_ipd_head_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

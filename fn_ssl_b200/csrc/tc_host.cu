@@ -160,6 +160,14 @@ extern "C" int fnssl_lstm_tc_supported(int hidden, int c0, int c1) {
   return fnssl::lstm_tc4_supports(hidden, c0, c1) ? 1 : 0;
 }
 
+extern "C" int fnssl_lstm_tc_kernel_for(const fnssl_lstm_args* a) {
+  if (!a || a->dtype != FNSSL_F16 || a->c0 <= 0 || a->c0 % 16 || a->c1 < 0 || a->c1 % 16) return 0;
+  if (!fnssl::lstm_tc4_supports(a->hidden, a->c0, a->c1)) return 0;
+  if (fnssl::lstm_tc5_wants(a)) return 5;
+  if (fnssl::lstm_tc6_wants(a)) return 6;
+  return 4;
+}
+
 extern "C" int fnssl_lstm_tc_error_site(void) {
   // site code recorded by a timed-out mbarrier wait (0 = none); resets the flag
   if (!fnssl::g_flag_host) return 0;

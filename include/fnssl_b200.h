@@ -161,6 +161,11 @@ int fnssl_lstm_forward(const fnssl_lstm_args* args, void* stream);
 
 /* 1 if the tcgen05 engine is built for this layer shape (fp16 grids; hidden, c0, c1 as in fnssl_lstm_args) */
 int fnssl_lstm_tc_supported(int hidden, int c0, int c1);
+/* Which tensor-core kernel fnssl_lstm_forward would launch for these arguments (no launch, no GPU needed): 4 = lstm_tc4.cu
+ * (cluster kernel: small grids, carried state), 5 = lstm_tc5.cu (CTA pairs, H = 128, >= 30 clusters), 6 = lstm_tc6.cu (CTA pairs
+ * with M = 128: H = 256 by wave count, mid-size two-source H = 128 layers); 0 if the engine is not built for the shape (the
+ * fp32 kernel runs).  Honours FNSSL_TC_PAIR / FNSSL_TC_PAIR256 / *_MIN like the dispatcher itself. */
+int fnssl_lstm_tc_kernel_for(const fnssl_lstm_args* args);
 /* diagnostic: site code written by a timed-out pipeline wait inside the tcgen05 kernel (0 = none) */
 int fnssl_lstm_tc_error_site(void);
 /* diagnostic: last in-kernel timeline of the cluster kernel (lstm_tc4.cu; 16 slots x 16 SM-clock stamps) recorded when
