@@ -26,6 +26,7 @@ LSTM = {  # axis, nb, nt, nf, c0, c1, H, bidir, addend(in place)
     "pair128f": (0, 1, 300, 6, 64, 16, 128, True, False),
     "pair256": (1, 1, 5, 300, 256, 0, 256, False, True),
     "pair256n": (1, 1, 5, 300, 256, 16, 256, False, True),
+    "pair128n6": (1, 1, 5, 300, 256, 16, 128, True, True),      # lstm_tc6.cu's H = 128 instantiation (two-source layer)
 }
 
 
@@ -33,7 +34,8 @@ def lstm_case(name):
     axis, nb, nt, nf, c0, c1, H, bidir, add = LSTM[name]
     dev = "cuda"
     os.environ["FNSSL_TC_PAIR"] = "1" if name.startswith("pair") else "0"
-    os.environ["FNSSL_TC_PAIR_MIN"] = "1"
+    os.environ["FNSSL_TC_PAIR_MIN"] = "1000000" if name.endswith("6") else "1"
+    os.environ["FNSSL_TC_PAIR128_MIN"] = "1"
     os.environ["FNSSL_TC_PAIR256_MIN"] = "1" if name.startswith("pair") else "1000000"
     torch.manual_seed(1)
     p = LSTMParams(c0 + c1, H, bidirectional=bidir).to(dev)
