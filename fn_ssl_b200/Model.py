@@ -59,13 +59,16 @@ class FNblock(nn.Module):
         Returns (N, N + F [if next_full_addend], F)."""
         fh = self.full_hidden_size
         if self.is_first:
-            F_, _ = run_lstm(self.fullLstm, eng, ops.ALONG_FREQ, x_full_in, c_in, None, 0)
+            # F_ is the narrow-band layer's INPUT, so the residual sum N + F cannot be accumulated onto it in place.  The
+            # full-band layer writes its output twice (a second TMA tile store per quadrant out of the same shared-memory
+            # tile: the 16-channel layer is epilogue-bound, its stores are free) and the sum is accumulated onto the copy
+            # with the TMA reduce-add path instead of per-thread read-modify-write stores from the epilogue warps
+            # (round 1: a separate HBM-rate copy kernel, 2.8 ms = 3.9 % of a cfg4 step).
+            dup = bool(next_full_addend) and eng == "tcgen05"
+            F_, F2 = run_lstm(self.fullLstm, eng, ops.ALONG_FREQ, x_full_in, c_in, None, 0, duplicate=dup)
             addend, inplace = (F_ if next_full_addend else None), False
-            if next_full_addend and eng == "tcgen05":
-                # F_ is this layer's INPUT, so the residual sum N + F cannot be accumulated onto it in place.  A copy of F_
-                # (one HBM-rate pass) lets the layer still use the TMA reduce-add output path instead of per-thread
-                # read-modify-write stores from the epilogue warps (measured: 1.28 -> 1.01 + 0.17 ms at cfg2).
-                addend, inplace = ops.grid_copy(F_, F_.shape[-1], F_.dtype), True
+            if dup:
+                addend, inplace = F2, True
             N_, S_ = run_lstm(self.narrLstm, eng, ops.ALONG_TIME, F_, 2 * fh, raw, c_in,
                               addend=addend, state=state, inplace_addend=inplace)
         else:

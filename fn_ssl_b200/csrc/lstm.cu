@@ -20,7 +20,7 @@ extern "C" int fnssl_lstm_forward(const fnssl_lstm_args* a, void* stream) {
   const int oc = a->num_dirs * a->hidden;
   FNSSL_REQUIRE(!a->out0 || (a->out0_off >= 0 && a->out0_ld >= a->out0_off + oc), "lstm: out0 window (off %d + %d channels) exceeds ld %d",
                 a->out0_off, oc, a->out0_ld);
-  FNSSL_REQUIRE(!a->out1 || (a->addend && a->addend_ld >= oc && a->out1_ld >= oc), "lstm: bad out1/addend");
+  FNSSL_REQUIRE(!a->out1 || (a->out1_ld >= oc && (!a->addend || a->addend_ld >= oc)), "lstm: bad out1/addend");      // (addend == NULL: out1 = h)
   if (a->state_flags) {
     FNSSL_REQUIRE((a->state_flags & ~3) == 0, "lstm: bad state_flags %d", a->state_flags);
     FNSSL_REQUIRE(a->num_dirs == 1, "lstm: recurrent state is carried for uni-directional layers only");

@@ -132,7 +132,7 @@ lstm_simt_kernel(const SimtParams p) {
         const int ch = dir * H + j;
         if (p.out0) st_act<T>(reinterpret_cast<T*>(p.out0) + pos * p.out0_ld + p.out0_off + ch, h);
         if (p.out1) {
-          const float a = ld_act<T>(reinterpret_cast<const T*>(p.addend) + pos * p.addend_ld + ch);
+          const float a = p.addend ? ld_act<T>(reinterpret_cast<const T*>(p.addend) + pos * p.addend_ld + ch) : 0.0f;
           st_act<T>(reinterpret_cast<T*>(p.out1) + pos * p.out1_ld + ch, h + a);
         }
       }

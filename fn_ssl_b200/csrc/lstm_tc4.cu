@@ -541,6 +541,10 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
                 if (along_f) tma_reduce_add_4d(&map_out1, hs_base + off, out1_c, s, r0, 0);
                 else tma_reduce_add_4d(&map_out1, hs_base + off, out1_c, r0, s, coord_b);
               }
+              if (p.tma_out & 4) {      // out1 = a second copy of h (no residual operand)
+                if (along_f) tma_store_4d(&map_out1, hs_base + off, out1_c, s, r0, 0);
+                else tma_store_4d(&map_out1, hs_base + off, out1_c, r0, s, coord_b);
+              }
             }
             bulk_commit_group();
           }
@@ -604,6 +608,10 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
               if (along_f) tma_reduce_add_4d(&map_out1, buf + hquad, out1_c, s, r0, 0);
               else tma_reduce_add_4d(&map_out1, buf + hquad, out1_c, r0, s, coord_b);
             }
+            if (p.tma_out & 4) {
+              if (along_f) tma_store_4d(&map_out1, buf + hquad, out1_c, s, r0, 0);
+              else tma_store_4d(&map_out1, buf + hquad, out1_c, r0, s, coord_b);
+            }
             bulk_commit_group();
           }
         }
@@ -611,7 +619,8 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
 #endif
     };
     const bool thr_out0 = p.out0 && !(p.tma_out & 1);     // per-thread stores (fallback paths)
-    const bool thr_out1 = p.out1 && !(p.tma_out & 2);
+    const bool thr_out1 = p.out1 && !(p.tma_out & 6);
+    const bool thr_add = thr_out1 && p.addend != nullptr;      // (out1 without a residual operand is a second copy of h)
     const bool tma_any = p.tma_out != 0;
 
     int a = 0;
@@ -630,7 +639,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         valid[sub] = R < valid_rows;
         base[sub] = (p.axis == FNSSL_ALONG_FREQ) ? (row0 + R) * p.nf : ((long long)coord_b * p.nt * p.nf + coord_r0 + R);
         addv_next[sub] = make_uint4(0, 0, 0, 0);
-        if (thr_out1 && valid[sub]) {
+        if (thr_add && valid[sub]) {
           const long long pos0 = base[sub] + (long long)(dir ? (L - 1) : 0) * sstride;
           addv_next[sub] = __ldg(reinterpret_cast<const uint4*>(p.addend + pos0 * p.addend_ld + dir * H + ua));
         }
@@ -664,7 +673,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           long long* tp = (tr && t >= 8 && t < 16) ? p.trace + ((t - 8) * 2 + sub) * 16 : nullptr;
           const long long pos = base[sub] + (long long)s * sstride;
           const uint4 addv = addv_next[sub];
-          if (thr_out1 && valid[sub] && t + 1 < L) {     // residual operand of the next layer, fetched one step ahead
+          if (thr_add && valid[sub] && t + 1 < L) {     // residual operand of the next layer, fetched one step ahead
             const long long posn = base[sub] + (long long)(dir ? (L - 2 - t) : (t + 1)) * sstride;
             addv_next[sub] = __ldg(reinterpret_cast<const uint4*>(p.addend + posn * p.addend_ld + dir * H + ua));
           }
@@ -778,7 +787,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           valid[sub][i] = R < valid_rows;
           base[sub][i] = (p.axis == FNSSL_ALONG_FREQ) ? (row0 + R) * p.nf : ((long long)coord_b * p.nt * p.nf + coord_r0 + R);
           addn[sub][i] = 0u;
-          if (thr_out1 && valid[sub][i]) {
+          if (thr_add && valid[sub][i]) {
             const long long pos0 = base[sub][i] + (long long)(dir ? (L - 1) : 0) * sstride;
             addn[sub][i] = __ldg(reinterpret_cast<const unsigned int*>(p.addend + pos0 * p.addend_ld + dir * H + ua));
           }
@@ -809,7 +818,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         for (int sub = 0; sub < 2; ++sub) {
           long long* tp = (tr && t >= 8 && t < 16) ? p.trace + ((t - 8) * 2 + sub) * 16 : nullptr;
           const uint32_t addc[2] = {addn[sub][0], addn[sub][1]};
-          if (thr_out1 && t + 1 < L) {     // residual operand of the next layer, fetched one step ahead
+          if (thr_add && t + 1 < L) {     // residual operand of the next layer, fetched one step ahead
 #pragma unroll
             for (int i = 0; i < 2; ++i)
               if (valid[sub][i]) {
@@ -1037,6 +1046,9 @@ static int launch_t(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
   if (a->out1 && a->out1 == a->addend && a->out1_ld == a->addend_ld && !no_tma_out) {
     if (make_out_map(&mo1, a->out1, a->out1_ld, a->nb, a->nt, a->nf, a->axis, SUB / 4)) return 1;
     p.tma_out |= 2;
+  } else if (a->out1 && !a->addend && !no_tma_out) {      // out1 = second copy of h: plain tile stores
+    if (make_out_map(&mo1, a->out1, a->out1_ld, a->nb, a->nt, a->nf, a->axis, SUB / 4)) return 1;
+    p.tma_out |= 4;
   }
 
   auto kern = lstm_tc4_kernel<H, SUB, TRACE, NARROW>;

@@ -79,7 +79,7 @@ struct Params {
   int nchains;                     // chain tiles of the layer (the last cluster may own an empty second chain)
   const float* bias;               // [dirs][4H], accumulator column order [chunk][gate][unit]
   int out0_off;
-  int tma_out;                     // bit 0: out0 tile stores; bit 1: in-place reduce-add onto out1 == addend
+  int tma_out;                     // bit 0: out0 tile stores; bit 1: in-place reduce-add onto out1 == addend; bit 2: out1 = second copy of h
   int* error_flag;
   long long* trace;                // FNSSL_TC_TRACE: clock64 stamps of cluster 0 / CTA rank 0 (pair leader): [half-slot 32..47][16 events]
   int debug;                       // timing experiments (FNSSL_TC_DEBUG; wrong results): 1 = no gate math, 2 = no fence.proxy.async, 4 = no TMA stores
@@ -403,6 +403,10 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
                 if (along_f) tma_reduce_add_4d(&map_out1, hs_base + off, out_c, s, r0, 0);
                 else tma_reduce_add_4d(&map_out1, hs_base + off, out_c, r0, s, CB(c));
               }
+              if (p.tma_out & 4) {
+                if (along_f) tma_store_4d(&map_out1, hs_base + off, out_c, s, r0, 0);
+                else tma_store_4d(&map_out1, hs_base + off, out_c, r0, s, CB(c));
+              }
             }
             bulk_commit_group();
           }
@@ -658,7 +662,7 @@ bool lstm_tc5_wants(const fnssl_lstm_args* a) {
   if (a->hidden != 128 || a->state_flags) return false;
   if (!tc5::make_plan(a->c0, a->c1).ok) return false;
   if (a->out0 && a->out0_off % 8) return false;
-  if (a->out1 && !(a->out1 == a->addend && a->out1_ld == a->addend_ld)) return false;      // only the in-place residual output
+  if (a->out1 && a->addend && !(a->out1 == a->addend && a->out1_ld == a->addend_ld)) return false;      // residual output: in place only
   const long long chains = a->axis == FNSSL_ALONG_FREQ ? ((long long)a->nb * a->nt + 255) / 256 : (long long)a->nb * ((a->nf + 255) / 256);
   const long long clusters = (chains + 1) / 2 * a->num_dirs;
   int min_clusters = 30;       // 33 clusters of 4 CTAs are co-resident; below ~one wave lstm_tc4.cu's smaller tiles win
@@ -723,7 +727,7 @@ int lstm_forward_tc5(const fnssl_lstm_args* a, cudaStream_t st) {
   }
   if (a->out1) {
     if (make_out_map(&mo1, a->out1, a->out1_ld, a->nb, a->nt, a->nf, a->axis, 32)) return 1;
-    p.tma_out |= 2;
+    p.tma_out |= a->addend ? 2 : 4;      // in-place reduce-add onto the residual operand / plain second copy of h
   }
   FNSSL_CUDA(cudaFuncSetAttribute(lstm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   cudaLaunchConfig_t cfg{};

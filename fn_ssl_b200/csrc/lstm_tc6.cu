@@ -63,7 +63,7 @@ struct Params {
   int chains_per_b, nchains;
   const float* bias;               // [dirs][4H], accumulator column order [chunk][gate][unit]
   int out0_off;
-  int tma_out;                     // bit 0: out0 tile stores; bit 1: in-place reduce-add onto out1 == addend
+  int tma_out;                     // bit 0: out0 tile stores; bit 1: in-place reduce-add onto out1 == addend; bit 2: out1 = second copy of h
   int* error_flag;
   int debug;
 };
@@ -407,6 +407,10 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
                 if (along_f) tma_reduce_add_4d(&map_out1, hs_base + off, out_c, s, r0, 0);
                 else tma_reduce_add_4d(&map_out1, hs_base + off, out_c, r0, s, CB(c));
               }
+              if (p.tma_out & 4) {
+                if (along_f) tma_store_4d(&map_out1, hs_base + off, out_c, s, r0, 0);
+                else tma_store_4d(&map_out1, hs_base + off, out_c, r0, s, CB(c));
+              }
             }
             bulk_commit_group();
           }
@@ -602,7 +606,7 @@ static int launch(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
   }
   if (a->out1) {
     if (make_out_map(&mo1, a->out1, a->out1_ld, a->nb, a->nt, a->nf, a->axis, 32)) return 1;
-    p.tma_out |= 2;
+    p.tma_out |= a->addend ? 2 : 4;      // in-place reduce-add onto the residual operand / plain second copy of h
   }
   FNSSL_CUDA(cudaFuncSetAttribute(lstm_tc6_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   cudaLaunchConfig_t cfg{};
@@ -637,7 +641,7 @@ bool lstm_tc6_wants(const fnssl_lstm_args* a) {
   if (a->state_flags) return false;
   if (!tc6::make_plan(a->hidden, a->c0, a->c1).ok) return false;
   if (a->out0 && a->out0_off % 8) return false;
-  if (a->out1 && !(a->out1 == a->addend && a->out1_ld == a->addend_ld)) return false;
+  if (a->out1 && a->addend && !(a->out1 == a->addend && a->out1_ld == a->addend_ld)) return false;
   const long long chains = a->axis == FNSSL_ALONG_FREQ ? ((long long)a->nb * a->nt + 127) / 128 : (long long)a->nb * ((a->nf + 127) / 128);
   const long long clusters = (chains + 1) / 2 * a->num_dirs;
   if (a->hidden == 128) {

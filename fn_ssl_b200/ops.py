@@ -297,11 +297,13 @@ def grid_add(a: Tensor, b: Tensor) -> Tensor:
 def lstm(engine: int, axis: int, src0: Tensor, c0: int, src1: Optional[Tensor], c1: int, weights: Tensor, hidden: int,
          num_dirs: int, addend: Optional[Tensor] = None, want_h: bool = True,
          out0: Optional[Tensor] = None, out0_off: int = 0,
-         state: Optional[Tuple[Tensor, Tensor]] = None, inplace_addend: bool = False
+         state: Optional[Tuple[Tensor, Tensor]] = None, inplace_addend: bool = False, duplicate: bool = False
          ) -> Tuple[Optional[Tensor], Optional[Tensor]]:
     """One LSTM layer over a grid (see fnssl_lstm_forward).  Returns (h grid, h + addend grid).
     inplace_addend: the sum is accumulated into `addend` itself (out1 aliases addend; tensor-core engine only) -- the
     caller must not need the residual operand afterwards and it must not be one of the layer's inputs.
+    duplicate (no addend): the second result is a second copy of h, written by the kernel itself (for a consumer that reads
+    h as an input AND accumulates onto a copy of it in place -- block 1's narrow-band layer).
     state = (h, c): float32 (rows, hidden) tensors the layer starts from and overwrites with its final state
     (nn.LSTM's (h_0, c_0) -> (h_n, c_n); uni-directional layers only)."""
     _need_cuda(src0, src1, weights, addend)
@@ -321,7 +323,9 @@ def lstm(engine: int, axis: int, src0: Tensor, c0: int, src1: Optional[Tensor], 
             raise RuntimeError("lstm: in-place residual operand must be a contiguous (nb, nt, nf, dirs*hidden) grid")
         out1 = addend
     else:
-        out1 = torch.empty((nb, nt, nf, oc), dtype=dt, device=dev) if addend is not None else None
+        if duplicate and addend is not None:
+            raise RuntimeError("lstm: duplicate=True is the addend-less form of the second output")
+        out1 = torch.empty((nb, nt, nf, oc), dtype=dt, device=dev) if (addend is not None or duplicate) else None
     a = _lib.LstmArgs()
     a.engine, a.axis = engine, axis
     a.nb, a.nt, a.nf = nb, nt, nf
@@ -350,7 +354,8 @@ def lstm(engine: int, axis: int, src0: Tensor, c0: int, src1: Optional[Tensor], 
         rows, steps = (nb * nt, nf) if axis == ALONG_FREQ else (nb * nf, nt)
         flops = 2.0 * rows * steps * num_dirs * 4 * hidden * (c0 + c1 + hidden)
         esz = src0.element_size()
-        nbytes = float(rows) * steps * esz * ((c0 + c1) + oc * ((1 if out0 is not None else 0) + (2 if addend is not None else 0)))
+        nbytes = float(rows) * steps * esz * ((c0 + c1) + oc * ((1 if out0 is not None else 0) + (2 if addend is not None else 0)
+                                                                + (1 if duplicate else 0)))
         label = "lstm_%s_%s_H%d_x%d_in%d" % ("tc" if engine == ENGINE_TCGEN05 else "simt",
                                              "full" if axis == ALONG_FREQ else "narrow", hidden, num_dirs, c0 + c1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -120,7 +120,7 @@ def _pad16(c: int) -> int:
 
 
 def run_lstm(params: "LSTMParams", eng: str, axis: int, src0: Tensor, c0: int, src1, c1: int,
-             addend=None, want_h: bool = True, state=None, inplace_addend: bool = False):
+             addend=None, want_h: bool = True, state=None, inplace_addend: bool = False, duplicate: bool = False):
     """Run one LSTM layer with the model-level engine `eng` ("tcgen05" | "simt").  In tcgen05 mode the layer
     uses the tensor-core kernel when it is built for this shape (fnssl_lstm_tc_supported) and the fp32
     CUDA-core kernel (on the same fp16 grids) otherwise.  c0/c1 are the REAL channel counts; fp16 grids are
@@ -135,7 +135,7 @@ def run_lstm(params: "LSTMParams", eng: str, axis: int, src0: Tensor, c0: int, s
             splits = ((c0, p0),) + (((c1, p1),) if src1 is not None else ())
             w = params.packed(ops.ENGINE_TCGEN05, splits)
             return ops.lstm(ops.ENGINE_TCGEN05, axis, src0, p0, src1, p1, w, H, params.num_dirs, addend=addend, want_h=want_h,
-                            state=state, inplace_addend=inplace_addend)
+                            state=state, inplace_addend=inplace_addend, duplicate=duplicate)
     w = params.packed(ops.ENGINE_SIMT, (c0, c1))
     return ops.lstm(ops.ENGINE_SIMT, axis, src0, c0, src1, c1, w, H, params.num_dirs, addend=addend, want_h=want_h,
-                    state=state)
+                    state=state, duplicate=duplicate)

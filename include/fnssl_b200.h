@@ -131,7 +131,9 @@ int fnssl_grid_add(const void* a, const void* b, void* dst, int dtype, int64_t n
  *   input   x_t  = concat(src0[c0 channels], src1[c1 channels])         (src1 may be NULL, c1 = 0)
  *   output  out0 = h                  (dirs*hidden channels at channel offset out0_off, stride out0_ld)
  *           out1 = h + addend         (optional; same channel count, its own stride)  -- the operand of
- *                                      the next layer in FN-SSL's additive-skip blocks
+ *                                      the next layer in FN-SSL's additive-skip blocks.  With addend == NULL
+ *                                      out1 is a second copy of h (block 1's narrow-band layer reads h as its
+ *                                      input AND accumulates its residual sum onto a copy of it, Model.py:41-45)
  *   weights: engine-specific packed buffer produced by fn_ssl_b200.packing (layout in DESIGN.md) from
  *            nn.LSTM-shaped weight_ih_l0 (4H,in), weight_hh_l0 (4H,H), bias_ih_l0, bias_hh_l0 [+ _reverse];
  *            gate order i,f,g,o; zero initial state.

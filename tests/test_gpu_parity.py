@@ -261,6 +261,50 @@ def test_lstm_layer_tcgen05_pair_kernel_m128_h128(monkeypatch, axis, bidir, c0, 
         assert _lstm_case("tcgen05", axis, nb, nt, nf, c0, c1, 128, bidir, addend, inplace=addend) <= 1e-3
 
 
+@pytest.mark.parametrize("kernel", ["simt", "tc4", "tc4_threads", "tc5", "tc6_h256", "tc6_h128"])
+@pytest.mark.parametrize("axis", [0, 1])
+def test_lstm_second_copy_of_the_output(monkeypatch, kernel, axis):
+    """fnssl_lstm_forward with out1 and NO residual operand: out1 is a second copy of h, written by the kernel itself (TMA tile
+    stores out of the same shared-memory tile; per-thread stores on the fallback paths) -- what FNblock 1 uses instead of a
+    copy kernel.  Every LSTM kernel: both outputs are bit-identical, equal the single-output run, and match the oracle."""
+    from fn_ssl_b200 import config, ops
+    from fn_ssl_b200.packing import LSTMParams, run_lstm
+    if kernel != "simt" and not config.TC_AVAILABLE:
+        pytest.skip("tcgen05 engine not built")
+    eng = "simt" if kernel == "simt" else "tcgen05"
+    H, c0, c1, bidir = {"simt": (64, 20, 4, True), "tc4": (128, 16, 0, True), "tc4_threads": (128, 64, 0, True), "tc5": (128, 16, 0, True),
+                        "tc6_h256": (256, 64, 0, False), "tc6_h128": (128, 64, 16, True)}[kernel]
+    _tc4_only(monkeypatch)
+    if kernel == "tc4_threads":
+        monkeypatch.setenv("FNSSL_TC_NO_TMA_OUT", "1")
+    elif kernel == "tc5":
+        monkeypatch.setenv("FNSSL_TC_PAIR", "1"); monkeypatch.setenv("FNSSL_TC_PAIR_MIN", "1")
+    elif kernel == "tc6_h256":
+        monkeypatch.setenv("FNSSL_TC_PAIR256", "1"); monkeypatch.setenv("FNSSL_TC_PAIR256_MIN", "1")
+    elif kernel == "tc6_h128":
+        monkeypatch.setenv("FNSSL_TC_PAIR", "1"); monkeypatch.setenv("FNSSL_TC_PAIR_MIN", "1000000"); monkeypatch.setenv("FNSSL_TC_PAIR128_MIN", "1")
+    nb, nt, nf = (2, 70, 40) if axis == 0 else (3, 5, 300)
+    dt = config.grid_dtype(eng)
+    torch.manual_seed(5)
+    p = LSTMParams(c0 + c1, H, bidirectional=bidir).to(DEV)
+    g0 = ops.grid_copy(_randn((nb, nt, nf, c0), 6).to(DEV), c0, dt)
+    g1 = ops.grid_copy(_randn((nb, nt, nf, c1), 7).to(DEV), c1, dt) if c1 else None
+    h, h2 = run_lstm(p, eng, axis, g0, c0, g1, c1, duplicate=True)
+    h_single, none = run_lstm(p, eng, axis, g0, c0, g1, c1)
+    assert none is None and h2 is not None and h2.data_ptr() != h.data_ptr()
+    assert torch.equal(h, h2) and torch.equal(h, h_single) and torch.isfinite(h).all()
+    oc = H * (2 if bidir else 1)
+    x = torch.cat([t for t in (g0[..., :c0].float().cpu(), g1[..., :c1].float().cpu() if c1 else None) if t is not None], -1)
+    sd = {"l." + k: v.detach().cpu() for k, v in p.state_dict().items()}
+    if axis == 0:
+        ref = orc.lstm(x.reshape(nb * nt, nf, -1), sd, "l.").reshape(nb, nt, nf, oc)
+    else:
+        ref = orc.lstm(x.permute(0, 2, 1, 3).reshape(nb * nf, nt, -1), sd, "l.").reshape(nb, nf, nt, oc).permute(0, 2, 1, 3)
+    assert _relerr(h2, ref) <= TOL[eng]
+    with pytest.raises(RuntimeError, match="duplicate"):
+        run_lstm(p, eng, axis, g0, c0, g1, c1, addend=h, duplicate=True)
+
+
 @pytest.mark.parametrize("small1", ["1", "0"])
 @pytest.mark.parametrize("axis", [0, 1])
 @pytest.mark.parametrize("H,bidir,c0,c1,addend", [(128, True, 256, 4, True), (64, True, 128, 8, True), (256, False, 256, 8, True),
