@@ -56,6 +56,9 @@ constexpr int kWHalf = 64 * 128;           // [64 gate columns x 64] fp16: this 
 constexpr int kXSlab = kRows * 128;        // [128 rows x 64] fp16
 constexpr int kHTile = kRows * 64;         // [128 rows x 32 units] fp16 (64B swizzle)
 constexpr int kChunkN = 128;
+#ifndef TC5_STORE_QUADRANTS
+#define TC5_STORE_QUADRANTS 0      // 1: four [32 x 32] output boxes per tile and destination (A/B; 0 = one [128 x 32] box)
+#endif
 #ifndef TC5_ACCBUFS
 #define TC5_ACCBUFS 4      // 4: one accumulator PAIR per chain (the x-part of one chain overlaps the other chain's h-part / epilogue)
 #endif
@@ -390,11 +393,19 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           }
           TP(n, 13);
           if (tma_any) {
+            // ONE [128 rows x 32 channels] box per destination: a TMA store costs the issuing lane ~170 cycles (timeline: 0.7 k for
+            // four per-quadrant stores), and with two destinations per-quadrant stores made the publisher the slowest role
             const int out_c = dir * H + kc * 32;
+#if TC5_STORE_QUADRANTS
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint32_t off = tile_off + (uint32_t)q * 2048u;
               const int r0 = CR0(c) + q * 32;
+#else
+            {
+              const uint32_t off = tile_off;
+              const int r0 = CR0(c);
+#endif
               if (p.tma_out & 1) {
                 if (along_f) tma_store_4d(&map_out0, hs_base + off, p.out0_off + out_c, s, r0, 0);
                 else tma_store_4d(&map_out0, hs_base + off, p.out0_off + out_c, r0, s, CB(c));
@@ -722,11 +733,11 @@ int lstm_forward_tc5(const fnssl_lstm_args* a, cudaStream_t st) {
   if (make_half_weight_map(&mw, a->weights, nslabs, a->num_dirs * 4)) return 1;
   CUtensorMap mo0 = m0, mo1 = m0;
   if (a->out0) {
-    if (make_out_map(&mo0, a->out0, a->out0_ld, a->nb, a->nt, a->nf, a->axis, 32)) return 1;
+    if (make_out_map(&mo0, a->out0, a->out0_ld, a->nb, a->nt, a->nf, a->axis, TC5_STORE_QUADRANTS ? 32 : kRows)) return 1;
     p.tma_out |= 1;
   }
   if (a->out1) {
-    if (make_out_map(&mo1, a->out1, a->out1_ld, a->nb, a->nt, a->nf, a->axis, 32)) return 1;
+    if (make_out_map(&mo1, a->out1, a->out1_ld, a->nb, a->nt, a->nf, a->axis, TC5_STORE_QUADRANTS ? 32 : kRows)) return 1;
     p.tma_out |= a->addend ? 2 : 4;      // in-place reduce-add onto the residual operand / plain second copy of h
   }
   FNSSL_CUDA(cudaFuncSetAttribute(lstm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
