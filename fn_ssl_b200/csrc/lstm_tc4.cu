@@ -528,8 +528,11 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
             }
           }
           if (tma_any) {
+            // (one publisher warp: ONE [SUB x 32] box per destination -- the lane needs ~170 cycles per TMA store, tools/tc5_trace.py;
+            // two publisher warps: each stores its quadrants)
+            constexpr int kStores = (kQPerPub == 4) ? 1 : kQPerPub;
 #pragma unroll
-            for (int qq = 0; qq < kQPerPub; ++qq) {
+            for (int qq = 0; qq < kStores; ++qq) {
               const int q = kQPerPub * pw + qq;
               const uint32_t off = (uint32_t)(sub * C + (int)rank) * kHTile + (uint32_t)q * kQuadBytes;
               const int r0 = coord_r0 + sub * SUB + q * kQuadRows;
@@ -1037,17 +1040,18 @@ static int launch_t(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
   mw2 = mw;
   if (pl.small1 && make_small_weight_map(&mw2, a->weights, nslabs, a->num_dirs * C)) return 1;
   // outputs through TMA: out0 as tile stores, out1 as an in-place reduce-add when it aliases the residual operand
+  constexpr int kOutBoxRows = (TC4_PUB == 1) ? SUB : SUB / 4;      // one publisher warp stores whole tiles, otherwise per quadrant
   CUtensorMap mo0 = m0, mo1 = m0;
   const bool no_tma_out = getenv("FNSSL_TC_NO_TMA_OUT") != nullptr;
   if (a->out0 && !no_tma_out && a->out0_off % 8 == 0) {
-    if (make_out_map(&mo0, a->out0, a->out0_ld, a->nb, a->nt, a->nf, a->axis, SUB / 4)) return 1;
+    if (make_out_map(&mo0, a->out0, a->out0_ld, a->nb, a->nt, a->nf, a->axis, kOutBoxRows)) return 1;
     p.tma_out |= 1;
   }
   if (a->out1 && a->out1 == a->addend && a->out1_ld == a->addend_ld && !no_tma_out) {
-    if (make_out_map(&mo1, a->out1, a->out1_ld, a->nb, a->nt, a->nf, a->axis, SUB / 4)) return 1;
+    if (make_out_map(&mo1, a->out1, a->out1_ld, a->nb, a->nt, a->nf, a->axis, kOutBoxRows)) return 1;
     p.tma_out |= 2;
   } else if (a->out1 && !a->addend && !no_tma_out) {      // out1 = second copy of h: plain tile stores
-    if (make_out_map(&mo1, a->out1, a->out1_ld, a->nb, a->nt, a->nf, a->axis, SUB / 4)) return 1;
+    if (make_out_map(&mo1, a->out1, a->out1_ld, a->nb, a->nt, a->nf, a->axis, kOutBoxRows)) return 1;
     p.tma_out |= 4;
   }
 
