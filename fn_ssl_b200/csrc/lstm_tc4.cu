@@ -62,6 +62,9 @@ namespace tc4 {
 #ifndef TC4_XORDER
 #define TC4_XORDER 0
 #endif
+#ifndef TC4_PUSH_TILE
+#define TC4_PUSH_TILE 0      // 1 (single publisher warp): ONE DSMEM bulk copy of the whole h tile per peer instead of one per quadrant (measured: -8 %, off)
+#endif
 #ifndef TC4_HTILE
 #define TC4_HTILE 1
 #endif
@@ -515,6 +518,20 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           // the exchange first (it sits on the recurrence's critical path), the HBM stores of all quadrants afterwards: issuing a
           // TMA store / reduce-add costs this single lane ~50 cycles each, which used to delay the next quadrant's pushes
           // (measured: 0.82 -> 0.73 ms per 256-channel layer without the stores, profiles/r2_lstm_variants.txt)
+          if (TC4_PUSH_TILE && kQPerPub == 4) {
+            // the four quadrants finish within a few hundred cycles of each other, and every bulk copy costs this lane ~100-170
+            // cycles to issue: 3 copies of the whole tile instead of 12 quadrant copies per slot
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mbar_wait(H_READY(sub, q), (uint32_t)(t & 1), p.error_flag, 400 + sub * 4 + q);
+            if (push) {
+              const uint32_t off = (uint32_t)(sub * C + (int)rank) * kHTile;
+#pragma unroll
+              for (int dd = 1; dd < C; ++dd)
+                bulk_copy_s2c(peer_hs[dd - 1] + off, hs_base + off, (uint32_t)kHTile, sub ? peer_bar1[dd - 1] : peer_bar0[dd - 1]);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) mbar_arrive(H_IN(sub, (int)rank));     // the local copy of every quadrant is in place
+            }
+          } else {
 #pragma unroll
           for (int qq = 0; qq < kQPerPub; ++qq) {
             const int q = kQPerPub * pw + qq;
@@ -526,6 +543,7 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
                 bulk_copy_s2c(peer_hs[dd - 1] + off, hs_base + off, kQuadBytes, sub ? peer_bar1[dd - 1] : peer_bar0[dd - 1]);
               mbar_arrive(H_IN(sub, (int)rank));     // the local copy of this quadrant is in place
             }
+          }
           }
           if (tma_any) {
             // (one publisher warp: ONE [SUB x 32] box per destination -- the lane needs ~170 cycles per TMA store, tools/tc5_trace.py;

@@ -56,6 +56,9 @@ constexpr int kWHalf = 64 * 128;           // [64 gate columns x 64] fp16: this 
 constexpr int kXSlab = kRows * 128;        // [128 rows x 64] fp16
 constexpr int kHTile = kRows * 64;         // [128 rows x 32 units] fp16 (64B swizzle)
 constexpr int kChunkN = 128;
+#ifndef TC5_PUSH_TILE
+#define TC5_PUSH_TILE 0      // 1: one DSMEM bulk copy of the whole [128 x 32] tile to the peer instead of four quadrant copies (measured: a draw, off)
+#endif
 #ifndef TC5_STORE_QUADRANTS
 #define TC5_STORE_QUADRANTS 0      // 1: four [32 x 32] output boxes per tile and destination (A/B; 0 = one [128 x 32] box)
 #endif
@@ -382,6 +385,16 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         const uint32_t tile_off = (uint32_t)(c * 4 + kc) * kHTile;
         TP(n, 12);
         if (push || tma_any) {
+#if TC5_PUSH_TILE
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            mbar_wait(BAR(B_HREADY + (c * 2 + uh) * 4 + q), (uint32_t)(t & 1), p.error_flag, 400 + (c * 2 + uh) * 4 + q);
+          if (push) {
+            bulk_copy_s2c(peer_hs + tile_off, hs_base + tile_off, (uint32_t)kHTile, peer_hfull0 + 8u * (uint32_t)c);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mbar_arrive(BAR(B_HFULL + c));     // the local copy of every quadrant is in place
+          }
+#else
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             mbar_wait(BAR(B_HREADY + (c * 2 + uh) * 4 + q), (uint32_t)(t & 1), p.error_flag, 400 + (c * 2 + uh) * 4 + q);
@@ -391,6 +404,7 @@ lstm_tc5_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
               mbar_arrive(BAR(B_HFULL + c));     // the local copy of this quadrant is in place
             }
           }
+#endif
           TP(n, 13);
           if (tma_any) {
             // ONE [128 rows x 32 channels] box per destination: a TMA store costs the issuing lane ~170 cycles (timeline: 0.7 k for

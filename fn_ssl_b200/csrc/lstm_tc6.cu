@@ -29,6 +29,10 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
+#ifndef TC6_PUSH_TILE
+#define TC6_PUSH_TILE 0      // 1: one DSMEM bulk copy of the whole [64 x 32] tile per peer instead of one per row half (measured: a draw, off)
+#endif
+
 namespace fnssl {
 namespace tc6 {
 
@@ -383,6 +387,18 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
         const int kc = 2 * pair + uh;
         const uint32_t tile_off = (uint32_t)(c * kNH + kc) * kHTile;
         if (push || tma_any) {
+#if TC6_PUSH_TILE
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh)
+            mbar_wait(BAR(B_HREADY + (c * 2 + uh) * 2 + rh), (uint32_t)(t & 1), p.error_flag, 400 + (c * 2 + uh) * 2 + rh);
+          if (push) {
+#pragma unroll
+            for (int d = 0; d < kPairs - 1; ++d)
+              bulk_copy_s2c(peer_hs[d] + tile_off, hs_base + tile_off, (uint32_t)kHTile, peer_hfull0[d] + 8u * (uint32_t)c);
+            mbar_arrive(BAR(B_HFULL + c));
+            mbar_arrive(BAR(B_HFULL + c));
+          }
+#else
 #pragma unroll
           for (int rh = 0; rh < 2; ++rh) {       // rows 0-31 / 32-63 of the tile: 2 KB each
             mbar_wait(BAR(B_HREADY + (c * 2 + uh) * 2 + rh), (uint32_t)(t & 1), p.error_flag, 400 + (c * 2 + uh) * 2 + rh);
@@ -393,6 +409,7 @@ lstm_tc6_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
               mbar_arrive(BAR(B_HFULL + c));
             }
           }
+#endif
           if (tma_any) {
             const int out_c = dir * H + kc * 32;
             {      // one [64 rows x 32 channels] box per destination (a TMA store costs the issuing lane ~170 cycles)
