@@ -62,9 +62,6 @@ namespace tc4 {
 #ifndef TC4_XORDER
 #define TC4_XORDER 0
 #endif
-#ifndef TC4_STORE_TILE
-#define TC4_STORE_TILE 0
-#endif
 #ifndef TC4_PUSH_TILE
 #define TC4_PUSH_TILE 0      // 1 (single publisher warp): ONE DSMEM bulk copy of the whole h tile per peer instead of one per quadrant (measured: -8 %, off)
 #endif
@@ -549,11 +546,12 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           }
           }
           if (tma_any) {
-            // (TC4_STORE_TILE: ONE [SUB x 32] box per destination instead of one per quadrant -- pays in the pair kernels, where the
-            // publisher lane's ~170 cycles per TMA store made it the slowest role; here it measured +3..6 % on the 256-channel layers
-            // at cfg2 size (profiles/r2_lstm_variants.txt, calls 45-46), so the quadrant boxes stay)
-            constexpr int kStores = (TC4_STORE_TILE && kQPerPub == 4) ? 1 : kQPerPub;
-#pragma unroll
+            // Whole-tile boxes ([SUB x 32], one per destination) when the layer has TWO plain destinations (out0 + the second copy of h):
+            // the lane needs ~170 cycles per TMA store and eight of them per slot made the publisher the slowest role (16-channel layer:
+            // 0.56 -> 0.47 ms for one utterance, 0.75 -> 0.72 at B = 16).  With one destination the quadrant boxes stay: whole-tile boxes
+            // measured +3..6 % on the 256-channel layers at cfg2 size (profiles/r2_lstm_variants.txt, calls 45-47).
+            const int kStores = ((p.tma_out & 5) == 5 && kQPerPub == 4) ? 1 : kQPerPub;
+#pragma unroll 1
             for (int qq = 0; qq < kStores; ++qq) {
               const int q = kQPerPub * pw + qq;
               const uint32_t off = (uint32_t)(sub * C + (int)rank) * kHTile + (uint32_t)q * kQuadBytes;
@@ -1062,9 +1060,10 @@ static int launch_t(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
   mw2 = mw;
   if (pl.small1 && make_small_weight_map(&mw2, a->weights, nslabs, a->num_dirs * C)) return 1;
   // outputs through TMA: out0 as tile stores, out1 as an in-place reduce-add when it aliases the residual operand
-  constexpr int kOutBoxRows = (TC4_STORE_TILE && TC4_PUB == 1) ? SUB : SUB / 4;
-  CUtensorMap mo0 = m0, mo1 = m0;
   const bool no_tma_out = getenv("FNSSL_TC_NO_TMA_OUT") != nullptr;
+  const bool two_copies = a->out0 && a->out1 && !a->addend && !no_tma_out && a->out0_off % 8 == 0;      // -> whole-tile output boxes
+  const int kOutBoxRows = (two_copies && TC4_PUB == 1) ? SUB : SUB / 4;
+  CUtensorMap mo0 = m0, mo1 = m0;
   if (a->out0 && !no_tma_out && a->out0_off % 8 == 0) {
     if (make_out_map(&mo0, a->out0, a->out0_ld, a->nb, a->nt, a->nf, a->axis, kOutBoxRows)) return 1;
     p.tma_out |= 1;
