@@ -110,6 +110,7 @@ struct Params {
   const __half* addend; int addend_ld;
   __half* out1; int out1_ld;
   float* h_state; float* c_state; int state_flags;   // optional carried state, fp32 (rows, H); dirs == 1 (see lstm_tc2.cu)
+  int store_tile;                  // 1: one [SUB x 32] output box per tile and destination instead of one per quadrant (see the publisher)
   int tma_out;                     // bit 0: out0 is written by TMA tile stores out of the h exchange tiles; bit 1: out1 aliases
                                    // addend and is produced in place by TMA reduce-add (global += h)
   int* error_flag;
@@ -546,11 +547,12 @@ lstm_tc4_kernel(const __grid_constant__ CUtensorMap map_src0, const __grid_const
           }
           }
           if (tma_any) {
-            // Whole-tile boxes ([SUB x 32], one per destination) when the layer has TWO plain destinations (out0 + the second copy of h):
+            // Whole-tile boxes ([SUB x 32], one per destination; Params::store_tile) for small grids (latency-bound: fewer publisher
+            // operations per slot, one utterance 1.25 -> 1.16 ms per forward) and when the layer has TWO plain destinations (out0 + the second copy of h):
             // the lane needs ~170 cycles per TMA store and eight of them per slot made the publisher the slowest role (16-channel layer:
             // 0.56 -> 0.47 ms for one utterance, 0.75 -> 0.72 at B = 16).  With one destination the quadrant boxes stay: whole-tile boxes
             // measured +3..6 % on the 256-channel layers at cfg2 size (profiles/r2_lstm_variants.txt, calls 45-47).
-            const int kStores = ((p.tma_out & 5) == 5 && kQPerPub == 4) ? 1 : kQPerPub;
+            const int kStores = (p.store_tile && kQPerPub == 4) ? 1 : kQPerPub;
 #pragma unroll 1
             for (int qq = 0; qq < kStores; ++qq) {
               const int q = kQPerPub * pw + qq;
@@ -1062,7 +1064,8 @@ static int launch_t(const fnssl_lstm_args* a, const Plan& pl, cudaStream_t st) {
   // outputs through TMA: out0 as tile stores, out1 as an in-place reduce-add when it aliases the residual operand
   const bool no_tma_out = getenv("FNSSL_TC_NO_TMA_OUT") != nullptr;
   const bool two_copies = a->out0 && a->out1 && !a->addend && !no_tma_out && a->out0_off % 8 == 0;      // -> whole-tile output boxes
-  const int kOutBoxRows = (two_copies && TC4_PUB == 1) ? SUB : SUB / 4;
+  p.store_tile = (TC4_PUB == 1 && (two_copies || (SUB == 64 && H != 256))) ? 1 : 0;      // (SUB == 64 with H < 256: the small-grid plan)
+  const int kOutBoxRows = p.store_tile ? SUB : SUB / 4;
   CUtensorMap mo0 = m0, mo1 = m0;
   if (a->out0 && !no_tma_out && a->out0_off % 8 == 0) {
     if (make_out_map(&mo0, a->out0, a->out0_ld, a->nb, a->nt, a->nf, a->axis, kOutBoxRows)) return 1;
