@@ -5,7 +5,10 @@ arguments, forward layouts and state_dict keys), executed by the sm_100a kernels
     FN_SSL    (:53-90)
     FN_lightning (FN-SSL/Model.py:92-99)
 
-Inference only: forward in training mode raises (dropout is the identity in eval mode, the only mode on this path).
+Eval mode is the accelerated inference path (tensor-core or fp32 engine, fused residuals).  Train mode (`.train()`) runs the
+differentiable fp32 path of fn_ssl_b200.training -- every LSTM layer and the DP-IPD head are CUDA kernels with hand-written
+backward passes, the residual adds and dropout between them are torch elementwise ops -- so `loss.backward()` fills the
+`.grad` of every parameter as it does for the reference modules (FN-SSL/Lightning/main.py:95-109).
 """
 from __future__ import annotations
 
@@ -83,10 +86,32 @@ class FNblock(nn.Module):
                 F_ = None        # overwritten by S_
         return N_, S_, F_
 
+    def _run_train(self, x: Tensor, fb_skip: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+        """Train-mode block on fp32 grids, the reference's arithmetic line by line (Model.py:31-50): x (nb, nt, nf, ld >= nc),
+        fb_skip = the previous block's full-band output before dropout -> (dropout(narrow-band output), this block's fb_skip)."""
+        from . import training as T
+        nc = self.input_size
+        xin = x if self.is_first else x + fb_skip                                   # :36-37 (nb_skip = the block input itself, :34)
+        F_ = T.lstm_layer(xin, nc, None, 0, self.fullLstm, ops.ALONG_FREQ)          # :38
+        Fd = self.dropout_full(F_)                                                  # :40
+        if self.is_first:
+            N_ = T.lstm_layer(Fd, 2 * self.full_hidden_size, x, nc, self.narrLstm, ops.ALONG_TIME)    # cat, :42-43,46
+        else:
+            N_ = T.lstm_layer(Fd + x, 2 * self.full_hidden_size, None, 0, self.narrLstm, ops.ALONG_TIME)   # :44-46
+        return self.dropout_narr(N_), F_
+
     def forward(self, x: Tensor, nb_skip: Optional[Tensor] = None, fb_skip: Optional[Tensor] = None
                 ) -> Tuple[Tensor, Tensor, Tensor]:
-        _require_eval(self)
         nb, nt, nf, nc = x.shape
+        if self.training:
+            if not x.is_cuda:
+                raise RuntimeError("fn_ssl_b200 runs on CUDA (sm_100a) only -- no CPU fallback exists")
+            if not self.is_first and fb_skip is None:
+                raise RuntimeError("FNblock: fb_skip is required when is_first=False")
+            xg = x.float().contiguous()
+            y, fb = self._run_train(xg, None if self.is_first else fb_skip.reshape(nb, nt, nf, -1).float())
+            N_ = y
+            return y, fb.reshape(nb * nt, nf, -1), N_.permute(0, 2, 1, 3).reshape(nb * nf, nt, -1)
         eng = config.resolve(self.engine, (self.full_hidden_size, self.narr_hidden_size))
         dt = config.grid_dtype(eng)
         xg = ops.grid_copy(x, nc, dt)                                   # (nb,nt,nf,ld) grid of the engine's dtype
@@ -132,7 +157,10 @@ class FN_SSL(nn.Module):
     def forward_grid(self, g0: Tensor, eng: Optional[str] = None, states=None) -> Tensor:
         """g0: feature grid (nb, nt, nf, ld) already in the engine's dtype (fused front-end path).
         states: optional list of three (h, c) pairs -- the narrow-band LSTM states of a stream (fn_ssl_b200.streaming)."""
-        _require_eval(self)
+        if self.training:
+            if states is not None or g0.dtype != torch.float32:
+                raise RuntimeError("FN_SSL: train mode runs whole clips on float32 grids (fn_ssl_b200.training)")
+            return self._forward_train(g0)
         eng = eng or self._engine()
         ci = self.input_size
         st = states or (None, None, None)
@@ -144,10 +172,25 @@ class FN_SSL(nn.Module):
             out = ops.linear(out, self.ipd2doa.weight, self.ipd2doa.bias)
         return out
 
+    def _forward_train(self, g0: Tensor) -> Tensor:
+        """Differentiable forward on an fp32 grid (nb, nt, nf, ld >= input_size) -- Model.py:72-90 in train mode."""
+        from . import training as T
+        x, fb = self.block_1._run_train(g0, None)
+        x, fb = self.block_2._run_train(x, fb)
+        x, fb = self.block_3._run_train(x, fb)
+        out = T.ipd_head_train(x, self.emb2ipd.weight, self.emb2ipd.bias)
+        if self.is_doa:
+            # the DOA classifier (512 -> 180 per output frame, 1e-5 of a step) is torch's Linear in train mode
+            out = torch.nn.functional.linear(out, self.ipd2doa.weight, self.ipd2doa.bias)
+        return out
+
     def forward(self, x: Tensor) -> Tensor:
-        _require_eval(self)
         if x.dim() != 4 or x.shape[1] != self.input_size:
             raise RuntimeError(f"FN_SSL: expected (nb, {self.input_size}, nf, nt), got {tuple(x.shape)}")
+        if self.training:
+            if not x.is_cuda:
+                raise RuntimeError("fn_ssl_b200 runs on CUDA (sm_100a) only -- no CPU fallback exists")
+            return self._forward_train(x.float().permute(0, 3, 2, 1).contiguous())     # Model.py:73
         eng = self._engine()
         g0 = ops.cfirst_to_grid(x, config.grid_dtype(eng))              # x.permute(0,3,2,1), Model.py:73
         return self.forward_grid(g0, eng)

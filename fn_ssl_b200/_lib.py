@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libfnssl_b200.so")
 _lock = threading.Lock()
 _lib = None
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 F32, F16 = 0, 1
 ALONG_FREQ, ALONG_TIME = 0, 1
 ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
@@ -95,6 +95,10 @@ SIGNATURES = {
     "fnssl_grid_copy": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i64, _i, _vp]),
     "fnssl_grid_add": (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
     "fnssl_lstm_forward": (_i, [C.POINTER(LstmArgs), _vp]),
+    "fnssl_lstm_train_saved_bytes": (_i64, [_i, _i, _i, _i, _i]),
+    "fnssl_lstm_forward_train": (_i, [C.POINTER(LstmArgs), _vp, _i64, _vp]),
+    "fnssl_lstm_backward": (_i, [C.POINTER(LstmArgs), _vp, _i64, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
+    "fnssl_ipd_head_backward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "fnssl_lstm_tc_supported": (_i, [_i, _i, _i]),
     "fnssl_lstm_tc_kernel_for": (_i, [C.POINTER(LstmArgs)]),
     "fnssl_lstm_tc_error_site": (_i, []),

@@ -91,6 +91,62 @@ ipd_head_h8_kernel(const __half* __restrict__ x, int ld, int nb, int nt, int nf,
   }
 }
 
+// Backward of ipd_head_kernel on fp32 grids (training side; autograd of Model.py:79-87): one warp per (b, t2, f), grid-stride.
+//   g_o = dy_o (1 - y_o^2);  dx[b, 12 t2 + k, f, c] = (g_0 w[0][c] + g_1 w[1][c]) / 12;  dw[o][c] += g_o mean_k x;  db[o] += g_o
+// Per-lane register partial sums of dw over the warp's items, combined per CTA in shared memory, one global atomic per CTA and
+// channel.  dx frames beyond 12 * (nt / 12) are not written (the caller zero-fills them).
+constexpr int kHeadBwdMaxC = 512;
+__global__ void __launch_bounds__(256)
+ipd_head_bwd_kernel(const float* __restrict__ x, int ld, int nb, int nt, int nf, int C, const float* __restrict__ w,
+                    const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, int dld,
+                    float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float s_dw[2 * kHeadBwdMaxC + 2];
+  for (int i = threadIdx.x; i < 2 * C + 2; i += blockDim.x) s_dw[i] = 0.0f;
+  __syncthreads();
+  const int nt2 = nt / 12;
+  const int64_t total = (int64_t)nb * nt2 * nf;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float a0[kHeadBwdMaxC / 32], a1[kHeadBwdMaxC / 32];
+#pragma unroll
+  for (int i = 0; i < kHeadBwdMaxC / 32; ++i) { a0[i] = 0.0f; a1[i] = 0.0f; }
+  float b0 = 0.0f, b1 = 0.0f;
+  for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += nwarps) {
+    const int f = (int)(item % nf);
+    const int t2 = (int)((item / nf) % nt2);
+    const int b = (int)(item / ((int64_t)nf * nt2));
+    const float* yo = y + ((int64_t)b * nt2 + t2) * (2 * nf);
+    const float* go = dy + ((int64_t)b * nt2 + t2) * (2 * nf);
+    const float g0 = go[f] * (1.0f - yo[f] * yo[f]);
+    const float g1 = go[nf + f] * (1.0f - yo[nf + f] * yo[nf + f]);
+    b0 += g0; b1 += g1;
+#pragma unroll
+    for (int i = 0; i < kHeadBwdMaxC / 32; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) {
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) s += x[(((int64_t)b * nt + t2 * 12 + k) * nf + f) * ld + c];
+        s *= (1.0f / 12.0f);
+        a0[i] = fmaf(g0, s, a0[i]);
+        a1[i] = fmaf(g1, s, a1[i]);
+        const float d = (g0 * __ldg(w + c) + g1 * __ldg(w + C + c)) * (1.0f / 12.0f);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) dx[(((int64_t)b * nt + t2 * 12 + k) * nf + f) * dld + c] = d;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kHeadBwdMaxC / 32; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C) { atomicAdd(&s_dw[c], a0[i]); atomicAdd(&s_dw[C + c], a1[i]); }
+  }
+  if (lane == 0) { atomicAdd(&s_dw[2 * C], b0); atomicAdd(&s_dw[2 * C + 1], b1); }   // every lane holds the same b0 / b1
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(dw + i, s_dw[i]);
+  if (threadIdx.x < 2) atomicAdd(db + threadIdx.x, s_dw[2 * C + threadIdx.x]);
+}
+
 // y[r][o] = b[o] + sum_k x[r][k] w[o][k]; one CTA per row, x row staged in shared memory
 __global__ void __launch_bounds__(256)
 linear_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, int in_f,
@@ -132,6 +188,22 @@ int fnssl_ipd_head_forward(const void* x, int dtype, int ld, int nb, int nt, int
   else
     FNSSL_FAIL("ipd_head: bad dtype %d", dtype);
   FNSSL_LAUNCH_CHECK("ipd_head_kernel");
+  return 0;
+}
+
+int fnssl_ipd_head_backward(const float* x, int ld, int nb, int nt, int nf, int C, const float* w, const float* y, const float* dy,
+                            float* dx, int dld, float* dw, float* db, void* stream) {
+  FNSSL_REQUIRE(x && w && y && dy && dx && dw && db, "ipd_head_backward: null pointer");
+  FNSSL_REQUIRE(nb > 0 && nf > 0 && C > 0 && C <= kHeadBwdMaxC && ld >= C && dld >= C, "ipd_head_backward: bad shape (C <= %d)", kHeadBwdMaxC);
+  cudaStream_t st = (cudaStream_t)stream;
+  FNSSL_CUDA(cudaMemsetAsync(dw, 0, (size_t)2 * C * sizeof(float), st));
+  FNSSL_CUDA(cudaMemsetAsync(db, 0, 2 * sizeof(float), st));
+  if (nt / 12 == 0) return 0;
+  const int64_t warps = (int64_t)nb * (nt / 12) * nf;
+  int64_t blocks = (warps * 32 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ipd_head_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ld, nb, nt, nf, C, w, y, dy, dx, dld, dw, db);
+  FNSSL_LAUNCH_CHECK("ipd_head_bwd_kernel");
   return 0;
 }
 

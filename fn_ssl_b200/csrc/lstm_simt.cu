@@ -26,7 +26,8 @@ struct SimtParams {
   int64_t rows; int steps; int nf; int nt; int axis;
   int I, K, Kp;
   float* h_state; float* c_state; int state_flags;   // optional carried state, fp32 (rows, H)
-};
+  float4* save_gates; float* save_cells;             // training forward (lstm_train.cu): activated (i,f,g,o) and c_t per
+};                                                   // (dir, row, position, unit), NULL for inference
 
 template <typename T, int H>
 __global__ void __launch_bounds__(kSimtThreads)
@@ -128,6 +129,11 @@ lstm_simt_kernel(const SimtParams p) {
       smem_a[lr * Kp + I + j] = h;
       const int64_t base = s_base[lr];
       if (base >= 0) {
+        if (p.save_gates) {
+          const int64_t sidx = (((int64_t)dir * p.rows + row0 + lr) * p.steps + s) * H + j;
+          p.save_gates[sidx] = make_float4(ig, fg, gg, og);
+          p.save_cells[sidx] = c[i];
+        }
         const int64_t pos = base + (int64_t)s * sstride;
         const int ch = dir * H + j;
         if (p.out0) st_act<T>(reinterpret_cast<T*>(p.out0) + pos * p.out0_ld + p.out0_off + ch, h);
@@ -163,8 +169,10 @@ static int launch_simt(const SimtParams& p, int dirs, cudaStream_t st) {
   return 0;
 }
 
-int lstm_forward_simt(const fnssl_lstm_args* a, cudaStream_t st) {
+// gates / cells: NULL (inference) or the buffers of the training forward (fnssl_lstm_forward_train)
+int lstm_forward_simt_save(const fnssl_lstm_args* a, float* gates, float* cells, cudaStream_t st) {
   SimtParams p;
+  p.save_gates = reinterpret_cast<float4*>(gates); p.save_cells = cells;
   p.src0 = a->src0; p.c0 = a->c0; p.ld0 = a->ld0;
   p.src1 = a->src1; p.c1 = a->c1; p.ld1 = a->ld1;
   p.I = a->c0 + a->c1;
@@ -195,5 +203,7 @@ int lstm_forward_simt(const fnssl_lstm_args* a, cudaStream_t st) {
   }
 #undef FNSSL_SIMT_CASE
 }
+
+int lstm_forward_simt(const fnssl_lstm_args* a, cudaStream_t st) { return lstm_forward_simt_save(a, nullptr, nullptr, st); }
 
 }  // namespace fnssl

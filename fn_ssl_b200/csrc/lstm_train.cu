@@ -1,0 +1,358 @@
+// Training side of the LSTM layer: the forward that keeps what back-propagation needs, and the
+// backward pass (back-propagation through time) of one uni- / bi-directional layer over a grid -- what autograd does behind
+// nn.LSTM at FN-SSL/Lightning/Model.py:38,46 (training_step, FN-SSL/Lightning/main.py:95-109) and IPDnet/FixedAarryIPDnet.py:32,36.
+// fp32 CUDA cores (the exact engine, lstm_simt.cu): gradients are held to 1e-4 of torch's autograd on the oracle.
+//
+//   fnssl_lstm_forward_train : lstm_simt_kernel with two extra outputs per (direction, row, position, unit): the ACTIVATED gates
+//                              (i, f, g, o) as one float4 and the cell state c_t.
+//   fnssl_lstm_backward      : three kernels
+//     1. lstm_bwd_seq_kernel  the sequential part, one CTA per 16..64 sequences and direction, walking the steps backwards:
+//                             dh_t = dout_t + W_hh^T dG_{t+1};  dG_t (gradient w.r.t. the gate pre-activations) from the saved
+//                             gates / cells, written over the saved gates; the recurrent product reads dG_t of the CTA's rows
+//                             from shared memory and W_hh (transposed copy, coalesced float4 per unit pair) from L2.
+//     2. lstm_bwd_dx_kernel   dx = dG . W_ih for every position at once (a [positions x dirs*4H] x [dirs*4H x I] product)
+//                             scattered to the gradient grids of the two input sources.
+//     3. lstm_bwd_dw_kernel   dW_ih | dW_hh | db = [x | h_{t-1} | 1]^T . dG  reduced over all positions (split over CTAs,
+//                             fp32 atomics), in the packed layout of the forward weights.
+#include "common.cuh"
+
+namespace fnssl {
+
+int lstm_forward_simt_save(const fnssl_lstm_args* a, float* gates, float* cells, cudaStream_t st);   // lstm_simt.cu
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kRowsPerThread = 16;
+
+// sequence addressing of a (nb, nt, nf, C) grid, as in lstm_simt.cu
+struct SeqGeom {
+  int64_t rows; int steps; int nf; int nt; int axis;
+  __device__ __forceinline__ int64_t base(int64_t row) const {
+    return axis == FNSSL_ALONG_FREQ ? row * nf : (row / nf) * (int64_t)nt * nf + (row % nf);
+  }
+  __device__ __forceinline__ int64_t stride() const { return axis == FNSSL_ALONG_FREQ ? 1 : nf; }
+};
+
+// ---- 1. sequential pass ---------------------------------------------------------------------------------------------------
+struct BwdSeqParams {
+  SeqGeom g;
+  const float* dout; int dout_ld;   // grid, channels [dir*H, dir*H + H)
+  float4* gates;                    // in: activated (i,f,g,o);  out: gradient w.r.t. the gate pre-activations
+  const float* cells;               // c_t
+  const float4* whh_t;              // [dirs][H (unit j)][H (input k)] float4 over the gates: W_hh[gate*H + j][k]
+};
+
+template <int H>
+__global__ void __launch_bounds__(kThreads)
+lstm_bwd_seq_kernel(const BwdSeqParams p) {
+  constexpr int G = kThreads / H;
+  constexpr int R = kRowsPerThread * G;
+  extern __shared__ __align__(16) float4 sm_dg[];   // [R][H]
+  __shared__ int64_t s_base[R];
+  const int tid = threadIdx.x;
+  const int j = tid % H;
+  const int rg = tid / H;
+  const int dir = blockIdx.y;
+  const int64_t row0 = (int64_t)blockIdx.x * R;
+  const int steps = p.g.steps;
+  const int64_t ss = p.g.stride();
+  for (int lr = tid; lr < R; lr += kThreads) s_base[lr] = (row0 + lr < p.g.rows) ? p.g.base(row0 + lr) : -1;
+  __syncthreads();
+  const float4* wt = p.whh_t + (size_t)dir * H * H + j;
+  float dh_rec[kRowsPerThread], dc_next[kRowsPerThread];
+#pragma unroll
+  for (int i = 0; i < kRowsPerThread; ++i) { dh_rec[i] = 0.0f; dc_next[i] = 0.0f; }
+
+  for (int step = steps - 1; step >= 0; --step) {       // step = position in the order the forward processed the sequence
+    const int s = dir ? (steps - 1 - step) : step;
+    const int sprev = dir ? s + 1 : s - 1;              // where the forward came from (valid when step > 0)
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) {
+      const int lr = rg * kRowsPerThread + i;
+      const int64_t base = s_base[lr];
+      float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (base >= 0) {
+        const int64_t seq = ((int64_t)dir * p.g.rows + row0 + lr) * steps;
+        const int64_t idx = (seq + s) * H + j;
+        const float4 a = p.gates[idx];
+        const float ct = p.cells[idx];
+        const float cp = step > 0 ? p.cells[(seq + sprev) * H + j] : 0.0f;
+        const float dh = p.dout[(base + (int64_t)s * ss) * p.dout_ld + dir * H + j] + dh_rec[i];
+        const float tc = tanh_f(ct);
+        const float dc = dc_next[i] + dh * a.w * (1.0f - tc * tc);
+        d.x = dc * a.z * a.x * (1.0f - a.x);            // i
+        d.y = dc * cp * a.y * (1.0f - a.y);             // f
+        d.z = dc * a.x * (1.0f - a.z * a.z);            // g
+        d.w = dh * tc * a.w * (1.0f - a.w);             // o
+        dc_next[i] = dc * a.y;
+        p.gates[idx] = d;
+      }
+      sm_dg[lr * H + j] = d;
+    }
+    __syncthreads();
+    if (step > 0) {                                     // dh_{t-1} += W_hh^T dG_t
+      float acc[kRowsPerThread];
+#pragma unroll
+      for (int i = 0; i < kRowsPerThread; ++i) acc[i] = 0.0f;
+      const float4* drow = sm_dg + (size_t)(rg * kRowsPerThread) * H;
+#pragma unroll 2
+      for (int jj = 0; jj < H; ++jj) {
+        const float4 w = __ldg(wt + (size_t)jj * H);
+#pragma unroll
+        for (int i = 0; i < kRowsPerThread; ++i) {
+          const float4 a = drow[(size_t)i * H + jj];
+          acc[i] = fmaf(a.x, w.x, acc[i]); acc[i] = fmaf(a.y, w.y, acc[i]);
+          acc[i] = fmaf(a.z, w.z, acc[i]); acc[i] = fmaf(a.w, w.w, acc[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kRowsPerThread; ++i) dh_rec[i] = acc[i];
+    }
+    __syncthreads();
+  }
+}
+
+// ---- generic 64 x 64 x 16 fp32 tile product with functor operands ------------------------------------------------------------
+constexpr int TM = 64, TN = 64, TK = 16;
+
+// C(m, n) = sum_{k in [k_begin, k_end)} A(m, k) B(k, n) for the tile at (m0, n0); fa / fb return 0 outside their operand,
+// fc ignores positions outside the result.  *_KFAST: consecutive threads fetch consecutive k (operand contiguous along k).
+template <bool A_KFAST, bool B_KFAST, class FA, class FB, class FC>
+__device__ __forceinline__ void sgemm_tile(int64_t m0, int64_t n0, int64_t k_begin, int64_t k_end, FA fa, FB fb, FC fc) {
+  __shared__ float As[TK][TM + 1];
+  __shared__ float Bs[TK][TN + 1];
+  const int t = threadIdx.x, tx = t % 16, ty = t / 16;
+  float acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[u][v] = 0.0f;
+  for (int64_t k0 = k_begin; k0 < k_end; k0 += TK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = t + kThreads * r;
+      const int akk = A_KFAST ? e % TK : e / TM;
+      const int amm = A_KFAST ? e / TK : e % TM;
+      As[akk][amm] = (k0 + akk < k_end) ? fa(m0 + amm, k0 + akk) : 0.0f;
+      const int bkk = B_KFAST ? e % TK : e / TN;
+      const int bnn = B_KFAST ? e / TK : e % TN;
+      Bs[bkk][bnn] = (k0 + bkk < k_end) ? fb(k0 + bkk, n0 + bnn) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = As[kk][ty * 4 + u];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) b[v] = Bs[kk][tx * 4 + v];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], b[v], acc[u][v]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) fc(m0 + ty * 4 + u, n0 + tx * 4 + v, acc[u][v]);
+}
+
+// ---- 2. input gradient ------------------------------------------------------------------------------------------------------
+struct BwdDxParams {
+  SeqGeom g;
+  int H, dirs, I, c0, Kp;
+  const float* dgates;               // [dirs][rows*steps][4H]  (unit-major: column = unit*4 + gate)
+  const float* w;                    // packed forward weights: [dirs][Kp][4H] in the same column order
+  float* dsrc0; int dld0;
+  float* dsrc1; int dld1;
+};
+
+__global__ void __launch_bounds__(kThreads)
+lstm_bwd_dx_kernel(const BwdDxParams p) {
+  const int64_t M = p.g.rows * p.g.steps;
+  const int G4 = 4 * p.H;
+  auto fa = [&](int64_t m, int64_t kk) -> float {
+    if (m >= M) return 0.0f;
+    const int dir = (int)(kk / G4), cc = (int)(kk % G4);
+    return p.dgates[((int64_t)dir * M + m) * G4 + cc];
+  };
+  auto fb = [&](int64_t kk, int64_t n) -> float {
+    if (n >= p.I) return 0.0f;
+    const int dir = (int)(kk / G4), cc = (int)(kk % G4);
+    return __ldg(p.w + ((int64_t)dir * p.Kp + n) * G4 + cc);
+  };
+  auto fc = [&](int64_t m, int64_t n, float v) {
+    if (m >= M || n >= p.I) return;
+    const int64_t row = m / p.g.steps;
+    const int s = (int)(m % p.g.steps);
+    const int64_t pos = p.g.base(row) + (int64_t)s * p.g.stride();
+    if (n < p.c0) { if (p.dsrc0) p.dsrc0[pos * p.dld0 + n] = v; }
+    else if (p.dsrc1) p.dsrc1[pos * p.dld1 + (n - p.c0)] = v;
+  };
+  sgemm_tile<true, true>((int64_t)blockIdx.x * TM, (int64_t)blockIdx.y * TN, 0, (int64_t)p.dirs * G4, fa, fb, fc);
+}
+
+// ---- 3. weight gradient -----------------------------------------------------------------------------------------------------
+struct BwdDwParams {
+  SeqGeom g;
+  int H, dirs, I, c0, Kp;
+  const float* src0; int ld0;
+  const float* src1; int ld1;
+  const float* hout; int hld; int hoff;   // the forward's h grid (h_{t-1} operand of W_hh)
+  const float* dgates;
+  float* dw;                              // packed: [dirs][Kp][4H] weights ++ [dirs][4H] bias, zero on entry
+  int64_t chunk;                          // positions per CTA along the reduction
+};
+
+__global__ void __launch_bounds__(kThreads)
+lstm_bwd_dw_kernel(const BwdDwParams p) {
+  const int64_t M = p.g.rows * p.g.steps;
+  const int G4 = 4 * p.H;
+  const int K = p.I + p.H;
+  const int dir = blockIdx.z % p.dirs;
+  const int64_t split = blockIdx.z / p.dirs;
+  const int64_t mb = split * p.chunk;
+  const int64_t me = (mb + p.chunk < M) ? mb + p.chunk : M;
+  const int64_t ss = p.g.stride();
+  auto fa = [&](int64_t k, int64_t m) -> float {          // [x | h_{t-1} | 1] at position m, column k
+    if (k > K) return 0.0f;
+    if (k == K) return 1.0f;
+    const int64_t row = m / p.g.steps;
+    const int s = (int)(m % p.g.steps);
+    const int64_t pos = p.g.base(row) + (int64_t)s * ss;
+    if (k < p.c0) return p.src0[pos * p.ld0 + k];
+    if (k < p.I) return p.src1[pos * p.ld1 + (k - p.c0)];
+    const int step = dir ? (p.g.steps - 1 - s) : s;
+    if (step == 0) return 0.0f;
+    const int64_t pprev = dir ? pos + ss : pos - ss;
+    return p.hout[pprev * p.hld + p.hoff + dir * p.H + (k - p.I)];
+  };
+  auto fb = [&](int64_t m, int64_t cc) -> float { return p.dgates[((int64_t)dir * M + m) * G4 + cc]; };
+  float* db = p.dw + (size_t)p.dirs * p.Kp * G4;
+  auto fc = [&](int64_t k, int64_t cc, float v) {
+    if (k < K) atomicAdd(p.dw + ((int64_t)dir * p.Kp + k) * G4 + cc, v);
+    else if (k == K) atomicAdd(db + (int64_t)dir * G4 + cc, v);
+  };
+  if (mb < me) sgemm_tile<false, false>((int64_t)blockIdx.x * TM, (int64_t)blockIdx.y * TN, mb, me, fa, fb, fc);
+}
+
+template <int H>
+int launch_bwd_seq(const BwdSeqParams& p, int dirs, cudaStream_t st) {
+  constexpr int R = kRowsPerThread * (kThreads / H);
+  const size_t smem = (size_t)R * H * sizeof(float4);
+  FNSSL_CUDA(cudaFuncSetAttribute(lstm_bwd_seq_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div64(p.g.rows, R), dirs);
+  lstm_bwd_seq_kernel<H><<<grid, kThreads, smem, st>>>(p);
+  FNSSL_LAUNCH_CHECK("lstm_bwd_seq_kernel");
+  return 0;
+}
+
+int check_train_args(const fnssl_lstm_args* a, const char* who) {
+  FNSSL_REQUIRE(a != nullptr, "%s: null args", who);
+  FNSSL_REQUIRE(a->engine == FNSSL_ENGINE_SIMT && a->dtype == FNSSL_F32, "%s: the training path runs the fp32 engine on fp32 grids", who);
+  FNSSL_REQUIRE(a->axis == FNSSL_ALONG_FREQ || a->axis == FNSSL_ALONG_TIME, "%s: bad axis %d", who, a->axis);
+  FNSSL_REQUIRE(a->nb > 0 && a->nt > 0 && a->nf > 0, "%s: bad grid %d x %d x %d", who, a->nb, a->nt, a->nf);
+  FNSSL_REQUIRE(a->num_dirs == 1 || a->num_dirs == 2, "%s: num_dirs must be 1 or 2 (got %d)", who, a->num_dirs);
+  FNSSL_REQUIRE(a->hidden == 32 || a->hidden == 64 || a->hidden == 128 || a->hidden == 256, "%s: hidden size %d not supported (32, 64, 128, 256)",
+                who, a->hidden);
+  FNSSL_REQUIRE(a->src0 && a->c0 > 0 && a->ld0 >= a->c0, "%s: bad src0 (c0=%d ld0=%d)", who, a->c0, a->ld0);
+  FNSSL_REQUIRE(a->c1 >= 0 && (a->c1 == 0 || (a->src1 && a->ld1 >= a->c1)), "%s: bad src1 (c1=%d ld1=%d)", who, a->c1, a->ld1);
+  FNSSL_REQUIRE(a->weights && a->out0, "%s: null weights / h grid", who);
+  FNSSL_REQUIRE(a->out0_off >= 0 && a->out0_ld >= a->out0_off + a->num_dirs * a->hidden, "%s: out0 window exceeds its stride", who);
+  FNSSL_REQUIRE(a->state_flags == 0, "%s: a carried recurrent state is an inference (streaming) feature", who);
+  return 0;
+}
+
+int64_t positions_of(const fnssl_lstm_args* a) { return (int64_t)a->nb * a->nt * a->nf; }   // rows * steps on either axis
+
+}  // namespace
+}  // namespace fnssl
+
+using namespace fnssl;
+
+extern "C" {
+
+int64_t fnssl_lstm_train_saved_bytes(int nb, int nt, int nf, int hidden, int num_dirs) {
+  if (nb <= 0 || nt <= 0 || nf <= 0 || hidden <= 0 || num_dirs <= 0) return 0;
+  return (int64_t)num_dirs * nb * nt * nf * hidden * 5 * (int64_t)sizeof(float);   // float4 gates + float cell per unit
+}
+
+int fnssl_lstm_forward_train(const fnssl_lstm_args* a, void* saved, int64_t saved_bytes, void* stream) {
+  if (int rc = check_train_args(a, "lstm_forward_train")) return rc;
+  const int64_t units = (int64_t)a->num_dirs * positions_of(a) * a->hidden;
+  FNSSL_REQUIRE(saved && saved_bytes == units * 5 * (int64_t)sizeof(float) && (reinterpret_cast<uintptr_t>(saved) & 15) == 0,
+                "lstm_forward_train: `saved` must be a 16-byte aligned buffer of fnssl_lstm_train_saved_bytes() = %lld bytes (got %lld)",
+                (long long)(units * 5 * (int64_t)sizeof(float)), (long long)saved_bytes);
+  float* gates = reinterpret_cast<float*>(saved);
+  return lstm_forward_simt_save(a, gates, gates + units * 4, (cudaStream_t)stream);
+}
+
+int fnssl_lstm_backward(const fnssl_lstm_args* a, void* saved, int64_t saved_bytes, const float* whh_t, const float* dout, int dout_ld,
+                        float* dsrc0, int dsrc0_ld, float* dsrc1, int dsrc1_ld, float* dweights, void* stream) {
+  if (int rc = check_train_args(a, "lstm_backward")) return rc;
+  const int H = a->hidden, dirs = a->num_dirs;
+  const int64_t units = (int64_t)dirs * positions_of(a) * H;
+  FNSSL_REQUIRE(saved && saved_bytes == units * 5 * (int64_t)sizeof(float) && (reinterpret_cast<uintptr_t>(saved) & 15) == 0,
+                "lstm_backward: `saved` is not the buffer fnssl_lstm_forward_train filled for this layer");
+  FNSSL_REQUIRE(whh_t && (reinterpret_cast<uintptr_t>(whh_t) & 15) == 0, "lstm_backward: null / unaligned whh_t");
+  FNSSL_REQUIRE(dout && dout_ld >= dirs * H, "lstm_backward: bad dout (ld %d)", dout_ld);
+  FNSSL_REQUIRE(!dsrc0 || dsrc0_ld >= a->c0, "lstm_backward: bad dsrc0 stride %d", dsrc0_ld);
+  FNSSL_REQUIRE(!dsrc1 || (a->c1 > 0 && dsrc1_ld >= a->c1), "lstm_backward: bad dsrc1 (c1 %d, stride %d)", a->c1, dsrc1_ld);
+  FNSSL_REQUIRE(dweights != nullptr, "lstm_backward: null dweights");
+  const int I = a->c0 + a->c1, K = I + H, Kp = (K + 3) & ~3;
+  const int64_t need = ((int64_t)dirs * Kp * H + (int64_t)dirs * H) * 16;
+  FNSSL_REQUIRE(a->weights_bytes == need, "lstm_backward: packed weight buffer is %lld bytes, expected %lld", (long long)a->weights_bytes,
+                (long long)need);
+  cudaStream_t st = (cudaStream_t)stream;
+  SeqGeom g;
+  g.nf = a->nf; g.nt = a->nt; g.axis = a->axis;
+  if (a->axis == FNSSL_ALONG_FREQ) { g.rows = (int64_t)a->nb * a->nt; g.steps = a->nf; }
+  else { g.rows = (int64_t)a->nb * a->nf; g.steps = a->nt; }
+  float* gates = reinterpret_cast<float*>(saved);
+  const float* cells = gates + units * 4;
+
+  BwdSeqParams sp;
+  sp.g = g; sp.dout = dout; sp.dout_ld = dout_ld; sp.gates = reinterpret_cast<float4*>(gates); sp.cells = cells;
+  sp.whh_t = reinterpret_cast<const float4*>(whh_t);
+  int rc = 0;
+  switch (H) {
+    case 32: rc = launch_bwd_seq<32>(sp, dirs, st); break;
+    case 64: rc = launch_bwd_seq<64>(sp, dirs, st); break;
+    case 128: rc = launch_bwd_seq<128>(sp, dirs, st); break;
+    default: rc = launch_bwd_seq<256>(sp, dirs, st); break;
+  }
+  if (rc) return rc;
+
+  const int64_t M = g.rows * g.steps;
+  if (dsrc0 || dsrc1) {
+    BwdDxParams xp;
+    xp.g = g; xp.H = H; xp.dirs = dirs; xp.I = I; xp.c0 = a->c0; xp.Kp = Kp;
+    xp.dgates = gates; xp.w = reinterpret_cast<const float*>(a->weights);
+    xp.dsrc0 = dsrc0; xp.dld0 = dsrc0_ld; xp.dsrc1 = dsrc1; xp.dld1 = dsrc1_ld;
+    dim3 grid((unsigned)ceil_div64(M, TM), (unsigned)((I + TN - 1) / TN));
+    lstm_bwd_dx_kernel<<<grid, kThreads, 0, st>>>(xp);
+    FNSSL_LAUNCH_CHECK("lstm_bwd_dx_kernel");
+  }
+
+  FNSSL_CUDA(cudaMemsetAsync(dweights, 0, (size_t)need, st));
+  BwdDwParams wp;
+  wp.g = g; wp.H = H; wp.dirs = dirs; wp.I = I; wp.c0 = a->c0; wp.Kp = Kp;
+  wp.src0 = reinterpret_cast<const float*>(a->src0); wp.ld0 = a->ld0;
+  wp.src1 = reinterpret_cast<const float*>(a->src1); wp.ld1 = a->ld1;
+  wp.hout = reinterpret_cast<const float*>(a->out0); wp.hld = a->out0_ld; wp.hoff = a->out0_off;
+  wp.dgates = gates; wp.dw = dweights;
+  int64_t chunk = ceil_div64(M, 64);                       // <= 64 splits of the reduction
+  if (chunk < 2048) chunk = 2048;
+  chunk = ceil_div64(chunk, TK) * TK;
+  wp.chunk = chunk;
+  const int64_t splits = ceil_div64(M, chunk);
+  dim3 wgrid((unsigned)((K + 1 + TM - 1) / TM), (unsigned)(4 * H / TN), (unsigned)(dirs * splits));
+  lstm_bwd_dw_kernel<<<wgrid, kThreads, 0, st>>>(wp);
+  FNSSL_LAUNCH_CHECK("lstm_bwd_dw_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -80,6 +80,30 @@ def pack_lstm_simt(dirs: Sequence[Tuple[Tensor, Tensor, Tensor, Tensor]]) -> Ten
     return torch.cat((w4.reshape(-1), b4.reshape(-1))).contiguous()
 
 
+def pack_lstm_whh_t(dirs: Sequence[Tuple[Tensor, Tensor, Tensor, Tensor]]) -> Tensor:
+    """weight_hh transposed for the backward pass's recurrent product (fnssl_lstm_backward):
+    whh_t [dirs][H (unit j)][H (input k)][4 (gate)] = weight_hh[gate*H + j][k], fp32."""
+    H = dirs[0][1].shape[1]
+    return torch.stack([wh.detach().float().reshape(4, H, H).permute(1, 2, 0) for (_, wh, _, _) in dirs]).contiguous()
+
+
+def unpack_lstm_simt_grad(dw: Tensor, num_dirs: int, input_size: int, hidden: int) -> List[Tuple[Tensor, Tensor, Tensor, Tensor]]:
+    """Inverse of pack_lstm_simt for a gradient buffer: per direction (d weight_ih (4H, I), d weight_hh (4H, H), d bias_ih (4H),
+    d bias_hh (4H)); the two bias gradients are the same tensor values (the forward adds the biases)."""
+    I, H = input_size, hidden
+    K = I + H
+    Kp = (K + 3) // 4 * 4
+    w4 = dw[:num_dirs * Kp * H * 4].reshape(num_dirs, Kp, H, 4)
+    b4 = dw[num_dirs * Kp * H * 4:].reshape(num_dirs, H, 4)
+    out = []
+    for d in range(num_dirs):
+        gwi = w4[d, :I].permute(2, 1, 0).reshape(4 * H, I).contiguous()        # [k][j][gate] -> [gate*H + j][k]
+        gwh = w4[d, I:K].permute(2, 1, 0).reshape(4 * H, H).contiguous()
+        gb = b4[d].t().reshape(4 * H).contiguous()
+        out.append((gwi, gwh, gb, gb.clone()))
+    return out
+
+
 def pack_lstm_tc(dirs, splits) -> Tensor:
     """tcgen05 engine, fp16.  splits = ((c_real, c_padded), ...) per input source (c_padded % 16 == 0).
 

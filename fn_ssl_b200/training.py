@@ -5,10 +5,15 @@
     ipd_mse_loss(...)         cal_loss, FN-SSL/Lightning/main.py:191-198
     ipd_pit_mse_loss(...)     frame-level PIT loss, IPDnet/runIPDnetOn.py:188-206
 
-Scope: these are the FORWARD computations of the training step that sit next to the hot path (targets are built per batch on
-the host in the reference: float64 numpy loops + a host->device copy).  The backward pass of the fused LSTM kernels is not
-implemented -- `FN_SSL` / `IPDnet` still raise in train mode -- so the losses are exposed as plain functions (with an analytic
-gradient w.r.t. the prediction for callers that train a head on frozen features), not as a Lightning training_step.
+    lstm_layer(...)           one LSTM layer over a grid WITH its backward pass (torch.autograd.Function over
+                              fnssl_lstm_forward_train / fnssl_lstm_backward): what autograd does behind nn.LSTM in the
+                              reference's training_step (FN-SSL/Lightning/main.py:95-109 through Model.py:38,46)
+    ipd_head_train(...)       AvgPool(12) -> Linear(256,2) -> tanh -> [cos | sin] with its backward (Model.py:79-87)
+
+Scope: targets are built per batch on the host in the reference (float64 numpy loops + a host->device copy); here they and the
+losses are CUDA kernels.  The backward pass exists for the fp32 engine (lstm_train.cu, head.cu): `FN_SSL` / `FNblock` in train
+mode run it (fn_ssl_b200/Model.py: residual adds and dropout are torch elementwise ops between the layer kernels); the
+tensor-core kernels are inference kernels and IPDnet's causal conv block has no backward, so `IPDnet` still raises in train mode.
 """
 from __future__ import annotations
 
@@ -17,7 +22,10 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 import torch
 
+import ctypes as C
+
 from . import _lib, ops
+from .packing import pack_lstm_simt, pack_lstm_whh_t, unpack_lstm_simt_grad
 
 Tensor = torch.Tensor
 
@@ -141,3 +149,119 @@ def ipd_pit_mse_loss(pred_batch: Tensor, ipd_gt_batch: Tensor) -> Tuple[Tensor, 
     _lib.check(lib.fnssl_ipd_pit_mse_loss(p.data_ptr(), g.data_ptr(), rows, p.shape[1], ns, ws.data_ptr(), loss.data_ptr(),
                                           perm.data_ptr(), ops._stream()))
     return loss, perm
+
+
+# ---------------------------------------------------------------------------------------------
+# LSTM layer and DP-IPD head with their backward passes (fp32 engine)
+# ---------------------------------------------------------------------------------------------
+
+def _lstm_args(axis, src0, c0, src1, c1, w, hidden, num_dirs, out0):
+    nb, nt, nf, ld0 = src0.shape
+    a = _lib.LstmArgs()
+    a.engine, a.axis = ops.ENGINE_SIMT, axis
+    a.nb, a.nt, a.nf = nb, nt, nf
+    a.hidden, a.num_dirs, a.dtype = hidden, num_dirs, ops.F32
+    a.src0, a.c0, a.ld0 = src0.data_ptr(), c0, ld0
+    a.src1, a.c1, a.ld1 = (src1.data_ptr(), c1, src1.shape[-1]) if src1 is not None else (None, 0, 0)
+    a.weights, a.weights_bytes = w.data_ptr(), w.numel() * w.element_size()
+    a.out0, a.out0_ld, a.out0_off = out0.data_ptr(), out0.shape[-1], 0
+    return a
+
+
+class _LstmLayer(torch.autograd.Function):
+    """h = LSTM(concat(src0[..., :c0], src1[..., :c1])) over a grid; params = nn.LSTM's (weight_ih, weight_hh, bias_ih, bias_hh)
+    per direction.  Backward = fnssl_lstm_backward (BPTT kernel + two reduction products), once per forward."""
+
+    @staticmethod
+    def forward(ctx, src0, src1, axis, c0, c1, hidden, num_dirs, *params):
+        lib = _lib.load()
+        dirs = [tuple(p.detach().float() for p in params[4 * d:4 * d + 4]) for d in range(num_dirs)]
+        w = pack_lstm_simt(dirs)
+        nb, nt, nf, _ = src0.shape
+        out = torch.empty((nb, nt, nf, hidden * num_dirs), dtype=torch.float32, device=src0.device)
+        nbytes = int(lib.fnssl_lstm_train_saved_bytes(nb, nt, nf, hidden, num_dirs))
+        saved = torch.empty(nbytes // 4, dtype=torch.float32, device=src0.device)
+        a = _lstm_args(axis, src0, c0, src1, c1, w, hidden, num_dirs, out)
+        ops._count(1)
+        _lib.check(lib.fnssl_lstm_forward_train(C.byref(a), saved.data_ptr(), nbytes, ops._stream()))
+        ctx.save_for_backward(src0, src1, w, out, saved, pack_lstm_whh_t(dirs))
+        ctx.cfg = (axis, c0, c1, hidden, num_dirs)
+        ctx.consumed = False
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        if ctx.consumed:
+            raise RuntimeError("lstm_layer: the saved activations are consumed by the first backward pass (no retain_graph)")
+        ctx.consumed = True
+        src0, src1, w, out, saved, whh_t = ctx.saved_tensors
+        axis, c0, c1, hidden, num_dirs = ctx.cfg
+        lib = _lib.load()
+        with torch.cuda.device(src0.device):
+            dout = dout.contiguous().float()
+            d0 = d1 = None
+            if ctx.needs_input_grad[0]:
+                d0 = torch.empty_like(src0) if src0.shape[-1] == c0 else torch.zeros_like(src0)
+            if src1 is not None and ctx.needs_input_grad[1]:
+                d1 = torch.empty_like(src1) if src1.shape[-1] == c1 else torch.zeros_like(src1)
+            dw = torch.empty_like(w)
+            a = _lstm_args(axis, src0, c0, src1, c1, w, hidden, num_dirs, out)
+            ops._count(3)
+            _lib.check(lib.fnssl_lstm_backward(C.byref(a), saved.data_ptr(), saved.numel() * 4, whh_t.data_ptr(), dout.data_ptr(),
+                                               dout.shape[-1], ops._ptr(d0), d0.shape[-1] if d0 is not None else 0, ops._ptr(d1),
+                                               d1.shape[-1] if d1 is not None else 0, dw.data_ptr(), ops._stream()))
+        grads = []
+        for d, g4 in enumerate(unpack_lstm_simt_grad(dw, num_dirs, c0 + c1, hidden)):
+            grads += [g if ctx.needs_input_grad[7 + 4 * d + i] else None for i, g in enumerate(g4)]
+        return (d0, d1, None, None, None, None, None) + tuple(grads)
+
+
+@ops.on_tensor_device
+def lstm_layer(src0: Tensor, c0: int, src1: Optional[Tensor], c1: int, params, axis: int) -> Tensor:
+    """One differentiable LSTM layer over fp32 grids: src0 (nb, nt, nf, ld0 >= c0) [+ src1 (.., ld1 >= c1) concatenated],
+    params = fn_ssl_b200.packing.LSTMParams (nn.LSTM's parameter set) -> h (nb, nt, nf, dirs*hidden).
+    axis = ops.ALONG_FREQ (full-band: sequences over f) | ops.ALONG_TIME (narrow-band: sequences over t)."""
+    ops._need_cuda(src0, src1)
+    if src0.dtype != torch.float32 or (src1 is not None and src1.dtype != torch.float32):
+        raise RuntimeError("lstm_layer: the training path runs on float32 grids")
+    if params.hidden_size not in (32, 64, 128, 256):
+        raise RuntimeError(f"lstm_layer: hidden size {params.hidden_size} not supported (32, 64, 128, 256)")
+    if c0 + (c1 if src1 is not None else 0) != params.input_size:
+        raise RuntimeError(f"lstm_layer: {c0} + {c1} input channels, the layer takes {params.input_size}")
+    flat = [t for d in params.directions() for t in d]
+    return _LstmLayer.apply(src0.contiguous(), src1.contiguous() if src1 is not None else None, axis, c0, c1 if src1 is not None else 0,
+                            params.hidden_size, params.num_dirs, *flat)
+
+
+class _IpdHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        y = ops.ipd_head(x, x.shape[-1], weight, bias)
+        ctx.save_for_backward(x, weight.detach().float().contiguous(), y)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        nb, nt, nf, Cc = x.shape
+        with torch.cuda.device(x.device):
+            dy = dy.contiguous().float()
+            dx = torch.empty_like(x) if nt % 12 == 0 else torch.zeros_like(x)
+            dw = torch.empty_like(w)
+            db = torch.empty(2, dtype=torch.float32, device=x.device)
+            ops._count(1)
+            _lib.check(_lib.load().fnssl_ipd_head_backward(x.data_ptr(), Cc, nb, nt, nf, Cc, w.data_ptr(), y.data_ptr(), dy.data_ptr(),
+                                                           dx.data_ptr(), Cc, dw.data_ptr(), db.data_ptr(), ops._stream()))
+        return dx, dw, db
+
+
+@ops.on_tensor_device
+def ipd_head_train(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
+    """Differentiable FN-SSL head on an fp32 grid x (nb, nt, nf, C): AvgPool over 12 frames -> Linear(C, 2) -> tanh ->
+    (nb, nt//12, 2*nf) = [channel 0 over f | channel 1 over f] (Model.py:79-87)."""
+    ops._need_cuda(x, weight, bias)
+    if x.dtype != torch.float32 or x.shape[-1] != weight.shape[1] or x.shape[-1] > 512:
+        raise RuntimeError("ipd_head_train: x must be a float32 grid with C = weight.shape[1] <= 512 channels")
+    return _IpdHead.apply(x.contiguous(), weight, bias)

@@ -26,9 +26,10 @@
 extern "C" {
 #endif
 
-#define FNSSL_ABI_VERSION 4 /* 2: carried LSTM state; 3: IPDnet2 entry points (fnssl_reflect_pad, fnssl_sn_*); 4: one tcgen05 LSTM kernel
+#define FNSSL_ABI_VERSION 5 /* 2: carried LSTM state; 3: IPDnet2 entry points (fnssl_reflect_pad, fnssl_sn_*); 4: one tcgen05 LSTM kernel
                              (fnssl_lstm_tc_trace of the retired generations removed), training-side targets / losses,
-                             fused fnssl_stft_features_forward */
+                             fused fnssl_stft_features_forward; 5: training forward / backward of the LSTM layer and the
+                             DP-IPD head (fnssl_lstm_forward_train, fnssl_lstm_backward, fnssl_ipd_head_backward) */
 
 /* element types of grid tensors */
 #define FNSSL_F32 0
@@ -174,6 +175,28 @@ int fnssl_lstm_tc_error_site(void);
  * FNSSL_TC_TRACE is set; 0 if none */
 int fnssl_lstm_tc4_trace(long long* out256);
 
+/* ---- LSTM, training side ---------------------------------------------------------------------- */
+
+/* What autograd does behind nn.LSTM in the reference's training_step (FN-SSL/Lightning/main.py:95-109 through Model.py:38,46;
+ * IPDnet/runIPDnetOn.py:110-125 through FixedAarryIPDnet.py:32,36), as explicit entry points on the fp32 engine
+ * (args->engine == FNSSL_ENGINE_SIMT, args->dtype == FNSSL_F32, no carried state; addend / out1 are honoured by the forward
+ * but have no gradient path here -- the host adds the residuals, fn_ssl_b200/training.py).
+ *
+ * fnssl_lstm_forward_train: fnssl_lstm_forward + `saved`: per (direction, row, position, unit) the activated gates (i,f,g,o)
+ *   and the cell state c_t -- fnssl_lstm_train_saved_bytes() bytes, 16-byte aligned.
+ * fnssl_lstm_backward: args = the forward's arguments (src0 / src1 / weights as then, out0 = the h grid it produced);
+ *   saved   : the forward's buffer; CONSUMED (the gates are overwritten with the gate pre-activation gradients)
+ *   whh_t   : weight_hh transposed for the recurrent product: [dirs][H (unit j)][H (input k)][4 (gate)] f32
+ *             = weight_hh_l0[gate*H + j][k]   (fn_ssl_b200.packing.pack_lstm_whh_t)
+ *   dout    : gradient w.r.t. h, grid (nb, nt, nf, dout_ld) f32, dirs*H channels
+ *   dsrc0/1 : OUT gradient w.r.t. the two input sources, grids with c0 / c1 channels (either may be NULL: not needed)
+ *   dweights: OUT gradient in the layout of the packed forward weights (args->weights_bytes bytes: [dirs][Kp][H][4] for
+ *             weight_ih | weight_hh rows, then [dirs][H][4] for the bias = d bias_ih = d bias_hh); zeroed by the call. */
+int64_t fnssl_lstm_train_saved_bytes(int nb, int nt, int nf, int hidden, int num_dirs);
+int fnssl_lstm_forward_train(const fnssl_lstm_args* args, void* saved, int64_t saved_bytes, void* stream);
+int fnssl_lstm_backward(const fnssl_lstm_args* args, void* saved, int64_t saved_bytes, const float* whh_t, const float* dout,
+                        int dout_ld, float* dsrc0, int dsrc0_ld, float* dsrc1, int dsrc1_ld, float* dweights, void* stream);
+
 /* ---- heads ---------------------------------------------------------------------------------- */
 
 /* FN_SSL head (Model.py:79-87): AvgPool over 12 frames -> Linear(C,2) -> tanh -> [ch0 over f | ch1 over f].
@@ -181,6 +204,11 @@ int fnssl_lstm_tc4_trace(long long* out256);
  *   out : (nb, nt/12, 2*nf) f32 */
 int fnssl_ipd_head_forward(const void* x, int dtype, int ld, int nb, int nt, int nf, int C, const float* w,
                            const float* b, float* out, void* stream);
+/* Backward of fnssl_ipd_head_forward on an fp32 grid (training side): y = the forward's output, dy its gradient, both
+ * (nb, nt/12, 2*nf);  dx : grid (nb, nt, nf, dld) -- frames [12*(nt/12), nt) are not written;  dw : (2, C), db : (2), zeroed
+ * by the call.  C <= 512. */
+int fnssl_ipd_head_backward(const float* x, int ld, int nb, int nt, int nf, int C, const float* w, const float* y, const float* dy,
+                            float* dx, int dld, float* dw, float* db, void* stream);
 
 /* y = x @ w^T + b for small row counts; the DOA classifier Linear(512,180) (Model.py:71,88-89).
  *   x : (rows, in) f32, w : (out, in) f32, b : (out) f32, y : (rows, out) f32 */

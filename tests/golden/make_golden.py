@@ -283,9 +283,73 @@ def gen_train():
     print("wrote train_golden.npz:", {k: np.asarray(v).shape for k, v in out.items()})
 
 
+def gen_grad():
+    """Training step of the reference network (row f4): the UNMODIFIED reference FN_SSL / FNblock in TRAIN mode -- with the dropout
+    probability of its nn.Dropout modules set to 0 so that the step is deterministic -- forward, MSE loss against a seeded target
+    (cal_loss's F.mse_loss, main.py:191-198) and loss.backward().  Stored: output, loss, per-parameter gradient norms / sums, and a
+    few whole gradient tensors.  The oracle's autograd (same functional forward, seeded weights) is asserted against it here."""
+    _shim()
+    sys.path.insert(0, os.path.join(REF, "FN-SSL", "Lightning"))
+    import Model as ref_model          # FN-SSL/Lightning/Model.py
+    from oracle import fnssl_oracle as orc
+
+    out = {}
+    x = _randn((1, 4, 256, 24), 21)
+    tgt = _randn((1, 2, 512), 22).tanh()
+    for tag, kw in (("off", dict(is_online=False)), ("on", dict(is_online=True))):
+        torch.manual_seed(3)
+        net = ref_model.FN_SSL(**kw).train()
+        for m in net.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        y = net(x)
+        loss = torch.nn.functional.mse_loss(y, tgt)
+        loss.backward()
+        out[f"{tag}_out"], out[f"{tag}_loss"] = y.detach().numpy(), np.float32(loss.item())
+        names = [n for n, _ in net.named_parameters()]
+        out[f"{tag}_names"] = np.array(names)
+        out[f"{tag}_grad_norm"] = np.array([float(p.grad.double().norm()) for _, p in net.named_parameters()])
+        out[f"{tag}_grad_sum"] = np.array([float(p.grad.double().sum()) for _, p in net.named_parameters()])
+        for n in ("emb2ipd.weight", "emb2ipd.bias", "block_1.fullLstm.weight_ih_l0", "block_1.fullLstm.bias_hh_l0_reverse",
+                  "block_1.narrLstm.bias_ih_l0", "block_2.narrLstm.bias_hh_l0", "block_3.fullLstm.bias_ih_l0"):
+            out[f"{tag}_grad_{n}"] = dict(net.named_parameters())[n].grad.numpy()
+        out[f"{tag}_grad_block_2.fullLstm.weight_hh_l0[:, :4]"] = dict(net.named_parameters())["block_2.fullLstm.weight_hh_l0"].grad[:, :4].numpy()
+        # the oracle's autograd reproduces it (same seeded weights, functional forward)
+        sd = {k: v.clone().requires_grad_(True) for k, v in orc.seeded_fnssl_state_dict(3, **kw).items()}
+        yo = orc.fnssl_forward(x, sd, fast=True)
+        torch.nn.functional.mse_loss(yo, tgt).backward()
+        for n, p_ in net.named_parameters():
+            err = float((sd[n].grad - p_.grad).abs().max()) / max(float(p_.grad.abs().max()), 1e-30)
+            assert err <= 1e-4, (tag, n, err)
+    # one FNblock (hidden 64) through its module API, first and non-first, gradient w.r.t. the input too
+    torch.manual_seed(5)
+    blk = ref_model.FNblock(input_size=4, hidden_size=64, is_online=True, is_first=True).train()
+    blk2 = ref_model.FNblock(input_size=64, hidden_size=64, is_online=False, is_first=False).train()
+    for m in list(blk.modules()) + list(blk2.modules()):
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    xb = _randn((1, 10, 16, 4), 23).requires_grad_(True)
+    y, fb, nbs = blk(xb)
+    y2, fb2, nbs2 = blk2(y, fb_skip=fb, nb_skip=nbs)
+    wy, wf = _randn(tuple(y2.shape), 24), _randn(tuple(fb2.shape), 25)
+    ((y2 * wy).sum() + (fb2 * wf).sum()).backward()
+    out["blk_y2"], out["blk_fb2"], out["blk_dx"] = y2.detach().numpy(), fb2.detach().numpy(), xb.grad.numpy()
+    for n, p_ in blk.named_parameters():
+        out[f"blk1_grad_{n}"] = p_.grad.numpy()
+    for n, p_ in blk2.named_parameters():
+        out[f"blk2_grad_{n}"] = p_.grad.numpy()
+    out["blk1_sd_names"] = np.array([n for n, _ in blk.named_parameters()])
+    for n, p_ in blk.state_dict().items():
+        out[f"blk1_w_{n}"] = p_.numpy()
+    for n, p_ in blk2.state_dict().items():
+        out[f"blk2_w_{n}"] = p_.numpy()
+    np.savez_compressed(os.path.join(HERE, "grad_golden.npz"), **out)
+    print("wrote grad_golden.npz:", {k: np.asarray(v).shape for k, v in out.items() if "grad_norm" in k or k.endswith("_loss")})
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
-        {"fnssl": gen_fnssl, "ipdnet": gen_ipdnet, "train": gen_train}[sys.argv[1]]()
+        {"fnssl": gen_fnssl, "ipdnet": gen_ipdnet, "train": gen_train, "grad": gen_grad}[sys.argv[1]]()
     else:
-        for which in ("fnssl", "ipdnet", "train"):
+        for which in ("fnssl", "ipdnet", "train", "grad"):
             subprocess.check_call([sys.executable, os.path.abspath(__file__), which])

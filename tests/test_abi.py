@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in include/fnssl_b200.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(syms)
-    assert lib.fnssl_abi_version() == 4
+    assert lib.fnssl_abi_version() == 5
 
 
 def test_host_only_entry_points():
@@ -91,8 +91,10 @@ def test_aliases_and_errors():
     import fn_ssl_b200 as F
     assert F.FullNarrowBlock is F.FNblock and F.FixedArrayIPDnet is F.IPDnet and F.CausalConv1dBlock is F.CausCnnBlock
     net = F.FN_SSL()
-    with pytest.raises(RuntimeError, match="eval"):
+    with pytest.raises(RuntimeError, match="CUDA"):          # train mode = the differentiable fp32 CUDA path: no CPU fallback either
         net(torch.zeros(1, 4, 8, 24))
+    with pytest.raises(RuntimeError, match="eval"):          # IPDnet's causal conv block has no backward: inference only
+        F.IPDnet()(torch.zeros(1, 4, 256, 24))
     with pytest.raises(RuntimeError, match="CUDA"):
         net.eval()(torch.zeros(1, 4, 8, 24))                # CPU tensor: no fallback, loud failure
     with pytest.raises(RuntimeError, match="CUDA"):
@@ -201,4 +203,4 @@ def test_library_links_from_plain_c(tmp_path):
     res = subprocess.run([str(exe)], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     first, second = res.stdout.splitlines()[:2]
-    assert first.split() == ["4", "249", "18"] and "512" in second
+    assert first.split() == ["5", "249", "18"] and "512" in second

@@ -1,0 +1,252 @@
+"""Training step of the hot path: backward pass of the LSTM layers and the DP-IPD head.
+
+Goldens (tests/golden/grad_golden.npz, made by tests/golden/make_golden.py grad): the UNMODIFIED reference FN_SSL / FNblock in
+train mode (dropout probability 0 so the step is deterministic), MSE loss, loss.backward().
+CPU: the oracle's autograd against those goldens.  GPU: the CUDA backward kernels (through the C ABI, torch.autograd.Function
+wrappers of fn_ssl_b200.training) against torch's autograd of nn.LSTM on the CPU and against the goldens.
+Tolerance: max |g - g_ref| <= 1e-4 max |g_ref| per gradient tensor (fp32 kernels; weight gradients are reduced with fp32 atomics)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fnssl_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(ROOT, "tests", "golden", "grad_golden.npz"))
+
+
+def _rel(a, b):
+    a = torch.as_tensor(np.asarray(a.detach().cpu() if torch.is_tensor(a) else a)).double()
+    b = torch.as_tensor(np.asarray(b.detach().cpu() if torch.is_tensor(b) else b)).double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+
+
+def _randn(shape, seed):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed), dtype=torch.float32)
+
+
+def _check_against_golden(g, tag, named_grads, out, loss):
+    assert _rel(out, g[f"{tag}_out"]) <= 2e-5
+    assert abs(float(loss.detach()) - float(g[f"{tag}_loss"])) <= 2e-5 * float(g[f"{tag}_loss"])
+    names = [str(n) for n in g[f"{tag}_names"]]
+    assert list(named_grads.keys()) == names
+    for i, n in enumerate(names):
+        gr = named_grads[n].detach().cpu().double()
+        assert abs(float(gr.norm()) - g[f"{tag}_grad_norm"][i]) <= TOL * g[f"{tag}_grad_norm"][i], n
+        assert abs(float(gr.sum()) - g[f"{tag}_grad_sum"][i]) <= 5 * TOL * g[f"{tag}_grad_norm"][i], n
+    for k in g.files:
+        if k.startswith(f"{tag}_grad_") and k not in (f"{tag}_grad_norm", f"{tag}_grad_sum"):
+            n = k[len(f"{tag}_grad_"):]
+            if n.endswith("[:, :4]"):
+                assert _rel(named_grads[n[:-7]][:, :4], g[k]) <= TOL, k
+            else:
+                assert _rel(named_grads[n], g[k]) <= TOL, k
+
+
+# ---- CPU: the oracle's autograd is pinned to the reference's ------------------------------------------------------------------
+
+@pytest.mark.parametrize("tag,kw", [("off", dict(is_online=False)), ("on", dict(is_online=True))])
+def test_oracle_autograd_matches_reference_gradients(g, tag, kw):
+    x, tgt = _randn((1, 4, 256, 24), 21), _randn((1, 2, 512), 22).tanh()
+    sd = {k: v.clone().requires_grad_(True) for k, v in orc.seeded_fnssl_state_dict(3, **kw).items()}
+    y = orc.fnssl_forward(x, sd, fast=True)
+    loss = torch.nn.functional.mse_loss(y, tgt)
+    loss.backward()
+    _check_against_golden(g, tag, {k: v.grad for k, v in sd.items()}, y, loss)
+
+
+def test_backward_abi_symbols_and_validation():
+    import ctypes
+    from fn_ssl_b200 import _lib
+    lib = _lib.load()
+    assert lib.fnssl_lstm_train_saved_bytes(2, 3, 5, 32, 2) == 2 * 2 * 3 * 5 * 32 * 5 * 4
+    a = _lib.LstmArgs()
+    a.engine, a.dtype = _lib.ENGINE_TCGEN05, _lib.F16                 # the training path is the fp32 engine: rejected before any CUDA call
+    assert lib.fnssl_lstm_forward_train(ctypes.byref(a), None, 0, None) != 0 and b"fp32" in lib.fnssl_last_error()
+    assert lib.fnssl_lstm_backward(ctypes.byref(a), None, 0, None, None, 0, None, 0, None, 0, None, None) != 0
+    assert lib.fnssl_ipd_head_backward(None, 0, 1, 12, 4, 8, None, None, None, None, 0, None, None, None) != 0
+
+
+def test_gradient_unpacking_is_the_inverse_of_weight_packing():
+    from fn_ssl_b200.packing import pack_lstm_simt, pack_lstm_whh_t, unpack_lstm_simt_grad
+    H, I = 32, 5
+    dirs = [tuple(_randn(s, 40 + i) for i, s in enumerate(((4 * H, I), (4 * H, H), (4 * H,), (4 * H,)))) for _ in range(2)]
+    un = unpack_lstm_simt_grad(pack_lstm_simt(dirs), 2, I, H)
+    for d in range(2):
+        assert torch.equal(un[d][0], dirs[d][0]) and torch.equal(un[d][1], dirs[d][1])
+        assert torch.allclose(un[d][2], dirs[d][2] + dirs[d][3]) and torch.equal(un[d][2], un[d][3])
+    t = pack_lstm_whh_t(dirs)
+    assert t.shape == (2, H, H, 4) and float(t[1, 3, 7, 2]) == float(dirs[1][1][2 * H + 3, 7])
+
+
+# ---- GPU: one layer against torch's autograd of nn.LSTM ----------------------------------------------------------------------
+
+def _sequences(grid, axis):
+    """(nb, nt, nf, C) -> (rows, steps, C) as the reference reshapes it (Model.py:35,41)."""
+    nb, nt, nf, C = grid.shape
+    return grid.reshape(nb * nt, nf, C) if axis == 0 else grid.permute(0, 2, 1, 3).reshape(nb * nf, nt, C)
+
+
+def _grid_from_sequences(seq, axis, nb, nt, nf):
+    return seq.reshape(nb, nt, nf, -1) if axis == 0 else seq.reshape(nb, nf, nt, -1).permute(0, 2, 1, 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("axis", [0, 1])
+@pytest.mark.parametrize("H,bidir,c0,ld0,c1,ld1", [(32, True, 4, 4, 0, 0), (64, False, 20, 24, 0, 0), (128, True, 24, 24, 4, 8),
+                                                  (256, False, 12, 12, 3, 4), (128, True, 256, 256, 0, 0)])
+def test_lstm_layer_gradients_match_torch_autograd(axis, H, bidir, c0, ld0, c1, ld1):
+    from fn_ssl_b200 import training as T
+    from fn_ssl_b200.packing import LSTMParams
+    nb, nt, nf = 2, 9, 11                                    # 18 / 22 sequences: a partial row tile in every CTA
+    torch.manual_seed(7)
+    ref = torch.nn.LSTM(c0 + c1, H, batch_first=True, bidirectional=bidir)
+    params = LSTMParams(c0 + c1, H, bidirectional=bidir)
+    params.load_state_dict(ref.state_dict())
+    params = params.cuda()
+    s0, s1 = _randn((nb, nt, nf, ld0), 1), (_randn((nb, nt, nf, ld1), 2) if c1 else None)
+    dout = _randn((nb, nt, nf, H * (2 if bidir else 1)), 3)
+    # reference: nn.LSTM on the CPU over the reference's sequence layout
+    r0 = s0.clone().requires_grad_(True)
+    r1 = s1.clone().requires_grad_(True) if c1 else None
+    xin = r0[..., :c0] if not c1 else torch.cat((r0[..., :c0], r1[..., :c1]), dim=-1)
+    href = _grid_from_sequences(ref(_sequences(xin, axis))[0], axis, nb, nt, nf)
+    (href * dout).sum().backward()
+    # CUDA path
+    d0 = s0.cuda().requires_grad_(True)
+    d1 = s1.cuda().requires_grad_(True) if c1 else None
+    h = T.lstm_layer(d0, c0, d1, c1, params, axis)
+    (h * dout.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert _rel(h, href) <= 2e-5
+    assert _rel(d0.grad, r0.grad) <= TOL                      # padding channels (ld0 > c0) carry zero gradient on both sides
+    if c1:
+        assert _rel(d1.grad, r1.grad) <= TOL
+    for (n, p_), (_, q_) in zip(ref.named_parameters(), params.named_parameters()):
+        assert _rel(q_.grad, p_.grad) <= TOL, n
+    with pytest.raises(RuntimeError):                        # the saved activations are overwritten by the first backward
+        h.backward(dout.cuda())
+
+
+@pytest.mark.gpu
+def test_lstm_layer_without_input_gradient_and_weight_only_sources():
+    """First layer of the network: the feature grid needs no gradient (dsrc0 = NULL); second source with a gradient only."""
+    from fn_ssl_b200 import training as T
+    from fn_ssl_b200.packing import LSTMParams
+    torch.manual_seed(8)
+    ref = torch.nn.LSTM(36, 64, batch_first=True, bidirectional=True)
+    params = LSTMParams(36, 64, bidirectional=True)
+    params.load_state_dict(ref.state_dict())
+    params = params.cuda()
+    nb, nt, nf = 1, 7, 70
+    s0, s1, dout = _randn((nb, nt, nf, 32), 4), _randn((nb, nt, nf, 4), 5), _randn((nb, nt, nf, 128), 6)
+    r1 = s1.clone().requires_grad_(True)
+    href = _grid_from_sequences(ref(_sequences(torch.cat((s0, r1), -1), 1))[0], 1, nb, nt, nf)
+    (href * dout).sum().backward()
+    d1 = s1.cuda().requires_grad_(True)
+    h = T.lstm_layer(s0.cuda(), 32, d1, 4, params, 1)
+    (h * dout.cuda()).sum().backward()
+    assert _rel(d1.grad, r1.grad) <= TOL
+    for (n, p_), (_, q_) in zip(ref.named_parameters(), params.named_parameters()):
+        assert _rel(q_.grad, p_.grad) <= TOL, n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nt", [24, 31])
+def test_ipd_head_train_gradients(nt):
+    from fn_ssl_b200 import training as T
+    nb, nf, Cc = 2, 19, 256
+    x, w, b = _randn((nb, nt, nf, Cc), 9), 0.1 * _randn((2, Cc), 10), _randn((2,), 11)
+    dy = _randn((nb, nt // 12, 2 * nf), 12)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    seq = xr.permute(0, 2, 1, 3).reshape(nb * nf, nt, Cc)                           # Model.py:79-87
+    ipd = torch.tanh(torch.nn.functional.linear(torch.nn.AvgPool2d(kernel_size=(12, 1))(seq), wr, br))
+    ipd = ipd.view(nb, nf, nt // 12, 2).permute(0, 2, 1, 3)
+    yref = torch.cat((ipd[..., 0], ipd[..., 1]), dim=2)
+    (yref * dy).sum().backward()
+    xd, wd, bd = (t.cuda().requires_grad_(True) for t in (x, w, b))
+    y = T.ipd_head_train(xd, wd, bd)
+    (y * dy.cuda()).sum().backward()
+    assert _rel(y, yref) <= 1e-5
+    assert _rel(xd.grad, xr.grad) <= TOL and _rel(wd.grad, wr.grad) <= TOL and _rel(bd.grad, br.grad) <= TOL
+
+
+# ---- GPU: the network's training step against the reference's ----------------------------------------------------------------
+
+def _no_dropout(net):
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    return net
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,kw", [("off", dict(is_online=False)), ("on", dict(is_online=True))])
+def test_fnssl_training_step_matches_reference_golden(g, tag, kw):
+    import fn_ssl_b200 as F
+    net = F.FN_SSL(**kw)
+    net.load_state_dict(orc.seeded_fnssl_state_dict(3, **kw))
+    net = _no_dropout(net.cuda().train())
+    x, tgt = _randn((1, 4, 256, 24), 21).cuda(), _randn((1, 2, 512), 22).tanh().cuda()
+    y = net(x)
+    loss = torch.nn.functional.mse_loss(y, tgt)
+    loss.backward()
+    torch.cuda.synchronize()
+    _check_against_golden(g, tag, {n: p_.grad for n, p_ in net.named_parameters()}, y, loss)
+    # eval mode on the same module is still the inference path and agrees with the train-mode forward (dropout off)
+    with torch.no_grad():
+        net.eval().engine = "simt"
+        assert _rel(net(x), y) <= 2e-5
+
+
+@pytest.mark.gpu
+def test_fnblock_train_module_api_matches_reference_golden(g):
+    import fn_ssl_b200 as F
+    blk = F.FNblock(input_size=4, hidden_size=64, is_online=True, is_first=True)
+    blk2 = F.FNblock(input_size=64, hidden_size=64, is_online=False, is_first=False)
+    blk.load_state_dict({k[len("blk1_w_"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("blk1_w_")})
+    blk2.load_state_dict({k[len("blk2_w_"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("blk2_w_")})
+    blk, blk2 = _no_dropout(blk.cuda().train()), _no_dropout(blk2.cuda().train())
+    xb = _randn((1, 10, 16, 4), 23).cuda().requires_grad_(True)
+    y, fb, nbs = blk(xb)
+    y2, fb2, nbs2 = blk2(y, fb_skip=fb, nb_skip=nbs)
+    wy, wf = _randn(tuple(y2.shape), 24).cuda(), _randn(tuple(fb2.shape), 25).cuda()
+    ((y2 * wy).sum() + (fb2 * wf).sum()).backward()
+    assert _rel(y2, g["blk_y2"]) <= 2e-5 and _rel(fb2, g["blk_fb2"]) <= 2e-5
+    assert _rel(xb.grad, g["blk_dx"]) <= TOL
+    for n, p_ in blk.named_parameters():
+        assert _rel(p_.grad, g[f"blk1_grad_{n}"]) <= TOL, n
+    for n, p_ in blk2.named_parameters():
+        assert _rel(p_.grad, g[f"blk2_grad_{n}"]) <= TOL, n
+
+
+@pytest.mark.gpu
+def test_training_steps_reduce_the_loss_with_dropout_on():
+    """A few optimiser steps of the whole pipeline in train mode (default dropout 0.2): DP-IPD targets from the CUDA target
+    kernel, MSE loss kernel, backward kernels, torch.optim.Adam -- the loss on the fixed batch goes down, every gradient is finite."""
+    import fn_ssl_b200 as F
+    from fn_ssl_b200 import training as T
+    torch.manual_seed(0)
+    net = F.FN_SSL(is_online=False).cuda().train()
+    opt = torch.optim.Adam(net.parameters(), lr=3e-3)
+    sig = orc.white_noise(2, 512 + 256 * 23, 2, seed=3).cuda()
+    feats = F.data_preprocess_fnssl(sig)[0]                                         # (2, 4, 256, 24) reference layout
+    doa = torch.stack((torch.full((2, 2, 1), 1.5), torch.tensor([[[0.3], [0.35]], [[2.0], [2.1]]])), dim=2).cuda()   # (nb, nt2, 2, ns)
+    tgt = T.dpipd_targets(doa, [[-0.04, 0, 0], [0.04, 0, 0]], ch_mode="MM")         # (nb, nt2, 512, 1)
+    losses = []
+    for _ in range(8):
+        opt.zero_grad()
+        loss = T.ipd_mse_loss(net(feats), tgt)
+        loss.backward()
+        assert all(torch.isfinite(p_.grad).all() for p_ in net.parameters())
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0], losses
