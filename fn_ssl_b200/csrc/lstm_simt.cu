@@ -27,7 +27,7 @@ struct SimtParams {
   int I, K, Kp;
   float* h_state; float* c_state; int state_flags;   // optional carried state, fp32 (rows, H)
   float4* save_gates; float* save_cells;             // training forward (lstm_train.cu): activated (i,f,g,o) and c_t per
-};                                                   // (dir, row, position, unit), NULL for inference
+};                                                   // (dir, grid position, unit), NULL for inference
 
 template <typename T, int H>
 __global__ void __launch_bounds__(kSimtThreads)
@@ -129,12 +129,12 @@ lstm_simt_kernel(const SimtParams p) {
       smem_a[lr * Kp + I + j] = h;
       const int64_t base = s_base[lr];
       if (base >= 0) {
-        if (p.save_gates) {
-          const int64_t sidx = (((int64_t)dir * p.rows + row0 + lr) * p.steps + s) * H + j;
+        const int64_t pos = base + (int64_t)s * sstride;
+        if (p.save_gates) {      // grid-position order: [dir][(b, t, f)][unit]
+          const int64_t sidx = ((int64_t)dir * p.rows * p.steps + pos) * H + j;
           p.save_gates[sidx] = make_float4(ig, fg, gg, og);
           p.save_cells[sidx] = c[i];
         }
-        const int64_t pos = base + (int64_t)s * sstride;
         const int ch = dir * H + j;
         if (p.out0) st_act<T>(reinterpret_cast<T*>(p.out0) + pos * p.out0_ld + p.out0_off + ch, h);
         if (p.out1) {

@@ -14,6 +14,8 @@
 //                             scattered to the gradient grids of the two input sources.
 //     3. lstm_bwd_dw_kernel   dW_ih | dW_hh | db = [x | h_{t-1} | 1]^T . dG  reduced over all positions (split over CTAs,
 //                             fp32 atomics), in the packed layout of the forward weights.
+//     Both products are 128 x 128 x 16 register-tiled fp32 kernels (8 x 8 results per thread) whose operands are read in place:
+//     the saved buffer is laid out by grid position, so [x | h_prev] rows and dG rows of a position are plain strided reads.
 #include "common.cuh"
 
 namespace fnssl {
@@ -35,6 +37,8 @@ struct SeqGeom {
 };
 
 // ---- 1. sequential pass ---------------------------------------------------------------------------------------------------
+// `saved` is indexed by GRID POSITION: element (dir, pos, unit) with pos = (b*nt + t)*nf + f, so that the two products below
+// walk positions linearly (no per-element division back to (sequence, step)).
 struct BwdSeqParams {
   SeqGeom g;
   const float* dout; int dout_ld;   // grid, channels [dir*H, dir*H + H)
@@ -57,6 +61,7 @@ lstm_bwd_seq_kernel(const BwdSeqParams p) {
   const int64_t row0 = (int64_t)blockIdx.x * R;
   const int steps = p.g.steps;
   const int64_t ss = p.g.stride();
+  const int64_t plane = (int64_t)dir * p.g.rows * steps;   // positions of the directions before this one
   for (int lr = tid; lr < R; lr += kThreads) s_base[lr] = (row0 + lr < p.g.rows) ? p.g.base(row0 + lr) : -1;
   __syncthreads();
   const float4* wt = p.whh_t + (size_t)dir * H * H + j;
@@ -66,19 +71,19 @@ lstm_bwd_seq_kernel(const BwdSeqParams p) {
 
   for (int step = steps - 1; step >= 0; --step) {       // step = position in the order the forward processed the sequence
     const int s = dir ? (steps - 1 - step) : step;
-    const int sprev = dir ? s + 1 : s - 1;              // where the forward came from (valid when step > 0)
+    const int64_t dprev = dir ? ss : -ss;               // where the forward came from (valid when step > 0)
 #pragma unroll
     for (int i = 0; i < kRowsPerThread; ++i) {
       const int lr = rg * kRowsPerThread + i;
       const int64_t base = s_base[lr];
       float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       if (base >= 0) {
-        const int64_t seq = ((int64_t)dir * p.g.rows + row0 + lr) * steps;
-        const int64_t idx = (seq + s) * H + j;
+        const int64_t pos = base + (int64_t)s * ss;
+        const int64_t idx = (plane + pos) * H + j;
         const float4 a = p.gates[idx];
         const float ct = p.cells[idx];
-        const float cp = step > 0 ? p.cells[(seq + sprev) * H + j] : 0.0f;
-        const float dh = p.dout[(base + (int64_t)s * ss) * p.dout_ld + dir * H + j] + dh_rec[i];
+        const float cp = step > 0 ? p.cells[idx + dprev * H] : 0.0f;
+        const float dh = p.dout[pos * p.dout_ld + dir * H + j] + dh_rec[i];
         const float tc = tanh_f(ct);
         const float dc = dc_next[i] + dh * a.w * (1.0f - tc * tc);
         d.x = dc * a.z * a.x * (1.0f - a.x);            // i
@@ -113,58 +118,42 @@ lstm_bwd_seq_kernel(const BwdSeqParams p) {
   }
 }
 
-// ---- generic 64 x 64 x 16 fp32 tile product with functor operands ------------------------------------------------------------
-constexpr int TM = 64, TN = 64, TK = 16;
+// ---- 128 x 128 x 16 fp32 tile product: 256 threads, 8 x 8 results per thread (two 4-wide groups per dimension) --------------
+constexpr int TM = 128, TN = 128, TK = 16, TLD = TM + 4;     // +4 floats: rows stay 16-byte aligned
 
-// C(m, n) = sum_{k in [k_begin, k_end)} A(m, k) B(k, n) for the tile at (m0, n0); fa / fb return 0 outside their operand,
-// fc ignores positions outside the result.  *_KFAST: consecutive threads fetch consecutive k (operand contiguous along k).
-template <bool A_KFAST, bool B_KFAST, class FA, class FB, class FC>
-__device__ __forceinline__ void sgemm_tile(int64_t m0, int64_t n0, int64_t k_begin, int64_t k_end, FA fa, FB fb, FC fc) {
-  __shared__ float As[TK][TM + 1];
-  __shared__ float Bs[TK][TN + 1];
-  const int t = threadIdx.x, tx = t % 16, ty = t / 16;
-  float acc[4][4];
+struct TileAcc {
+  float v[8][8];
+  __device__ __forceinline__ void clear() {
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 8; ++u)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) acc[u][v] = 0.0f;
-  for (int64_t k0 = k_begin; k0 < k_end; k0 += TK) {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int e = t + kThreads * r;
-      const int akk = A_KFAST ? e % TK : e / TM;
-      const int amm = A_KFAST ? e / TK : e % TM;
-      As[akk][amm] = (k0 + akk < k_end) ? fa(m0 + amm, k0 + akk) : 0.0f;
-      const int bkk = B_KFAST ? e % TK : e / TN;
-      const int bnn = B_KFAST ? e / TK : e % TN;
-      Bs[bkk][bnn] = (k0 + bkk < k_end) ? fb(k0 + bkk, n0 + bnn) : 0.0f;
-    }
-    __syncthreads();
+      for (int w = 0; w < 8; ++w) v[u][w] = 0.0f;
+  }
+  // As[kk][m], Bs[kk][n]: one K = 16 slab.  Thread (ty, tx) owns rows {4 ty .. +3, 64 + 4 ty .. +3}, columns likewise with tx.
+  __device__ __forceinline__ void mac(const float (*As)[TLD], const float (*Bs)[TLD], int ty, int tx) {
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
-      float a[4], b[4];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] = As[kk][ty * 4 + u];
+      for (int u = 0; u < 8; ++u)
 #pragma unroll
-      for (int v = 0; v < 4; ++v) b[v] = Bs[kk][tx * 4 + v];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], b[v], acc[u][v]);
+        for (int w = 0; w < 8; ++w) v[u][w] = fmaf(a[u], b[w], v[u][w]);
     }
-    __syncthreads();
   }
-#pragma unroll
-  for (int u = 0; u < 4; ++u)
-#pragma unroll
-    for (int v = 0; v < 4; ++v) fc(m0 + ty * 4 + u, n0 + tx * 4 + v, acc[u][v]);
-}
+  __device__ __forceinline__ static int row_of(int ty, int u) { return (u < 4 ? 0 : 60) + ty * 4 + u; }   // u >= 4 -> 64 + 4 ty + (u - 4)
+};
 
-// ---- 2. input gradient ------------------------------------------------------------------------------------------------------
+// ---- 2. input gradient: dx[pos][n] = sum_{dir, cc} dG[dir][pos][cc] W[dir][n][cc] -------------------------------------------
 struct BwdDxParams {
-  SeqGeom g;
+  int64_t npos;                      // nb * nt * nf
   int H, dirs, I, c0, Kp;
-  const float* dgates;               // [dirs][rows*steps][4H]  (unit-major: column = unit*4 + gate)
+  int n_begin;                       // first input column that needs a gradient (c0 when dsrc0 == NULL)
+  const float* dgates;               // [dirs][npos][4H]  (column = unit*4 + gate)
   const float* w;                    // packed forward weights: [dirs][Kp][4H] in the same column order
   float* dsrc0; int dld0;
   float* dsrc1; int dld1;
@@ -172,71 +161,127 @@ struct BwdDxParams {
 
 __global__ void __launch_bounds__(kThreads)
 lstm_bwd_dx_kernel(const BwdDxParams p) {
-  const int64_t M = p.g.rows * p.g.steps;
+  __shared__ __align__(16) float As[TK][TLD];
+  __shared__ __align__(16) float Bs[TK][TLD];
+  const int t = threadIdx.x, tx = t % 16, ty = t / 16;
   const int G4 = 4 * p.H;
-  auto fa = [&](int64_t m, int64_t kk) -> float {
-    if (m >= M) return 0.0f;
-    const int dir = (int)(kk / G4), cc = (int)(kk % G4);
-    return p.dgates[((int64_t)dir * M + m) * G4 + cc];
-  };
-  auto fb = [&](int64_t kk, int64_t n) -> float {
-    if (n >= p.I) return 0.0f;
-    const int dir = (int)(kk / G4), cc = (int)(kk % G4);
-    return __ldg(p.w + ((int64_t)dir * p.Kp + n) * G4 + cc);
-  };
-  auto fc = [&](int64_t m, int64_t n, float v) {
-    if (m >= M || n >= p.I) return;
-    const int64_t row = m / p.g.steps;
-    const int s = (int)(m % p.g.steps);
-    const int64_t pos = p.g.base(row) + (int64_t)s * p.g.stride();
-    if (n < p.c0) { if (p.dsrc0) p.dsrc0[pos * p.dld0 + n] = v; }
-    else if (p.dsrc1) p.dsrc1[pos * p.dld1 + (n - p.c0)] = v;
-  };
-  sgemm_tile<true, true>((int64_t)blockIdx.x * TM, (int64_t)blockIdx.y * TN, 0, (int64_t)p.dirs * G4, fa, fb, fc);
+  const int64_t m0 = (int64_t)blockIdx.x * TM;
+  const int n0 = p.n_begin + blockIdx.y * TN;
+  const int lq = (t % 4) * 4;                          // this thread's 4 consecutive k of the slab
+  TileAcc acc;
+  acc.clear();
+  for (int dir = 0; dir < p.dirs; ++dir) {
+    const float* dg = p.dgates + (int64_t)dir * p.npos * G4;
+    const float* wd = p.w + (int64_t)dir * p.Kp * G4;
+    for (int cc0 = 0; cc0 < G4; cc0 += TK) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int mm = t / 4 + 64 * r;
+        const int64_t pos = m0 + mm;
+        float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (pos < p.npos) a = *reinterpret_cast<const float4*>(dg + pos * G4 + cc0 + lq);
+        As[lq + 0][mm] = a.x; As[lq + 1][mm] = a.y; As[lq + 2][mm] = a.z; As[lq + 3][mm] = a.w;
+        const int n = n0 + mm;
+        float4 b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (n < p.I) b = __ldg(reinterpret_cast<const float4*>(wd + (int64_t)n * G4 + cc0 + lq));
+        Bs[lq + 0][mm] = b.x; Bs[lq + 1][mm] = b.y; Bs[lq + 2][mm] = b.z; Bs[lq + 3][mm] = b.w;
+      }
+      __syncthreads();
+      acc.mac(As, Bs, ty, tx);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int64_t pos = m0 + TileAcc::row_of(ty, u);
+    if (pos >= p.npos) continue;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const int n = n0 + TileAcc::row_of(tx, w);
+      if (n >= p.I) continue;
+      if (n < p.c0) { if (p.dsrc0) p.dsrc0[pos * p.dld0 + n] = acc.v[u][w]; }
+      else if (p.dsrc1) p.dsrc1[pos * p.dld1 + (n - p.c0)] = acc.v[u][w];
+    }
+  }
 }
 
-// ---- 3. weight gradient -----------------------------------------------------------------------------------------------------
+// ---- 3. weight gradient: dW[dir][k][cc] = sum_pos [x | h_prev | 1][pos][k] dG[dir][pos][cc] -----------------------------------
 struct BwdDwParams {
   SeqGeom g;
+  int64_t npos;
   int H, dirs, I, c0, Kp;
   const float* src0; int ld0;
   const float* src1; int ld1;
   const float* hout; int hld; int hoff;   // the forward's h grid (h_{t-1} operand of W_hh)
   const float* dgates;
   float* dw;                              // packed: [dirs][Kp][4H] weights ++ [dirs][4H] bias, zero on entry
-  int64_t chunk;                          // positions per CTA along the reduction
+  int64_t chunk;                          // positions per CTA along the reduction (multiple of TK)
 };
 
 __global__ void __launch_bounds__(kThreads)
 lstm_bwd_dw_kernel(const BwdDwParams p) {
-  const int64_t M = p.g.rows * p.g.steps;
+  __shared__ __align__(16) float As[TK][TLD];
+  __shared__ __align__(16) float Bs[TK][TLD];
+  const int t = threadIdx.x, tx = t % 16, ty = t / 16;
   const int G4 = 4 * p.H;
   const int K = p.I + p.H;
   const int dir = blockIdx.z % p.dirs;
   const int64_t split = blockIdx.z / p.dirs;
   const int64_t mb = split * p.chunk;
-  const int64_t me = (mb + p.chunk < M) ? mb + p.chunk : M;
+  const int64_t me = (mb + p.chunk < p.npos) ? mb + p.chunk : p.npos;
+  const int k0 = blockIdx.x * TM;          // rows of the result: columns of [x | h_prev | 1]
+  const int n0 = blockIdx.y * TN;          // gate columns
   const int64_t ss = p.g.stride();
-  auto fa = [&](int64_t k, int64_t m) -> float {          // [x | h_{t-1} | 1] at position m, column k
-    if (k > K) return 0.0f;
-    if (k == K) return 1.0f;
-    const int64_t row = m / p.g.steps;
-    const int s = (int)(m % p.g.steps);
-    const int64_t pos = p.g.base(row) + (int64_t)s * ss;
-    if (k < p.c0) return p.src0[pos * p.ld0 + k];
-    if (k < p.I) return p.src1[pos * p.ld1 + (k - p.c0)];
-    const int step = dir ? (p.g.steps - 1 - s) : s;
-    if (step == 0) return 0.0f;
-    const int64_t pprev = dir ? pos + ss : pos - ss;
-    return p.hout[pprev * p.hld + p.hoff + dir * p.H + (k - p.I)];
-  };
-  auto fb = [&](int64_t m, int64_t cc) -> float { return p.dgates[((int64_t)dir * M + m) * G4 + cc]; };
+  const float* dg = p.dgates + (int64_t)dir * p.npos * G4;
+  const int pk = t / 16;                   // this thread's position within a slab of 16 (operand A: 8 columns k of ONE position)
+  const int kq = t % 16;
+  TileAcc acc;
+  acc.clear();
+  for (int64_t m0 = mb; m0 < me; m0 += TK) {
+    {   // A slab: As[pk][k - k0] = [x | h_prev | 1](pos, k)
+      const int64_t pos = m0 + pk;
+      const bool valid = pos < me;
+      bool first = true;                   // is `pos` the first step of its sequence in this direction (h_prev = 0)?
+      if (valid) {
+        const int s = p.g.axis == FNSSL_ALONG_FREQ ? (int)(pos % p.g.nf) : (int)((pos / p.g.nf) % p.g.nt);
+        first = dir ? (s == p.g.steps - 1) : (s == 0);
+      }
+      const float* hp = p.hout + (pos + (dir ? ss : -ss)) * p.hld + p.hoff + dir * p.H;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int kk = kq + 16 * r;
+        const int k = k0 + kk;
+        float v = 0.0f;
+        if (valid) {
+          if (k < p.c0) v = p.src0[pos * p.ld0 + k];
+          else if (k < p.I) v = p.src1[pos * p.ld1 + (k - p.c0)];
+          else if (k < K) v = first ? 0.0f : hp[k - p.I];
+          else if (k == K) v = 1.0f;
+        }
+        As[pk][kk] = v;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {          // B slab: Bs[pk][cc - n0] = dG(pos, cc), float4 per thread
+      const int64_t pos = m0 + pk;
+      const int nn = kq * 4 + 64 * r;
+      float4 b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (pos < me) b = *reinterpret_cast<const float4*>(dg + pos * G4 + n0 + nn);
+      *reinterpret_cast<float4*>(&Bs[pk][nn]) = b;
+    }
+    __syncthreads();
+    acc.mac(As, Bs, ty, tx);
+    __syncthreads();
+  }
   float* db = p.dw + (size_t)p.dirs * p.Kp * G4;
-  auto fc = [&](int64_t k, int64_t cc, float v) {
-    if (k < K) atomicAdd(p.dw + ((int64_t)dir * p.Kp + k) * G4 + cc, v);
-    else if (k == K) atomicAdd(db + (int64_t)dir * G4 + cc, v);
-  };
-  if (mb < me) sgemm_tile<false, false>((int64_t)blockIdx.x * TM, (int64_t)blockIdx.y * TN, mb, me, fa, fb, fc);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int k = k0 + TileAcc::row_of(ty, u);
+    if (k > K) continue;
+    float* dst = (k < K) ? p.dw + ((int64_t)dir * p.Kp + k) * G4 : db + (int64_t)dir * G4;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) atomicAdd(dst + n0 + TileAcc::row_of(tx, w), acc.v[u][w]);
+  }
 }
 
 template <int H>
@@ -326,26 +371,31 @@ int fnssl_lstm_backward(const fnssl_lstm_args* a, void* saved, int64_t saved_byt
   }
   if (rc) return rc;
 
-  const int64_t M = g.rows * g.steps;
+  const int64_t M = g.rows * g.steps;                       // = nb * nt * nf grid positions
   if (dsrc0 || dsrc1) {
     BwdDxParams xp;
-    xp.g = g; xp.H = H; xp.dirs = dirs; xp.I = I; xp.c0 = a->c0; xp.Kp = Kp;
+    xp.npos = M; xp.H = H; xp.dirs = dirs; xp.I = I; xp.c0 = a->c0; xp.Kp = Kp;
+    xp.n_begin = dsrc0 ? 0 : a->c0;
+    const int n_end = dsrc1 ? I : a->c0;                    // columns outside [n_begin, n_end) need no gradient
     xp.dgates = gates; xp.w = reinterpret_cast<const float*>(a->weights);
     xp.dsrc0 = dsrc0; xp.dld0 = dsrc0_ld; xp.dsrc1 = dsrc1; xp.dld1 = dsrc1_ld;
-    dim3 grid((unsigned)ceil_div64(M, TM), (unsigned)((I + TN - 1) / TN));
+    dim3 grid((unsigned)ceil_div64(M, TM), (unsigned)((n_end - xp.n_begin + TN - 1) / TN));
     lstm_bwd_dx_kernel<<<grid, kThreads, 0, st>>>(xp);
     FNSSL_LAUNCH_CHECK("lstm_bwd_dx_kernel");
   }
 
   FNSSL_CUDA(cudaMemsetAsync(dweights, 0, (size_t)need, st));
   BwdDwParams wp;
-  wp.g = g; wp.H = H; wp.dirs = dirs; wp.I = I; wp.c0 = a->c0; wp.Kp = Kp;
+  wp.g = g; wp.npos = M; wp.H = H; wp.dirs = dirs; wp.I = I; wp.c0 = a->c0; wp.Kp = Kp;
   wp.src0 = reinterpret_cast<const float*>(a->src0); wp.ld0 = a->ld0;
   wp.src1 = reinterpret_cast<const float*>(a->src1); wp.ld1 = a->ld1;
   wp.hout = reinterpret_cast<const float*>(a->out0); wp.hld = a->out0_ld; wp.hoff = a->out0_off;
   wp.dgates = gates; wp.dw = dweights;
-  int64_t chunk = ceil_div64(M, 64);                       // <= 64 splits of the reduction
-  if (chunk < 2048) chunk = 2048;
+  const int64_t tiles = (int64_t)((K + 1 + TM - 1) / TM) * (4 * H / TN) * dirs;
+  int64_t want = (148 * 4 + tiles - 1) / tiles;             // splits of the reduction: about four CTAs per SM in total
+  if (want < 1) want = 1;
+  int64_t chunk = ceil_div64(M, want);
+  if (chunk < 1024) chunk = 1024;
   chunk = ceil_div64(chunk, TK) * TK;
   wp.chunk = chunk;
   const int64_t splits = ceil_div64(M, chunk);
