@@ -8,12 +8,13 @@
 // registers, [x_t | h_{t-1}] in shared memory, and the (I+H) x 4H weight matrix is streamed from L2 every
 // step as float4 (i,f,g,o) per (k, unit).  It is the reference engine of the package: any I, H in
 // {32,64,128,256}, fp32 or fp16 grids.  The tensor-core engine (lstm_tc.cu) is the fast one.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace fnssl {
 
 constexpr int kSimtThreads = 256;
-constexpr int kRowsPerThread = 16;
 
 struct SimtParams {
   const void* src0; int c0; int ld0;
@@ -29,9 +30,12 @@ struct SimtParams {
   float4* save_gates; float* save_cells;             // training forward (lstm_train.cu): activated (i,f,g,o) and c_t per
 };                                                   // (dir, grid position, unit), NULL for inference
 
-template <typename T, int H>
+// RPT = rows per thread: 16 for inference (the weights streamed from L2 are reused by 16 rows); the training forward picks 8 / 4
+// on small batches so that the grid still covers the GPU (its CTAs are latency-bound otherwise).
+template <typename T, int H, int RPT = 16>
 __global__ void __launch_bounds__(kSimtThreads)
 lstm_simt_kernel(const SimtParams p) {
+  constexpr int kRowsPerThread = RPT;
   constexpr int G = kSimtThreads / H;          // row groups
   constexpr int R = kRowsPerThread * G;        // rows per CTA
   extern __shared__ __align__(16) float smem_a[];  // [R][Kp]
@@ -157,16 +161,30 @@ lstm_simt_kernel(const SimtParams p) {
   }
 }
 
-template <typename T, int H>
-static int launch_simt(const SimtParams& p, int dirs, cudaStream_t st) {
-  constexpr int R = kRowsPerThread * (kSimtThreads / H);
+template <typename T, int H, int RPT>
+static int launch_simt_rpt(const SimtParams& p, int dirs, cudaStream_t st) {
+  constexpr int R = RPT * (kSimtThreads / H);
   const size_t smem = (size_t)R * p.Kp * sizeof(float);
   FNSSL_REQUIRE(smem <= 220 * 1024, "lstm(simt): input size %d too large for H=%d", p.I, H);
-  FNSSL_CUDA(cudaFuncSetAttribute(lstm_simt_kernel<T, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FNSSL_CUDA(cudaFuncSetAttribute(lstm_simt_kernel<T, H, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div64(p.rows, R), dirs);
-  lstm_simt_kernel<T, H><<<grid, kSimtThreads, smem, st>>>(p);
+  lstm_simt_kernel<T, H, RPT><<<grid, kSimtThreads, smem, st>>>(p);
   FNSSL_LAUNCH_CHECK("lstm_simt_kernel");
   return 0;
+}
+
+template <typename T, int H>
+static int launch_simt(const SimtParams& p, int dirs, cudaStream_t st) {
+  if (p.save_gates) {   // training forward (fp32 grids): fewer rows per CTA while the 16-row grid would leave SMs idle
+    if constexpr (std::is_same<T, float>::value) {
+      constexpr int G = kSimtThreads / H;
+      if (ceil_div64(p.rows, 16 * G) * dirs < 148) {
+        if (ceil_div64(p.rows, 8 * G) * dirs >= 148) return launch_simt_rpt<T, H, 8>(p, dirs, st);
+        return launch_simt_rpt<T, H, 4>(p, dirs, st);
+      }
+    }
+  }
+  return launch_simt_rpt<T, H, 16>(p, dirs, st);
 }
 
 // gates / cells: NULL (inference) or the buffers of the training forward (fnssl_lstm_forward_train)

@@ -25,7 +25,6 @@ int lstm_forward_simt_save(const fnssl_lstm_args* a, float* gates, float* cells,
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kRowsPerThread = 16;
 
 // sequence addressing of a (nb, nt, nf, C) grid, as in lstm_simt.cu
 struct SeqGeom {
@@ -47,9 +46,10 @@ struct BwdSeqParams {
   const float4* whh_t;              // [dirs][H (unit j)][H (input k)] float4 over the gates: W_hh[gate*H + j][k]
 };
 
-template <int H>
+template <int H, int RPT>
 __global__ void __launch_bounds__(kThreads)
 lstm_bwd_seq_kernel(const BwdSeqParams p) {
+  constexpr int kRowsPerThread = RPT;          // 16, or 8 / 4 on small batches (grid coverage), as the training forward
   constexpr int G = kThreads / H;
   constexpr int R = kRowsPerThread * G;
   extern __shared__ __align__(16) float4 sm_dg[];   // [R][H]
@@ -205,7 +205,7 @@ lstm_bwd_dx_kernel(const BwdDxParams p) {
   }
 }
 
-// ---- 3. weight gradient: dW[dir][k][cc] = sum_pos [x | h_prev | 1][pos][k] dG[dir][pos][cc] -----------------------------------
+// ---- 3. weight gradient: dW[dir][k][cc] = sum_pos [x | h_prev][pos][k] dG[dir][pos][cc];  db[dir][cc] = sum_pos dG[dir][pos][cc] -----------------------------------
 struct BwdDwParams {
   SeqGeom g;
   int64_t npos;
@@ -237,8 +237,12 @@ lstm_bwd_dw_kernel(const BwdDwParams p) {
   const int kq = t % 16;
   TileAcc acc;
   acc.clear();
+  const bool bias_cta = blockIdx.x == 0 && ty == 0;   // d bias = column sums of dG: the first row of tiles adds them up on the side
+  float bsum[8];
+#pragma unroll
+  for (int w = 0; w < 8; ++w) bsum[w] = 0.0f;
   for (int64_t m0 = mb; m0 < me; m0 += TK) {
-    {   // A slab: As[pk][k - k0] = [x | h_prev | 1](pos, k)
+    {   // A slab: As[pk][k - k0] = [x | h_prev](pos, k)
       const int64_t pos = m0 + pk;
       const bool valid = pos < me;
       bool first = true;                   // is `pos` the first step of its sequence in this direction (h_prev = 0)?
@@ -256,7 +260,6 @@ lstm_bwd_dw_kernel(const BwdDwParams p) {
           if (k < p.c0) v = p.src0[pos * p.ld0 + k];
           else if (k < p.I) v = p.src1[pos * p.ld1 + (k - p.c0)];
           else if (k < K) v = first ? 0.0f : hp[k - p.I];
-          else if (k == K) v = 1.0f;
         }
         As[pk][kk] = v;
       }
@@ -271,28 +274,46 @@ lstm_bwd_dw_kernel(const BwdDwParams p) {
     }
     __syncthreads();
     acc.mac(As, Bs, ty, tx);
+    if (bias_cta) {
+#pragma unroll
+      for (int kk = 0; kk < TK; ++kk)
+#pragma unroll
+        for (int w = 0; w < 8; ++w) bsum[w] += Bs[kk][TileAcc::row_of(tx, w)];
+    }
     __syncthreads();
   }
-  float* db = p.dw + (size_t)p.dirs * p.Kp * G4;
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
     const int k = k0 + TileAcc::row_of(ty, u);
-    if (k > K) continue;
-    float* dst = (k < K) ? p.dw + ((int64_t)dir * p.Kp + k) * G4 : db + (int64_t)dir * G4;
+    if (k >= K) continue;
+    float* dst = p.dw + ((int64_t)dir * p.Kp + k) * G4;
 #pragma unroll
     for (int w = 0; w < 8; ++w) atomicAdd(dst + n0 + TileAcc::row_of(tx, w), acc.v[u][w]);
   }
+  if (bias_cta) {
+    float* db = p.dw + (size_t)p.dirs * p.Kp * G4 + (int64_t)dir * G4;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) atomicAdd(db + n0 + TileAcc::row_of(tx, w), bsum[w]);
+  }
+}
+
+template <int H, int RPT>
+int launch_bwd_seq_rpt(const BwdSeqParams& p, int dirs, cudaStream_t st) {
+  constexpr int R = RPT * (kThreads / H);
+  const size_t smem = (size_t)R * H * sizeof(float4);
+  FNSSL_CUDA(cudaFuncSetAttribute(lstm_bwd_seq_kernel<H, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div64(p.g.rows, R), dirs);
+  lstm_bwd_seq_kernel<H, RPT><<<grid, kThreads, smem, st>>>(p);
+  FNSSL_LAUNCH_CHECK("lstm_bwd_seq_kernel");
+  return 0;
 }
 
 template <int H>
 int launch_bwd_seq(const BwdSeqParams& p, int dirs, cudaStream_t st) {
-  constexpr int R = kRowsPerThread * (kThreads / H);
-  const size_t smem = (size_t)R * H * sizeof(float4);
-  FNSSL_CUDA(cudaFuncSetAttribute(lstm_bwd_seq_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div64(p.g.rows, R), dirs);
-  lstm_bwd_seq_kernel<H><<<grid, kThreads, smem, st>>>(p);
-  FNSSL_LAUNCH_CHECK("lstm_bwd_seq_kernel");
-  return 0;
+  constexpr int G = kThreads / H;
+  if (ceil_div64(p.g.rows, 16 * G) * dirs >= 148) return launch_bwd_seq_rpt<H, 16>(p, dirs, st);
+  if (ceil_div64(p.g.rows, 8 * G) * dirs >= 148) return launch_bwd_seq_rpt<H, 8>(p, dirs, st);
+  return launch_bwd_seq_rpt<H, 4>(p, dirs, st);
 }
 
 int check_train_args(const fnssl_lstm_args* a, const char* who) {
@@ -391,7 +412,7 @@ int fnssl_lstm_backward(const fnssl_lstm_args* a, void* saved, int64_t saved_byt
   wp.src1 = reinterpret_cast<const float*>(a->src1); wp.ld1 = a->ld1;
   wp.hout = reinterpret_cast<const float*>(a->out0); wp.hld = a->out0_ld; wp.hoff = a->out0_off;
   wp.dgates = gates; wp.dw = dweights;
-  const int64_t tiles = (int64_t)((K + 1 + TM - 1) / TM) * (4 * H / TN) * dirs;
+  const int64_t tiles = (int64_t)((K + TM - 1) / TM) * (4 * H / TN) * dirs;
   int64_t want = (148 * 4 + tiles - 1) / tiles;             // splits of the reduction: about four CTAs per SM in total
   if (want < 1) want = 1;
   int64_t chunk = ceil_div64(M, want);
@@ -399,7 +420,7 @@ int fnssl_lstm_backward(const fnssl_lstm_args* a, void* saved, int64_t saved_byt
   chunk = ceil_div64(chunk, TK) * TK;
   wp.chunk = chunk;
   const int64_t splits = ceil_div64(M, chunk);
-  dim3 wgrid((unsigned)((K + 1 + TM - 1) / TM), (unsigned)(4 * H / TN), (unsigned)(dirs * splits));
+  dim3 wgrid((unsigned)((K + TM - 1) / TM), (unsigned)(4 * H / TN), (unsigned)(dirs * splits));
   lstm_bwd_dw_kernel<<<wgrid, kThreads, 0, st>>>(wp);
   FNSSL_LAUNCH_CHECK("lstm_bwd_dw_kernel");
   return 0;
