@@ -6,7 +6,8 @@ Drop-in module surface (same names as the reference, Audio-WestlakeU/FN-SSL):
     fn_ssl_b200.FixedAarryIPDnet  FNblock, CausCnnBlock, IPDnet
     fn_ssl_b200.IPDnet2           OnlineSpatialNet, SpatialNetLayer, FreqInverse, CausalConv1d, Mamba (parameter holder)
 plus the fused end-to-end pipelines (fn_ssl_b200.pipeline), the multi-GPU helpers (fn_ssl_b200.distributed) and the
-training-side forward pieces (fn_ssl_b200.training: DP-IPD targets, MSE / frame-level PIT losses).
+training step (fn_ssl_b200.training: DP-IPD targets, MSE / frame-level PIT losses, LSTM layer / head with backward passes;
+FN_SSL / FNblock in train mode).
 All arithmetic runs in libfnssl_b200.so (hand-written CUDA, C ABI in include/fnssl_b200.h).
 """
 from . import config  # noqa: F401
@@ -17,6 +18,6 @@ from .Module import (DPIPD, STFT, AddChToBatch, RemoveChFromBatch, SourceDetectL
                      pred_ipd_to_doa)
 from .pipeline import FNSSLPipeline, IPDnetPipeline, data_preprocess_fnssl, data_preprocess_ipdnet  # noqa: F401
 from .streaming import FNSSLStream, IPDnetStream  # noqa: F401
-from .training import dpipd_targets, ipd_mse_loss, ipd_pit_mse_loss  # noqa: F401
+from .training import dpipd_targets, ipd_head_train, ipd_mse_loss, ipd_pit_mse_loss, lstm_layer  # noqa: F401
 
 __version__ = "0.1.0"

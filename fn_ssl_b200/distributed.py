@@ -1,10 +1,12 @@
-"""Multi-GPU inference plumbing: one process per GPU (torch.distributed, NCCL over NVLink 5 / NVSwitch).
+"""Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink 5 / NVSwitch).
 
 The path shards over utterances with no data-path exchange (every utterance / mic pair is independent through
 the whole forward); the only collectives are
     * one broadcast of the flat weight buffer at start-up (what Lightning's DDP wrapper does at wrap time,
       FN-SSL/Lightning/main.py:286-288), and
     * one all-gather of the per-utterance outputs per batch (<= 1.3 MB per rank).
+Training (fn_ssl_b200.training) is data-parallel the same way; its one exchange step is the gradient all-reduce that
+Lightning's DDP strategy performs after backward (main.py:286-288): `all_reduce_gradients` -- one flat fp32 bucket per call.
 Works with the gloo backend on CPU tensors too (used by the world_size-2 tests).
 """
 from __future__ import annotations
@@ -76,3 +78,29 @@ def all_gather_outputs(local_out: Tensor, counts: List[int]) -> Tensor:
     padded[: local_out.shape[0]] = local_out
     dist.all_gather_into_tensor(out, padded)
     return torch.cat([out[r * mx: r * mx + counts[r]] for r in range(world)], dim=0)
+
+
+@torch.no_grad()
+def all_reduce_gradients(module: nn.Module, average: bool = True) -> int:
+    """Data-parallel training step, the exchange DDP does (FN-SSL/Lightning/main.py:286-288): sum (average) the gradients of
+    every parameter over the ranks as ONE flat fp32 bucket (2.5 M parameters = 10 MB: a single NVSwitch all-reduce, sized for
+    launch latency rather than overlap -- the backward pass of a step is hundreds of milliseconds).  Parameters without a
+    gradient on this rank contribute zeros and receive the reduced value, as under DDP.  Returns the bucket's bytes."""
+    params = [p for p in module.parameters() if p.requires_grad]
+    if not params:
+        return 0
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params])
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if average:
+            flat /= dist.get_world_size()
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = flat[off:off + n].reshape(p.shape).to(p.dtype)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
+    return flat.numel() * 4

@@ -182,7 +182,7 @@ int fnssl_lstm_tc4_trace(long long* out256);
  * (args->engine == FNSSL_ENGINE_SIMT, args->dtype == FNSSL_F32, no carried state; addend / out1 are honoured by the forward
  * but have no gradient path here -- the host adds the residuals, fn_ssl_b200/training.py).
  *
- * fnssl_lstm_forward_train: fnssl_lstm_forward + `saved`: per (direction, row, position, unit) the activated gates (i,f,g,o)
+ * fnssl_lstm_forward_train: fnssl_lstm_forward + `saved`: per (direction, grid position, unit) the activated gates (i,f,g,o)
  *   and the cell state c_t -- fnssl_lstm_train_saved_bytes() bytes, 16-byte aligned.
  * fnssl_lstm_backward: args = the forward's arguments (src0 / src1 / weights as then, out0 = the h grid it produced);
  *   saved   : the forward's buffer; CONSUMED (the gates are overwritten with the gate pre-activation gradients)

@@ -66,3 +66,52 @@ def test_shard_range_covers_everything():
             spans = [shard_range(n, r, w) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+def _grad_worker(rank, world, port, q):
+    """Data-parallel training step on two ranks == the same step on the concatenated batch (what DDP guarantees): per-rank
+    gradients of a mean loss over the local shard, averaged by all_reduce_gradients, equal the full-batch gradient."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from fn_ssl_b200 import distributed as D
+    from fn_ssl_b200.packing import LSTMParams
+    D.init_from_env(backend="gloo")
+    torch.manual_seed(7)                                 # same parameters on every rank (as after broadcast_weights)
+    layer = LSTMParams(6, 32, bidirectional=True)        # the package's nn.LSTM-shaped parameter holder
+    head = torch.nn.Linear(64, 3)
+    frozen = torch.nn.Linear(3, 3)
+    for p in frozen.parameters():
+        p.requires_grad_(False)
+    model = torch.nn.ModuleList([layer, head, frozen])
+
+    def forward(x):                                      # host-side stand-in for the CUDA layer: same parameters through ATen
+        flat = [t for d in layer.directions() for t in d]
+        h = torch.zeros(2, x.shape[0], 32)
+        y = torch._VF.lstm(x, (h, h), flat, True, 1, 0.0, False, True, True)[0]
+        return head(y).pow(2).mean()
+
+    full = torch.randn(4, 5, 6, generator=torch.Generator().manual_seed(3))
+    lo, hi = D.shard_range(4, rank, world)
+    forward(full[lo:hi]).backward()
+    nbytes = D.all_reduce_gradients(model)
+    got = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.requires_grad])
+    model.zero_grad()
+    forward(full).backward()
+    want = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.requires_grad])
+    ok = torch.allclose(got, want, rtol=1e-5, atol=1e-7) and all(p.grad is None for p in frozen.parameters())
+    q.put((rank, ok, nbytes, int(want.numel())))
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_equals_full_batch_gloo():
+    world, port = 2, 29733
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(60)
+    for rank, ok, nbytes, n in res:
+        assert ok and nbytes == 4 * n
