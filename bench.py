@@ -504,6 +504,21 @@ def main():
         except Exception as exc:
             torch_base = {"error": str(exc)[:300]}
 
+    # training step at batch 8 x 4 s, forward + MSE loss + backward, next to cuDNN + autograd on the same GPU: run
+    # in a child process (tools/bench_train.py) so that nothing it does can disturb this line; informational, never fatal.
+    train_step = None
+    if world == 1 and not args.no_extra and args.workload == "cfg4":
+        try:
+            torch.cuda.empty_cache()
+            res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_train.py"), "8"], capture_output=True, text=True,
+                                 timeout=180)
+            last = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+            train_step = json.loads(last[-1]) if last else {"error": (res.stderr or "no output")[-300:]}
+        except Exception as exc:
+            train_step = {"error": str(exc)[:300]}
+        if extra is not None:
+            extra["training_step_b8"] = train_step
+
     cfg = workload_config(args, world)
     run = {"engine": eng, "per_gpu_batch": main_res["per_gpu_batch"], "weights_broadcast_bytes": main_res["weights_broadcast_bytes"]}
     fpf = flops_per_frame(online, wl["blocks"])

@@ -16,6 +16,8 @@
 //                             fp32 atomics), in the packed layout of the forward weights.
 //     Both products are 128 x 128 x 16 register-tiled fp32 kernels (8 x 8 results per thread) whose operands are read in place:
 //     the saved buffer is laid out by grid position, so [x | h_prev] rows and dG rows of a position are plain strided reads.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fnssl {
@@ -297,6 +299,114 @@ lstm_bwd_dw_kernel(const BwdDwParams p) {
   }
 }
 
+// Second version of the weight-gradient product for layers whose channel counts and strides are multiples of 4 (every layer of
+// the networks; the first version above stays for odd shapes): the [x | h_prev] operand is gathered as float4 -- a group of 4
+// columns never straddles the src0 / src1 / h boundaries --, the position -> (step-of-sequence) bookkeeping is incremental
+// instead of a 64-bit division per slab, and the global loads of slab i+1 are issued before the FMAs of slab i (register
+// double buffering).
+__global__ void __launch_bounds__(kThreads, 2)
+lstm_bwd_dw2_kernel(const BwdDwParams p) {
+  __shared__ __align__(16) float As[TK][TLD];
+  __shared__ __align__(16) float Bs[TK][TLD];
+  const int t = threadIdx.x, tx = t % 16, ty = t / 16;
+  const int G4 = 4 * p.H;
+  const int K = p.I + p.H;
+  const int dir = blockIdx.z % p.dirs;
+  const int64_t split = blockIdx.z / p.dirs;
+  const int64_t mb = split * p.chunk;
+  const int64_t me = (mb + p.chunk < p.npos) ? mb + p.chunk : p.npos;
+  const int k0 = blockIdx.x * TM;
+  const int n0 = blockIdx.y * TN;
+  const int64_t ss = p.g.stride();
+  const float* dg = p.dgates + (int64_t)dir * p.npos * G4;
+  const int pk = t / 16;                   // this thread's position within a slab of 16
+  const int kq = t % 16;                   // its float4 column groups: 4 (kq + 16 r), r = 0, 1
+  // step-of-sequence bookkeeping of position mb + pk, advanced by 16 positions per slab
+  int f_idx, s_idx;                        // ALONG_FREQ: s_idx = f;  ALONG_TIME: (f_idx, s_idx = t)
+  {
+    const int64_t pos = mb + pk;
+    f_idx = (int)(pos % p.g.nf);
+    s_idx = p.g.axis == FNSSL_ALONG_FREQ ? f_idx : (int)((pos / p.g.nf) % p.g.nt);
+  }
+  const int s_first = dir ? p.g.steps - 1 : 0;
+  const int64_t dprev = dir ? ss : -ss;
+
+  float4 ra[2], rb[2];
+  auto fetch = [&](int64_t m0) {
+    const int64_t pos = m0 + pk;
+    const bool valid = pos < me;
+    const bool first = s_idx == s_first;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int k = k0 + 4 * (kq + 16 * r);
+      float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (valid) {
+        if (k < p.c0) v = *reinterpret_cast<const float4*>(p.src0 + pos * p.ld0 + k);
+        else if (k < p.I) v = *reinterpret_cast<const float4*>(p.src1 + pos * p.ld1 + (k - p.c0));
+        else if (k < K && !first) v = *reinterpret_cast<const float4*>(p.hout + (pos + dprev) * p.hld + p.hoff + dir * p.H + (k - p.I));
+      }
+      ra[r] = v;
+      float4 b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (valid) b = *reinterpret_cast<const float4*>(dg + pos * G4 + n0 + kq * 4 + 64 * r);
+      rb[r] = b;
+    }
+    // advance the bookkeeping to the next slab
+    f_idx += TK;
+    if (p.g.axis == FNSSL_ALONG_FREQ) {
+      while (f_idx >= p.g.nf) f_idx -= p.g.nf;
+      s_idx = f_idx;
+    } else {
+      while (f_idx >= p.g.nf) { f_idx -= p.g.nf; if (++s_idx == p.g.nt) s_idx = 0; }
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      *reinterpret_cast<float4*>(&As[pk][4 * (kq + 16 * r)]) = ra[r];
+      *reinterpret_cast<float4*>(&Bs[pk][kq * 4 + 64 * r]) = rb[r];
+    }
+  };
+
+  TileAcc acc;
+  acc.clear();
+  const bool bias_cta = blockIdx.x == 0 && ty == 0;
+  float bsum[8];
+#pragma unroll
+  for (int w = 0; w < 8; ++w) bsum[w] = 0.0f;
+  if (mb < me) {
+    fetch(mb);
+    stash();
+    __syncthreads();
+    for (int64_t m0 = mb; m0 < me; m0 += TK) {
+      const bool more = m0 + TK < me;
+      if (more) fetch(m0 + TK);
+      acc.mac(As, Bs, ty, tx);
+      if (bias_cta) {
+#pragma unroll
+        for (int kk = 0; kk < TK; ++kk)
+#pragma unroll
+          for (int w = 0; w < 8; ++w) bsum[w] += Bs[kk][TileAcc::row_of(tx, w)];
+      }
+      __syncthreads();
+      if (more) stash();
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int k = k0 + TileAcc::row_of(ty, u);
+    if (k >= K) continue;
+    float* dst = p.dw + ((int64_t)dir * p.Kp + k) * G4;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) atomicAdd(dst + n0 + TileAcc::row_of(tx, w), acc.v[u][w]);
+  }
+  if (bias_cta) {
+    float* db = p.dw + (size_t)p.dirs * p.Kp * G4 + (int64_t)dir * G4;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) atomicAdd(db + n0 + TileAcc::row_of(tx, w), bsum[w]);
+  }
+}
+
 template <int H, int RPT>
 int launch_bwd_seq_rpt(const BwdSeqParams& p, int dirs, cudaStream_t st) {
   constexpr int R = RPT * (kThreads / H);
@@ -421,8 +531,18 @@ int fnssl_lstm_backward(const fnssl_lstm_args* a, void* saved, int64_t saved_byt
   wp.chunk = chunk;
   const int64_t splits = ceil_div64(M, chunk);
   dim3 wgrid((unsigned)((K + TM - 1) / TM), (unsigned)(4 * H / TN), (unsigned)(dirs * splits));
-  lstm_bwd_dw_kernel<<<wgrid, kThreads, 0, st>>>(wp);
-  FNSSL_LAUNCH_CHECK("lstm_bwd_dw_kernel");
+  // float4 operand gathers need every channel count / stride / pointer to be a multiple of 4 floats
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool vec_ok = a->c0 % 4 == 0 && a->c1 % 4 == 0 && a->ld0 % 4 == 0 && (a->c1 == 0 || a->ld1 % 4 == 0) && a->out0_ld % 4 == 0 &&
+                      a->out0_off % 4 == 0 && al16(a->src0) && (a->c1 == 0 || al16(a->src1)) && al16(a->out0);
+  static const int dw_version = [] { const char* e = getenv("FNSSL_TRAIN_DW"); return e ? atoi(e) : 1; }();
+  if (vec_ok && dw_version == 2) {
+    lstm_bwd_dw2_kernel<<<wgrid, kThreads, 0, st>>>(wp);
+    FNSSL_LAUNCH_CHECK("lstm_bwd_dw2_kernel");
+  } else {
+    lstm_bwd_dw_kernel<<<wgrid, kThreads, 0, st>>>(wp);
+    FNSSL_LAUNCH_CHECK("lstm_bwd_dw_kernel");
+  }
   return 0;
 }
 
