@@ -2,7 +2,9 @@
 
     FNblock       (reference :7-40)      CausCnnBlock (:42-73)  alias CausalConv1dBlock
     IPDnet        (:76-120)              alias FixedArrayIPDnet
-Same constructor arguments, forward layouts and state_dict keys; inference only.
+Same constructor arguments, forward layouts and state_dict keys.  Eval mode = the accelerated inference path; train mode = the
+differentiable fp32 path of fn_ssl_b200.training (LSTM layers and the three causal convs as CUDA kernels with backward passes;
+dropout, ReLU, pooling, tanh and the concatenations around them are torch elementwise / view ops).
 """
 from __future__ import annotations
 
@@ -51,9 +53,22 @@ class FNblock(nn.Module):
         N_, _ = run_lstm(self.narrLstm, eng, ops.ALONG_TIME, F_, 2 * fh, raw, craw, state=state)
         return N_
 
+    def _run_train(self, x: Tensor, cx: int, x1: Optional[Tensor], cx1: int, raw: Tensor, craw: int) -> Tensor:
+        """Train-mode block on fp32 grids (reference :29-39): full-band input = concat(x[cx], x1[cx1]); returns
+        dropout(narrow-band output) -- the concatenation with the raw skip (:37) stays virtual, as in `_run`."""
+        from . import training as T
+        F_ = self.dropout_full(T.lstm_layer(x, cx, x1, cx1, self.fullLstm, ops.ALONG_FREQ))
+        N_ = T.lstm_layer(F_, 2 * self.full_hidden_size, raw, craw, self.narrLstm, ops.ALONG_TIME)
+        return self.dropout_narr(N_)
+
     def forward(self, x: Tensor, fb_skip: Tensor, nb_skip: Tensor) -> Tensor:
-        _require_eval(self)
         nb, nt, nf, nc = x.shape
+        if self.training:
+            if not x.is_cuda:
+                raise RuntimeError("fn_ssl_b200 runs on CUDA (sm_100a) only -- no CPU fallback exists")
+            skip = fb_skip.reshape(nb, nt, nf, -1).float().contiguous()
+            N_ = self._run_train(x.float().contiguous(), nc, None, 0, skip, skip.shape[-1])
+            return torch.cat((N_, nb_skip.reshape(nb, nf, nt, -1).permute(0, 2, 1, 3).float()), dim=-1)
         eng = config.resolve(self.engine, (self.full_hidden_size, self.narr_hidden_size))
         dt = config.grid_dtype(eng)
         skip = fb_skip.reshape(nb, nt, nf, -1)
@@ -88,7 +103,12 @@ class CausCnnBlock(nn.Module):
         return ops.causcnn(src0, c0, src1, c1, self.conv1.weight, self.conv2.weight, self.conv3.weight)
 
     def forward(self, x: Tensor) -> Tensor:
-        _require_eval(self)
+        if self.training:
+            from . import training as T
+            if not x.is_cuda:
+                raise RuntimeError("fn_ssl_b200 runs on CUDA (sm_100a) only -- no CPU fallback exists")
+            g = x.float().permute(0, 3, 2, 1).contiguous()
+            return T.causcnn_train(g, x.shape[1], None, 0, self.conv1.weight, self.conv2.weight, self.conv3.weight)
         g = ops.cfirst_to_grid(x, torch.float32)
         return self.forward_grid(g, x.shape[1], None, 0)
 
@@ -150,10 +170,27 @@ class IPDnet(nn.Module):
             return x[:, :ou_frame, :, :, :]
         return x.reshape(nbp, nt2, 2, nf * 2, -1).permute(0, 1, 3, 4, 2)
 
+    def _forward_train(self, g0: Tensor) -> Tensor:
+        """Differentiable forward on an fp32 feature grid (nb, nt, nf, ld >= input_size): reference :91-120 in train mode."""
+        from . import training as T
+        nb, nt, nf, _ = g0.shape
+        ci = self.input_size
+        N1 = self.block_1._run_train(g0, ci, None, 0, g0, ci)                     # block 1: x = the raw grid itself
+        N2 = self.block_2._run_train(N1, self.hidden_size, g0, ci, g0, ci)        # block 2: x = [N1 | raw]
+        y = T.causcnn_train(N2, self.hidden_size, g0, ci, self.conv.conv1.weight, self.conv.conv2.weight, self.conv.conv3.weight)
+        nt2 = y.shape[3]
+        x = y.permute(0, 3, 2, 1).reshape(nb, nt2, nf, 2, -1).permute(0, 1, 3, 2, 4)     # :114
+        return x.reshape(nb, nt2, 2, nf * 2, -1).permute(0, 1, 3, 4, 2)
+
     def forward(self, x: Tensor, offline_inference: bool = False) -> Tensor:
-        _require_eval(self)
         if x.dim() != 4 or x.shape[1] != self.input_size:
             raise RuntimeError(f"IPDnet: expected (nb, {self.input_size}, nf, nt), got {tuple(x.shape)}")
+        if self.training:
+            if not x.is_cuda:
+                raise RuntimeError("fn_ssl_b200 runs on CUDA (sm_100a) only -- no CPU fallback exists")
+            if offline_inference:
+                raise RuntimeError("IPDnet: offline_inference (chunked) is an eval-mode feature")
+            return self._forward_train(x.float().permute(0, 3, 2, 1).contiguous())
         eng = self._engine()
         nt = x.shape[3]
         chunked = (not self.is_online) and offline_inference

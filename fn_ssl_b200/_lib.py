@@ -113,6 +113,10 @@ SIGNATURES = {
     "fnssl_dpipd_targets": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _i, _i, _f, _i, _vp, _vp, _vp]),
     "fnssl_ipd_mse_loss": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "fnssl_ipd_pit_mse_loss": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "fnssl_conv3x3_train_workspace_bytes": (_sz, [_i, _i]),
+    "fnssl_conv3x3_forward": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
+    "fnssl_conv3x3_backward_data": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
+    "fnssl_conv3x3_backward_weight": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "fnssl_causcnn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "fnssl_causcnn_forward": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
 }

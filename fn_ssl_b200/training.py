@@ -129,26 +129,48 @@ def ipd_mse_loss(pred_ipd: Tensor, gt_ipd: Tensor) -> Tensor:
     return _MseLoss.apply(pred_ipd, gt_ipd, nb)
 
 
+class _PitLoss(torch.autograd.Function):
+    """Loss and permutation from the CUDA kernel; the gradient w.r.t. the prediction is analytic: with the per-frame permutation
+    fixed (as torchmetrics' pit_permutate does, runIPDnetOn.py:203-205) it is 2 (pred_perm - gt) / N routed back through it."""
+
+    @staticmethod
+    def forward(ctx, pred, gt):
+        nb, nt, _, _, ns = pred.shape
+        rows = nb * nt
+        p = pred.detach().float().reshape(rows, -1, ns).contiguous()
+        g = gt.detach().float().reshape(rows, -1, ns).contiguous()
+        if p.shape != g.shape:
+            raise RuntimeError(f"ipd_pit_mse_loss: prediction {tuple(p.shape)} and target {tuple(g.shape)} differ")
+        lib = _lib.load()
+        ws = torch.empty(rows, dtype=torch.float32, device=p.device)
+        loss = torch.empty((), dtype=torch.float32, device=p.device)
+        perm = torch.empty((rows, ns), dtype=torch.int32, device=p.device)
+        ops._count(2)
+        _lib.check(lib.fnssl_ipd_pit_mse_loss(p.data_ptr(), g.data_ptr(), rows, p.shape[1], ns, ws.data_ptr(), loss.data_ptr(),
+                                              perm.data_ptr(), ops._stream()))
+        ctx.save_for_backward(p, g, perm)
+        ctx.shape = tuple(pred.shape)
+        ctx.mark_non_differentiable(perm)
+        return loss, perm
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad, _grad_perm):
+        p, g, perm = ctx.saved_tensors
+        idx = perm.long().unsqueeze(1).expand_as(p)                     # pred_perm[r, :, s] = p[r, :, perm[r, s]]
+        d = (torch.gather(p, 2, idx) - g) * (2.0 / p.numel())
+        gp = torch.zeros_like(p).scatter_(2, idx, d)
+        return (grad * gp).reshape(ctx.shape), None
+
+
 @ops.on_tensor_device
 def ipd_pit_mse_loss(pred_batch: Tensor, ipd_gt_batch: Tensor) -> Tuple[Tensor, Tensor]:
     """Frame-level PIT loss of IPDnet (runIPDnetOn.py:196-206): pred (nb, nt, 2nf, nmic-1, ns), target (nb*nt, 2nf, nmic-1, ns)
     [or the same 5-D shape]; per frame the source permutation with the smallest MSE is applied to the prediction, the loss is
-    the MSE after permuting.  Returns (loss 0-d, best_perm (nb*nt, ns) int32 with pred index per target source)."""
+    the MSE after permuting.  Returns (loss 0-d, best_perm (nb*nt, ns) int32 with pred index per target source); the loss
+    back-propagates to the prediction."""
     ops._need_cuda(pred_batch, ipd_gt_batch)
-    nb, nt, _, _, ns = pred_batch.shape
-    rows = nb * nt
-    p = pred_batch.detach().float().reshape(rows, -1, ns).contiguous()
-    g = ipd_gt_batch.detach().float().reshape(rows, -1, ns).contiguous()
-    if p.shape != g.shape:
-        raise RuntimeError(f"ipd_pit_mse_loss: prediction {tuple(p.shape)} and target {tuple(g.shape)} differ")
-    lib = _lib.load()
-    ws = torch.empty(rows, dtype=torch.float32, device=p.device)
-    loss = torch.empty((), dtype=torch.float32, device=p.device)
-    perm = torch.empty((rows, ns), dtype=torch.int32, device=p.device)
-    ops._count(2)
-    _lib.check(lib.fnssl_ipd_pit_mse_loss(p.data_ptr(), g.data_ptr(), rows, p.shape[1], ns, ws.data_ptr(), loss.data_ptr(),
-                                          perm.data_ptr(), ops._stream()))
-    return loss, perm
+    return _PitLoss.apply(pred_batch, ipd_gt_batch)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -265,3 +287,82 @@ def ipd_head_train(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
     if x.dtype != torch.float32 or x.shape[-1] != weight.shape[1] or x.shape[-1] > 512:
         raise RuntimeError("ipd_head_train: x must be a float32 grid with C = weight.shape[1] <= 512 channels")
     return _IpdHead.apply(x.contiguous(), weight, bias)
+
+
+# ---------------------------------------------------------------------------------------------
+# IPDnet's causal conv block with its backward pass
+# ---------------------------------------------------------------------------------------------
+
+class _Conv3x3(torch.autograd.Function):
+    """y = causal conv3x3(concat(in0[..., :c0], in1[..., :c1])) on fp32 grids (nb, nt, nf, C): nn.Conv2d(kernel 3x3, padding (1,2),
+    bias=False) + crop of the last two frames (FixedAarryIPDnet.py:50-52,62-64); weight (O, C, 3, 3)."""
+
+    @staticmethod
+    def forward(ctx, in0, in1, c0, c1, weight):
+        lib = _lib.load()
+        nb, nt, nf, ld0 = in0.shape
+        w = weight.detach().float().contiguous()
+        O = w.shape[0]
+        out = torch.empty((nb, nt, nf, O), dtype=torch.float32, device=in0.device)
+        work = torch.empty(9 * (c0 + c1) * O, dtype=torch.float32, device=in0.device)
+        ops._count(2)
+        _lib.check(lib.fnssl_conv3x3_forward(in0.data_ptr(), c0, ld0, ops._ptr(in1), c1, in1.shape[-1] if in1 is not None else 0,
+                                             nb, nt, nf, w.data_ptr(), O, work.data_ptr(), out.data_ptr(), O, ops._stream()))
+        ctx.save_for_backward(in0, in1, w)
+        ctx.cfg = (c0, c1)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        in0, in1, w = ctx.saved_tensors
+        c0, c1 = ctx.cfg
+        lib = _lib.load()
+        nb, nt, nf, ld0 = in0.shape
+        O = w.shape[0]
+        with torch.cuda.device(in0.device):
+            dy = dy.contiguous().float()
+            work = torch.empty(9 * (c0 + c1) * O, dtype=torch.float32, device=in0.device)
+            d0 = d1 = dw = None
+            if ctx.needs_input_grad[0]:
+                d0 = torch.empty_like(in0) if ld0 == c0 else torch.zeros_like(in0)
+            if in1 is not None and ctx.needs_input_grad[1]:
+                d1 = torch.empty_like(in1) if in1.shape[-1] == c1 else torch.zeros_like(in1)
+            if d0 is not None or d1 is not None:
+                ops._count(2)
+                _lib.check(lib.fnssl_conv3x3_backward_data(dy.data_ptr(), O, O, nb, nt, nf, w.data_ptr(), c0, c1, work.data_ptr(),
+                                                           ops._ptr(d0), d0.shape[-1] if d0 is not None else 0, ops._ptr(d1),
+                                                           d1.shape[-1] if d1 is not None else 0, ops._stream()))
+            if ctx.needs_input_grad[4]:
+                dw = torch.empty_like(w)
+                ops._count(2)
+                _lib.check(lib.fnssl_conv3x3_backward_weight(in0.data_ptr(), c0, ld0, ops._ptr(in1), c1,
+                                                             in1.shape[-1] if in1 is not None else 0, dy.data_ptr(), O, O, nb, nt, nf,
+                                                             work.data_ptr(), dw.data_ptr(), ops._stream()))
+        return d0, d1, None, None, dw
+
+
+@ops.on_tensor_device
+def conv3x3_causal(in0: Tensor, c0: int, in1: Optional[Tensor], c1: int, weight: Tensor) -> Tensor:
+    """Differentiable causal 3x3 conv over fp32 grids: (nb, nt, nf, ld0 >= c0) [+ (.., ld1 >= c1) concatenated] -> (nb, nt, nf, O)."""
+    ops._need_cuda(in0, in1, weight)
+    if in0.dtype != torch.float32 or (in1 is not None and in1.dtype != torch.float32):
+        raise RuntimeError("conv3x3_causal: the training path runs on float32 grids")
+    if tuple(weight.shape[1:]) != (c0 + (c1 if in1 is not None else 0), 3, 3):
+        raise RuntimeError("conv3x3_causal: weight shape does not match the input channels / 3x3 kernel")
+    return _Conv3x3.apply(in0.contiguous(), in1.contiguous() if in1 is not None else None, c0, c1 if in1 is not None else 0, weight)
+
+
+def causcnn_train(src0: Tensor, c0: int, src1: Optional[Tensor], c1: int, w1: Tensor, w2: Tensor, w3: Tensor) -> Tensor:
+    """CausCnnBlock.forward (FixedAarryIPDnet.py:61-73) with a backward pass: grids in, (nb, cout, nf, nt//12) out (the reference's
+    layout).  The three convs are the CUDA products of conv_train.cu; ReLU, the two average poolings over 3 and 4 frames and tanh
+    are torch elementwise / view ops on the grids."""
+    nb, nt, nf, _ = src0.shape
+    a = torch.relu(conv3x3_causal(src0, c0, src1, c1, w1))
+    nt1 = nt // 3
+    a = a[:, :nt1 * 3].reshape(nb, nt1, 3, nf, a.shape[-1]).mean(dim=2)          # AvgPool2d((1, 3)) over time
+    a = torch.relu(conv3x3_causal(a, a.shape[-1], None, 0, w2))
+    nt2 = nt1 // 4
+    a = a[:, :nt2 * 4].reshape(nb, nt2, 4, nf, a.shape[-1]).mean(dim=2)          # AvgPool2d((1, 4))
+    y = torch.tanh(conv3x3_causal(a, a.shape[-1], None, 0, w3))
+    return y.permute(0, 3, 2, 1)

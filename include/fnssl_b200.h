@@ -29,7 +29,7 @@ extern "C" {
 #define FNSSL_ABI_VERSION 5 /* 2: carried LSTM state; 3: IPDnet2 entry points (fnssl_reflect_pad, fnssl_sn_*); 4: one tcgen05 LSTM kernel
                              (fnssl_lstm_tc_trace of the retired generations removed), training-side targets / losses,
                              fused fnssl_stft_features_forward; 5: training forward / backward of the LSTM layer and the
-                             DP-IPD head (fnssl_lstm_forward_train, fnssl_lstm_backward, fnssl_ipd_head_backward) */
+                             DP-IPD head (fnssl_lstm_forward_train, fnssl_lstm_backward, fnssl_ipd_head_backward), of the causal conv (fnssl_conv3x3_*) */
 
 /* element types of grid tensors */
 #define FNSSL_F32 0
@@ -225,6 +225,22 @@ size_t fnssl_causcnn_workspace_bytes(int nb, int nt, int nf, int cin, int hid, i
 int fnssl_causcnn_forward(const void* src0, int c0, int ld0, const void* src1, int c1, int ld1, int dtype,
                           int nb, int nt, int nf, const float* w1, const float* w2, const float* w3, int hid,
                           int cout, void* work, float* out, void* stream);
+
+/* Training side of CausCnnBlock: the three products autograd runs behind each nn.Conv2d(kernel 3x3, padding (1,2), bias=False)
+ * + crop of the last two frames (IPDnet/FixedAarryIPDnet.py:50-52,61-72; training_step IPDnet/runIPDnetOn.py:110-125), on fp32
+ * channels-last grids (nb, nt, nf, C); ReLU / AvgPool / tanh between them are host-side elementwise ops
+ * (fn_ssl_b200.training.causcnn_train).  w, dw : (cout, c0+c1, 3, 3) f32 in PyTorch's layout.
+ *   forward         out[b,t,f,o] = sum w[o,c,kf,kt] in[b, t+kt-2, f+kf-1, c],   in = concat(in0[c0], in1[c1])
+ *   backward_data   din[b,t,f,c] = sum w[o,c,kf,kt] dy[b, t-kt+2, f-kf+1, o]    (din0: c < c0, din1: the rest; either may be NULL)
+ *   backward_weight dw[o,c,kf,kt] = sum_{b,t,f} dy[b,t,f,o] in[b, t+kt-2, f+kf-1, c]
+ * work : scratch of fnssl_conv3x3_train_workspace_bytes(c0+c1, cout) bytes (a re-packed copy of w / the unreduced dw). */
+size_t fnssl_conv3x3_train_workspace_bytes(int cin, int cout);
+int fnssl_conv3x3_forward(const float* in0, int c0, int ld0, const float* in1, int c1, int ld1, int nb, int nt, int nf, const float* w,
+                          int cout, float* work, float* out, int out_ld, void* stream);
+int fnssl_conv3x3_backward_data(const float* dy, int cout, int dy_ld, int nb, int nt, int nf, const float* w, int c0, int c1, float* work,
+                                float* din0, int din0_ld, float* din1, int din1_ld, void* stream);
+int fnssl_conv3x3_backward_weight(const float* in0, int c0, int ld0, const float* in1, int c1, int ld1, const float* dy, int cout, int dy_ld,
+                                  int nb, int nt, int nf, float* work, float* dw, void* stream);
 
 /* ---- IPD -> DOA decoding ("next" row of the scope contract) ------------------------------------- */
 

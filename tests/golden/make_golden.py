@@ -347,9 +347,63 @@ def gen_grad():
     print("wrote grad_golden.npz:", {k: np.asarray(v).shape for k, v in out.items() if "grad_norm" in k or k.endswith("_loss")})
 
 
+def gen_grad_ipdnet():
+    """Training step of the reference IPDnet (row f4): the UNMODIFIED reference IPDnet (online 4-mic-style hidden 128 / 2-mic default,
+    and offline) and a CausCnnBlock alone in TRAIN mode with dropout probability 0: forward, MSE loss against a seeded target,
+    loss.backward().  (The reference's own loss is the frame-level PIT loss through torchmetrics, absent here: its gradient is
+    checked against the oracle's restatement in tests/test_training_backward.py.)"""
+    _shim()
+    sys.path.insert(0, os.path.join(REF, "IPDnet"))
+    import FixedAarryIPDnet as ref_ipd
+    from oracle import fnssl_oracle as orc
+
+    out = {}
+    cfgs = {"d2": dict(input_size=4, hidden_size=128, max_track=2, is_online=True),
+            "off6": dict(input_size=6, hidden_size=64, max_track=2, is_online=False)}
+    for tag, kw in cfgs.items():
+        torch.manual_seed(4)
+        net = ref_ipd.IPDnet(**kw).train()
+        for m in net.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        x = _randn((1, kw["input_size"], 40, 25), 31)                  # 25 frames -> 2 output frames (the 25th is dropped by pooling)
+        y = net(x)
+        tgt = _randn(tuple(y.shape), 32).tanh()
+        loss = torch.nn.functional.mse_loss(y, tgt)
+        loss.backward()
+        out[f"{tag}_out"], out[f"{tag}_loss"] = y.detach().numpy(), np.float32(loss.item())
+        out[f"{tag}_names"] = np.array([n for n, _ in net.named_parameters()])
+        out[f"{tag}_grad_norm"] = np.array([float(p.grad.double().norm()) for _, p in net.named_parameters()])
+        out[f"{tag}_grad_sum"] = np.array([float(p.grad.double().sum()) for _, p in net.named_parameters()])
+        for n in ("conv.conv3.weight", "conv.conv2.weight", "block_1.fullLstm.weight_ih_l0", "block_2.fullLstm.bias_hh_l0_reverse",
+                  "block_2.narrLstm.bias_ih_l0"):
+            out[f"{tag}_grad_{n}"] = dict(net.named_parameters())[n].grad.numpy()
+        out[f"{tag}_grad_conv.conv1.weight[:, :4]"] = dict(net.named_parameters())["conv.conv1.weight"].grad[:, :4].numpy()
+        sd = {k: v.clone().requires_grad_(True) for k, v in orc.seeded_ipdnet_state_dict(4, **kw).items()}
+        yo = orc.ipdnet_forward(x, sd, is_online=kw["is_online"], fast=True)
+        torch.nn.functional.mse_loss(yo, tgt).backward()
+        for n, p_ in net.named_parameters():
+            err = float((sd[n].grad - p_.grad).abs().max()) / max(float(p_.grad.abs().max()), 1e-30)
+            assert err <= 1e-4, (tag, n, err)
+    # CausCnnBlock alone, gradient w.r.t. the input too (odd sizes: 13 bins, 38 frames -> 3 output frames)
+    torch.manual_seed(9)
+    cnn = ref_ipd.CausCnnBlock(inp_dim=20, out_dim=4, cnn_hidden_dim=128).train()
+    xc = _randn((2, 20, 13, 38), 33).requires_grad_(True)
+    yc = cnn(xc)
+    wc = _randn(tuple(yc.shape), 34)
+    (yc * wc).sum().backward()
+    out["cnn_y"], out["cnn_dx"] = yc.detach().numpy(), xc.grad.numpy()
+    for k, v in cnn.state_dict().items():
+        out["cnn_sd." + k] = v.numpy()
+    for k, p_ in cnn.named_parameters():
+        out["cnn_grad." + k] = p_.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "grad_ipdnet_golden.npz"), **out)
+    print("wrote grad_ipdnet_golden.npz:", {k: np.asarray(v).shape for k, v in out.items() if k.endswith("_out") or k.startswith("cnn_d")})
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
-        {"fnssl": gen_fnssl, "ipdnet": gen_ipdnet, "train": gen_train, "grad": gen_grad}[sys.argv[1]]()
+        {"fnssl": gen_fnssl, "ipdnet": gen_ipdnet, "train": gen_train, "grad": gen_grad, "grad_ipdnet": gen_grad_ipdnet}[sys.argv[1]]()
     else:
-        for which in ("fnssl", "ipdnet", "train", "grad"):
+        for which in ("fnssl", "ipdnet", "train", "grad", "grad_ipdnet"):
             subprocess.check_call([sys.executable, os.path.abspath(__file__), which])

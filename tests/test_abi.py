@@ -93,8 +93,10 @@ def test_aliases_and_errors():
     net = F.FN_SSL()
     with pytest.raises(RuntimeError, match="CUDA"):          # train mode = the differentiable fp32 CUDA path: no CPU fallback either
         net(torch.zeros(1, 4, 8, 24))
-    with pytest.raises(RuntimeError, match="eval"):          # IPDnet's causal conv block has no backward: inference only
+    with pytest.raises(RuntimeError, match="CUDA"):
         F.IPDnet()(torch.zeros(1, 4, 256, 24))
+    with pytest.raises(RuntimeError, match="eval"):          # IPDnet2 has no backward kernels: inference only
+        F.IPDnet2_lightning()(torch.zeros(1, 10, 256, 10))
     with pytest.raises(RuntimeError, match="CUDA"):
         net.eval()(torch.zeros(1, 4, 8, 24))                # CPU tensor: no fallback, loud failure
     with pytest.raises(RuntimeError, match="CUDA"):

@@ -250,3 +250,95 @@ def test_training_steps_reduce_the_loss_with_dropout_on():
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0], losses
+
+
+# ---- IPDnet: causal conv block and network training step ---------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def gi():
+    return np.load(os.path.join(ROOT, "tests", "golden", "grad_ipdnet_golden.npz"))
+
+
+IPD_CFGS = [("d2", dict(input_size=4, hidden_size=128, max_track=2, is_online=True)),
+            ("off6", dict(input_size=6, hidden_size=64, max_track=2, is_online=False))]
+
+
+@pytest.mark.parametrize("tag,kw", IPD_CFGS)
+def test_oracle_autograd_matches_reference_ipdnet_gradients(gi, tag, kw):
+    x = _randn((1, kw["input_size"], 40, 25), 31)
+    sd = {k: v.clone().requires_grad_(True) for k, v in orc.seeded_ipdnet_state_dict(4, **kw).items()}
+    y = orc.ipdnet_forward(x, sd, is_online=kw["is_online"], fast=True)
+    loss = torch.nn.functional.mse_loss(y, _randn(tuple(y.shape), 32).tanh())
+    loss.backward()
+    _check_against_golden(gi, tag, {k: v.grad for k, v in sd.items()}, y.detach(), loss.detach())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c0,ld0,c1,ld1,O", [(5, 5, 0, 0, 7), (20, 24, 3, 4, 128), (128, 128, 0, 0, 130), (6, 8, 130, 132, 4)])
+def test_conv3x3_causal_gradients_match_torch_autograd(c0, ld0, c1, ld1, O):
+    from fn_ssl_b200 import training as T
+    nb, nt, nf = 2, 13, 9
+    s0, s1 = _randn((nb, nt, nf, ld0), 50), (_randn((nb, nt, nf, ld1), 51) if c1 else None)
+    w, dy = 0.2 * _randn((O, c0 + c1, 3, 3), 52), _randn((nb, nt, nf, O), 53)
+    r0, rw = s0.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    r1 = s1.clone().requires_grad_(True) if c1 else None
+    xin = r0[..., :c0] if not c1 else torch.cat((r0[..., :c0], r1[..., :c1]), dim=-1)
+    yref = torch.nn.functional.conv2d(xin.permute(0, 3, 2, 1), rw, padding=(1, 2))[:, :, :, :-2].permute(0, 3, 2, 1)   # (nb,C,F,T) conv
+    (yref * dy).sum().backward()
+    d0, dw = s0.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    d1 = s1.cuda().requires_grad_(True) if c1 else None
+    y = T.conv3x3_causal(d0, c0, d1, c1, dw)
+    (y * dy.cuda()).sum().backward()
+    assert _rel(y, yref) <= 2e-5
+    assert _rel(d0.grad, r0.grad) <= TOL and _rel(dw.grad, rw.grad) <= TOL
+    if c1:
+        assert _rel(d1.grad, r1.grad) <= TOL
+
+
+@pytest.mark.gpu
+def test_causcnn_block_training_matches_reference_golden(gi):
+    import fn_ssl_b200 as F
+    cnn = F.CausCnnBlock(inp_dim=20, out_dim=4, cnn_hidden_dim=128)
+    cnn.load_state_dict({k[len("cnn_sd."):]: torch.from_numpy(gi[k]) for k in gi.files if k.startswith("cnn_sd.")})
+    cnn = cnn.cuda().train()
+    xc = _randn((2, 20, 13, 38), 33).cuda().requires_grad_(True)
+    yc = cnn(xc)
+    (yc * _randn(tuple(yc.shape), 34).cuda()).sum().backward()
+    assert _rel(yc, gi["cnn_y"]) <= 2e-5 and _rel(xc.grad, gi["cnn_dx"]) <= TOL
+    for n, p_ in cnn.named_parameters():
+        assert _rel(p_.grad, gi["cnn_grad." + n]) <= TOL, n
+    with torch.no_grad():                                    # eval mode on the same module = the fused inference kernels
+        assert _rel(cnn.eval()(xc.detach()), yc) <= 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,kw", IPD_CFGS)
+def test_ipdnet_training_step_matches_reference_golden(gi, tag, kw):
+    import fn_ssl_b200 as F
+    net = F.IPDnet(**kw)
+    net.load_state_dict(orc.seeded_ipdnet_state_dict(4, **kw))
+    net = _no_dropout(net.cuda().train())
+    x = _randn((1, kw["input_size"], 40, 25), 31).cuda()
+    y = net(x)
+    loss = torch.nn.functional.mse_loss(y, _randn(tuple(y.shape), 32).tanh().cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    _check_against_golden(gi, tag, {n: p_.grad for n, p_ in net.named_parameters()}, y.detach(), loss.detach())
+
+
+@pytest.mark.gpu
+def test_pit_loss_gradient_matches_oracle_autograd():
+    from fn_ssl_b200 import training as T
+    from oracle import training_oracle as tro
+    gt = _randn((2, 5, 64, 2, 3), 60)
+    order = torch.stack([torch.randperm(3, generator=torch.Generator().manual_seed(70 + r)) for r in range(10)])
+    pred = torch.stack([gt.reshape(10, -1, 3)[r][:, order[r]] for r in range(10)]).reshape(gt.shape) + 0.1 * _randn(tuple(gt.shape), 61)
+    pr = pred.clone().requires_grad_(True)
+    lref, pref = tro.ipdnet_pit_loss(pr, gt)
+    lref.backward()
+    pd = pred.cuda().requires_grad_(True)
+    loss, perm = T.ipd_pit_mse_loss(pd, gt.cuda())
+    (3.0 * loss).backward()
+    assert np.array_equal(perm.cpu().numpy(), pref.numpy())
+    assert abs(float(loss.detach()) - float(lref.detach())) <= 1e-5 * float(lref.detach())
+    assert _rel(pd.grad, 3.0 * pr.grad) <= 1e-5
