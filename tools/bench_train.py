@@ -1,7 +1,9 @@
 """Training-step timing (not the contract bench): FN_SSL (offline, 3 blocks) forward + MSE loss + backward on one GPU at a few
 batch sizes -- the fp32 training path of fn_ssl_b200 (CUDA kernels with hand-written backward passes) next to the reference's own
 library path restated with stock torch modules (nn.LSTM -> cuDNN, autograd), fp32 and TF32, same shapes, same GPU.
-Prints one JSON object per batch size.      python tools/bench_train.py [B ...] [--once]   (--once: a single step, for ncu)"""
+Prints one JSON object per batch size.      python tools/bench_train.py [B ...] [--once] [--ours-only] [--dw-compare] [--ipdnet]
+(--once: a single step, for ncu; --ours-only: skip the cuDNN comparator; --dw-compare: time the step with both weight-gradient
+kernels, FNSSL_TRAIN_DW=1 / 2; --ipdnet: also time IPDnet's training step, 4-mic hidden 256 online, batch 4)"""
 import json
 import os
 import sys
@@ -101,11 +103,20 @@ def main():
             continue
         res = {"workload": f"FN-SSL offline (3 blocks, BLSTM 2x128), training step, batch {B} x 4 s, fp32", "batch": B,
                "frames": B * NT}
-        f_ms, b_ms = timed(ours, steps=3, warmup=1)
-        res["fn_ssl_b200_fp32"] = {"forward_ms": round(f_ms, 2), "backward_ms": round(b_ms, 2), "step_ms": round(f_ms + b_ms, 2),
-                                   "frames_per_s": round(B * NT / (f_ms + b_ms) * 1e3, 1)}
+        variants = [("fn_ssl_b200_fp32", None)]
+        if "--dw-compare" in sys.argv:
+            variants = [("fn_ssl_b200_fp32_dw1", "1"), ("fn_ssl_b200_fp32_dw2", "2")]
+        for key, dw in variants:
+            if dw is not None:
+                os.environ["FNSSL_TRAIN_DW"] = dw          # read by fnssl_lstm_backward on every call
+            f_ms, b_ms = timed(ours, steps=3, warmup=1)
+            res[key] = {"forward_ms": round(f_ms, 2), "backward_ms": round(b_ms, 2), "step_ms": round(f_ms + b_ms, 2),
+                        "frames_per_s": round(B * NT / (f_ms + b_ms) * 1e3, 1)}
         del net
         torch.cuda.empty_cache()
+        if "--ours-only" in sys.argv:
+            print(json.dumps(res), flush=True)
+            continue
         ref = TorchNet().to(dev).train()
         for tag, tf32 in (("fp32", False), ("tf32", True)):
             torch.backends.cudnn.allow_tf32 = tf32
@@ -128,5 +139,29 @@ def main():
         print(json.dumps(res), flush=True)
 
 
+def ipdnet_step():
+    """IPDnet 4-mic, hidden 256, online (BASELINE configs[2]'s network) training step at batch 4 x 4 s: forward + frame-level PIT
+    loss + backward, fp32 kernels."""
+    dev = "cuda"
+    B = 4
+    torch.manual_seed(0)
+    net = F.IPDnet(input_size=8, hidden_size=256, max_track=2, is_online=True).to(dev).train()
+    x = torch.randn(B, 8, NF, NT, device=dev)
+    gt = torch.randn(B, NT // 12, 2 * NF, 3, 2, device=dev).tanh()
+
+    def step(fwd_only=False):
+        net.zero_grad(set_to_none=True)
+        loss, _ = T.ipd_pit_mse_loss(net(x), gt)
+        if not fwd_only:
+            loss.backward()
+        return loss
+    f_ms, b_ms = timed(step, steps=2, warmup=1)
+    print(json.dumps({"workload": f"IPDnet 4-mic hidden 256 online, training step (PIT loss), batch {B} x 4 s, fp32", "batch": B,
+                      "fn_ssl_b200_fp32": {"forward_ms": round(f_ms, 2), "backward_ms": round(b_ms, 2), "step_ms": round(f_ms + b_ms, 2),
+                                           "frames_per_s": round(B * NT / (f_ms + b_ms) * 1e3, 1)}}), flush=True)
+
+
 if __name__ == "__main__":
     main()
+    if "--ipdnet" in sys.argv:
+        ipdnet_step()
