@@ -68,12 +68,14 @@ def _grid(seq, axis, nb, nt, nf):
 
 @pytest.mark.parametrize("dw_version", ["1", "2"])
 @pytest.mark.parametrize("axis", [0, 1])
-@pytest.mark.parametrize("H,bidir,c0,ld0,c1,ld1", [(32, True, 4, 4, 0, 0), (32, False, 8, 12, 4, 4), (64, True, 5, 6, 3, 3)])
-def test_emulated_lstm_layer_backward(emu, monkeypatch, dw_version, axis, H, bidir, c0, ld0, c1, ld1):
+@pytest.mark.parametrize("H,bidir,c0,ld0,c1,ld1,geom", [(32, True, 4, 4, 0, 0, (2, 5, 7)), (32, False, 8, 12, 4, 4, (2, 5, 7)),
+                                                       (64, True, 5, 6, 3, 3, (2, 5, 7)),
+                                                       (32, False, 8, 12, 4, 4, (1, 30, 41))])   # 1230 positions: the reduction is split
+def test_emulated_lstm_layer_backward(emu, monkeypatch, dw_version, axis, H, bidir, c0, ld0, c1, ld1, geom):
     from fn_ssl_b200 import _lib
     from fn_ssl_b200.packing import pack_lstm_simt, pack_lstm_whh_t, unpack_lstm_simt_grad
     monkeypatch.setenv("FNSSL_TRAIN_DW", dw_version)      # (5, 6, 3, 3) is not a multiple-of-4 shape: it takes kernel 1 either way
-    nb, nt, nf = 2, 5, 7
+    nb, nt, nf = geom
     dirs_n = 2 if bidir else 1
     torch.manual_seed(11)
     ref = torch.nn.LSTM(c0 + c1, H, batch_first=True, bidirectional=bidir)
@@ -117,9 +119,10 @@ def test_emulated_lstm_layer_backward(emu, monkeypatch, dw_version, axis, H, bid
             assert _rel(g4[k], list(ref.parameters())[4 * d + k].grad) <= 1e-4, (d, k)
 
 
-@pytest.mark.parametrize("c0,ld0,c1,ld1,O", [(5, 5, 0, 0, 7), (6, 8, 3, 4, 130), (130, 132, 2, 2, 4)])
-def test_emulated_conv3x3_products(emu, c0, ld0, c1, ld1, O):
-    nb, nt, nf = 2, 6, 5
+@pytest.mark.parametrize("c0,ld0,c1,ld1,O,geom", [(5, 5, 0, 0, 7, (2, 6, 5)), (6, 8, 3, 4, 130, (2, 6, 5)), (130, 132, 2, 2, 4, (2, 6, 5)),
+                                                  (6, 8, 3, 4, 130, (2, 30, 40))])               # 2400 positions: several splits
+def test_emulated_conv3x3_products(emu, c0, ld0, c1, ld1, O, geom):
+    nb, nt, nf = geom
     Cc = c0 + c1
     s0, s1 = _randn((nb, nt, nf, ld0), 50), (_randn((nb, nt, nf, ld1), 51) if c1 else None)
     w, dy = 0.2 * _randn((O, Cc, 3, 3), 52), _randn((nb, nt, nf, O), 53)
