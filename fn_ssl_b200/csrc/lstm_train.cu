@@ -535,8 +535,8 @@ int fnssl_lstm_backward(const fnssl_lstm_args* a, void* saved, int64_t saved_byt
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const bool vec_ok = a->c0 % 4 == 0 && a->c1 % 4 == 0 && a->ld0 % 4 == 0 && (a->c1 == 0 || a->ld1 % 4 == 0) && a->out0_ld % 4 == 0 &&
                       a->out0_off % 4 == 0 && al16(a->src0) && (a->c1 == 0 || al16(a->src1)) && al16(a->out0);
-  const char* dw_env = getenv("FNSSL_TRAIN_DW");            // 1: lstm_bwd_dw_kernel (any shape), 2: lstm_bwd_dw2_kernel when vec_ok
-  const int dw_version = dw_env ? atoi(dw_env) : 1;
+  const char* dw_env = getenv("FNSSL_TRAIN_DW");            // 2 (default): lstm_bwd_dw2_kernel when vec_ok; 1: lstm_bwd_dw_kernel always
+  const int dw_version = dw_env ? atoi(dw_env) : 2;         // (B = 16: 514 -> 416 ms per training step, profiles/r2_train_bench_v55.jsonl)
   if (vec_ok && dw_version == 2) {
     lstm_bwd_dw2_kernel<<<wgrid, kThreads, 0, st>>>(wp);
     FNSSL_LAUNCH_CHECK("lstm_bwd_dw2_kernel");
