@@ -511,7 +511,7 @@ def main():
         try:
             torch.cuda.empty_cache()
             res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_train.py"), "8"], capture_output=True, text=True,
-                                 timeout=180)
+                                 timeout=90)
             last = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
             train_step = json.loads(last[-1]) if last else {"error": (res.stderr or "no output")[-300:]}
         except Exception as exc:

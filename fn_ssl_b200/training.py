@@ -1,4 +1,5 @@
-"""Training-side forward pieces on the GPU: DP-IPD regression targets and the losses.
+"""The training step on the GPU: DP-IPD regression targets, the losses, and the layers with their
+backward passes.
 
     dpipd_targets(...)        DPIPD.forward(source_doa) + the ground-truth branch of data_preprocess
                               (FN-SSL/Lightning/Module.py:464-497, main.py:227-265; IPDnet/runIPDnetOn.py:256-290)
@@ -9,11 +10,13 @@
                               fnssl_lstm_forward_train / fnssl_lstm_backward): what autograd does behind nn.LSTM in the
                               reference's training_step (FN-SSL/Lightning/main.py:95-109 through Model.py:38,46)
     ipd_head_train(...)       AvgPool(12) -> Linear(256,2) -> tanh -> [cos | sin] with its backward (Model.py:79-87)
+    conv3x3_causal(...), causcnn_train(...)   IPDnet's causal conv block with its backward (IPDnet/FixedAarryIPDnet.py:42-73)
 
 Scope: targets are built per batch on the host in the reference (float64 numpy loops + a host->device copy); here they and the
 losses are CUDA kernels.  The backward pass exists for the fp32 engine (lstm_train.cu, head.cu): `FN_SSL` / `FNblock` in train
-mode run it (fn_ssl_b200/Model.py: residual adds and dropout are torch elementwise ops between the layer kernels); the
-tensor-core kernels are inference kernels and IPDnet's causal conv block has no backward, so `IPDnet` still raises in train mode.
+mode run it (fn_ssl_b200/Model.py: residual adds and dropout are torch elementwise ops between the layer kernels), and so does
+`IPDnet` (conv_train.cu; ReLU / pooling / tanh are torch ops).  The tensor-core kernels are inference kernels; IPDnet2 has no
+backward kernels and raises in train mode.
 """
 from __future__ import annotations
 
