@@ -369,3 +369,80 @@ def causcnn_train(src0: Tensor, c0: int, src1: Optional[Tensor], c1: int, w1: Te
     a = a[:, :nt2 * 4].reshape(nb, nt2, 4, nf, a.shape[-1]).mean(dim=2)          # AvgPool2d((1, 4))
     y = torch.tanh(conv3x3_causal(a, a.shape[-1], None, 0, w3))
     return y.permute(0, 3, 2, 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's LightningModule surface for training, without Lightning
+# ---------------------------------------------------------------------------------------------
+
+class FNSSLTrainModule(torch.nn.Module):
+    """Plain-PyTorch counterpart of the training-relevant surface of the reference's LightningModule `MyModel`
+    (FN-SSL/Lightning/main.py:80-279; pytorch_lightning is not a dependency of this package): `forward`, `data_preprocess`
+    (features AND the DP-IPD targets, both on the device), `cal_loss`, `training_step`, `validation_step`, `predict_step`,
+    `configure_optimizers` -- same names, argument meaning and return values, so a Lightning subclass only has to forward to them.
+
+        batch = (mic_sig_batch (nb, nsample, nch) f32,
+                 {'doa': (nb, nseg, 2, nsource) [elevation, azimuth] rad, 'vad_sources': (nb, nseg, nvad, nsource)})
+        step  = module.training_step(batch, 0)["loss"];  step.backward();  distributed.all_reduce_gradients(module.arch);  opt.step()
+    """
+
+    def __init__(self, tar_useVAD: bool = True, ch_mode: str = 'MM', fs: int = 16000, win_len: int = 512, nfft: int = 512,
+                 win_shift_ratio: float = 0.5, mic_location=((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0)), speed: float = 340.0,
+                 arch: Optional[torch.nn.Module] = None):
+        super().__init__()
+        if (win_len, nfft, win_shift_ratio) != (512, 512, 0.5):
+            raise RuntimeError("FNSSLTrainModule: the front end is built for win_len = nfft = 512, hop 256")
+        if arch is None:
+            from .Model import FN_SSL
+            arch = FN_SSL()                                                # main.py:100
+        self.arch = arch
+        self.tar_useVAD, self.ch_mode, self.nfft, self.fre_max, self.speed = tar_useVAD, ch_mode, nfft, fs / 2, speed
+        self.mic_location = np.asarray(mic_location, dtype=np.float64)
+        self.fre_range_used = range(1, nfft // 2 + 1, 1)                   # main.py:128
+
+    def _device(self) -> torch.device:
+        return next(self.arch.parameters()).device
+
+    def forward(self, x: Tensor) -> Tensor:
+        return self.arch(x)
+
+    def data_preprocess(self, mic_sig_batch: Optional[Tensor] = None, gt_batch: Optional[dict] = None, eps: float = 1e-6,
+                        nor_flag: bool = True) -> list:
+        """main.py:200-266: [network input (nb*P, 4, 256, nt)] + [gt dict with 'ipd' (nb, nseg, 2*256, P) added] -- STFT, pair
+        re-batching, forgetting_norm and the feature assembly are the CUDA front end; the targets come from `dpipd_targets`."""
+        from .pipeline import data_preprocess_fnssl
+        dev = self._device()
+        data = []
+        if mic_sig_batch is not None:
+            data += data_preprocess_fnssl(mic_sig_batch.to(dev), ch_mode=self.ch_mode, eps=eps, nor_flag=nor_flag)
+        if gt_batch is not None:
+            doa = gt_batch['doa'].to(dev).float()
+            vad = gt_batch['vad_sources'].to(dev).float().mean(dim=2)      # (nb, nseg, nsource), main.py:241
+            ipd = dpipd_targets(doa, self.mic_location, vad=vad if self.tar_useVAD else None, ch_mode=self.ch_mode,
+                                nf=self.nfft // 2 + 1, fre_max=self.fre_max, speed=self.speed, fre_range_used=self.fre_range_used)
+            gt_batch = dict(gt_batch)
+            gt_batch['doa'], gt_batch['ipd'], gt_batch['vad_sources'] = doa, ipd, vad
+            data += [gt_batch]
+        return data
+
+    def cal_loss(self, pred_batch: Tensor, gt_batch: dict) -> Tensor:
+        return ipd_mse_loss(pred_batch, gt_batch['ipd'])                   # main.py:191-198
+
+    def _step(self, batch) -> Tensor:
+        in_batch, gt_batch = self.data_preprocess(batch[0], batch[1])
+        return self.cal_loss(self(in_batch), gt_batch)
+
+    def training_step(self, batch, batch_idx: int = 0) -> dict:
+        return {"loss": self._step(batch)}                                 # main.py:95-103
+
+    def validation_step(self, batch, batch_idx: int = 0) -> Tensor:
+        with torch.no_grad():
+            return self._step(batch)                                       # main.py:105-115 without the DOA metrics
+
+    def predict_step(self, batch: Tensor, batch_idx: int = 0) -> Tensor:
+        return self(self.data_preprocess(mic_sig_batch=batch.permute(0, 2, 1))[0])     # main.py:183-189
+
+    def configure_optimizers(self) -> dict:
+        optimizer = torch.optim.Adam(self.arch.parameters(), lr=0.001)     # main.py:268-279
+        lr_scheduler = torch.optim.lr_scheduler.ExponentialLR(optimizer, gamma=0.8988, last_epoch=-1)
+        return {'optimizer': optimizer, 'lr_scheduler': {'scheduler': lr_scheduler, 'monitor': 'valid/loss'}}

@@ -342,3 +342,54 @@ def test_pit_loss_gradient_matches_oracle_autograd():
     assert np.array_equal(perm.cpu().numpy(), pref.numpy())
     assert abs(float(loss.detach()) - float(lref.detach())) <= 1e-5 * float(lref.detach())
     assert _rel(pd.grad, 3.0 * pr.grad) <= 1e-5
+
+
+# ---- the reference's LightningModule surface (training_step) -----------------------------------------------------------------
+
+def _train_batch():
+    gen = torch.Generator().manual_seed(5)
+    sig = orc.white_noise(2, 512 + 256 * 23, 2, seed=3)
+    doa = torch.stack((torch.rand(2, 2, 1, generator=gen) * 3.1, torch.rand(2, 2, 1, generator=gen) * 3.1), dim=2)     # (nb, nseg, 2, ns)
+    vad = torch.rand(2, 2, 12, 1, generator=gen)
+    return sig, {'doa': doa, 'vad_sources': vad}
+
+
+def test_training_module_surface():
+    from fn_ssl_b200 import training as T
+    mod = T.FNSSLTrainModule()
+    for name in ("forward", "data_preprocess", "cal_loss", "training_step", "validation_step", "predict_step", "configure_optimizers"):
+        assert callable(getattr(mod, name))                                          # MyModel's names, FN-SSL/Lightning/main.py:80-279
+    cfg = mod.configure_optimizers()
+    assert isinstance(cfg['optimizer'], torch.optim.Adam) and cfg['optimizer'].defaults['lr'] == 0.001
+    assert isinstance(cfg['lr_scheduler']['scheduler'], torch.optim.lr_scheduler.ExponentialLR) and cfg['lr_scheduler']['monitor'] == 'valid/loss'
+    assert list(mod.state_dict().keys())[0].startswith("arch.")                     # checkpoints carry the `arch.` prefix, as Lightning's
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mod.training_step(_train_batch(), 0)                                         # no CPU fallback here either
+
+
+@pytest.mark.gpu
+def test_training_module_step_matches_the_oracle_composition():
+    """training_step = CUDA front end -> train-mode network -> CUDA DP-IPD targets -> CUDA MSE loss; against the same chain of
+    oracle functions (main.py:95-103,191-266), loss and gradients."""
+    import fn_ssl_b200 as F
+    from fn_ssl_b200 import training as T
+    from oracle import training_oracle as tro
+    net = F.FN_SSL(is_online=False)
+    net.load_state_dict(orc.seeded_fnssl_state_dict(0, is_online=False))
+    mod = T.FNSSLTrainModule(arch=_no_dropout(net)).cuda().train()
+    sig, gt = _train_batch()
+    loss = mod.training_step((sig, gt), 0)["loss"]
+    sd = {k: v.clone().requires_grad_(True) for k, v in orc.seeded_fnssl_state_dict(0, is_online=False).items()}
+    ref_gt = tro.fnssl_targets(gt['doa'].numpy(), gt['vad_sources'].mean(2).numpy(), np.array(((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0))), 'MM')
+    ref_loss = tro.fnssl_loss(orc.fnssl_forward(orc.preprocess_fnssl(sig), sd, fast=True), ref_gt)
+    assert abs(float(loss.detach()) - float(ref_loss.detach())) <= 1e-4 * float(ref_loss.detach())
+    loss.backward()
+    ref_loss.backward()
+    for n, p_ in net.named_parameters():
+        assert _rel(p_.grad, sd[n].grad) <= 2e-4, n
+    cfg = mod.configure_optimizers()
+    cfg['optimizer'].step()
+    cfg['lr_scheduler']['scheduler'].step()
+    assert float(mod.validation_step((sig, gt))) != float(loss.detach())             # the parameters moved
+    with torch.no_grad():
+        assert tuple(mod.eval().predict_step(sig.permute(0, 2, 1).cuda()).shape) == (2, 2, 512)
