@@ -446,3 +446,85 @@ class FNSSLTrainModule(torch.nn.Module):
         optimizer = torch.optim.Adam(self.arch.parameters(), lr=0.001)     # main.py:268-279
         lr_scheduler = torch.optim.lr_scheduler.ExponentialLR(optimizer, gamma=0.8988, last_epoch=-1)
         return {'optimizer': optimizer, 'lr_scheduler': {'scheduler': lr_scheduler, 'monitor': 'valid/loss'}}
+
+
+class IPDnetTrainModule(torch.nn.Module):
+    """The same for IPDnet: the training-relevant surface of `MyModel` in IPDnet/runIPDnetOn.py:80-304 -- `data_preprocess` returns
+    [network input (nb, 2M, 256, nt), doa, per-source DP-IPD targets (nb*nt2, 512, M-1, nsrc) with silent sources replaced by the
+    non-source (Bessel) target, dp_vad], `cal_loss` is the frame-level PIT loss, `training_step(batch)` -> {"loss": ...}.
+
+        batch = (mic_sig_batch (nb, nsample, M) f32,
+                 {'doa': (nb, nt2, 2, nsrc) rad, 'dp_signal': (nb, nsample, M, nsrc) direct-path signals for the VAD})"""
+
+    def __init__(self, tar_useVAD: bool = True, ch_mode: str = 'M', fs: int = 16000, win_len: int = 512, nfft: int = 512,
+                 win_shift_ratio: float = 0.5, max_source: int = 2, mic_pos=((-0.04, 0.0, 0.0), (0.04, 0.0, 0.0)),
+                 arch: Optional[torch.nn.Module] = None):
+        super().__init__()
+        if (win_len, nfft, win_shift_ratio) != (512, 512, 0.5):
+            raise RuntimeError("IPDnetTrainModule: the front end is built for win_len = nfft = 512, hop 256")
+        if arch is None:
+            from .FixedAarryIPDnet import IPDnet
+            arch = IPDnet()                                                # runIPDnetOn.py:101 (2-mic IPDnet)
+        self.arch = arch
+        self.tar_useVAD, self.ch_mode, self.nfft, self.fre_max, self.max_source = tar_useVAD, ch_mode, nfft, fs / 2, max_source
+        self.mic_pos = np.asarray(mic_pos.cpu().numpy() if torch.is_tensor(mic_pos) else mic_pos, dtype=np.float64)
+        self.fre_range_used = range(1, nfft // 2 + 1, 1)
+        self.register_buffer("non_source_tar", torch.from_numpy(non_source_target(self.mic_pos, self.fre_range_used)).float(),
+                             persistent=False)                             # euclidean_distances_to_bessel, :209-222
+
+    def _device(self) -> torch.device:
+        return next(self.arch.parameters()).device
+
+    def forward(self, x: Tensor) -> Tensor:
+        return self.arch(x)
+
+    def cal_vad(self, dp_mic_sig_batch: Tensor, spec: Tensor) -> Tensor:
+        """runIPDnetOn.py:224-235: per source, mean over the 257 bins of |STFT(direct path)| / |STFT(mixture)| on microphone 0,
+        averaged over the 12 frames of an output frame -> (nb, nt // 12, max_source).  The STFTs are the CUDA kernel."""
+        nb, nf, nt, _ = spec.shape
+        mix = spec[:, :, :, 0].abs()
+        vad = torch.stack([(ops.stft(dp_mic_sig_batch[:, :, :, s].contiguous())[0][:, :, :, 0].abs() / mix).mean(dim=1)
+                           for s in range(self.max_source)], dim=2)         # (nb, nt, nsrc)
+        nt2 = nt // 12
+        return vad[:, :nt2 * 12].reshape(nb, nt2, 12, self.max_source).mean(dim=2)
+
+    def data_preprocess(self, mic_sig_batch: Tensor, acoustic_scene_batch: Optional[dict] = None, eps: float = 1e-6) -> list:
+        dev = self._device()
+        sig = mic_sig_batch.to(dev)
+        spec, magsum = ops.stft(sig, want_magsum=True)
+        _, _, cf = ops.features(spec, magsum, 'ALL', ops.NORM_FORGETTING, 280, eps, torch.float32, want_cfirst=True)     # :240-254
+        data = [cf]
+        if acoustic_scene_batch is None:
+            return data
+        dp_vad = self.cal_vad(acoustic_scene_batch['dp_signal'].to(dev).float(), spec)
+        doa = acoustic_scene_batch['doa'].to(dev).float()
+        ipd = dpipd_targets(doa, self.mic_pos, vad=dp_vad, ch_mode=self.ch_mode, nf=self.nfft // 2 + 1, fre_max=self.fre_max,
+                            speed=340.0, fre_range_used=self.fre_range_used, vad_threshold=0.001, per_source=True,
+                            non_source=self.non_source_tar.to(dev))        # :256-283
+        nb, nt2 = ipd.shape[0], ipd.shape[1]
+        data += [doa, ipd.reshape(nb * nt2, ipd.shape[2], ipd.shape[3], ipd.shape[4])]
+        if self.tar_useVAD:
+            data += [dp_vad]
+        return data
+
+    def cal_loss(self, pred_batch: Tensor, gt_batch: list) -> Tensor:
+        return ipd_pit_mse_loss(pred_batch, gt_batch[1])[0]                # :196-206
+
+    def _step(self, batch) -> Tensor:
+        data = self.data_preprocess(batch[0], batch[1])
+        return self.cal_loss(self(data[0]), data[1:])
+
+    def training_step(self, batch, batch_idx: int = 0) -> dict:
+        return {"loss": self._step(batch)}                                 # :144-154
+
+    def validation_step(self, batch, batch_idx: int = 0) -> Tensor:
+        with torch.no_grad():
+            return self._step(batch)
+
+    def predict_step(self, batch: Tensor, batch_idx: int = 0) -> Tensor:
+        return self(self.data_preprocess(mic_sig_batch=batch.permute(0, 2, 1))[0])[0]      # :182-186 (first utterance, as there)
+
+    def configure_optimizers(self) -> dict:
+        optimizer = torch.optim.Adam(self.arch.parameters(), lr=0.0005)    # :293-304
+        lr_scheduler = torch.optim.lr_scheduler.ExponentialLR(optimizer, gamma=0.975, last_epoch=-1)
+        return {'optimizer': optimizer, 'lr_scheduler': {'scheduler': lr_scheduler, 'monitor': 'valid/loss'}}

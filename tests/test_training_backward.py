@@ -393,3 +393,57 @@ def test_training_module_step_matches_the_oracle_composition():
     assert float(mod.validation_step((sig, gt))) != float(loss.detach())             # the parameters moved
     with torch.no_grad():
         assert tuple(mod.eval().predict_step(sig.permute(0, 2, 1).cuda()).shape) == (2, 2, 512)
+
+
+def _ipdnet_train_batch():
+    gen = torch.Generator().manual_seed(6)
+    sig = orc.white_noise(2, 512 + 256 * 23, 3, seed=3)
+    dp = 0.3 * torch.randn(2, sig.shape[1], 3, 2, generator=gen)
+    dp[0, :, :, 1] = 0.0                                                             # source 1 of utterance 0 is silent: non-source target
+    doa = torch.stack((torch.full((2, 2, 2), 1.57), torch.rand(2, 2, 2, generator=gen) * 3.1), dim=2)     # (nb, nt2, 2, nsrc)
+    return sig, {'doa': doa, 'dp_signal': dp}
+
+
+IPD_MIC3 = np.array(((0.0, 0.0, 0.0), (0.03, 0.0, 0.0), (0.0, 0.04, 0.0)))
+
+
+def test_ipdnet_training_module_surface():
+    from fn_ssl_b200 import training as T
+    mod = T.IPDnetTrainModule(mic_pos=torch.tensor(IPD_MIC3))
+    cfg = mod.configure_optimizers()
+    assert cfg['optimizer'].defaults['lr'] == 0.0005 and isinstance(cfg['lr_scheduler']['scheduler'], torch.optim.lr_scheduler.ExponentialLR)
+    assert tuple(mod.non_source_tar.shape) == (512, 2) and "non_source_tar" not in mod.state_dict()
+    assert all(k.startswith("arch.") for k in mod.state_dict())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mod.training_step(_ipdnet_train_batch(), 0)
+
+
+@pytest.mark.gpu
+def test_ipdnet_training_module_step_matches_the_oracle_composition():
+    """training_step of IPDnet = CUDA front end + dp-VAD (CUDA STFTs) -> train-mode network -> per-source targets with the
+    non-source target -> frame-level PIT loss; against the reference's lines restated with oracle functions
+    (runIPDnetOn.py:144-154,196-206,224-283), loss and gradients."""
+    import fn_ssl_b200 as F
+    from fn_ssl_b200 import training as T
+    from oracle import training_oracle as tro
+    kw = dict(input_size=6, hidden_size=64, max_track=2, is_online=True)
+    net = F.IPDnet(**kw)
+    net.load_state_dict(orc.seeded_ipdnet_state_dict(4, **kw))
+    mod = T.IPDnetTrainModule(mic_pos=IPD_MIC3, arch=_no_dropout(net)).cuda().train()
+    sig, scene = _ipdnet_train_batch()
+    loss = mod.training_step((sig, scene), 0)["loss"]
+    st = orc.stft(sig)
+    vad = torch.zeros(2, st.shape[2], 2)
+    for s in range(2):                                                               # cal_vad, :224-235
+        vad[:, :, s] = torch.mean(torch.abs(orc.stft(scene['dp_signal'][:, :, :, s]))[:, :, :, 0] / torch.abs(st[:, :, :, 0]), dim=1)
+    vad = torch.nn.AvgPool2d(kernel_size=(12, 1))(vad)
+    tgt = tro.ipdnet_targets(scene['doa'].numpy(), vad.numpy(), IPD_MIC3, T.non_source_target(IPD_MIC3), 'M')
+    sd = {k: v.clone().requires_grad_(True) for k, v in orc.seeded_ipdnet_state_dict(4, **kw).items()}
+    ref_loss, _ = tro.ipdnet_pit_loss(orc.ipdnet_forward(orc.preprocess_ipdnet(sig), sd, is_online=True, fast=True), tgt)
+    assert abs(float(loss.detach()) - float(ref_loss.detach())) <= 1e-4 * float(ref_loss.detach())
+    loss.backward()
+    ref_loss.backward()
+    for n, p_ in net.named_parameters():
+        assert _rel(p_.grad, sd[n].grad) <= 2e-4, n
+    mod.configure_optimizers()['optimizer'].step()
+    assert float(mod.validation_step((sig, scene))) != float(loss.detach())
