@@ -147,3 +147,50 @@ def test_emulated_conv3x3_products(emu, c0, ld0, c1, ld1, O, geom):
     assert emu.fnssl_conv3x3_backward_weight(a0.ctypes.data, c0, ld0, _ptr(a1), c1, ld1, dyn.ctypes.data, O, O, nb, nt, nf,
                                              work.ctypes.data, dw.ctypes.data, None) == 0, emu.emu_last_error()
     assert _rel(dw, rw.grad) <= 1e-4
+
+
+# ---- train.cu: DP-IPD targets and the losses against the reference goldens ----------------------------------------------------
+
+@pytest.fixture(scope="module")
+def tg():
+    return np.load(os.path.join(ROOT, "tests", "golden", "train_golden.npz"))
+
+
+@pytest.mark.parametrize("tag,mode", [("2mic", "MM"), ("3mic", "MM"), ("3micM", "M")])
+def test_emulated_targets_and_mse_loss(emu, tg, tag, mode):
+    from fn_ssl_b200.training import mic_pairs
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    emu.fnssl_dpipd_targets.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, f, f, i, i, f, i, vp, vp, vp]
+    emu.fnssl_ipd_mse_loss.argtypes = [vp, vp, i, i, i, i, vp, vp, vp]
+    doa, vad, mic = np.ascontiguousarray(tg[f"{tag}_doa"], np.float32), np.ascontiguousarray(tg[f"{tag}_vad"], np.float32), tg[f"{tag}_mic"]
+    nb, nt, _, ns = doa.shape
+    pairs = np.ascontiguousarray(mic_pairs(mic.shape[0], mode))
+    micf = np.ascontiguousarray(mic, np.float32)
+    P = pairs.shape[0]
+    out = np.zeros((nb, nt, 512, P), np.float32)
+    assert emu.fnssl_dpipd_targets(doa.ctypes.data, vad.ctypes.data, micf.ctypes.data, pairs.ctypes.data, nb, nt, ns, mic.shape[0], P, 257,
+                                   8000.0, 340.0, 1, 256, 0.0, 0, None, out.ctypes.data, None) == 0, emu.emu_last_error()
+    assert float(np.abs(out - tg[f"{tag}_ipd_gt"]).max()) <= 2e-6
+    per = np.zeros((nb, nt, 512, P, ns), np.float32)
+    assert emu.fnssl_dpipd_targets(doa.ctypes.data, None, micf.ctypes.data, pairs.ctypes.data, nb, nt, ns, mic.shape[0], P, 257,
+                                   8000.0, 340.0, 1, 256, 0.0, 1, None, per.ctypes.data, None) == 0, emu.emu_last_error()
+    assert float(np.abs(per - tg[f"{tag}_ipd_per_source"]).max()) <= 2e-6
+    pred, gt = np.ascontiguousarray(tg[f"{tag}_pred"], np.float32), np.ascontiguousarray(tg[f"{tag}_ipd_gt"], np.float32)
+    ws, loss = np.zeros(nb * nt, np.float32), np.zeros(1, np.float32)
+    assert emu.fnssl_ipd_mse_loss(pred.ctypes.data, gt.ctypes.data, nb, P, nt, 512, ws.ctypes.data, loss.ctypes.data, None) == 0
+    assert abs(float(loss[0]) - float(tg[f"{tag}_loss"])) <= 2e-6 * float(tg[f"{tag}_loss"])
+
+
+def test_emulated_pit_loss(emu, tg):
+    vp, i = C.c_void_p, C.c_int
+    emu.fnssl_ipd_pit_mse_loss.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp]
+    pred = np.ascontiguousarray(tg["ipdnet_pred"], np.float32)
+    gt = np.ascontiguousarray(tg["ipdnet_ipd_gt"], np.float32)
+    nb, nt, _, _, ns = pred.shape
+    rows = nb * nt
+    p, g = pred.reshape(rows, -1, ns), gt.reshape(rows, -1, ns)
+    ws, loss, perm = np.zeros(rows, np.float32), np.zeros(1, np.float32), np.zeros((rows, ns), np.int32)
+    assert emu.fnssl_ipd_pit_mse_loss(p.ctypes.data, g.ctypes.data, rows, p.shape[1], ns, ws.ctypes.data, loss.ctypes.data,
+                                      perm.ctypes.data, None) == 0, emu.emu_last_error()
+    assert abs(float(loss[0]) - float(tg["ipdnet_pit_loss"])) <= 2e-6 * float(tg["ipdnet_pit_loss"])
+    assert np.array_equal(perm, tg["ipdnet_pit_perm"])
