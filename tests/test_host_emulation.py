@@ -194,3 +194,36 @@ def test_emulated_pit_loss(emu, tg):
                                       perm.ctypes.data, None) == 0, emu.emu_last_error()
     assert abs(float(loss[0]) - float(tg["ipdnet_pit_loss"])) <= 2e-6 * float(tg["ipdnet_pit_loss"])
     assert np.array_equal(perm, tg["ipdnet_pit_perm"])
+
+
+# ---- head.cu: DP-IPD head forward / backward and the DOA linear (warp shuffles emulated with per-warp barriers) ------------------
+
+@pytest.mark.parametrize("nt,Cc,ld", [(24, 64, 64), (31, 40, 44)])
+def test_emulated_ipd_head_forward_backward_and_linear(emu, nt, Cc, ld):
+    vp, i = C.c_void_p, C.c_int
+    emu.fnssl_ipd_head_forward.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp, vp]
+    emu.fnssl_ipd_head_backward.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp, i, vp, vp, vp]
+    emu.fnssl_linear_forward.argtypes = [vp, vp, vp, i, i, i, vp, vp]
+    nb, nf = 2, 7
+    x, w, b = _randn((nb, nt, nf, ld), 9), 0.1 * _randn((2, Cc), 10), _randn((2,), 11)
+    dy = _randn((nb, nt // 12, 2 * nf), 12)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    seq = xr[..., :Cc].permute(0, 2, 1, 3).reshape(nb * nf, nt, Cc)                 # Model.py:79-87
+    ipd = torch.tanh(torch.nn.functional.linear(torch.nn.AvgPool2d(kernel_size=(12, 1))(seq), wr, br))
+    ipd = ipd.view(nb, nf, nt // 12, 2).permute(0, 2, 1, 3)
+    yref = torch.cat((ipd[..., 0], ipd[..., 1]), dim=2)
+    (yref * dy).sum().backward()
+    xn, wn, bn, dyn = _np(x), _np(w), _np(b), _np(dy)
+    y = np.zeros((nb, nt // 12, 2 * nf), np.float32)
+    assert emu.fnssl_ipd_head_forward(xn.ctypes.data, 0, ld, nb, nt, nf, Cc, wn.ctypes.data, bn.ctypes.data, y.ctypes.data, None) == 0
+    assert _rel(y, yref) <= 1e-5
+    dx, dw, db = np.zeros_like(xn), np.full_like(wn, 5.0), np.full(2, 5.0, np.float32)
+    assert emu.fnssl_ipd_head_backward(xn.ctypes.data, ld, nb, nt, nf, Cc, wn.ctypes.data, y.ctypes.data, dyn.ctypes.data, dx.ctypes.data, ld,
+                                       dw.ctypes.data, db.ctypes.data, None) == 0, emu.emu_last_error()
+    assert _rel(dx, xr.grad) <= 1e-4 and _rel(dw, wr.grad) <= 1e-4 and _rel(db, br.grad) <= 1e-4
+    # DOA classifier Linear(2 nf -> 9) on the head's output rows
+    lw, lb = _randn((9, 2 * nf), 13), _randn((9,), 14)
+    rows = y.reshape(-1, 2 * nf)
+    z = np.zeros((rows.shape[0], 9), np.float32)
+    assert emu.fnssl_linear_forward(rows.ctypes.data, _np(lw).ctypes.data, _np(lb).ctypes.data, rows.shape[0], 2 * nf, 9, z.ctypes.data, None) == 0
+    assert _rel(z, torch.nn.functional.linear(torch.from_numpy(rows), lw, lb)) <= 1e-5

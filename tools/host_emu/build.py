@@ -13,11 +13,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "fn_ssl_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-SOURCES = ["lstm_simt.cu", "lstm_train.cu", "conv_train.cu", "train.cu"]
+SOURCES = ["lstm_simt.cu", "lstm_train.cu", "conv_train.cu", "train.cu", "head.cu"]
 LIB = os.path.join(OUT, "libfnssl_emu.so")
 
 LAUNCH = re.compile(r"^(\s*)([\w:]+(?:<[^<>;]*>)?)<<<(.+?),\s*([^,]+?),\s*([^,]+?),\s*([^,]+?)>>>\((.*?)\);", re.M | re.S)
-DYN_SHARED = re.compile(r"extern __shared__ __align__\(16\) (\w+) (\w+)\[\];")
+DYN_SHARED = re.compile(r"extern __shared__ (?:__align__\(16\) )?(\w+) (\w+)\[\];")
 
 
 def transform(text: str) -> str:

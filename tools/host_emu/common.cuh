@@ -26,6 +26,10 @@ struct dim3 {
 struct alignas(16) float4 { float x, y, z, w; };
 inline float4 make_float4(float a, float b, float c, float d) { float4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 struct __half { unsigned short v; };
+struct __half2 { __half x, y; };
+struct float2 { float x, y; };
+struct uint4 { unsigned x, y, z, w; };
+inline float2 __half22float2(__half2) { float2 r; r.x = 0.0f; r.y = 0.0f; return r; }     // fp16 grids are not emulated
 
 inline thread_local dim3 threadIdx, blockIdx;
 inline dim3 blockDim, gridDim;
@@ -51,7 +55,21 @@ template <class F> int cudaFuncSetAttribute(F, int, int) { return 0; }
 inline int cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline float __expf(float x) { return expf(x); }
+inline float tanhf_emu_unused(float x) { return tanhf(x); }
 inline float atomicAdd(float* p, float v) { std::lock_guard<std::mutex> g(g_emu_atomic); float o = *p; *p = o + v; return o; }
+
+// warp shuffles: the 32 threads of a warp meet on a per-warp barrier around a per-warp exchange buffer (converged code only)
+inline float g_emu_shfl[32][32];
+inline pthread_barrier_t g_emu_warp_barrier[32];
+inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+  const unsigned t = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  const unsigned w = t / 32, l = t % 32;
+  g_emu_shfl[w][l] = v;
+  pthread_barrier_wait(&g_emu_warp_barrier[w]);
+  const float r = g_emu_shfl[w][l ^ (unsigned)lane_mask];
+  pthread_barrier_wait(&g_emu_warp_barrier[w]);
+  return r;
+}
 
 inline char g_emu_log[4096];                      // names of the kernels launched since the last emu_launch_log_reset()
 inline void emu_launch(const char* name, const std::function<void()>& body, dim3 grid, dim3 block) {
@@ -60,6 +78,8 @@ inline void emu_launch(const char* name, const std::function<void()>& body, dim3
   blockDim = block;
   gridDim = grid;
   pthread_barrier_init(&g_emu_barrier, nullptr, nthreads);
+  for (unsigned w = 0; w < (nthreads + 31) / 32 && w < 32; ++w)
+    pthread_barrier_init(&g_emu_warp_barrier[w], nullptr, nthreads - 32 * w < 32 ? nthreads - 32 * w : 32);
   std::vector<std::thread> pool;
   for (unsigned t = 0; t < nthreads; ++t)
     pool.emplace_back([&, t] {
@@ -74,6 +94,7 @@ inline void emu_launch(const char* name, const std::function<void()>& body, dim3
     });
   for (auto& th : pool) th.join();
   pthread_barrier_destroy(&g_emu_barrier);
+  for (unsigned w = 0; w < (nthreads + 31) / 32 && w < 32; ++w) pthread_barrier_destroy(&g_emu_warp_barrier[w]);
 }
 
 namespace fnssl {
