@@ -8,6 +8,8 @@
 // registers, [x_t | h_{t-1}] in shared memory, and the (I+H) x 4H weight matrix is streamed from L2 every
 // step as float4 (i,f,g,o) per (k, unit).  It is the reference engine of the package: any I, H in
 // {32,64,128,256}, fp32 or fp16 grids.  The tensor-core engine (lstm_tc.cu) is the fast one.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -178,10 +180,10 @@ static int launch_simt(const SimtParams& p, int dirs, cudaStream_t st) {
   if (p.save_gates) {   // training forward (fp32 grids): fewer rows per CTA while the 16-row grid would leave SMs idle
     if constexpr (std::is_same<T, float>::value) {
       constexpr int G = kSimtThreads / H;
-      if (ceil_div64(p.rows, 16 * G) * dirs < 148) {
-        if (ceil_div64(p.rows, 8 * G) * dirs >= 148) return launch_simt_rpt<T, H, 8>(p, dirs, st);
-        return launch_simt_rpt<T, H, 4>(p, dirs, st);
-      }
+      int rpt = ceil_div64(p.rows, 16 * G) * dirs >= 148 ? 16 : ceil_div64(p.rows, 8 * G) * dirs >= 148 ? 8 : 4;
+      if (const char* e = getenv("FNSSL_TRAIN_RPT")) rpt = atoi(e);      // tests: force a variant on a small grid
+      if (rpt == 8) return launch_simt_rpt<T, H, 8>(p, dirs, st);
+      if (rpt == 4) return launch_simt_rpt<T, H, 4>(p, dirs, st);
     }
   }
   return launch_simt_rpt<T, H, 16>(p, dirs, st);

@@ -421,8 +421,10 @@ int launch_bwd_seq_rpt(const BwdSeqParams& p, int dirs, cudaStream_t st) {
 template <int H>
 int launch_bwd_seq(const BwdSeqParams& p, int dirs, cudaStream_t st) {
   constexpr int G = kThreads / H;
-  if (ceil_div64(p.g.rows, 16 * G) * dirs >= 148) return launch_bwd_seq_rpt<H, 16>(p, dirs, st);
-  if (ceil_div64(p.g.rows, 8 * G) * dirs >= 148) return launch_bwd_seq_rpt<H, 8>(p, dirs, st);
+  int rpt = ceil_div64(p.g.rows, 16 * G) * dirs >= 148 ? 16 : ceil_div64(p.g.rows, 8 * G) * dirs >= 148 ? 8 : 4;
+  if (const char* e = getenv("FNSSL_TRAIN_RPT")) rpt = atoi(e);          // tests: force a variant on a small grid
+  if (rpt == 16) return launch_bwd_seq_rpt<H, 16>(p, dirs, st);
+  if (rpt == 8) return launch_bwd_seq_rpt<H, 8>(p, dirs, st);
   return launch_bwd_seq_rpt<H, 4>(p, dirs, st);
 }
 

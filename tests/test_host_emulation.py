@@ -66,6 +66,18 @@ def _grid(seq, axis, nb, nt, nf):
     return seq.reshape(nb, nt, nf, -1) if axis == 0 else seq.reshape(nb, nf, nt, -1).permute(0, 2, 1, 3)
 
 
+@pytest.mark.parametrize("rpt", ["8", "16"])
+@pytest.mark.parametrize("axis", [0, 1])
+def test_emulated_lstm_rows_per_thread_variants(emu, monkeypatch, rpt, axis):
+    """The 8- and 16-rows-per-thread instantiations of the training forward and the BPTT kernel (picked by grid coverage at
+    batch >= 8 / 16) forced onto a small grid with a partial row tile."""
+    monkeypatch.setenv("FNSSL_TRAIN_RPT", rpt)
+    test_emulated_lstm_layer_backward(emu, monkeypatch, "2", axis, 64, True, 8, 8, 4, 4, (2, 9, 11))
+    rows = 2 * 9 if axis == 0 else 2 * 11
+    blocks = -(-rows // (int(rpt) * 4))                                   # H = 64: 4 row groups per CTA
+    assert f"lstm_bwd_seq_kernel<H, RPT>[{blocks},2,1]" in emu.emu_launch_log().decode(), emu.emu_launch_log().decode()
+
+
 @pytest.mark.parametrize("dw_version", ["1", "2"])
 @pytest.mark.parametrize("axis", [0, 1])
 @pytest.mark.parametrize("H,bidir,c0,ld0,c1,ld1,geom", [(32, True, 4, 4, 0, 0, (2, 5, 7)), (32, False, 8, 12, 4, 4, (2, 5, 7)),

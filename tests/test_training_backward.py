@@ -137,6 +137,16 @@ def test_lstm_layer_gradients_match_torch_autograd(axis, H, bidir, c0, ld0, c1, 
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("rpt", ["8", "16"])
+@pytest.mark.parametrize("axis", [0, 1])
+def test_lstm_layer_rows_per_thread_variants(monkeypatch, rpt, axis):
+    """The 8- / 16-rows-per-thread instantiations of the training forward and the BPTT kernel (chosen by grid coverage from batch
+    8 / 16 up, i.e. never on test-sized grids) forced onto a small grid with a partial row tile."""
+    monkeypatch.setenv("FNSSL_TRAIN_RPT", rpt)
+    test_lstm_layer_gradients_match_torch_autograd(axis, 128, True, 24, 24, 4, 8)
+
+
+@pytest.mark.gpu
 def test_lstm_layer_without_input_gradient_and_weight_only_sources():
     """First layer of the network: the feature grid needs no gradient (dsrc0 = NULL); second source with a gradient only."""
     from fn_ssl_b200 import training as T

@@ -73,7 +73,8 @@ inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
 
 inline char g_emu_log[4096];                      // names of the kernels launched since the last emu_launch_log_reset()
 inline void emu_launch(const char* name, const std::function<void()>& body, dim3 grid, dim3 block) {
-  if (strlen(g_emu_log) + strlen(name) + 2 < sizeof(g_emu_log)) { strcat(g_emu_log, name); strcat(g_emu_log, ";"); }
+  if (strlen(g_emu_log) + strlen(name) + 40 < sizeof(g_emu_log))          // "name[gx,gy,gz];"
+    snprintf(g_emu_log + strlen(g_emu_log), 40 + strlen(name), "%s[%u,%u,%u];", name, grid.x, grid.y, grid.z);
   const unsigned nthreads = block.x * block.y * block.z;
   blockDim = block;
   gridDim = grid;
