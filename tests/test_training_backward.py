@@ -457,3 +457,27 @@ def test_ipdnet_training_module_step_matches_the_oracle_composition():
         assert _rel(p_.grad, sd[n].grad) <= 2e-4, n
     mod.configure_optimizers()['optimizer'].step()
     assert float(mod.validation_step((sig, scene))) != float(loss.detach())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("first,nc", [(True, 6), (False, 70)])
+def test_ipdnet_fnblock_train_module_api_matches_oracle_autograd(first, nc):
+    """IPDnet's FNblock through its module API in train mode (FixedAarryIPDnet.py:29-40): output and the gradient w.r.t. the
+    block input against the oracle's autograd."""
+    from fn_ssl_b200.FixedAarryIPDnet import FNblock
+    torch.manual_seed(1)
+    blk = _no_dropout(FNblock(input_size=6 if first else 64, hidden_size=64, add_skip_dim=6, is_online=True, is_first=first))
+    nb, nt, nf = 2, 5, 7
+    x, raw, wy = _randn((nb, nt, nf, nc), 80), _randn((nb, nt, nf, 6), 81), _randn((nb, nt, nf, 70), 82)
+    fb, nbs = raw.reshape(nb * nt, nf, 6), raw.permute(0, 2, 1, 3).reshape(nb * nf, nt, 6)
+    sd = {("b." + k): v.clone().requires_grad_(True) for k, v in blk.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    (orc.ipdnet_block(xr, sd, "b.", fb, nbs, fast=True) * wy).sum().backward()
+    blk = blk.cuda().train()
+    xd = x.cuda().requires_grad_(True)
+    y = blk(xd, fb.cuda(), nbs.cuda())
+    (y * wy.cuda()).sum().backward()
+    assert _rel(y, orc.ipdnet_block(x, {k: v.detach() for k, v in sd.items()}, "b.", fb, nbs, fast=True)) <= 2e-5
+    assert _rel(xd.grad, xr.grad) <= TOL
+    for n, p_ in blk.named_parameters():
+        assert _rel(p_.grad, sd["b." + n].grad) <= TOL, n
