@@ -180,8 +180,7 @@ class FN_SSL(nn.Module):
         x, fb = self.block_3._run_train(x, fb)
         out = T.ipd_head_train(x, self.emb2ipd.weight, self.emb2ipd.bias)
         if self.is_doa:
-            # the DOA classifier (512 -> 180 per output frame, 1e-5 of a step) is torch's Linear in train mode
-            out = torch.nn.functional.linear(out, self.ipd2doa.weight, self.ipd2doa.bias)
+            out = T.linear_train(out, self.ipd2doa.weight, self.ipd2doa.bias)
         return out
 
     def forward(self, x: Tensor) -> Tensor:

@@ -19,6 +19,6 @@ from .Module import (DPIPD, STFT, AddChToBatch, RemoveChFromBatch, SourceDetectL
 from .pipeline import FNSSLPipeline, IPDnetPipeline, data_preprocess_fnssl, data_preprocess_ipdnet  # noqa: F401
 from .streaming import FNSSLStream, IPDnetStream  # noqa: F401
 from .training import (FNSSLTrainModule, IPDnetTrainModule, causcnn_train, conv3x3_causal, dpipd_targets, ipd_head_train, ipd_mse_loss,  # noqa: F401
-                       ipd_pit_mse_loss, lstm_layer)
+                       ipd_pit_mse_loss, linear_train, lstm_layer)
 
 __version__ = "0.1.0"

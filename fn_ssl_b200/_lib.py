@@ -105,6 +105,7 @@ SIGNATURES = {
     "fnssl_lstm_tc4_trace": (_i, [C.POINTER(C.c_longlong)]),
     "fnssl_ipd_head_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "fnssl_linear_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "fnssl_linear_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "fnssl_doa_decode_idl": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fnssl_reflect_pad": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "fnssl_sn_freq_forward": (_i, [C.POINTER(SnFreqArgs), _vp]),

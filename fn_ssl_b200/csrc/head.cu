@@ -165,6 +165,38 @@ linear_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, con
   }
 }
 
+// Backward of linear_rows_kernel (training side: the DOA classifier Linear(512,180), Model.py:71,88-89).
+//   dx[r][k] = sum_o dy[r][o] w[o][k]         one CTA per row, threads over k (w rows read coalesced)
+//   dw[o][k] = sum_r dy[r][o] x[r][k],  db[o] = sum_r dy[r][o]      one CTA per output o, threads over k: no atomics
+__global__ void __launch_bounds__(256)
+linear_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ w, int in_f, int out_f, float* __restrict__ dx) {
+  extern __shared__ float gs[];                       // dy row
+  const int r = blockIdx.x;
+  for (int o = threadIdx.x; o < out_f; o += blockDim.x) gs[o] = dy[(size_t)r * out_f + o];
+  __syncthreads();
+  for (int k = threadIdx.x; k < in_f; k += blockDim.x) {
+    float a = 0.0f;
+    for (int o = 0; o < out_f; ++o) a = fmaf(gs[o], __ldg(w + (size_t)o * in_f + k), a);
+    dx[(size_t)r * in_f + k] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+linear_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ dy, int rows, int in_f, int out_f, float* __restrict__ dw,
+                     float* __restrict__ db) {
+  const int o = blockIdx.x;
+  for (int k = threadIdx.x; k < in_f; k += blockDim.x) {
+    float a = 0.0f;
+    for (int r = 0; r < rows; ++r) a = fmaf(__ldg(dy + (size_t)r * out_f + o), __ldg(x + (size_t)r * in_f + k), a);
+    dw[(size_t)o * in_f + k] = a;
+  }
+  if (threadIdx.x == 0) {
+    float a = 0.0f;
+    for (int r = 0; r < rows; ++r) a += dy[(size_t)r * out_f + o];
+    db[o] = a;
+  }
+}
+
 }  // namespace fnssl
 
 using namespace fnssl;
@@ -214,6 +246,20 @@ int fnssl_linear_forward(const float* x, const float* w, const float* b, int row
   if (rows == 0) return 0;
   linear_rows_kernel<<<rows, 256, in_features * sizeof(float), (cudaStream_t)stream>>>(x, w, b, in_features, out_features, y);
   FNSSL_LAUNCH_CHECK("linear_rows_kernel");
+  return 0;
+}
+
+int fnssl_linear_backward(const float* x, const float* w, const float* dy, int rows, int in_features, int out_features, float* dx,
+                          float* dw, float* db, void* stream) {
+  FNSSL_REQUIRE(x && w && dy && dw && db, "linear_backward: null pointer");
+  FNSSL_REQUIRE(rows >= 0 && in_features > 0 && out_features > 0 && out_features <= 12288, "linear_backward: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dx && rows > 0) {
+    linear_bwd_dx_kernel<<<rows, 256, out_features * sizeof(float), st>>>(dy, w, in_features, out_features, dx);
+    FNSSL_LAUNCH_CHECK("linear_bwd_dx_kernel");
+  }
+  linear_bwd_dw_kernel<<<out_features, 256, 0, st>>>(x, dy, rows, in_features, out_features, dw, db);
+  FNSSL_LAUNCH_CHECK("linear_bwd_dw_kernel");
   return 0;
 }
 

@@ -292,6 +292,37 @@ def ipd_head_train(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
     return _IpdHead.apply(x.contiguous(), weight, bias)
 
 
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        y = ops.linear(x, weight, bias)
+        ctx.save_for_backward(x.detach().float().reshape(-1, x.shape[-1]).contiguous(), weight.detach().float().contiguous())
+        ctx.xshape = tuple(x.shape)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        rows, inf = x2.shape
+        outf = w.shape[0]
+        with torch.cuda.device(x2.device):
+            dy2 = dy.contiguous().float().reshape(rows, outf)
+            dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+            dw, db = torch.empty_like(w), torch.empty(outf, dtype=torch.float32, device=w.device)
+            ops._count(2)
+            _lib.check(_lib.load().fnssl_linear_backward(x2.data_ptr(), w.data_ptr(), dy2.data_ptr(), rows, inf, outf, ops._ptr(dx),
+                                                         dw.data_ptr(), db.data_ptr(), ops._stream()))
+        return (dx.reshape(ctx.xshape) if dx is not None else None), dw, db
+
+
+@ops.on_tensor_device
+def linear_train(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
+    """Differentiable y = x @ weight^T + bias on the CUDA kernels of head.cu (the DOA classifier Linear(512,180), Model.py:71,88-89)."""
+    ops._need_cuda(x, weight, bias)
+    return _Linear.apply(x, weight, bias)
+
+
 # ---------------------------------------------------------------------------------------------
 # IPDnet's causal conv block with its backward pass
 # ---------------------------------------------------------------------------------------------

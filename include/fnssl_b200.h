@@ -214,6 +214,9 @@ int fnssl_ipd_head_backward(const float* x, int ld, int nb, int nt, int nf, int 
  *   x : (rows, in) f32, w : (out, in) f32, b : (out) f32, y : (rows, out) f32 */
 int fnssl_linear_forward(const float* x, const float* w, const float* b, int rows, int in_features,
                          int out_features, float* y, void* stream);
+/* Backward of fnssl_linear_forward (training side, the DOA classifier): dx (rows, in) [may be NULL], dw (out, in), db (out). */
+int fnssl_linear_backward(const float* x, const float* w, const float* dy, int rows, int in_features, int out_features, float* dx,
+                          float* dw, float* db, void* stream);
 
 /* CausCnnBlock.forward (IPDnet/FixedAarryIPDnet.py:61-73): 3x (Conv2d 3x3, pad (1,2), no bias, crop 2)
  * with ReLU+AvgPool(1,3), ReLU+AvgPool(1,4), tanh.

@@ -239,3 +239,17 @@ def test_emulated_ipd_head_forward_backward_and_linear(emu, nt, Cc, ld):
     z = np.zeros((rows.shape[0], 9), np.float32)
     assert emu.fnssl_linear_forward(rows.ctypes.data, _np(lw).ctypes.data, _np(lb).ctypes.data, rows.shape[0], 2 * nf, 9, z.ctypes.data, None) == 0
     assert _rel(z, torch.nn.functional.linear(torch.from_numpy(rows), lw, lb)) <= 1e-5
+
+
+def test_emulated_linear_backward(emu):
+    vp, i = C.c_void_p, C.c_int
+    emu.fnssl_linear_backward.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp]
+    rows, inf, outf = 5, 300, 19
+    x, w, dy = _randn((rows, inf), 90), _randn((outf, inf), 91), _randn((rows, outf), 92)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), torch.zeros(outf, requires_grad=True)
+    (torch.nn.functional.linear(xr, wr, br) * dy).sum().backward()
+    xn, wn, dyn = _np(x), _np(w), _np(dy)
+    dx, dw, db = np.zeros_like(xn), np.zeros_like(wn), np.zeros(outf, np.float32)
+    assert emu.fnssl_linear_backward(xn.ctypes.data, wn.ctypes.data, dyn.ctypes.data, rows, inf, outf, dx.ctypes.data, dw.ctypes.data,
+                                     db.ctypes.data, None) == 0, emu.emu_last_error()
+    assert _rel(dx, xr.grad) <= 1e-5 and _rel(dw, wr.grad) <= 1e-5 and _rel(db, br.grad) <= 1e-5

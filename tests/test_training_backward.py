@@ -481,3 +481,23 @@ def test_ipdnet_fnblock_train_module_api_matches_oracle_autograd(first, nc):
     assert _rel(xd.grad, xr.grad) <= TOL
     for n, p_ in blk.named_parameters():
         assert _rel(p_.grad, sd["b." + n].grad) <= TOL, n
+
+
+@pytest.mark.gpu
+def test_fnssl_doa_head_training_step_matches_oracle_autograd():
+    """`is_doa=True` (BASELINE configs[3]'s head) in train mode: the DOA classifier Linear(512,180) runs the head.cu kernels forward
+    and backward (fnssl_linear_backward); every gradient against the oracle's autograd."""
+    import fn_ssl_b200 as F
+    kw = dict(is_online=True, is_doa=True)
+    net = F.FN_SSL(**kw)
+    net.load_state_dict(orc.seeded_fnssl_state_dict(3, **kw))
+    net = _no_dropout(net.cuda().train())
+    x, tgt = _randn((2, 4, 256, 24), 95), _randn((2, 2, 180), 96)
+    sd = {k: v.clone().requires_grad_(True) for k, v in orc.seeded_fnssl_state_dict(3, **kw).items()}
+    yref = orc.fnssl_forward(x, sd, fast=True)
+    torch.nn.functional.mse_loss(yref, tgt).backward()
+    y = net(x.cuda())
+    torch.nn.functional.mse_loss(y, tgt.cuda()).backward()
+    assert tuple(y.shape) == (2, 2, 180) and _rel(y, yref) <= 2e-5
+    for n, p_ in net.named_parameters():
+        assert _rel(p_.grad, sd[n].grad) <= TOL, n
