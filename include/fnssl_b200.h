@@ -29,7 +29,8 @@ extern "C" {
 #define FNSSL_ABI_VERSION 5 /* 2: carried LSTM state; 3: IPDnet2 entry points (fnssl_reflect_pad, fnssl_sn_*); 4: one tcgen05 LSTM kernel
                              (fnssl_lstm_tc_trace of the retired generations removed), training-side targets / losses,
                              fused fnssl_stft_features_forward; 5: training forward / backward of the LSTM layer and the
-                             DP-IPD head (fnssl_lstm_forward_train, fnssl_lstm_backward, fnssl_ipd_head_backward), of the causal conv (fnssl_conv3x3_*) */
+                             DP-IPD head (fnssl_lstm_forward_train, fnssl_lstm_backward, fnssl_ipd_head_backward), of the causal conv (fnssl_conv3x3_*)
+                             and of the DOA linear (fnssl_linear_backward) */
 
 /* element types of grid tensors */
 #define FNSSL_F32 0
