@@ -253,3 +253,17 @@ def test_emulated_linear_backward(emu):
     assert emu.fnssl_linear_backward(xn.ctypes.data, wn.ctypes.data, dyn.ctypes.data, rows, inf, outf, dx.ctypes.data, dw.ctypes.data,
                                      db.ctypes.data, None) == 0, emu.emu_last_error()
     assert _rel(dx, xr.grad) <= 1e-5 and _rel(dw, wr.grad) <= 1e-5 and _rel(db, br.grad) <= 1e-5
+
+
+# ---- `-m gpu` test bodies against the emulated library (a patched child process; tools/host_emu/run_tests_on_emulator.py) --------
+
+@pytest.mark.parametrize("args", [
+    ["--module", "test_training_backward", "-k", "ipd_head_train", "-k", "pit_loss_gradient", "-k", "rows_per_thread", "-k", "ipdnet_fnblock_train"],
+    ["--module", "test_gpu_ipdnet2", "-k", "single_layer"],      # IPDnet2: SpatialNetLayer (frequency stage + both Mamba blocks) vs the oracle
+])
+def test_gpu_test_bodies_on_the_emulator(args):
+    import subprocess
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "host_emu", "run_tests_on_emulator.py")] + args,
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("test_")]
+    assert res.returncode == 0 and lines and all(": ok" in ln for ln in lines), res.stdout[-3000:] + res.stderr[-2000:]

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "fn_ssl_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-SOURCES = ["lstm_simt.cu", "lstm_train.cu", "conv_train.cu", "train.cu", "head.cu"]
+SOURCES = ["lstm_simt.cu", "lstm_train.cu", "conv_train.cu", "train.cu", "head.cu", "spatialnet.cu"]
 LIB = os.path.join(OUT, "libfnssl_emu.so")
 
 LAUNCH = re.compile(r"^(\s*)([\w:]+(?:<[^<>;]*>)?)<<<(.+?),\s*([^,]+?),\s*([^,]+?),\s*([^,]+?)>>>\((.*?)\);", re.M | re.S)
@@ -25,6 +25,8 @@ def transform(text: str) -> str:
     assert "<<<" not in text, "an unconverted kernel launch is left"
     text = DYN_SHARED.sub(lambda m: f"static __attribute__((aligned(16))) {m.group(1)} {m.group(2)}[57344];", text)
     assert "extern __shared__" not in text
+    text = re.sub(r'asm\("ex2\.approx\.ftz\.f32 %0, %1;" : "=f"\((\w+)\) : "f"\((\w+)\)\);', r"\1 = exp2f(\2);", text)   # the one PTX line
+    assert "asm(" not in text and "asm volatile" not in text, "inline PTX cannot be emulated"
     return text
 
 

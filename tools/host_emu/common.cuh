@@ -55,6 +55,9 @@ template <class F> int cudaFuncSetAttribute(F, int, int) { return 0; }
 inline int cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline float __expf(float x) { return expf(x); }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
 inline float tanhf_emu_unused(float x) { return tanhf(x); }
 inline float atomicAdd(float* p, float v) { std::lock_guard<std::mutex> g(g_emu_atomic); float o = *p; *p = o + v; return o; }
 

@@ -4,7 +4,7 @@ of any test suite: it monkeypatches this process only (Tensor.cuda -> identity, 
 CUDA-only guards off) and then calls the selected test functions with their real bodies, so the Python side (autograd Functions,
 packing, ctypes signatures, module wiring) runs exactly as on the GPU while the kernels run as OS threads.
 
-    python tools/host_emu/run_tests_on_emulator.py [-k substring] ... [--oracle-frontend]
+    python tools/host_emu/run_tests_on_emulator.py [--module test_training_backward | test_gpu_ipdnet2] [-k substring] ... [--oracle-frontend]
 
 Tests that need kernels outside the emulated set (front end, tcgen05 engine) fail with "not emulated"; --oracle-frontend stands the
 oracle's STFT / feature assembly in for the (TMA-staged, not emulatable) front-end kernels so that the training-module tests can
@@ -52,6 +52,22 @@ def install():
     ops._stream = lambda: None
     torch.Tensor.cuda = lambda self, *a, **k: self
     torch.nn.Module.cuda = lambda self, *a, **k: self
+    _tensor_to, _module_to = torch.Tensor.to, torch.nn.Module.to
+
+    def _strip(args, kwargs):           # .to("cuda") / .to(device=...) -> stay where we are
+        args = tuple(a for a in args if not (isinstance(a, (str, torch.device)) and str(a).startswith("cuda")))
+        kwargs = {k: v for k, v in kwargs.items() if not (k == "device" and str(v).startswith("cuda"))}
+        return args, kwargs
+
+    def tensor_to(self, *a, **k):
+        a, k = _strip(a, k)
+        return _tensor_to(self, *a, **k) if (a or k) else self
+
+    def module_to(self, *a, **k):
+        a, k = _strip(a, k)
+        return _module_to(self, *a, **k) if (a or k) else self
+
+    torch.Tensor.to, torch.nn.Module.to = tensor_to, module_to
     torch.cuda.synchronize = lambda *a, **k: None
     torch.cuda.current_device = lambda: None            # == torch.device('cpu').index: on_tensor_device takes the direct path
     torch.cuda.device = lambda *a, **k: contextlib.nullcontext()
@@ -99,12 +115,15 @@ def main():
     install()
     if "--oracle-frontend" in sys.argv:
         install_oracle_frontend()
-    import test_training_backward as T
+    modname = sys.argv[sys.argv.index("--module") + 1] if "--module" in sys.argv else "test_training_backward"
+    T = __import__(modname)
     g = np.load(os.path.join(ROOT, "tests", "golden", "grad_golden.npz"))
     gi = np.load(os.path.join(ROOT, "tests", "golden", "grad_ipdnet_golden.npz"))
+    fixtures = {"golden_ipdnet2": "ipdnet2_golden.npz", "golden_fnssl": "fnssl_golden.npz", "golden_ipdnet": "ipdnet_golden.npz"}
+    module_gpu = any(getattr(m, "name", "") == "gpu" for m in ([getattr(T, "pytestmark", None)] if not isinstance(getattr(T, "pytestmark", None), list) else T.pytestmark) if m is not None)
     failed = 0
     for name, fn in sorted(vars(T).items()):
-        if not name.startswith("test_") or not callable(fn) or not any(m.name == "gpu" for m in getattr(fn, "pytestmark", [])):
+        if not name.startswith("test_") or not callable(fn) or not (module_gpu or any(m.name == "gpu" for m in getattr(fn, "pytestmark", []))):
             continue
         if keys and not any(k in name for k in keys):
             continue
@@ -123,6 +142,8 @@ def main():
                     kwargs[p] = gi
                 elif p == "monkeypatch":
                     kwargs[p] = mp
+                elif p in fixtures:
+                    kwargs[p] = np.load(os.path.join(ROOT, "tests", "golden", fixtures[p]))
             t0 = time.time()
             try:
                 fn(**kwargs)
